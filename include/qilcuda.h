@@ -1,0 +1,95 @@
+/* qilcuda.h -- C ABI of libqilcuda.so, the B200 (sm_100a) implementation of the QILaplace.jl hot path.
+ *
+ * The reference (SUTD-MDQS/QILaplace.jl) has no FFI of its own: every function below replaces the
+ * BODY of one Julia function, whose Index bookkeeping stays in Julia (see INTEGRATION.md for the
+ * `ccall` stubs).  Citations are file:line inside the reference repository.
+ *
+ * Conventions
+ *   - All entry points return an int status (QIL_OK == 0).  On failure `qil_last_error()` returns a
+ *     thread-local message.  Status codes map onto the Julia exception types the reference's tests
+ *     assert (ArgumentError, DomainError, ErrorException, AssertionError).
+ *   - Buffers are plain host pointers unless the name ends in `_dev` (device pointers on the
+ *     context's device).  The caller owns every buffer it passes; the library owns everything
+ *     behind a handle.  Sizes of data-dependent results come from a `*_dims` query first.
+ *   - Tensors are C-order (row-major): MPS core [l][s][r], MPO core [l][p][s][r] with p the
+ *     primed/input leg and s the unprimed/output leg.  For a Julia caller that is exactly
+ *     `Array(T, r, s, l)` / `Array(T, r, s, p, l)` of the ITensor (column-major, reversed order).
+ *   - Scalars are float64 (`is_complex == 0`) or interleaved complex128 (`is_complex == 1`).
+ *   - Signals are read MSB-first: sample j of a length-2^n vector has site-1 bit = top bit of j
+ *     (src/signals/SignalConverters.jl:39-41, docs/src/core_concepts.md:34-41).
+ *   - One host thread per context; every call is synchronous with respect to the host unless it
+ *     ends in `_dev` (those are stream-ordered on the context's stream).
+ */
+#ifndef QILCUDA_H
+#define QILCUDA_H
+
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#define QIL_MAX_SITES 128
+
+/* status codes */
+#define QIL_OK 0
+#define QIL_ERR_ARGUMENT 1    /* Julia ArgumentError  */
+#define QIL_ERR_DOMAIN 2      /* Julia DomainError    */
+#define QIL_ERR_RUNTIME 3     /* Julia ErrorException */
+#define QIL_ERR_ASSERT 4      /* Julia AssertionError */
+#define QIL_ERR_CUDA 5        /* CUDA runtime / driver failure */
+#define QIL_ERR_UNSUPPORTED 6 /* shape outside what this build implements (never a silent fallback) */
+
+typedef struct qil_ctx qil_ctx;
+typedef struct qil_mps qil_mps;
+typedef struct qil_mpo qil_mpo;
+
+/* ---- context ------------------------------------------------------------------------------- */
+const char* qil_last_error(void);
+const char* qil_version(void);
+int qil_create(int device, qil_ctx** out);
+/* Same, but all work is ordered on an existing CUDA stream (e.g. torch's current stream). */
+int qil_create_on_stream(int device, void* cuda_stream, qil_ctx** out);
+int qil_destroy(qil_ctx* ctx);
+int qil_sync(qil_ctx* ctx);
+/* Number of kernels this library has launched on the context since creation. */
+int qil_launch_count(qil_ctx* ctx, uint64_t* out);
+
+/* ---- MPS / MPO containers (replace Vector{ITensor} storage; src/mps.jl:70-130, src/mpo.jl:26-99) -- */
+/* bond has n+1 entries with bond[0] == bond[n] == 1; cores[i] points at bond[i]*2*bond[i+1] scalars */
+int qil_mps_from_host(qil_ctx* ctx, int n, int is_complex, const int64_t* bond,
+                      const void* const* cores, double amplitude, qil_mps** out);
+int qil_mps_info(const qil_mps* m, int* n, int* is_complex, double* amplitude);
+int qil_mps_dims(const qil_mps* m, int64_t* bond /* n+1 */);
+int qil_mps_get_core(const qil_mps* m, int site, void* host_buf);
+int qil_mps_set_amplitude(qil_mps* m, double amplitude);
+int qil_mps_clone(const qil_mps* m, qil_mps** out);
+int qil_mps_free(qil_mps* m);
+
+int qil_mpo_from_host(qil_ctx* ctx, int n, int is_complex, const int64_t* bond,
+                      const void* const* cores, qil_mpo** out);
+int qil_mpo_info(const qil_mpo* m, int* n, int* is_complex);
+int qil_mpo_dims(const qil_mpo* m, int64_t* bond /* n+1 */);
+int qil_mpo_get_core(const qil_mpo* m, int site, void* host_buf);
+int qil_mpo_free(qil_mpo* m);
+
+/* ---- coefficient (src/mps.jl:669-693) --------------------------------------------------------
+ * bits is uint8[B][n] with entries in {0,1}; out receives B scalars of the MPS element type,
+ * already multiplied by the stored amplitude.  A ZTMPS is passed as its 2n-site chain
+ * (main1, copy1, main2, ...; src/mps.jl:421-445). */
+int qil_coefficient_batch(qil_ctx* ctx, const qil_mps* psi, const uint8_t* bits, int64_t B, void* out);
+int qil_coefficient_batch_dev(qil_ctx* ctx, const qil_mps* psi, const uint8_t* d_bits, int64_t B,
+                              void* d_out);
+
+/* ---- apply (src/linalg/apply.jl:75-122, 124-199, 201-236) ----------------------------------
+ * Exact MPO x MPS: out core = [D_l*chi_l][2][D_r*chi_r] with the MPO bond fastest; never truncates;
+ * amplitude is copied.  Paired operands are passed as 2n-site chains. */
+int qil_apply_mpo_mps(qil_ctx* ctx, const qil_mpo* W, const qil_mps* psi, qil_mps** out);
+/* MPO o MPO over the matching window; W1 acts first; start1/start2 = first matching site (0-based). */
+int qil_apply_mpo_mpo(qil_ctx* ctx, const qil_mpo* W1, const qil_mpo* W2, int start1, int start2,
+                      qil_mpo** out);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* QILCUDA_H */

@@ -1,0 +1,10 @@
+"""qilaplace_b200 -- B200-native (sm_100a) hot path of QILaplace.jl behind the reference's API.
+
+The package directory is named ``qilaplace.jl_b200`` (not a legal module name); import it through
+the repository-root shim ``qilaplace_b200``.
+"""
+from ._lib import (ArgumentError, DomainError, ErrorException, CudaError, UnsupportedError,
+                   LIB_PATH, declared_symbols, load as load_library)
+from .api import *  # noqa: F401,F403
+from .api import (Context, default_context, SignalMPS, ZTMPS, SingleSiteMPO, PairedSiteMPO,
+                  coefficient, coefficients, apply, generate_signal)

@@ -1,0 +1,102 @@
+"""ctypes binding of libqilcuda.so (include/qilcuda.h).  No CPU fallback: a missing library or a
+missing GPU raises."""
+from __future__ import annotations
+
+import ctypes as C
+import os
+
+HERE = os.path.dirname(os.path.abspath(__file__))
+LIB_PATH = os.path.join(HERE, "libqilcuda.so")
+
+
+class ArgumentError(ValueError):
+    """Julia ArgumentError (QIL_ERR_ARGUMENT)."""
+
+
+class DomainError(ValueError):
+    """Julia DomainError (QIL_ERR_DOMAIN)."""
+
+
+class ErrorException(RuntimeError):
+    """Julia ErrorException (QIL_ERR_RUNTIME)."""
+
+
+class CudaError(RuntimeError):
+    """CUDA runtime/driver failure (QIL_ERR_CUDA)."""
+
+
+class UnsupportedError(NotImplementedError):
+    """Shape outside what the library implements (QIL_ERR_UNSUPPORTED); never a silent fallback."""
+
+
+_ERRMAP = {1: ArgumentError, 2: DomainError, 3: ErrorException, 4: AssertionError, 5: CudaError,
+           6: UnsupportedError}
+
+_lib = None
+
+c_ctx = C.c_void_p
+c_mps = C.c_void_p
+c_mpo = C.c_void_p
+i64p = C.POINTER(C.c_int64)
+
+# name -> (argtypes, ) ; every function returns int status except the two string getters
+_SIGS = {
+    "qil_create": [C.c_int, C.POINTER(c_ctx)],
+    "qil_create_on_stream": [C.c_int, C.c_void_p, C.POINTER(c_ctx)],
+    "qil_destroy": [c_ctx],
+    "qil_sync": [c_ctx],
+    "qil_launch_count": [c_ctx, C.POINTER(C.c_uint64)],
+    "qil_mps_from_host": [c_ctx, C.c_int, C.c_int, i64p, C.POINTER(C.c_void_p), C.c_double, C.POINTER(c_mps)],
+    "qil_mps_info": [c_mps, C.POINTER(C.c_int), C.POINTER(C.c_int), C.POINTER(C.c_double)],
+    "qil_mps_dims": [c_mps, i64p],
+    "qil_mps_get_core": [c_mps, C.c_int, C.c_void_p],
+    "qil_mps_set_amplitude": [c_mps, C.c_double],
+    "qil_mps_clone": [c_mps, C.POINTER(c_mps)],
+    "qil_mps_free": [c_mps],
+    "qil_mpo_from_host": [c_ctx, C.c_int, C.c_int, i64p, C.POINTER(C.c_void_p), C.POINTER(c_mpo)],
+    "qil_mpo_info": [c_mpo, C.POINTER(C.c_int), C.POINTER(C.c_int)],
+    "qil_mpo_dims": [c_mpo, i64p],
+    "qil_mpo_get_core": [c_mpo, C.c_int, C.c_void_p],
+    "qil_mpo_free": [c_mpo],
+    "qil_coefficient_batch": [c_ctx, c_mps, C.c_void_p, C.c_int64, C.c_void_p],
+    "qil_coefficient_batch_dev": [c_ctx, c_mps, C.c_void_p, C.c_int64, C.c_void_p],
+    "qil_apply_mpo_mps": [c_ctx, c_mpo, c_mps, C.POINTER(c_mps)],
+    "qil_apply_mpo_mpo": [c_ctx, c_mpo, c_mpo, C.c_int, C.c_int, C.POINTER(c_mpo)],
+}
+
+
+def declared_symbols():
+    """Every entry point include/qilcuda.h declares (used by the CPU-side ABI test)."""
+    return sorted(list(_SIGS) + ["qil_last_error", "qil_version"])
+
+
+def load():
+    """Load libqilcuda.so (building is the job of __graft_entry__.build / build.py)."""
+    global _lib
+    if _lib is not None:
+        return _lib
+    if not os.path.exists(LIB_PATH):
+        raise ImportError(
+            f"{LIB_PATH} not found: build it with `python qilaplace.jl_b200/build.py` "
+            "(there is no CPU fallback for the CUDA path)")
+    lib = C.CDLL(LIB_PATH)
+    for name, args in _SIGS.items():
+        fn = getattr(lib, name)
+        fn.argtypes = args
+        fn.restype = C.c_int
+    lib.qil_last_error.restype = C.c_char_p
+    lib.qil_last_error.argtypes = []
+    lib.qil_version.restype = C.c_char_p
+    lib.qil_version.argtypes = []
+    _lib = lib
+    return lib
+
+
+def check(status):
+    if status != 0:
+        msg = load().qil_last_error().decode("utf-8", "replace")
+        raise _ERRMAP.get(status, RuntimeError)(msg)
+
+
+def call(name, *args):
+    check(getattr(load(), name)(*args))

@@ -1,0 +1,376 @@
+"""Host-side mirror of the QILaplace.jl public API over the C ABI of libqilcuda.so.
+
+The reference keeps ITensor `Index` bookkeeping on the host; here the host objects only hold an
+opaque device handle plus dimensions.  Names, argument meaning and error behaviour follow the
+reference (file:line cited per function); Julia's `f!` is spelled `f_` / `f` returning the mutated
+object, `W * psi` is `W * psi` (or `apply(W, psi)`).
+"""
+from __future__ import annotations
+
+import ctypes as C
+import math
+import re
+
+import numpy as np
+
+from . import _lib
+from ._lib import ArgumentError, DomainError, ErrorException, UnsupportedError, CudaError, call
+
+BIG = 2**62
+
+
+# ------------------------------------------------------------------------------------------
+# context
+# ------------------------------------------------------------------------------------------
+class Context:
+    """One CUDA device + stream + memory pool (qil_create)."""
+
+    def __init__(self, device=0, stream=None):
+        self.handle = _lib.c_ctx()
+        if stream is None:
+            call("qil_create", int(device), C.byref(self.handle))
+        else:
+            call("qil_create_on_stream", int(device), C.c_void_p(int(stream)), C.byref(self.handle))
+        self.device = int(device)
+
+    def sync(self):
+        call("qil_sync", self.handle)
+
+    def launch_count(self):
+        v = C.c_uint64(0)
+        call("qil_launch_count", self.handle, C.byref(v))
+        return int(v.value)
+
+    def close(self):
+        if self.handle:
+            _lib.load().qil_destroy(self.handle)
+            self.handle = None
+
+
+_default_ctx = {}
+
+
+def default_context(device=0):
+    if device not in _default_ctx:
+        _default_ctx[device] = Context(device)
+    return _default_ctx[device]
+
+
+def _np_dtype(is_complex):
+    return np.complex128 if is_complex else np.float64
+
+
+def _core_ptrs(cores, is_complex, ndim):
+    dt = _np_dtype(is_complex)
+    keep = [np.ascontiguousarray(c, dtype=dt) for c in cores]
+    for c in keep:
+        if c.ndim != ndim:
+            raise ArgumentError(f"core must have {ndim} legs, got shape {c.shape}")
+    bond = [int(keep[0].shape[0])] + [int(c.shape[-1]) for c in keep]
+    for i, c in enumerate(keep):
+        if c.shape[0] != bond[i] or any(d != 2 for d in c.shape[1:-1]):
+            raise ArgumentError(f"core {i} has inconsistent shape {c.shape}")
+    arr = (C.c_void_p * len(keep))(*[c.ctypes.data for c in keep])
+    b = (C.c_int64 * len(bond))(*bond)
+    return keep, arr, b
+
+
+# ------------------------------------------------------------------------------------------
+# containers (src/mps.jl:37-130, src/mpo.jl:26-99)
+# ------------------------------------------------------------------------------------------
+class _DeviceChain:
+    _free = None
+    _dims = None
+    _get = None
+    _legs = 3
+
+    def __init__(self, ctx, handle):
+        self.ctx = ctx
+        self.handle = handle
+
+    def __del__(self):
+        h = getattr(self, "handle", None)
+        if h:
+            try:
+                getattr(_lib.load(), self._free)(h)
+            except Exception:
+                pass
+            self.handle = None
+
+    def _bond_dims(self):
+        n = self.nsites_flat
+        b = (C.c_int64 * (n + 1))()
+        call(self._dims, self.handle, b)
+        return [int(v) for v in b]
+
+    def cores(self):
+        """Download every core as a numpy array ([l,2,r] or [l,2,2,r])."""
+        b = self._bond_dims()
+        out = []
+        dt = _np_dtype(self.is_complex)
+        for i in range(self.nsites_flat):
+            shape = (b[i],) + (2,) * (self._legs - 2) + (b[i + 1],)
+            a = np.empty(shape, dtype=dt)
+            call(self._get, self.handle, i, C.c_void_p(a.ctypes.data))
+            out.append(a)
+        return out
+
+
+class SignalMPS(_DeviceChain):
+    """SignalMPS (src/mps.jl:70-81): n cores [chi_l, 2, chi_r] on the device + `amplitude`."""
+    _free, _dims, _get, _legs = "qil_mps_free", "qil_mps_dims", "qil_mps_get_core", 3
+
+    @classmethod
+    def from_cores(cls, cores, amplitude=1.0, ctx=None):
+        ctx = ctx or default_context()
+        is_complex = any(np.iscomplexobj(c) for c in cores)
+        keep, arr, b = _core_ptrs(cores, is_complex, 3)
+        h = _lib.c_mps()
+        call("qil_mps_from_host", ctx.handle, len(keep), int(is_complex), b, arr, float(amplitude), C.byref(h))
+        return cls(ctx, h)
+
+    def _info(self):
+        n, c, a = C.c_int(), C.c_int(), C.c_double()
+        call("qil_mps_info", self.handle, C.byref(n), C.byref(c), C.byref(a))
+        return n.value, c.value, a.value
+
+    @property
+    def nsites_flat(self):
+        return self._info()[0]
+
+    def __len__(self):
+        return self.nsites_flat
+
+    @property
+    def is_complex(self):
+        return bool(self._info()[1])
+
+    @property
+    def amplitude(self):
+        return self._info()[2]
+
+    @amplitude.setter
+    def amplitude(self, v):
+        call("qil_mps_set_amplitude", self.handle, float(v))
+
+    @property
+    def bonds(self):
+        """Inner bond dimensions (length n-1), like `dim.(psi.bonds)`."""
+        return self._bond_dims()[1:-1]
+
+    def copy(self):
+        h = _lib.c_mps()
+        call("qil_mps_clone", self.handle, C.byref(h))
+        return type(self)(self.ctx, h)
+
+    def __getitem__(self, config):
+        if not isinstance(config, tuple):
+            config = (config,)
+        return coefficient(self, list(config))
+
+
+class ZTMPS(SignalMPS):
+    """ZTMPS (src/mps.jl:98-121) stored as its 2n-site chain main1, copy1, main2, ... (mps.jl:421-445)."""
+
+    def __len__(self):
+        return self.nsites_flat // 2
+
+    @property
+    def bonds_main(self):
+        return self._bond_dims()[2:-1:2]
+
+    @property
+    def bonds_copy(self):
+        return self._bond_dims()[1:-1:2]
+
+
+class SingleSiteMPO(_DeviceChain):
+    """SingleSiteMPO (src/mpo.jl:26-46): n cores [D_l, 2(in), 2(out), D_r] on the device."""
+    _free, _dims, _get, _legs = "qil_mpo_free", "qil_mpo_dims", "qil_mpo_get_core", 4
+
+    @classmethod
+    def from_cores(cls, cores, ctx=None):
+        ctx = ctx or default_context()
+        is_complex = any(np.iscomplexobj(c) for c in cores)
+        keep, arr, b = _core_ptrs(cores, is_complex, 4)
+        h = _lib.c_mpo()
+        call("qil_mpo_from_host", ctx.handle, len(keep), int(is_complex), b, arr, C.byref(h))
+        return cls(ctx, h)
+
+    def _info(self):
+        n, c = C.c_int(), C.c_int()
+        call("qil_mpo_info", self.handle, C.byref(n), C.byref(c))
+        return n.value, c.value
+
+    @property
+    def nsites_flat(self):
+        return self._info()[0]
+
+    def __len__(self):
+        return self.nsites_flat
+
+    @property
+    def is_complex(self):
+        return bool(self._info()[1])
+
+    @property
+    def bonds(self):
+        return self._bond_dims()[1:-1]
+
+    def __mul__(self, other):
+        return apply(self, other)
+
+
+class PairedSiteMPO(SingleSiteMPO):
+    """PairedSiteMPO (src/mpo.jl:54-75) stored as its 2n-site chain (apply.jl:16-33)."""
+
+    def __len__(self):
+        return self.nsites_flat // 2
+
+    @property
+    def bonds_main(self):
+        return self._bond_dims()[2:-1:2]
+
+    @property
+    def bonds_copy(self):
+        return self._bond_dims()[1:-1:2]
+
+
+# ------------------------------------------------------------------------------------------
+# coefficient (src/mps.jl:609-693)
+# ------------------------------------------------------------------------------------------
+def _parse_config_string(spec):
+    """_parse_config_string (mps.jl:616-631)."""
+    s = spec.strip().strip("[](){}")
+    if not s:
+        raise ArgumentError("coefficient: configuration string is empty")
+    if re.search(r"[,\s]", s):
+        toks = [t for t in re.split(r"[,\s]+", s) if t]
+        if not toks:
+            raise ArgumentError("coefficient: configuration string did not contain any entries")
+        return [int(t) for t in toks]
+    if any(ch not in "01" for ch in s):
+        raise ArgumentError("coefficient: bit strings may contain only '0' or '1'")
+    return [1 if ch == "1" else 0 for ch in s]
+
+
+def _bits_from_integer(value, n):
+    """_bits_from_integer (mps.jl:633-645): n-bit big-endian pattern."""
+    if value < 0:
+        raise ArgumentError("coefficient: integer configuration must be non-negative")
+    if value >> n:
+        raise ArgumentError(f"coefficient: integer {value} requires more than {n} bits")
+    return [(value >> (n - 1 - i)) & 1 for i in range(n)]
+
+
+def coefficients(psi, bits):
+    """Batched `coefficient`: bits is a (B, n) array of 0/1 (2n interleaved columns for a ZTMPS)."""
+    b = np.ascontiguousarray(bits)
+    if b.ndim != 2:
+        raise ArgumentError("coefficients: expected a (B, n) array of bits")
+    N = psi.nsites_flat
+    if b.shape[1] != N:
+        raise ArgumentError(f"coefficient: expected {N} entries, got {b.shape[1]}")
+    if b.size and (b.min() < 0 or b.max() > 1):
+        bad = int(b.max() if b.max() > 1 else b.min())
+        raise ArgumentError(f"coefficient: bit value {bad} outside [0,1]")
+    b8 = np.ascontiguousarray(b, dtype=np.uint8)
+    out = np.empty(b8.shape[0], dtype=_np_dtype(psi.is_complex))
+    call("qil_coefficient_batch", psi.ctx.handle, psi.handle, C.c_void_p(b8.ctypes.data),
+         C.c_int64(b8.shape[0]), C.c_void_p(out.ctypes.data))
+    return out
+
+
+def coefficient(psi, *config):
+    """coefficient(psi, config) (mps.jl:669-693): vector / tuple / varargs / string / integer."""
+    N = psi.nsites_flat
+    if len(config) == 1:
+        c = config[0]
+        if isinstance(c, str):
+            bits = _parse_config_string(c)
+        elif isinstance(c, (int, np.integer)):
+            bits = _bits_from_integer(int(c), N)
+        else:
+            bits = [int(v) for v in c]
+    else:
+        bits = [int(v) for v in config]
+    if len(bits) != N:
+        raise ArgumentError(f"coefficient: expected {N} entries, got {len(bits)}")
+    for v in bits:
+        if not 0 <= v <= 1:
+            raise ArgumentError(f"coefficient: bit value {v} outside [0,1]")
+    v = coefficients(psi, np.asarray([bits], dtype=np.uint8))[0]
+    return complex(v) if psi.is_complex else float(v)
+
+
+# ------------------------------------------------------------------------------------------
+# apply (src/linalg/apply.jl)
+# ------------------------------------------------------------------------------------------
+def apply(W, other, **kwargs):
+    """apply(W, psi) / apply(W1, W2) (apply.jl:75-236).  kwargs are accepted and ignored, as in the
+    reference (`apply` never truncates)."""
+    if isinstance(other, SignalMPS):
+        paired = isinstance(W, PairedSiteMPO)
+        if paired != isinstance(other, ZTMPS):
+            raise ArgumentError("apply: PairedSiteMPO needs a ZTMPS and SingleSiteMPO a SignalMPS")
+        if paired and W.nsites_flat != 2 * len(other):
+            raise ArgumentError("apply: MPO and MPS must have compatible sizes.")
+        h = _lib.c_mps()
+        call("qil_apply_mpo_mps", W.ctx.handle, W.handle, other.handle, C.byref(h))
+        return type(other)(W.ctx, h)
+    if isinstance(other, SingleSiteMPO):
+        h = _lib.c_mpo()
+        s1 = int(kwargs.get("start1", 0))
+        s2 = int(kwargs.get("start2", 0))
+        call("qil_apply_mpo_mpo", W.ctx.handle, W.handle, other.handle, s1, s2, C.byref(h))
+        cls = PairedSiteMPO if isinstance(W, PairedSiteMPO) and isinstance(other, PairedSiteMPO) else SingleSiteMPO
+        return cls(W.ctx, h)
+    raise ArgumentError("apply: unsupported operand types")
+
+
+# ------------------------------------------------------------------------------------------
+# signals (src/signals/Signals.jl:188-235) -- trivial elementwise host code, out of kernel scope
+# ------------------------------------------------------------------------------------------
+def generate_signal(n, kind="sin", dt=None, freq=None, **kw):
+    """generate_signal(n; kind, dt, freq, kwargs...) for the deterministic kinds of the reference
+    (:sin, :sin_decay, :abs_cos_power_p8) plus :random via numpy's generator (the reference's
+    Xoshiro stream is Julia-specific)."""
+    kind = str(kind).lstrip(":")
+    N = 2**n
+    if kind == "random":
+        return np.random.default_rng(kw.get("seed", 1234)).standard_normal(N)
+    f = 2 * math.pi if freq is None else freq
+    is_vec = isinstance(f, (list, tuple, np.ndarray))
+    if dt is None:
+        fmax = max(abs(float(v)) for v in f) if is_vec else abs(float(f))
+        dt = 1.0 if fmax == 0 else 1.0 / (fmax * N)
+    j = np.arange(N, dtype=np.float64)
+    if kind == "sin":
+        if is_vec:
+            ph = kw.get("phase", [0.0] * len(f))
+            if len(ph) != len(f):
+                raise ArgumentError("Frequency and phase vectors must be of the same length.")
+            x = sum(np.sin(w * dt * j + p) for w, p in zip(f, ph))
+        else:
+            x = np.sin(f * dt * j + kw.get("phase", 0.0))
+        nl = kw.get("noise_level", 0.0)
+        if nl:
+            x = x + nl * np.random.default_rng(kw.get("seed")).standard_normal(N)
+        return x
+    if kind == "sin_decay":
+        dr = kw["decay_rate"]
+        if is_vec:
+            if len(dr) != len(f):
+                raise ArgumentError("Frequency and decay_rate vectors must be of the same length.")
+            ph = kw.get("phase")
+            if ph is None:
+                ph = [0.0] * len(f)
+            elif len(ph) != len(f):
+                raise ArgumentError("Frequency and phase vectors must be of the same length.")
+            return sum(np.sin(w * dt * j + p) * np.exp(-l * dt * j) for w, l, p in zip(f, dr, ph))
+        return np.sin(f * dt * j + kw.get("phase", 0.0)) * np.exp(-dr * dt * j)
+    if kind == "abs_cos_power_p8":
+        return np.abs(np.cos(2 * math.pi * dt * j)) ** kw.get("power", 0.8)
+    raise ArgumentError(
+        f"Unsupported signal kind: {kind}. Supported kinds are :sin, :multi_sin, :sin_decay, "
+        ":multi_sin_exp, :abs_cos_power_p8, :random.")

@@ -1,0 +1,180 @@
+// qil_apply.cu -- K6 / K7: exact MPO x MPS and MPO o MPO (reference: src/linalg/apply.jl:75-199).
+//
+// out[(l,a), s, (r,b)] = sum_p W[a,p,s,b] * psi[l,p,r]      (MPO bond fastest in the fused bonds,
+// `combiner(W.bonds[i], psi.bonds[i])`, apply.jl:105-119).  Contraction depth is 2, so this is a
+// write-bound Kronecker-style expansion: all sites go in ONE launch, one thread per pair of output
+// elements (s = 0,1), consecutive threads along the fused right bond for coalesced stores.
+#include "qil_common.cuh"
+
+namespace qil {
+
+struct ApplyDesc {
+    int n;
+    int wb[kMaxSites + 1];   // MPO bonds
+    int pb[kMaxSites + 1];   // MPS (or second MPO) bonds
+    const void* w[kMaxSites];
+    const void* p[kMaxSites];
+    void* o[kMaxSites];
+};
+
+template <typename TW, typename TP, typename TO>
+__global__ void __launch_bounds__(256) apply_mpo_mps_kernel(const ApplyDesc d) {
+    const int i = blockIdx.y;
+    const int Da = d.wb[i], Db = d.wb[i + 1], cl = d.pb[i], cr = d.pb[i + 1];
+    const TW* __restrict__ W = reinterpret_cast<const TW*>(d.w[i]);
+    const TP* __restrict__ P = reinterpret_cast<const TP*>(d.p[i]);
+    TO* __restrict__ O = reinterpret_cast<TO*>(d.o[i]);
+    const long long R = (long long)cr * Db;       // fused right bond
+    const long long L = (long long)cl * Da;       // fused left bond
+    const long long total = L * R;
+    for (long long idx = (long long)blockIdx.x * blockDim.x + threadIdx.x; idx < total;
+         idx += (long long)gridDim.x * blockDim.x) {
+        const long long LA = idx / R, RB = idx - LA * R;
+        const int l = (int)(LA / Da), a = (int)(LA - (long long)l * Da);
+        const int r = (int)(RB / Db), b = (int)(RB - (long long)r * Db);
+        const TO p0 = promote<TO, TP>(P[((size_t)l * 2 + 0) * cr + r]);
+        const TO p1 = promote<TO, TP>(P[((size_t)l * 2 + 1) * cr + r]);
+        // W[a][p][s][b]
+        const size_t wbase = (size_t)a * 4 * Db + b;
+        const TO w00 = promote<TO, TW>(W[wbase + 0 * Db]);  // p=0,s=0
+        const TO w01 = promote<TO, TW>(W[wbase + 1 * Db]);  // p=0,s=1
+        const TO w10 = promote<TO, TW>(W[wbase + 2 * Db]);  // p=1,s=0
+        const TO w11 = promote<TO, TW>(W[wbase + 3 * Db]);  // p=1,s=1
+        TO o0 = Scalar<TO>::mul(w00, p0);
+        o0 = Scalar<TO>::fma(w10, p1, o0);
+        TO o1 = Scalar<TO>::mul(w01, p0);
+        o1 = Scalar<TO>::fma(w11, p1, o1);
+        O[((size_t)LA * 2 + 0) * R + RB] = o0;
+        O[((size_t)LA * 2 + 1) * R + RB] = o1;
+    }
+}
+
+// out[(c,a), p, s, (d,b)] = sum_m W1[a,p,m,b] * W2[c,m,s,d]   (W1 acts first; W1 bond fastest)
+template <typename T1, typename T2, typename TO>
+__global__ void __launch_bounds__(256) apply_mpo_mpo_kernel(const ApplyDesc d) {
+    const int i = blockIdx.y;
+    const int Da = d.wb[i], Db = d.wb[i + 1], Dc = d.pb[i], Dd = d.pb[i + 1];
+    const T1* __restrict__ W1 = reinterpret_cast<const T1*>(d.w[i]);
+    const T2* __restrict__ W2 = reinterpret_cast<const T2*>(d.p[i]);
+    TO* __restrict__ O = reinterpret_cast<TO*>(d.o[i]);
+    const long long R = (long long)Dd * Db;
+    const long long L = (long long)Dc * Da;
+    const long long total = L * R;
+    for (long long idx = (long long)blockIdx.x * blockDim.x + threadIdx.x; idx < total;
+         idx += (long long)gridDim.x * blockDim.x) {
+        const long long CA = idx / R, DB = idx - CA * R;
+        const int c = (int)(CA / Da), a = (int)(CA - (long long)c * Da);
+        const int dd = (int)(DB / Db), b = (int)(DB - (long long)dd * Db);
+        TO w1[2][2], w2[2][2];
+#pragma unroll
+        for (int x = 0; x < 2; ++x)
+#pragma unroll
+            for (int y = 0; y < 2; ++y) {
+                w1[x][y] = promote<TO, T1>(W1[((size_t)a * 4 + x * 2 + y) * Db + b]);
+                w2[x][y] = promote<TO, T2>(W2[((size_t)c * 4 + x * 2 + y) * Dd + dd]);
+            }
+#pragma unroll
+        for (int p = 0; p < 2; ++p)
+#pragma unroll
+            for (int s = 0; s < 2; ++s) {
+                TO v = Scalar<TO>::mul(w1[p][0], w2[0][s]);
+                v = Scalar<TO>::fma(w1[p][1], w2[1][s], v);
+                O[((size_t)CA * 4 + p * 2 + s) * R + DB] = v;
+            }
+    }
+}
+
+template <typename K>
+static void launch_sites(qil_ctx* ctx, K kern, const ApplyDesc& d, long long max_total) {
+    int bx = (int)std::min<long long>((max_total + 255) / 256, (long long)ctx->sm_count * 8);
+    if (bx < 1) bx = 1;
+    dim3 grid(bx, d.n);
+    kern<<<grid, 256, 0, ctx->stream>>>(d);
+    QIL_LAUNCH_CHECK(ctx);
+}
+
+qil_mps* apply_mpo_mps(qil_ctx* ctx, const qil_mpo* W, const qil_mps* psi) {
+    QIL_REQUIRE(W->n == psi->n, QIL_ERR_ARGUMENT,
+                "apply: MPO and MPS must have the same number of sites. Found length(W)=%d, length(psi)=%d",
+                W->n, psi->n);
+    const int n = psi->n;
+    std::vector<int64_t> ob(n + 1);
+    for (int i = 0; i <= n; ++i) ob[i] = W->bond[i] * psi->bond[i];
+    const int oc = (W->is_complex || psi->is_complex) ? 1 : 0;
+    qil_mps* out = new_mps(ctx, n, oc, ob.data(), true);
+    out->amplitude = psi->amplitude;
+    ApplyDesc d;
+    d.n = n;
+    long long mx = 1;
+    for (int i = 0; i <= n; ++i) {
+        d.wb[i] = (int)W->bond[i];
+        d.pb[i] = (int)psi->bond[i];
+    }
+    for (int i = 0; i < n; ++i) {
+        d.w[i] = W->core[i];
+        d.p[i] = psi->core[i];
+        d.o[i] = out->core[i];
+        mx = std::max<long long>(mx, ob[i] * ob[i + 1]);
+    }
+    if (W->is_complex && psi->is_complex)
+        launch_sites(ctx, apply_mpo_mps_kernel<cplx, cplx, cplx>, d, mx);
+    else if (W->is_complex)
+        launch_sites(ctx, apply_mpo_mps_kernel<cplx, double, cplx>, d, mx);
+    else if (psi->is_complex)
+        launch_sites(ctx, apply_mpo_mps_kernel<double, cplx, cplx>, d, mx);
+    else
+        launch_sites(ctx, apply_mpo_mps_kernel<double, double, double>, d, mx);
+    return out;
+}
+
+qil_mpo* apply_mpo_mpo(qil_ctx* ctx, const qil_mpo* W1, const qil_mpo* W2, int start1, int start2) {
+    QIL_REQUIRE(start1 >= 0 && start1 < W1->n && start2 >= 0 && start2 < W2->n, QIL_ERR_ARGUMENT,
+                "apply: No matching sites found");
+    const int n1 = W1->n, n2 = W2->n;
+    const int match = std::min(n1 - start1, n2 - start2);
+    const bool base1 = n1 >= n2;
+    const qil_mpo* base = base1 ? W1 : W2;
+    const int bstart = base1 ? start1 : start2;
+    const int oc = (W1->is_complex || W2->is_complex) ? 1 : 0;
+    // the operand that is not the base must lie inside the window with closed boundary bonds
+    const qil_mpo* other = base1 ? W2 : W1;
+    const int ostart = base1 ? start2 : start1;
+    QIL_REQUIRE(ostart == 0 && match == other->n, QIL_ERR_UNSUPPORTED,
+                "apply(MPO,MPO): the shorter operator must lie entirely inside the longer one");
+    std::vector<int64_t> ob(base->bond);
+    for (int i = 0; i <= match; ++i) ob[bstart + i] = W1->bond[start1 + i] * W2->bond[start2 + i];
+    qil_mpo* out = new_mpo(ctx, base->n, oc, ob.data(), true);
+    // copy the cores outside the window (promoting to complex when needed)
+    ApplyDesc d;
+    d.n = match;
+    long long mx = 1;
+    for (int i = 0; i <= match; ++i) {
+        d.wb[i] = (int)W1->bond[start1 + i];
+        d.pb[i] = (int)W2->bond[start2 + i];
+    }
+    for (int i = 0; i < match; ++i) {
+        d.w[i] = W1->core[start1 + i];
+        d.p[i] = W2->core[start2 + i];
+        d.o[i] = out->core[bstart + i];
+        mx = std::max<long long>(mx, ob[bstart + i] * ob[bstart + i + 1]);
+    }
+    if (W1->is_complex && W2->is_complex)
+        launch_sites(ctx, apply_mpo_mpo_kernel<cplx, cplx, cplx>, d, mx);
+    else if (W1->is_complex)
+        launch_sites(ctx, apply_mpo_mpo_kernel<cplx, double, cplx>, d, mx);
+    else if (W2->is_complex)
+        launch_sites(ctx, apply_mpo_mpo_kernel<double, cplx, cplx>, d, mx);
+    else
+        launch_sites(ctx, apply_mpo_mpo_kernel<double, double, double>, d, mx);
+    // sites of the base outside the window are kept as they are
+    for (int i = 0; i < base->n; ++i) {
+        if (i >= bstart && i < bstart + match) continue;
+        QIL_REQUIRE(base->is_complex == oc, QIL_ERR_UNSUPPORTED,
+                    "apply(MPO,MPO): mixed real/complex operands with a partial window");
+        QIL_CUDA(cudaMemcpyAsync(out->core[i], base->core[i], base->core_elems(i) * elem_size(oc),
+                                 cudaMemcpyDeviceToDevice, ctx->stream));
+    }
+    return out;
+}
+
+}  // namespace qil

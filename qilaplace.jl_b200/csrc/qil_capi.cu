@@ -1,0 +1,274 @@
+// qil_capi.cu -- extern "C" boundary of libqilcuda.so (see include/qilcuda.h).
+#include "qil_common.cuh"
+
+#include <cstring>
+
+static thread_local std::string g_last_error;
+
+#define QIL_API_BEGIN try {
+#define QIL_API_END                                         \
+    }                                                       \
+    catch (const qil::Error& e) {                           \
+        g_last_error = e.msg;                               \
+        return e.code;                                      \
+    }                                                       \
+    catch (const std::bad_alloc&) {                         \
+        g_last_error = "host allocation failed";            \
+        return QIL_ERR_RUNTIME;                             \
+    }                                                       \
+    catch (const std::exception& e) {                       \
+        g_last_error = e.what();                            \
+        return QIL_ERR_RUNTIME;                             \
+    }                                                       \
+    return QIL_OK;
+
+#define QIL_NONNULL(p) QIL_REQUIRE((p) != nullptr, QIL_ERR_ARGUMENT, "null pointer: %s", #p)
+
+using namespace qil;
+
+extern "C" {
+
+const char* qil_last_error(void) { return g_last_error.c_str(); }
+const char* qil_version(void) { return "qilcuda 0.1 (sm_100a)"; }
+
+static int create_impl(int device, void* stream, bool have_stream, qil_ctx** out) {
+    QIL_API_BEGIN
+    QIL_NONNULL(out);
+    int count = 0;
+    cudaError_t e = cudaGetDeviceCount(&count);
+    if (e != cudaSuccess || count == 0)
+        QIL_THROW(QIL_ERR_CUDA, "no CUDA device available (%s): libqilcuda has no CPU fallback",
+                  cudaGetErrorString(e));
+    QIL_REQUIRE(device >= 0 && device < count, QIL_ERR_ARGUMENT, "device %d out of range [0,%d)", device, count);
+    QIL_CUDA(cudaSetDevice(device));
+    cudaDeviceProp prop;
+    QIL_CUDA(cudaGetDeviceProperties(&prop, device));
+    QIL_REQUIRE(prop.major >= 10, QIL_ERR_UNSUPPORTED,
+                "device %d is sm_%d%d; libqilcuda is built for sm_100a only", device, prop.major, prop.minor);
+    qil_ctx* ctx = new qil_ctx();
+    ctx->device = device;
+    ctx->sm_count = prop.multiProcessorCount;
+    ctx->smem_optin = prop.sharedMemPerBlockOptin;
+    if (have_stream) {
+        ctx->stream = (cudaStream_t)stream;
+        ctx->own_stream = false;
+    } else {
+        QIL_CUDA(cudaStreamCreateWithFlags(&ctx->stream, cudaStreamNonBlocking));
+        ctx->own_stream = true;
+    }
+    // keep freed blocks in the pool instead of returning them to the driver at every sync
+    cudaMemPool_t pool;
+    if (cudaDeviceGetDefaultMemPool(&pool, device) == cudaSuccess) {
+        uint64_t thr = UINT64_MAX;
+        cudaMemPoolSetAttribute(pool, cudaMemPoolAttrReleaseThreshold, &thr);
+    }
+    *out = ctx;
+    QIL_API_END
+}
+
+int qil_create(int device, qil_ctx** out) { return create_impl(device, nullptr, false, out); }
+int qil_create_on_stream(int device, void* cuda_stream, qil_ctx** out) {
+    return create_impl(device, cuda_stream, true, out);
+}
+
+int qil_destroy(qil_ctx* ctx) {
+    QIL_API_BEGIN
+    if (!ctx) return QIL_OK;
+    cudaSetDevice(ctx->device);
+    cudaStreamSynchronize(ctx->stream);
+    if (ctx->scratch) cudaFreeAsync(ctx->scratch, ctx->stream);
+    cudaStreamSynchronize(ctx->stream);
+    if (ctx->own_stream) cudaStreamDestroy(ctx->stream);
+    delete ctx;
+    QIL_API_END
+}
+
+int qil_sync(qil_ctx* ctx) {
+    QIL_API_BEGIN
+    QIL_NONNULL(ctx);
+    ctx->sync();
+    QIL_API_END
+}
+
+int qil_launch_count(qil_ctx* ctx, uint64_t* out) {
+    QIL_API_BEGIN
+    QIL_NONNULL(ctx);
+    QIL_NONNULL(out);
+    *out = ctx->launches;
+    QIL_API_END
+}
+
+// ---- containers ----------------------------------------------------------------------------
+int qil_mps_from_host(qil_ctx* ctx, int n, int is_complex, const int64_t* bond, const void* const* cores,
+                      double amplitude, qil_mps** out) {
+    QIL_API_BEGIN
+    QIL_NONNULL(ctx); QIL_NONNULL(bond); QIL_NONNULL(cores); QIL_NONNULL(out);
+    QIL_CUDA(cudaSetDevice(ctx->device));
+    qil_mps* m = new_mps(ctx, n, is_complex, bond, true);
+    m->amplitude = amplitude;
+    for (int i = 0; i < n; ++i)
+        QIL_CUDA(cudaMemcpyAsync(m->core[i], cores[i], m->core_elems(i) * elem_size(is_complex),
+                                 cudaMemcpyHostToDevice, ctx->stream));
+    ctx->sync();
+    *out = m;
+    QIL_API_END
+}
+
+int qil_mps_info(const qil_mps* m, int* n, int* is_complex, double* amplitude) {
+    QIL_API_BEGIN
+    QIL_NONNULL(m);
+    if (n) *n = m->n;
+    if (is_complex) *is_complex = m->is_complex;
+    if (amplitude) *amplitude = m->amplitude;
+    QIL_API_END
+}
+
+int qil_mps_dims(const qil_mps* m, int64_t* bond) {
+    QIL_API_BEGIN
+    QIL_NONNULL(m); QIL_NONNULL(bond);
+    for (int i = 0; i <= m->n; ++i) bond[i] = m->bond[i];
+    QIL_API_END
+}
+
+int qil_mps_get_core(const qil_mps* m, int site, void* host_buf) {
+    QIL_API_BEGIN
+    QIL_NONNULL(m); QIL_NONNULL(host_buf);
+    QIL_REQUIRE(site >= 0 && site < m->n, QIL_ERR_ARGUMENT, "site %d out of range [0,%d)", site, m->n);
+    QIL_CUDA(cudaSetDevice(m->ctx->device));
+    QIL_CUDA(cudaMemcpyAsync(host_buf, m->core[site], m->core_elems(site) * elem_size(m->is_complex),
+                             cudaMemcpyDeviceToHost, m->ctx->stream));
+    m->ctx->sync();
+    QIL_API_END
+}
+
+int qil_mps_set_amplitude(qil_mps* m, double amplitude) {
+    QIL_API_BEGIN
+    QIL_NONNULL(m);
+    m->amplitude = amplitude;
+    QIL_API_END
+}
+
+int qil_mps_clone(const qil_mps* m, qil_mps** out) {
+    QIL_API_BEGIN
+    QIL_NONNULL(m); QIL_NONNULL(out);
+    QIL_CUDA(cudaSetDevice(m->ctx->device));
+    qil_mps* c = new_mps(m->ctx, m->n, m->is_complex, m->bond.data(), true);
+    c->amplitude = m->amplitude;
+    for (int i = 0; i < m->n; ++i)
+        QIL_CUDA(cudaMemcpyAsync(c->core[i], m->core[i], m->core_elems(i) * elem_size(m->is_complex),
+                                 cudaMemcpyDeviceToDevice, m->ctx->stream));
+    *out = c;
+    QIL_API_END
+}
+
+int qil_mps_free(qil_mps* m) {
+    QIL_API_BEGIN
+    if (m) {
+        cudaSetDevice(m->ctx->device);
+        destroy(m);
+    }
+    QIL_API_END
+}
+
+int qil_mpo_from_host(qil_ctx* ctx, int n, int is_complex, const int64_t* bond, const void* const* cores,
+                      qil_mpo** out) {
+    QIL_API_BEGIN
+    QIL_NONNULL(ctx); QIL_NONNULL(bond); QIL_NONNULL(cores); QIL_NONNULL(out);
+    QIL_CUDA(cudaSetDevice(ctx->device));
+    qil_mpo* m = new_mpo(ctx, n, is_complex, bond, true);
+    for (int i = 0; i < n; ++i)
+        QIL_CUDA(cudaMemcpyAsync(m->core[i], cores[i], m->core_elems(i) * elem_size(is_complex),
+                                 cudaMemcpyHostToDevice, ctx->stream));
+    ctx->sync();
+    *out = m;
+    QIL_API_END
+}
+
+int qil_mpo_info(const qil_mpo* m, int* n, int* is_complex) {
+    QIL_API_BEGIN
+    QIL_NONNULL(m);
+    if (n) *n = m->n;
+    if (is_complex) *is_complex = m->is_complex;
+    QIL_API_END
+}
+
+int qil_mpo_dims(const qil_mpo* m, int64_t* bond) {
+    QIL_API_BEGIN
+    QIL_NONNULL(m); QIL_NONNULL(bond);
+    for (int i = 0; i <= m->n; ++i) bond[i] = m->bond[i];
+    QIL_API_END
+}
+
+int qil_mpo_get_core(const qil_mpo* m, int site, void* host_buf) {
+    QIL_API_BEGIN
+    QIL_NONNULL(m); QIL_NONNULL(host_buf);
+    QIL_REQUIRE(site >= 0 && site < m->n, QIL_ERR_ARGUMENT, "site %d out of range [0,%d)", site, m->n);
+    QIL_CUDA(cudaSetDevice(m->ctx->device));
+    QIL_CUDA(cudaMemcpyAsync(host_buf, m->core[site], m->core_elems(site) * elem_size(m->is_complex),
+                             cudaMemcpyDeviceToHost, m->ctx->stream));
+    m->ctx->sync();
+    QIL_API_END
+}
+
+int qil_mpo_free(qil_mpo* m) {
+    QIL_API_BEGIN
+    if (m) {
+        cudaSetDevice(m->ctx->device);
+        destroy(m);
+    }
+    QIL_API_END
+}
+
+// ---- coefficient ---------------------------------------------------------------------------
+int qil_coefficient_batch_dev(qil_ctx* ctx, const qil_mps* psi, const uint8_t* d_bits, int64_t B, void* d_out) {
+    QIL_API_BEGIN
+    QIL_NONNULL(ctx); QIL_NONNULL(psi);
+    QIL_REQUIRE(B >= 0, QIL_ERR_ARGUMENT, "coefficient: negative batch size");
+    if (B == 0) return QIL_OK;
+    QIL_NONNULL(d_bits); QIL_NONNULL(d_out);
+    QIL_CUDA(cudaSetDevice(ctx->device));
+    coefficient_batch_dev(ctx, psi, d_bits, B, d_out);
+    QIL_API_END
+}
+
+int qil_coefficient_batch(qil_ctx* ctx, const qil_mps* psi, const uint8_t* bits, int64_t B, void* out) {
+    QIL_API_BEGIN
+    QIL_NONNULL(ctx); QIL_NONNULL(psi);
+    QIL_REQUIRE(B >= 0, QIL_ERR_ARGUMENT, "coefficient: negative batch size");
+    if (B == 0) return QIL_OK;
+    QIL_NONNULL(bits); QIL_NONNULL(out);
+    QIL_CUDA(cudaSetDevice(ctx->device));
+    const size_t nb = (size_t)B * psi->n;
+    for (size_t i = 0; i < nb; ++i)
+        QIL_REQUIRE(bits[i] <= 1, QIL_ERR_ARGUMENT, "coefficient: bit value %d outside [0,1]", (int)bits[i]);
+    const size_t ob = (size_t)B * elem_size(psi->is_complex);
+    uint8_t* d_bits = (uint8_t*)ctx->alloc(nb);
+    void* d_out = ctx->alloc(ob);
+    QIL_CUDA(cudaMemcpyAsync(d_bits, bits, nb, cudaMemcpyHostToDevice, ctx->stream));
+    coefficient_batch_dev(ctx, psi, d_bits, B, d_out);
+    QIL_CUDA(cudaMemcpyAsync(out, d_out, ob, cudaMemcpyDeviceToHost, ctx->stream));
+    ctx->sync();
+    ctx->free(d_bits);
+    ctx->free(d_out);
+    QIL_API_END
+}
+
+// ---- apply ---------------------------------------------------------------------------------
+int qil_apply_mpo_mps(qil_ctx* ctx, const qil_mpo* W, const qil_mps* psi, qil_mps** out) {
+    QIL_API_BEGIN
+    QIL_NONNULL(ctx); QIL_NONNULL(W); QIL_NONNULL(psi); QIL_NONNULL(out);
+    QIL_CUDA(cudaSetDevice(ctx->device));
+    *out = apply_mpo_mps(ctx, W, psi);
+    QIL_API_END
+}
+
+int qil_apply_mpo_mpo(qil_ctx* ctx, const qil_mpo* W1, const qil_mpo* W2, int start1, int start2,
+                      qil_mpo** out) {
+    QIL_API_BEGIN
+    QIL_NONNULL(ctx); QIL_NONNULL(W1); QIL_NONNULL(W2); QIL_NONNULL(out);
+    QIL_CUDA(cudaSetDevice(ctx->device));
+    *out = apply_mpo_mpo(ctx, W1, W2, start1, start2);
+    QIL_API_END
+}
+
+}  // extern "C"

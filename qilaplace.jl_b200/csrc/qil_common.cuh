@@ -1,0 +1,169 @@
+// qil_common.cuh -- shared declarations for libqilcuda (sm_100a only).
+//
+// Layout conventions (row-major / C order everywhere on the device):
+//   MPS core i : M[l][s][r]      dims bond[i] x 2 x bond[i+1]          (reference: ITensor (l,s,r))
+//   MPO core i : W[l][p][s][r]   dims bond[i] x 2 x 2 x bond[i+1], p = primed/input, s = output
+//   signal     : x[j], j MSB-first == site 1 is the most significant bit
+// Scalars are double or interleaved complex double (cuDoubleComplex-compatible double2).
+#pragma once
+#include <cuda_runtime.h>
+#include <cstdint>
+#include <cstdio>
+#include <exception>
+#include <string>
+#include <vector>
+
+#include "../../include/qilcuda.h"
+
+namespace qil {
+
+struct Error : public std::exception {
+    int code;
+    std::string msg;
+    Error(int c, std::string m) : code(c), msg(std::move(m)) {}
+    const char* what() const noexcept override { return msg.c_str(); }
+};
+
+#define QIL_THROW(code, ...)                                   \
+    do {                                                       \
+        char _b[512];                                          \
+        snprintf(_b, sizeof(_b), __VA_ARGS__);                 \
+        throw ::qil::Error((code), std::string(_b));           \
+    } while (0)
+
+#define QIL_CUDA(expr)                                                                    \
+    do {                                                                                  \
+        cudaError_t _e = (expr);                                                          \
+        if (_e != cudaSuccess)                                                            \
+            QIL_THROW(QIL_ERR_CUDA, "%s failed: %s (%s:%d)", #expr, cudaGetErrorString(_e), \
+                      __FILE__, __LINE__);                                                \
+    } while (0)
+
+#define QIL_REQUIRE(cond, code, ...) \
+    do {                             \
+        if (!(cond)) QIL_THROW(code, __VA_ARGS__); \
+    } while (0)
+
+constexpr int kMaxSites = QIL_MAX_SITES;
+
+// ---- complex helpers (double2 == interleaved complex) -------------------------------------
+typedef double2 cplx;
+
+template <typename T> struct Scalar;
+template <> struct Scalar<double> {
+    static constexpr bool is_complex = false;
+    __host__ __device__ static inline double zero() { return 0.0; }
+    __host__ __device__ static inline double one() { return 1.0; }
+    __host__ __device__ static inline double conj(double a) { return a; }
+    __host__ __device__ static inline double mul(double a, double b) { return a * b; }
+    __host__ __device__ static inline double fma(double a, double b, double c) { return a * b + c; }
+    __host__ __device__ static inline double add(double a, double b) { return a + b; }
+    __host__ __device__ static inline double sub(double a, double b) { return a - b; }
+    __host__ __device__ static inline double scale(double a, double s) { return a * s; }
+    __host__ __device__ static inline double abs2(double a) { return a * a; }
+    __host__ __device__ static inline double real(double a) { return a; }
+    __host__ __device__ static inline double from_real(double a) { return a; }
+};
+template <> struct Scalar<cplx> {
+    static constexpr bool is_complex = true;
+    __host__ __device__ static inline cplx zero() { return make_double2(0.0, 0.0); }
+    __host__ __device__ static inline cplx one() { return make_double2(1.0, 0.0); }
+    __host__ __device__ static inline cplx conj(cplx a) { return make_double2(a.x, -a.y); }
+    __host__ __device__ static inline cplx mul(cplx a, cplx b) {
+        return make_double2(a.x * b.x - a.y * b.y, a.x * b.y + a.y * b.x);
+    }
+    __host__ __device__ static inline cplx fma(cplx a, cplx b, cplx c) {
+        c.x = ::fma(a.x, b.x, c.x);
+        c.x = ::fma(-a.y, b.y, c.x);
+        c.y = ::fma(a.x, b.y, c.y);
+        c.y = ::fma(a.y, b.x, c.y);
+        return c;
+    }
+    __host__ __device__ static inline cplx add(cplx a, cplx b) { return make_double2(a.x + b.x, a.y + b.y); }
+    __host__ __device__ static inline cplx sub(cplx a, cplx b) { return make_double2(a.x - b.x, a.y - b.y); }
+    __host__ __device__ static inline cplx scale(cplx a, double s) { return make_double2(a.x * s, a.y * s); }
+    __host__ __device__ static inline double abs2(cplx a) { return a.x * a.x + a.y * a.y; }
+    __host__ __device__ static inline double real(cplx a) { return a.x; }
+    __host__ __device__ static inline cplx from_real(double a) { return make_double2(a, 0.0); }
+};
+
+// promote real -> complex on load
+template <typename TO, typename TI> __host__ __device__ inline TO promote(TI v);
+template <> __host__ __device__ inline double promote<double, double>(double v) { return v; }
+template <> __host__ __device__ inline cplx promote<cplx, double>(double v) { return make_double2(v, 0.0); }
+template <> __host__ __device__ inline cplx promote<cplx, cplx>(cplx v) { return v; }
+
+inline size_t elem_size(int is_complex) { return is_complex ? 16 : 8; }
+
+}  // namespace qil
+
+// ---- opaque handles --------------------------------------------------------------------------
+struct qil_ctx {
+    int device = 0;
+    cudaStream_t stream = nullptr;
+    bool own_stream = false;
+    int sm_count = 148;
+    size_t smem_optin = 0;
+    unsigned long long launches = 0;  // kernels launched by this library on this context
+    // scratch that lives as long as the context
+    void* scratch = nullptr;
+    size_t scratch_bytes = 0;
+
+    void* alloc(size_t bytes);           // stream-ordered device allocation
+    void free(void* p);                  // stream-ordered free
+    void* get_scratch(size_t bytes);     // grow-only scratch (valid until next get_scratch)
+    void sync();
+};
+
+struct qil_mps {
+    qil_ctx* ctx = nullptr;
+    int n = 0;
+    int is_complex = 0;
+    std::vector<int64_t> bond;  // n+1 entries, bond[0] = bond[n] = 1
+    std::vector<void*> core;    // device pointers, core[i] is [bond[i]][2][bond[i+1]]
+    double amplitude = 1.0;
+    size_t core_elems(int i) const { return (size_t)bond[i] * 2 * (size_t)bond[i + 1]; }
+};
+
+struct qil_mpo {
+    qil_ctx* ctx = nullptr;
+    int n = 0;
+    int is_complex = 0;
+    std::vector<int64_t> bond;  // n+1 entries
+    std::vector<void*> core;    // core[i] is [bond[i]][2][2][bond[i+1]]
+    size_t core_elems(int i) const { return (size_t)bond[i] * 4 * (size_t)bond[i + 1]; }
+};
+
+namespace qil {
+
+// chain descriptor passed by value to kernels that walk all sites in one launch
+struct ChainDesc {
+    int n;
+    int bond[kMaxSites + 1];
+    const void* core[kMaxSites];
+};
+
+ChainDesc make_desc(const qil_mps* m);
+ChainDesc make_desc(const qil_mpo* m);
+
+qil_mps* new_mps(qil_ctx* ctx, int n, int is_complex, const int64_t* bond /* n+1 */, bool allocate);
+qil_mpo* new_mpo(qil_ctx* ctx, int n, int is_complex, const int64_t* bond /* n+1 */, bool allocate);
+void destroy(qil_mps* m);
+void destroy(qil_mpo* m);
+
+#define QIL_LAUNCH_CHECK(ctx)            \
+    do {                                 \
+        (ctx)->launches++;               \
+        QIL_CUDA(cudaGetLastError());    \
+    } while (0)
+
+// ---- kernels / device-side ops implemented across the .cu files -----------------------------
+// K8: batched coefficient extraction (mps.jl:669-678)
+void coefficient_batch_dev(qil_ctx* ctx, const qil_mps* psi, const uint8_t* d_bits, int64_t B,
+                           void* d_out /* B scalars of psi's type */);
+// K6: exact MPO x MPS (apply.jl:75-122)
+qil_mps* apply_mpo_mps(qil_ctx* ctx, const qil_mpo* W, const qil_mps* psi);
+// K7: MPO o MPO (apply.jl:124-199), W1 acts first, equal lengths or windowed
+qil_mpo* apply_mpo_mpo(qil_ctx* ctx, const qil_mpo* W1, const qil_mpo* W2, int start1, int start2);
+
+}  // namespace qil

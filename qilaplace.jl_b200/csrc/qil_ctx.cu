@@ -1,0 +1,93 @@
+// qil_ctx.cu -- context, device memory and MPS/MPO handle management.
+#include "qil_common.cuh"
+
+#include <cstring>
+
+void* qil_ctx::alloc(size_t bytes) {
+    if (bytes == 0) bytes = 16;
+    void* p = nullptr;
+    QIL_CUDA(cudaMallocAsync(&p, bytes, stream));
+    return p;
+}
+
+void qil_ctx::free(void* p) {
+    if (p) cudaFreeAsync(p, stream);
+}
+
+void* qil_ctx::get_scratch(size_t bytes) {
+    if (bytes > scratch_bytes) {
+        if (scratch) cudaFreeAsync(scratch, stream);
+        scratch = nullptr;
+        size_t nb = bytes + (bytes >> 2) + 256;
+        QIL_CUDA(cudaMallocAsync(&scratch, nb, stream));
+        scratch_bytes = nb;
+    }
+    return scratch;
+}
+
+void qil_ctx::sync() { QIL_CUDA(cudaStreamSynchronize(stream)); }
+
+namespace qil {
+
+static void check_bonds(int n, const int64_t* bond) {
+    QIL_REQUIRE(n >= 1 && n <= kMaxSites, QIL_ERR_ARGUMENT, "number of sites %d outside [1,%d]", n, kMaxSites);
+    QIL_REQUIRE(bond[0] == 1 && bond[n] == 1, QIL_ERR_ARGUMENT, "boundary bonds must have dimension 1");
+    for (int i = 0; i <= n; ++i)
+        QIL_REQUIRE(bond[i] >= 1 && bond[i] < (1ll << 30), QIL_ERR_ARGUMENT, "bond %d has invalid dimension", i);
+}
+
+qil_mps* new_mps(qil_ctx* ctx, int n, int is_complex, const int64_t* bond, bool allocate) {
+    check_bonds(n, bond);
+    qil_mps* m = new qil_mps();
+    m->ctx = ctx;
+    m->n = n;
+    m->is_complex = is_complex ? 1 : 0;
+    m->bond.assign(bond, bond + n + 1);
+    m->core.assign(n, nullptr);
+    if (allocate)
+        for (int i = 0; i < n; ++i) m->core[i] = ctx->alloc(m->core_elems(i) * elem_size(is_complex));
+    return m;
+}
+
+qil_mpo* new_mpo(qil_ctx* ctx, int n, int is_complex, const int64_t* bond, bool allocate) {
+    check_bonds(n, bond);
+    qil_mpo* m = new qil_mpo();
+    m->ctx = ctx;
+    m->n = n;
+    m->is_complex = is_complex ? 1 : 0;
+    m->bond.assign(bond, bond + n + 1);
+    m->core.assign(n, nullptr);
+    if (allocate)
+        for (int i = 0; i < n; ++i) m->core[i] = ctx->alloc(m->core_elems(i) * elem_size(is_complex));
+    return m;
+}
+
+void destroy(qil_mps* m) {
+    if (!m) return;
+    for (void* p : m->core) m->ctx->free(p);
+    delete m;
+}
+
+void destroy(qil_mpo* m) {
+    if (!m) return;
+    for (void* p : m->core) m->ctx->free(p);
+    delete m;
+}
+
+ChainDesc make_desc(const qil_mps* m) {
+    ChainDesc d;
+    d.n = m->n;
+    for (int i = 0; i <= m->n; ++i) d.bond[i] = (int)m->bond[i];
+    for (int i = 0; i < m->n; ++i) d.core[i] = m->core[i];
+    return d;
+}
+
+ChainDesc make_desc(const qil_mpo* m) {
+    ChainDesc d;
+    d.n = m->n;
+    for (int i = 0; i <= m->n; ++i) d.bond[i] = (int)m->bond[i];
+    for (int i = 0; i < m->n; ++i) d.core[i] = m->core[i];
+    return d;
+}
+
+}  // namespace qil
