@@ -89,6 +89,37 @@ int qil_apply_mpo_mps(qil_ctx* ctx, const qil_mpo* W, const qil_mps* psi, qil_mp
 int qil_apply_mpo_mpo(qil_ctx* ctx, const qil_mpo* W1, const qil_mpo* W2, int start1, int start2,
                       qil_mpo** out);
 
+/* ---- signal -> MPS (src/signals/SignalConverters.jl:16-104, 228-283) ------------------------
+ * x holds N scalars (zero-padded to 2^round(log2 N) like the reference; N > 2^n is an AssertionError).
+ * The result carries amplitude = ||x||_2.  maxdim <= 0 means "no limit" (typemax(Int)). */
+int qil_encode_svd(qil_ctx* ctx, int is_complex, const void* x, int64_t N, double cutoff, int64_t maxdim,
+                   qil_mps** out);
+int qil_encode_svd_dev(qil_ctx* ctx, int is_complex, const void* d_x, int64_t N, double cutoff,
+                       int64_t maxdim, qil_mps** out);
+/* Per-site copy-tensor split of signal_ztmps (SignalConverters.jl:258-277): n-site MPS -> 2n-site chain. */
+int qil_ztmps_split(qil_ctx* ctx, const qil_mps* psi, double cutoff, int64_t maxdim, qil_mps** out);
+
+/* ---- gauge / compression (src/mps.jl:754-999), in place on the handle ------------------------ */
+/* direction: 0 = :left (sweep N..center+1), 1 = :right (sweep 1..center-1); center 1-based, 0 = default */
+int qil_canonicalize(qil_ctx* ctx, qil_mps* psi, int direction_right, int center, double cutoff, int64_t maxdim);
+int qil_compress(qil_ctx* ctx, qil_mps* psi, int64_t maxdim, double tol, int sweeps);
+int qil_norm(qil_ctx* ctx, const qil_mps* psi, double* out);
+
+/* ---- transform MPO builders (src/transforms/{qft,dt,zt}_transformer.jl) ------------------------
+ * dt/zt return the 2n-site chain of the PairedSiteMPO (main1, copy1, main2, ...). */
+int qil_build_qft_mpo(qil_ctx* ctx, int n, double cutoff, int64_t maxdim, qil_mpo** out);
+int qil_build_dt_mpo(qil_ctx* ctx, int n, double omega_r, double cutoff, int64_t maxdim, qil_mpo** out);
+int qil_build_zt_mpo(qil_ctx* ctx, int n, double omega_r, double cutoff, int64_t maxdim, qil_mpo** out);
+
+/* ---- dense factorizations on host matrices (row-major), the ITensors calls of the path ----------
+ * qil_qr: thin QR, k = min(m,n); Q is m x k, R is k x n; positive != 0 => diag(R) >= 0 (rsvd.jl:83).
+ * qil_svd_trunc: truncated SVD with the NDTensors rule (relative cumulative cutoff on sigma^2, maxdim,
+ * mindim).  U / S / Vh must have room for min(m,n) columns / values / rows; they are written
+ * compactly as m x r, r, r x n and *rank receives r. */
+int qil_qr(qil_ctx* ctx, int is_complex, int64_t m, int64_t n, const void* A, int positive, void* Q, void* R);
+int qil_svd_trunc(qil_ctx* ctx, int is_complex, int64_t m, int64_t n, const void* A, double cutoff,
+                  int64_t maxdim, int64_t mindim, int64_t* rank, void* U, double* S, void* Vh);
+
 #ifdef __cplusplus
 }
 #endif

@@ -374,3 +374,176 @@ def generate_signal(n, kind="sin", dt=None, freq=None, **kw):
     raise ArgumentError(
         f"Unsupported signal kind: {kind}. Supported kinds are :sin, :multi_sin, :sin_decay, "
         ":multi_sin_exp, :abs_cos_power_p8, :random.")
+
+
+# ------------------------------------------------------------------------------------------
+# signal -> MPS (src/signals/SignalConverters.jl:228-283)
+# ------------------------------------------------------------------------------------------
+def _maxdim_arg(maxdim):
+    return 0 if maxdim is None or maxdim >= BIG else int(maxdim)
+
+
+def _signal_array(x):
+    x = np.asarray(x)
+    if x.ndim != 1:
+        raise ArgumentError("signal must be a vector")
+    is_complex = np.iscomplexobj(x)
+    return np.ascontiguousarray(x, dtype=_np_dtype(is_complex)), is_complex
+
+
+def signal_mps(x, method="svd", ctx=None, **kwargs):
+    """signal_mps(x; method=:svd, kwargs...) (SignalConverters.jl:228-233).
+
+    method "svd": cutoff=1e-15, maxdim.  method "rsvd": additionally k=20, p=10, q=0, random_seed=1234,
+    mindim=1 (rsvd.jl:38-50); cutoff/maxdim always override (SignalConverters.jl:133)."""
+    ctx = ctx or default_context()
+    method = str(method).lstrip(":")
+    if method not in ("svd", "rsvd"):
+        raise ArgumentError(f"tensor_to_mps: unknown method {method}. Use :svd or :rsvd.")
+    xa, is_complex = _signal_array(x)
+    cutoff = float(kwargs.pop("cutoff", 1e-15))
+    maxdim = _maxdim_arg(kwargs.pop("maxdim", None))
+    h = _lib.c_mps()
+    if method == "svd":
+        if kwargs:
+            raise TypeError(f"signal_mps(method=:svd): unexpected keyword(s) {sorted(kwargs)}")
+        call("qil_encode_svd", ctx.handle, int(is_complex), C.c_void_p(xa.ctypes.data), C.c_int64(xa.size),
+             cutoff, C.c_int64(maxdim), C.byref(h))
+    else:
+        k = int(kwargs.pop("k", 20)); p = int(kwargs.pop("p", 10)); q = int(kwargs.pop("q", 0))
+        seed = int(kwargs.pop("random_seed", 1234)); mindim = int(kwargs.pop("mindim", 1))
+        kwargs.pop("verbose", None); kwargs.pop("bondtag", None)
+        omega = kwargs.pop("omega", None)
+        if kwargs:
+            raise TypeError(f"signal_mps(method=:rsvd): unexpected keyword(s) {sorted(kwargs)}")
+        if omega is not None:
+            om = np.ascontiguousarray(omega, dtype=_np_dtype(is_complex))
+            op, orows, ocols = C.c_void_p(om.ctypes.data), om.shape[0], om.shape[1]
+        else:
+            op, orows, ocols = None, 0, 0
+        call("qil_encode_rsvd", ctx.handle, int(is_complex), C.c_void_p(xa.ctypes.data), C.c_int64(xa.size),
+             k, p, q, C.c_int64(seed), cutoff, C.c_int64(maxdim), C.c_int64(mindim), op, C.c_int64(orows),
+             C.c_int64(ocols), C.byref(h))
+    return SignalMPS(ctx, h)
+
+
+def signal_ztmps(x, cutoff=1e-10, maxdim=None, ctx=None, **kwargs):
+    """signal_ztmps(x; cutoff=1e-10, maxdim, kwargs...) (SignalConverters.jl:247-283)."""
+    psi = signal_mps(x, ctx=ctx, cutoff=cutoff, maxdim=maxdim, **kwargs)
+    h = _lib.c_mps()
+    call("qil_ztmps_split", psi.ctx.handle, psi.handle, float(cutoff), C.c_int64(_maxdim_arg(maxdim)), C.byref(h))
+    return ZTMPS(psi.ctx, h)
+
+
+# ------------------------------------------------------------------------------------------
+# canonicalize! / compress! / norm (src/mps.jl:754-999)
+# ------------------------------------------------------------------------------------------
+def canonicalize(psi, direction, center=None, cutoff=1e-12, maxdim=None):
+    """canonicalize!(psi, direction; center, cutoff=1e-12, maxdim) -- in place, returns psi."""
+    d = str(direction).lstrip(":")
+    if d not in ("right", "left"):
+        raise ArgumentError("Direction must be :right or :left")
+    n = psi.nsites_flat
+    c = 0 if center is None else int(center)
+    if center is not None and not 1 <= c <= n:
+        raise DomainError(f"Center out of range [1,{n}]")
+    call("qil_canonicalize", psi.ctx.handle, psi.handle, 1 if d == "right" else 0, c, float(cutoff),
+         C.c_int64(_maxdim_arg(maxdim)))
+    return psi
+
+
+def compress(psi, maxdim=None, tol=1e-12, sweeps=1):
+    """compress!(psi; maxdim, tol=1e-12, sweeps=1) -- in place, returns psi."""
+    call("qil_compress", psi.ctx.handle, psi.handle, C.c_int64(_maxdim_arg(maxdim)), float(tol), int(sweeps))
+    return psi
+
+
+canonicalize_ = canonicalize
+compress_ = compress
+
+
+def norm(psi):
+    """norm(psi) (mps.jl:754-771): sqrt(|<psi|psi>|); ignores `amplitude`."""
+    v = C.c_double()
+    call("qil_norm", psi.ctx.handle, psi.handle, C.byref(v))
+    return float(v.value)
+
+
+def mps_to_vector(psi, reverse=False):
+    """mps_to_vector(psi; reverse=false) (mps.jl:716-743): every coefficient, MSB-first by default,
+    bit-reversed ordering with reverse=true.  Runs the batched coefficient kernel over all 2^n strings."""
+    n = psi.nsites_flat
+    if n > 26:
+        raise UnsupportedError("mps_to_vector: refusing to materialise more than 2^26 amplitudes")
+    idx = np.arange(2**n, dtype=np.int64)
+    shifts = np.arange(n - 1, -1, -1) if not reverse else np.arange(n)
+    bits = ((idx[:, None] >> shifts[None, :]) & 1).astype(np.uint8)
+    return coefficients(psi, bits)
+
+
+# ------------------------------------------------------------------------------------------
+# transform MPOs (src/transforms/*.jl)
+# ------------------------------------------------------------------------------------------
+def _n_from(arg):
+    return len(arg) if isinstance(arg, (SignalMPS, ZTMPS)) else int(arg)
+
+
+def build_qft_mpo(n_or_psi, cutoff=1e-14, maxdim=1000, ctx=None):
+    """build_qft_mpo(n, sites; cutoff=1e-14, maxdim=1000) / build_qft_mpo(psi; ...) (qft_transformer.jl:121-165)."""
+    ctx = ctx or (n_or_psi.ctx if isinstance(n_or_psi, SignalMPS) else default_context())
+    h = _lib.c_mpo()
+    call("qil_build_qft_mpo", ctx.handle, _n_from(n_or_psi), float(cutoff), C.c_int64(_maxdim_arg(maxdim)), C.byref(h))
+    return SingleSiteMPO(ctx, h)
+
+
+def build_dt_mpo(n_or_psi, omega_r, cutoff=1e-14, maxdim=1000, ctx=None):
+    """build_dt_mpo(n, wr, sites_main, sites_copy; ...) / build_dt_mpo(psi::ZTMPS, wr; ...) (dt_transformer.jl:312-412)."""
+    ctx = ctx or (n_or_psi.ctx if isinstance(n_or_psi, SignalMPS) else default_context())
+    h = _lib.c_mpo()
+    call("qil_build_dt_mpo", ctx.handle, _n_from(n_or_psi), float(omega_r), float(cutoff),
+         C.c_int64(_maxdim_arg(maxdim)), C.byref(h))
+    return PairedSiteMPO(ctx, h)
+
+
+def build_zt_mpo(n_or_psi, omega_r, cutoff=1e-14, maxdim=1000, ctx=None):
+    """build_zt_mpo(n, wr, sites_main, sites_copy; ...) / build_zt_mpo(psi::ZTMPS, wr; ...) (zt_transformer.jl:41-112)."""
+    ctx = ctx or (n_or_psi.ctx if isinstance(n_or_psi, SignalMPS) else default_context())
+    h = _lib.c_mpo()
+    call("qil_build_zt_mpo", ctx.handle, _n_from(n_or_psi), float(omega_r), float(cutoff),
+         C.c_int64(_maxdim_arg(maxdim)), C.byref(h))
+    return PairedSiteMPO(ctx, h)
+
+
+# ------------------------------------------------------------------------------------------
+# dense factorizations (the ITensors calls of the path)
+# ------------------------------------------------------------------------------------------
+def qr(A, positive=False, ctx=None):
+    ctx = ctx or default_context()
+    A = np.asarray(A)
+    ic = np.iscomplexobj(A)
+    A = np.ascontiguousarray(A, dtype=_np_dtype(ic))
+    m, n = A.shape
+    k = min(m, n)
+    Q = np.empty((m, k), dtype=A.dtype)
+    R = np.empty((k, n), dtype=A.dtype)
+    call("qil_qr", ctx.handle, int(ic), C.c_int64(m), C.c_int64(n), C.c_void_p(A.ctypes.data), int(positive),
+         C.c_void_p(Q.ctypes.data), C.c_void_p(R.ctypes.data))
+    return Q, R
+
+
+def svd_trunc(A, cutoff=0.0, maxdim=None, mindim=1, ctx=None):
+    ctx = ctx or default_context()
+    A = np.asarray(A)
+    ic = np.iscomplexobj(A)
+    A = np.ascontiguousarray(A, dtype=_np_dtype(ic))
+    m, n = A.shape
+    k = min(m, n)
+    U = np.empty(m * k, dtype=A.dtype)
+    S = np.empty(k, dtype=np.float64)
+    Vh = np.empty(k * n, dtype=A.dtype)
+    r = C.c_int64(0)
+    call("qil_svd_trunc", ctx.handle, int(ic), C.c_int64(m), C.c_int64(n), C.c_void_p(A.ctypes.data), float(cutoff),
+         C.c_int64(_maxdim_arg(maxdim)), C.c_int64(mindim), C.byref(r), C.c_void_p(U.ctypes.data),
+         C.c_void_p(S.ctypes.data), C.c_void_p(Vh.ctypes.data))
+    r = int(r.value)
+    return U[: m * r].reshape(m, r), S[:r], Vh[: r * n].reshape(r, n)

@@ -1,5 +1,5 @@
 // qil_capi.cu -- extern "C" boundary of libqilcuda.so (see include/qilcuda.h).
-#include "qil_common.cuh"
+#include "qil_mpsops.cuh"
 
 #include <cstring>
 
@@ -25,6 +25,34 @@ static thread_local std::string g_last_error;
 #define QIL_NONNULL(p) QIL_REQUIRE((p) != nullptr, QIL_ERR_ARGUMENT, "null pointer: %s", #p)
 
 using namespace qil;
+
+static inline int64_t fix_maxdim(int64_t maxdim) { return maxdim <= 0 ? ((int64_t)1 << 62) : maxdim; }
+
+template <typename T>
+static void qr_host(qil_ctx* ctx, int64_t m, int64_t n, const void* A, int positive, void* Qh, void* Rh) {
+    Mat<T> dA(ctx, m, n), Q, R;
+    QIL_CUDA(cudaMemcpyAsync(dA.p, A, (size_t)m * n * sizeof(T), cudaMemcpyHostToDevice, ctx->stream));
+    qr_thin<T>(ctx, m, n, dA.p, n, positive != 0, Q, R);
+    const int64_t k = std::min(m, n);
+    QIL_CUDA(cudaMemcpyAsync(Qh, Q.p, (size_t)m * k * sizeof(T), cudaMemcpyDeviceToHost, ctx->stream));
+    QIL_CUDA(cudaMemcpyAsync(Rh, R.p, (size_t)k * n * sizeof(T), cudaMemcpyDeviceToHost, ctx->stream));
+    ctx->sync();
+}
+
+template <typename T>
+static int svd_host(qil_ctx* ctx, int64_t m, int64_t n, const void* A, double cutoff, int64_t maxdim, int64_t mindim,
+                    void* Uh, double* Sh, void* Vhh) {
+    Mat<T> dA(ctx, m, n), U, Vh;
+    Mat<double> S;
+    QIL_CUDA(cudaMemcpyAsync(dA.p, A, (size_t)m * n * sizeof(T), cudaMemcpyHostToDevice, ctx->stream));
+    const int r = svd_trunc<T>(ctx, m, n, dA.p, n, cutoff, maxdim, mindim, Uh ? &U : nullptr, nullptr,
+                               Vhh ? &Vh : nullptr, nullptr, Sh ? &S : nullptr);
+    if (Uh) QIL_CUDA(cudaMemcpyAsync(Uh, U.p, (size_t)m * r * sizeof(T), cudaMemcpyDeviceToHost, ctx->stream));
+    if (Sh) QIL_CUDA(cudaMemcpyAsync(Sh, S.p, (size_t)r * sizeof(double), cudaMemcpyDeviceToHost, ctx->stream));
+    if (Vhh) QIL_CUDA(cudaMemcpyAsync(Vhh, Vh.p, (size_t)r * n * sizeof(T), cudaMemcpyDeviceToHost, ctx->stream));
+    ctx->sync();
+    return r;
+}
 
 extern "C" {
 
@@ -268,6 +296,127 @@ int qil_apply_mpo_mpo(qil_ctx* ctx, const qil_mpo* W1, const qil_mpo* W2, int st
     QIL_NONNULL(ctx); QIL_NONNULL(W1); QIL_NONNULL(W2); QIL_NONNULL(out);
     QIL_CUDA(cudaSetDevice(ctx->device));
     *out = apply_mpo_mpo(ctx, W1, W2, start1, start2);
+    QIL_API_END
+}
+
+// ---- encode ----------------------------------------------------------------------------------
+
+int qil_encode_svd_dev(qil_ctx* ctx, int is_complex, const void* d_x, int64_t N, double cutoff, int64_t maxdim,
+                       qil_mps** out) {
+    QIL_API_BEGIN
+    QIL_NONNULL(ctx); QIL_NONNULL(d_x); QIL_NONNULL(out);
+    QIL_CUDA(cudaSetDevice(ctx->device));
+    *out = is_complex ? encode_svd<cplx>(ctx, (const cplx*)d_x, N, cutoff, fix_maxdim(maxdim))
+                      : encode_svd<double>(ctx, (const double*)d_x, N, cutoff, fix_maxdim(maxdim));
+    QIL_API_END
+}
+
+int qil_encode_svd(qil_ctx* ctx, int is_complex, const void* x, int64_t N, double cutoff, int64_t maxdim,
+                   qil_mps** out) {
+    QIL_API_BEGIN
+    QIL_NONNULL(ctx); QIL_NONNULL(x); QIL_NONNULL(out);
+    QIL_REQUIRE(N >= 1, QIL_ERR_ARGUMENT, "signal_mps: empty signal");
+    QIL_CUDA(cudaSetDevice(ctx->device));
+    const size_t bytes = (size_t)N * elem_size(is_complex);
+    void* d_x = ctx->alloc(bytes);
+    QIL_CUDA(cudaMemcpyAsync(d_x, x, bytes, cudaMemcpyHostToDevice, ctx->stream));
+    qil_mps* m = nullptr;
+    try {
+        m = is_complex ? encode_svd<cplx>(ctx, (const cplx*)d_x, N, cutoff, fix_maxdim(maxdim))
+                       : encode_svd<double>(ctx, (const double*)d_x, N, cutoff, fix_maxdim(maxdim));
+    } catch (...) {
+        ctx->free(d_x);
+        throw;
+    }
+    ctx->free(d_x);
+    ctx->sync();
+    *out = m;
+    QIL_API_END
+}
+
+int qil_ztmps_split(qil_ctx* ctx, const qil_mps* psi, double cutoff, int64_t maxdim, qil_mps** out) {
+    QIL_API_BEGIN
+    QIL_NONNULL(ctx); QIL_NONNULL(psi); QIL_NONNULL(out);
+    QIL_CUDA(cudaSetDevice(ctx->device));
+    *out = ztmps_split(ctx, psi, cutoff, fix_maxdim(maxdim));
+    ctx->sync();
+    QIL_API_END
+}
+
+// ---- gauge / compression -----------------------------------------------------------------------
+int qil_canonicalize(qil_ctx* ctx, qil_mps* psi, int direction_right, int center, double cutoff, int64_t maxdim) {
+    QIL_API_BEGIN
+    QIL_NONNULL(ctx); QIL_NONNULL(psi);
+    QIL_CUDA(cudaSetDevice(ctx->device));
+    canonicalize(ctx, psi, direction_right ? 1 : 0, center, cutoff, fix_maxdim(maxdim));
+    ctx->sync();
+    QIL_API_END
+}
+
+int qil_compress(qil_ctx* ctx, qil_mps* psi, int64_t maxdim, double tol, int sweeps) {
+    QIL_API_BEGIN
+    QIL_NONNULL(ctx); QIL_NONNULL(psi);
+    QIL_CUDA(cudaSetDevice(ctx->device));
+    compress(ctx, psi, fix_maxdim(maxdim), tol, sweeps);
+    ctx->sync();
+    QIL_API_END
+}
+
+int qil_norm(qil_ctx* ctx, const qil_mps* psi, double* out) {
+    QIL_API_BEGIN
+    QIL_NONNULL(ctx); QIL_NONNULL(psi); QIL_NONNULL(out);
+    QIL_CUDA(cudaSetDevice(ctx->device));
+    *out = mps_norm(ctx, psi);
+    QIL_API_END
+}
+
+// ---- builders --------------------------------------------------------------------------------------
+int qil_build_qft_mpo(qil_ctx* ctx, int n, double cutoff, int64_t maxdim, qil_mpo** out) {
+    QIL_API_BEGIN
+    QIL_NONNULL(ctx); QIL_NONNULL(out);
+    QIL_CUDA(cudaSetDevice(ctx->device));
+    *out = build_qft_mpo(ctx, n, cutoff, fix_maxdim(maxdim));
+    ctx->sync();
+    QIL_API_END
+}
+
+int qil_build_dt_mpo(qil_ctx* ctx, int n, double omega_r, double cutoff, int64_t maxdim, qil_mpo** out) {
+    QIL_API_BEGIN
+    QIL_NONNULL(ctx); QIL_NONNULL(out);
+    QIL_CUDA(cudaSetDevice(ctx->device));
+    *out = build_dt_mpo(ctx, n, omega_r, cutoff, fix_maxdim(maxdim));
+    ctx->sync();
+    QIL_API_END
+}
+
+int qil_build_zt_mpo(qil_ctx* ctx, int n, double omega_r, double cutoff, int64_t maxdim, qil_mpo** out) {
+    QIL_API_BEGIN
+    QIL_NONNULL(ctx); QIL_NONNULL(out);
+    QIL_CUDA(cudaSetDevice(ctx->device));
+    *out = build_zt_mpo(ctx, n, omega_r, cutoff, fix_maxdim(maxdim));
+    ctx->sync();
+    QIL_API_END
+}
+
+// ---- dense factorizations -----------------------------------------------------------------------
+int qil_qr(qil_ctx* ctx, int is_complex, int64_t m, int64_t n, const void* A, int positive, void* Q, void* R) {
+    QIL_API_BEGIN
+    QIL_NONNULL(ctx); QIL_NONNULL(A); QIL_NONNULL(Q); QIL_NONNULL(R);
+    QIL_REQUIRE(m >= 1 && n >= 1, QIL_ERR_ARGUMENT, "qr: empty matrix");
+    QIL_CUDA(cudaSetDevice(ctx->device));
+    if (is_complex) qr_host<cplx>(ctx, m, n, A, positive, Q, R);
+    else qr_host<double>(ctx, m, n, A, positive, Q, R);
+    QIL_API_END
+}
+
+int qil_svd_trunc(qil_ctx* ctx, int is_complex, int64_t m, int64_t n, const void* A, double cutoff, int64_t maxdim,
+                  int64_t mindim, int64_t* rank, void* U, double* S, void* Vh) {
+    QIL_API_BEGIN
+    QIL_NONNULL(ctx); QIL_NONNULL(A); QIL_NONNULL(rank);
+    QIL_REQUIRE(m >= 1 && n >= 1, QIL_ERR_ARGUMENT, "svd: empty matrix");
+    QIL_CUDA(cudaSetDevice(ctx->device));
+    *rank = is_complex ? svd_host<cplx>(ctx, m, n, A, cutoff, fix_maxdim(maxdim), mindim, U, S, Vh)
+                       : svd_host<double>(ctx, m, n, A, cutoff, fix_maxdim(maxdim), mindim, U, S, Vh);
     QIL_API_END
 }
 

@@ -1,0 +1,34 @@
+// qil_mpsops.cuh -- MPS-level algorithms (see qil_mpsops.cu, qil_encode.cu, qil_builders.cu).
+#pragma once
+#include "qil_dense.cuh"
+
+namespace qil {
+
+int ilog2_round(int64_t N);
+template <typename T> double device_norm2(qil_ctx* ctx, const T* x, int64_t n);
+
+// signal_mps(x; method=:svd) -- d_x is a device pointer to N scalars
+template <typename T> qil_mps* encode_svd(qil_ctx* ctx, const T* d_x, int64_t N, double cutoff, int64_t maxdim);
+
+struct RsvdOpts {
+    int k = 20, p = 10, q = 0;
+    long long seed = 1234;
+    double cutoff = 1e-15;
+    int64_t maxdim = (int64_t)1 << 62;
+    int64_t mindim = 1;
+    const void* omega = nullptr;   // optional host-supplied test matrix (cols x l, row-major), device pointer
+    int64_t omega_rows = 0, omega_cols = 0;
+};
+// signal_mps(x; method=:rsvd, ...)
+template <typename T> qil_mps* encode_rsvd(qil_ctx* ctx, const T* d_x, int64_t N, const RsvdOpts& o);
+
+qil_mps* ztmps_split(qil_ctx* ctx, const qil_mps* psi, double cutoff, int64_t maxdim);
+void canonicalize(qil_ctx* ctx, qil_mps* psi, int dir_right, int center, double cutoff, int64_t maxdim);
+void compress(qil_ctx* ctx, qil_mps* psi, int64_t maxdim, double tol, int sweeps);
+double mps_norm(qil_ctx* ctx, const qil_mps* psi);
+
+qil_mpo* build_qft_mpo(qil_ctx* ctx, int n, double cutoff, int64_t maxdim);
+qil_mpo* build_dt_mpo(qil_ctx* ctx, int n, double wr, double cutoff, int64_t maxdim);
+qil_mpo* build_zt_mpo(qil_ctx* ctx, int n, double wr, double cutoff, int64_t maxdim);
+
+}  // namespace qil

@@ -1,0 +1,299 @@
+// qil_qr.cu -- K3 / K5: Householder thin QR in shared memory and TSQR for tall-skinny matrices.
+//
+// Replaces ITensors `qr` at rsvd.jl:83,90,94 (positive=true), dt_transformer.jl:73,131,190,237 and the
+// QR branch of `factorize` (qft_transformer.jl:52).  Householder reflectors keep Q orthonormal to
+// rounding even when the matrix is numerically rank deficient (the usual case for Y = A*Omega of a
+// structured signal), which Gram/Cholesky shortcuts do not.
+#include "qil_dense.cuh"
+
+namespace qil {
+
+constexpr int kQrThreads = 256;        // shared-memory variant
+constexpr int kQrWarps = kQrThreads / 32;
+constexpr int kQrThreadsGlobal = 1024; // single-CTA variant on an L2-resident scratch copy (large bond matrices)
+
+template <typename T>
+struct QrParams {
+    const T* A;          // input, row-major
+    long long lda;
+    int nsum;            // number of partial matrices summed on load
+    long long sum_stride;
+    long long m;         // total rows
+    int n;               // columns
+    int nblk;            // row blocks (balanced split); block b owns rows [b*m/nblk, (b+1)*m/nblk)
+    T* Q;                // m x kq, row-major (ldq); may be null
+    long long ldq;
+    T* R;                // block b writes rows [b*rrows, b*rrows + min(mloc,n)) of an (nblk*rrows) x n matrix
+    int rrows;
+    int positive;
+    int mpad;            // smem column pitch (elements)
+    T* gscratch;         // if non-null: the (n + nwarps) x mpad work area lives here instead of shared memory
+};
+
+template <typename T>
+__device__ __forceinline__ T warp_sum(T v);
+template <>
+__device__ __forceinline__ double warp_sum<double>(double v) {
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) v += __shfl_xor_sync(0xffffffffu, v, o);
+    return v;
+}
+template <>
+__device__ __forceinline__ cplx warp_sum<cplx>(cplx v) {
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) {
+        v.x += __shfl_xor_sync(0xffffffffu, v.x, o);
+        v.y += __shfl_xor_sync(0xffffffffu, v.y, o);
+    }
+    return v;
+}
+
+template <typename T>
+__global__ void __launch_bounds__(kQrThreadsGlobal) hhqr_kernel(const QrParams<T> p) {
+    extern __shared__ __align__(16) unsigned char smem_raw[];
+    const int n = p.n, mpad = p.mpad;
+    const int kQrThreads = blockDim.x, kQrWarps = blockDim.x >> 5;
+    T* As;                                                 // [n][mpad] column-major
+    T* sbeta;                                              // [n]
+    if (p.gscratch) {
+        As = p.gscratch;
+        sbeta = reinterpret_cast<T*>(smem_raw);
+    } else {
+        As = reinterpret_cast<T*>(smem_raw);
+        sbeta = As + (size_t)(n + kQrWarps) * mpad;
+    }
+    T* qb = As + (size_t)n * mpad;                         // [kQrWarps][mpad]
+    T* su0 = sbeta + n;                                    // [n]
+    double* ss = reinterpret_cast<double*>(su0 + n);       // [n]
+
+    const int b = blockIdx.x;
+    const long long r0 = ((long long)b * p.m) / p.nblk;
+    const long long r1 = ((long long)(b + 1) * p.m) / p.nblk;
+    const int mloc = (int)(r1 - r0);
+    const int k = min(mloc, n);
+    const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
+
+    // ---- load (sum of partials), transposing into column-major smem
+    for (long long idx = tid; idx < (long long)mloc * n; idx += kQrThreads) {
+        const int i = (int)(idx / n), j = (int)(idx - (long long)i * n);
+        const T* src = p.A + (r0 + i) * p.lda + j;
+        T v = src[0];
+        for (int s = 1; s < p.nsum; ++s) v = Scalar<T>::add(v, src[(long long)s * p.sum_stride]);
+        As[(size_t)j * mpad + i] = v;
+    }
+    __syncthreads();
+
+    // ---- factorisation: H_j = I - s_j u_j u_j^H,  H_j x = beta_j e_1
+    for (int j = 0; j < k; ++j) {
+        T* col = As + (size_t)j * mpad;
+        if (warp == 0) {
+            double xn2 = 0.0;
+            for (int i = j + 1 + lane; i < mloc; i += 32) xn2 += Scalar<T>::abs2(col[i]);
+            xn2 = warp_sum<double>(xn2);
+            if (lane == 0) {
+                const T x0 = col[j];
+                const double a0 = sqrt(Scalar<T>::abs2(x0));
+                const double nx = sqrt(a0 * a0 + xn2);
+                if (nx == 0.0) {
+                    sbeta[j] = Scalar<T>::zero();
+                    su0[j] = Scalar<T>::zero();
+                    ss[j] = 0.0;
+                } else {
+                    const T ph = (a0 > 0.0) ? Scalar<T>::scale(x0, 1.0 / a0) : Scalar<T>::one();
+                    const T beta = Scalar<T>::scale(ph, -nx);
+                    sbeta[j] = beta;
+                    const T u0 = Scalar<T>::sub(x0, beta);
+                    su0[j] = u0;
+                    col[j] = u0;
+                    ss[j] = 1.0 / (nx * (nx + a0));
+                }
+            }
+        }
+        __syncthreads();
+        const double s = ss[j];
+        if (s != 0.0) {
+            for (int c = j + 1 + warp; c < n; c += kQrWarps) {
+                T* cc = As + (size_t)c * mpad;
+                T w = Scalar<T>::zero();
+                for (int i = j + lane; i < mloc; i += 32) w = Scalar<T>::fma(Scalar<T>::conj(col[i]), cc[i], w);
+                w = warp_sum<T>(w);
+                w = Scalar<T>::scale(w, -s);
+                for (int i = j + lane; i < mloc; i += 32) cc[i] = Scalar<T>::fma(w, col[i], cc[i]);
+            }
+        }
+        __syncthreads();
+    }
+
+    // ---- R (k x n), optional positive diagonal
+    if (p.R) {
+        for (int idx = tid; idx < k * n; idx += kQrThreads) {
+            const int j = idx / n, c = idx - j * n;
+            T v = Scalar<T>::zero();
+            if (c == j) v = sbeta[j];
+            else if (c > j) v = As[(size_t)c * mpad + j];
+            if (p.positive) {
+                const T bj = sbeta[j];
+                const double ab = sqrt(Scalar<T>::abs2(bj));
+                if (ab > 0.0) v = Scalar<T>::mul(Scalar<T>::conj(Scalar<T>::scale(bj, 1.0 / ab)), v);
+            }
+            p.R[((long long)b * p.rrows + j) * n + c] = v;
+        }
+    }
+
+    // ---- explicit Q (mloc x k): column c = H_0 ... H_c e_c, groups of kQrWarps columns
+    if (p.Q) {
+        T* q = qb + (size_t)warp * mpad;
+        for (int c0 = 0; c0 < k; c0 += kQrWarps) {
+            const int c = c0 + warp;
+            if (c < k) {
+                for (int i = lane; i < mloc; i += 32) q[i] = (i == c) ? Scalar<T>::one() : Scalar<T>::zero();
+                __syncwarp();
+                for (int j = c; j >= 0; --j) {
+                    const double s = ss[j];
+                    if (s == 0.0) continue;
+                    const T* col = As + (size_t)j * mpad;
+                    T w = Scalar<T>::zero();
+                    for (int i = j + lane; i < mloc; i += 32) w = Scalar<T>::fma(Scalar<T>::conj(col[i]), q[i], w);
+                    w = warp_sum<T>(w);
+                    w = Scalar<T>::scale(w, -s);
+                    for (int i = j + lane; i < mloc; i += 32) q[i] = Scalar<T>::fma(w, col[i], q[i]);
+                    __syncwarp();
+                }
+                if (p.positive) {
+                    const T bj = sbeta[c];
+                    const double ab = sqrt(Scalar<T>::abs2(bj));
+                    if (ab > 0.0) {
+                        const T ph = Scalar<T>::scale(bj, 1.0 / ab);
+                        for (int i = lane; i < mloc; i += 32) q[i] = Scalar<T>::mul(q[i], ph);
+                    }
+                }
+            }
+            __syncthreads();
+            const int nc = min(kQrWarps, k - c0);
+            for (int idx = tid; idx < mloc * nc; idx += kQrThreads) {
+                const int i = idx / nc, w = idx - i * nc;
+                p.Q[(r0 + i) * p.ldq + c0 + w] = qb[(size_t)w * mpad + i];
+            }
+            __syncthreads();
+        }
+    }
+}
+
+// out[b-th row block] = Q0[b] (mloc x n) * Q1[b*n : (b+1)*n, :] (n x n)
+template <typename T>
+__global__ void __launch_bounds__(256) tsqr_combine_kernel(const T* __restrict__ Q0, const T* __restrict__ Q1,
+                                                           T* __restrict__ out, long long m, int n, int nblk) {
+    extern __shared__ __align__(16) unsigned char smem_raw[];
+    T* s1 = reinterpret_cast<T*>(smem_raw);  // [n][n]
+    const int b = blockIdx.x;
+    const long long r0 = ((long long)b * m) / nblk, r1 = ((long long)(b + 1) * m) / nblk;
+    for (int idx = threadIdx.x; idx < n * n; idx += blockDim.x) s1[idx] = Q1[(long long)b * n * n + idx];
+    __syncthreads();
+    const long long tot = (r1 - r0) * n;
+    for (long long idx = (long long)blockIdx.y * blockDim.x + threadIdx.x; idx < tot;
+         idx += (long long)gridDim.y * blockDim.x) {
+        const long long i = idx / n;
+        const int c = (int)(idx - i * n);
+        const T* row = Q0 + (r0 + i) * n;
+        T acc = Scalar<T>::zero();
+        for (int j = 0; j < n; ++j) acc = Scalar<T>::fma(row[j], s1[j * n + c], acc);
+        out[(r0 + i) * n + c] = acc;
+    }
+}
+
+template <typename T>
+static size_t qr_smem(int n, int mloc) {
+    const int mpad = mloc | 1;
+    return ((size_t)n * mpad + (size_t)kQrWarps * mpad + 2 * (size_t)n) * sizeof(T) + (size_t)n * sizeof(double) + 32;
+}
+
+template <typename T>
+static int qr_capacity(qil_ctx* ctx, int n) {
+    const size_t budget = std::min<size_t>(ctx->smem_optin, 220 * 1024);
+    // rows that fit: (n + warps) * mpad * sizeof(T) <= budget - small
+    long long fixed = (2ll * n) * sizeof(T) + (long long)n * 8 + 64;
+    long long rows = ((long long)budget - fixed) / ((long long)(n + kQrWarps) * sizeof(T));
+    rows -= 2;
+    return (int)std::max<long long>(rows, 0);
+}
+
+template <typename T>
+static void launch_hhqr(qil_ctx* ctx, const QrParams<T>& p, int max_mloc, bool use_global = false) {
+    QrParams<T> q = p;
+    q.mpad = max_mloc | 1;
+    auto kern = hhqr_kernel<T>;
+    if (!use_global) {
+        const size_t smem = qr_smem<T>(p.n, max_mloc);
+        q.gscratch = nullptr;
+        QIL_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+        kern<<<p.nblk, kQrThreads, smem, ctx->stream>>>(q);
+        QIL_LAUNCH_CHECK(ctx);
+        return;
+    }
+    // one CTA, 32 warps, work area in global memory (stays in L2): slow but shape-agnostic
+    QIL_REQUIRE(p.nblk == 1, QIL_ERR_RUNTIME, "qr: global-scratch variant handles a single block");
+    const int nw = kQrThreadsGlobal / 32;
+    Mat<T> scratch(ctx, (int64_t)p.n + nw, q.mpad);
+    q.gscratch = scratch.p;
+    const size_t smem = 2 * (size_t)p.n * sizeof(T) + (size_t)p.n * sizeof(double) + 32;
+    QIL_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+    kern<<<1, kQrThreadsGlobal, smem, ctx->stream>>>(q);
+    QIL_LAUNCH_CHECK(ctx);
+}
+
+template <typename T>
+void qr_thin(qil_ctx* ctx, int64_t m, int64_t n64, const T* A, int64_t lda, bool positive, Mat<T>& Q, Mat<T>& R,
+             int nsum, int64_t sum_stride, bool want_q) {
+    QIL_REQUIRE(m >= 1 && n64 >= 1, QIL_ERR_ARGUMENT, "qr: empty matrix");
+    QIL_REQUIRE(n64 < (1 << 20), QIL_ERR_UNSUPPORTED, "qr: too many columns");
+    const int n = (int)n64;
+    const int cap = qr_capacity<T>(ctx, n);
+    const int64_t k = std::min<int64_t>(m, n);
+    if (m <= cap) {
+        if (want_q) Q = Mat<T>(ctx, m, k);
+        R = Mat<T>(ctx, k, n);
+        QrParams<T> p{A, lda, nsum, sum_stride, m, n, 1, want_q ? Q.p : nullptr, k, R.p, (int)k, positive ? 1 : 0, 0, nullptr};
+        launch_hhqr(ctx, p, (int)m);
+        return;
+    }
+    if (cap < 2 * n) {
+        // wide bond matrices of the zT builder / large compress!: single CTA on a global work area
+        QIL_REQUIRE(m * (int64_t)n <= ((int64_t)1 << 26), QIL_ERR_UNSUPPORTED,
+                    "qr: %lld x %d exceeds the global-scratch Householder path", (long long)m, n);
+        if (want_q) Q = Mat<T>(ctx, m, k);
+        R = Mat<T>(ctx, k, n);
+        QrParams<T> p{A, lda, nsum, sum_stride, m, n, 1, want_q ? Q.p : nullptr, k, R.p, (int)k, positive ? 1 : 0, 0, nullptr};
+        launch_hhqr(ctx, p, (int)m, true);
+        return;
+    }
+    // TSQR: balanced row blocks of at most mb rows, each with at least n rows
+    int mb = std::min(cap, std::max(2 * n, 256));
+    int64_t nblk = (m + mb - 1) / mb;
+    while (nblk > 1 && m / nblk < n) --nblk;
+    const int max_mloc = (int)((m + nblk - 1) / nblk);
+    QIL_REQUIRE(max_mloc <= cap, QIL_ERR_UNSUPPORTED, "qr: TSQR block of %d rows exceeds capacity %d", max_mloc, cap);
+    Mat<T> Q0;
+    if (want_q) Q0 = Mat<T>(ctx, m, n);
+    Mat<T> Rst(ctx, nblk * n, n);
+    QrParams<T> p{A, lda, nsum, sum_stride, m, n, (int)nblk, want_q ? Q0.p : nullptr, n, Rst.p, n, 0, 0, nullptr};
+    launch_hhqr(ctx, p, max_mloc);
+    Mat<T> Q1;
+    qr_thin<T>(ctx, nblk * n, n, Rst.p, n, positive, Q1, R, 1, 0, want_q);
+    if (want_q) {
+        Q = Mat<T>(ctx, m, n);
+        const size_t smem = (size_t)n * n * sizeof(T);
+        auto kern = tsqr_combine_kernel<T>;
+        QIL_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+        int gy = (int)std::max<int64_t>(1, std::min<int64_t>(8, ((int64_t)max_mloc * n + 255) / 256));
+        dim3 grid((unsigned)nblk, gy);
+        kern<<<grid, 256, smem, ctx->stream>>>(Q0.p, Q1.p, Q.p, (long long)m, n, (int)nblk);
+        QIL_LAUNCH_CHECK(ctx);
+    }
+}
+
+template void qr_thin<double>(qil_ctx*, int64_t, int64_t, const double*, int64_t, bool, Mat<double>&, Mat<double>&,
+                              int, int64_t, bool);
+template void qr_thin<cplx>(qil_ctx*, int64_t, int64_t, const cplx*, int64_t, bool, Mat<cplx>&, Mat<cplx>&, int,
+                            int64_t, bool);
+
+}  // namespace qil

@@ -1,0 +1,346 @@
+// qil_svd.cu -- K4: truncated SVD = Householder QR + one-sided (Hestenes) Jacobi in shared memory with
+// the ITensors/NDTensors truncation rule evaluated on the device.
+//
+// Replaces every `ITensors.svd(...; cutoff, maxdim[, mindim])` on the path: rsvd.jl:103,
+// SignalConverters.jl:84,266, mps.jl:929,946 (+ factorize -> svd at :804,:824), qft_transformer.jl:82,
+// dt_transformer.jl:213,261.  One-sided Jacobi on the triangular factor delivers small singular
+// values to high relative accuracy, which the cutoffs used here (down to ~1e-25 on sigma^2) need.
+//
+// With A = Q R (m >= n) and G = R^H, the kernel finds V with G V = W (orthogonal columns):
+//   A = (Q V) W^H,  sigma_j = |W_j|,  U = Q V,  S*Vh = W^H      -- no division by sigma anywhere.
+#include "qil_dense.cuh"
+
+namespace qil {
+
+constexpr int kJacThreads = 256;        // shared-memory variant
+constexpr int kJacThreadsGlobal = 1024; // single-CTA variant working on an L2-resident scratch copy
+constexpr int kMaxSweeps = 60;
+
+// NDTensors truncate!! on P = sigma^2 (descending): drop while n > maxdim, then while the discarded
+// weight stays <= cutoff * sum(P) and n > mindim.
+__device__ inline int truncate_rank_dev(const double* sig, int n, double cutoff, long long maxdim, long long mindim) {
+    if (n <= 1) return n;
+    int r = n;
+    double err = 0.0;
+    while ((long long)r > maxdim) { err += sig[r - 1] * sig[r - 1]; --r; }
+    double scale = 0.0;
+    for (int i = 0; i < n; ++i) scale += sig[i] * sig[i];
+    if (scale == 0.0) scale = 1.0;
+    while ((long long)r > mindim && err + sig[r - 1] * sig[r - 1] <= cutoff * scale) {
+        err += sig[r - 1] * sig[r - 1];
+        --r;
+    }
+    return r < 1 ? 1 : r;
+}
+
+template <typename T>
+struct JacParams {
+    const T* R;      // ns x ns row-major (ld); the kernel works on G = R^H
+    long long ld;
+    int ns;
+    int pad;         // smem column pitch
+    T* V;            // out: ns x ns row-major, columns sorted by descending sigma
+    T* W;            // out: ns x ns row-major, W = G V (same column order)
+    double* S;       // out: ns singular values, descending
+    int* rank;       // out: kept rank
+    double cutoff;
+    long long maxdim, mindim;
+    int gl;          // lanes per column pair (8, 16 or 32)
+    T* gscratch;     // if non-null: G and V live here (2 * ns * pad elements) instead of shared memory
+};
+
+// reductions inside an aligned group of `gl` lanes; `mask` names exactly that group so that groups of
+// one warp may diverge (different pairs, dummy pairs) without deadlocking the shuffle
+template <typename T>
+__device__ __forceinline__ T group_sum(T v, int gl, unsigned mask);
+template <>
+__device__ __forceinline__ double group_sum<double>(double v, int gl, unsigned mask) {
+    for (int o = gl >> 1; o > 0; o >>= 1) v += __shfl_xor_sync(mask, v, o);
+    return v;
+}
+template <>
+__device__ __forceinline__ cplx group_sum<cplx>(cplx v, int gl, unsigned mask) {
+    for (int o = gl >> 1; o > 0; o >>= 1) {
+        v.x += __shfl_xor_sync(mask, v.x, o);
+        v.y += __shfl_xor_sync(mask, v.y, o);
+    }
+    return v;
+}
+
+template <typename T>
+__global__ void __launch_bounds__(kJacThreadsGlobal) jacobi_kernel(const JacParams<T> p) {
+    extern __shared__ __align__(16) unsigned char smem_raw[];
+    const int ns = p.ns, pad = p.pad;
+    const int kJacThreads = blockDim.x;
+    T* G;                                         // [ns][pad] column-major
+    double* sig;                                  // [ns]
+    if (p.gscratch) {
+        G = p.gscratch;
+        sig = reinterpret_cast<double*>(smem_raw);
+    } else {
+        G = reinterpret_cast<T*>(smem_raw);
+        sig = reinterpret_cast<double*>(G + (size_t)2 * ns * pad);
+    }
+    T* V = G + (size_t)ns * pad;                  // [ns][pad]
+    int* order = reinterpret_cast<int*>(sig + ns);                  // [ns]
+    __shared__ int s_rot;
+
+    const int tid = threadIdx.x;
+    for (int idx = tid; idx < ns * ns; idx += kJacThreads) {
+        const int j = idx / ns, i = idx - j * ns;
+        G[(size_t)j * pad + i] = Scalar<T>::conj(p.R[(long long)j * p.ld + i]);
+        V[(size_t)j * pad + i] = (i == j) ? Scalar<T>::one() : Scalar<T>::zero();
+    }
+    __syncthreads();
+
+    const int gl = p.gl;
+    const int grp = tid / gl, gln = tid % gl;
+    const unsigned gmask = (gl == 32) ? 0xffffffffu : (((1u << gl) - 1u) << ((tid & 31) / gl * gl));
+    const int ngroups = kJacThreads / gl;
+    const int ne = ns + (ns & 1);
+    const int npairs = ne / 2;
+    const double tol = sqrt((double)ns) * 2.220446049250313e-16;
+
+    for (int sweep = 0; sweep < kMaxSweeps; ++sweep) {
+        if (tid == 0) s_rot = 0;
+        __syncthreads();
+        for (int r = 0; r < ne - 1; ++r) {
+            for (int pi = grp; pi < npairs; pi += ngroups) {
+                int a, b;
+                if (pi == 0) { a = ne - 1; b = r; }
+                else { a = (r + pi) % (ne - 1); b = (r - pi + (ne - 1)) % (ne - 1); }
+                if (a >= ns || b >= ns) continue;   // group-uniform
+                const int cp = min(a, b), cq = max(a, b);
+                T* gp = G + (size_t)cp * pad;
+                T* gq = G + (size_t)cq * pad;
+                double al = 0.0, be = 0.0;
+                T ga = Scalar<T>::zero();
+                for (int i = gln; i < ns; i += gl) {
+                    const T x = gp[i], y = gq[i];
+                    al += Scalar<T>::abs2(x);
+                    be += Scalar<T>::abs2(y);
+                    ga = Scalar<T>::fma(Scalar<T>::conj(x), y, ga);
+                }
+                al = group_sum<double>(al, gl, gmask);
+                be = group_sum<double>(be, gl, gmask);
+                ga = group_sum<T>(ga, gl, gmask);
+                const double g2 = Scalar<T>::abs2(ga);
+                if (g2 > tol * tol * al * be && g2 > 0.0) {
+                    const double ag = sqrt(g2);
+                    const T ph = Scalar<T>::scale(ga, 1.0 / ag);          // e^{i phi}
+                    const double zeta = (be - al) / (2.0 * ag);
+                    const double t = (zeta >= 0.0 ? 1.0 : -1.0) / (fabs(zeta) + sqrt(1.0 + zeta * zeta));
+                    const double c = 1.0 / sqrt(1.0 + t * t);
+                    const double s = c * t;
+                    const T sp = Scalar<T>::scale(ph, s);                 // s e^{i phi}
+                    const T spc = Scalar<T>::conj(sp);                    // s e^{-i phi}
+                    for (int i = gln; i < ns; i += gl) {
+                        const T x = gp[i], y = gq[i];
+                        gp[i] = Scalar<T>::sub(Scalar<T>::scale(x, c), Scalar<T>::mul(spc, y));
+                        gq[i] = Scalar<T>::add(Scalar<T>::mul(sp, x), Scalar<T>::scale(y, c));
+                    }
+                    T* vp = V + (size_t)cp * pad;
+                    T* vq = V + (size_t)cq * pad;
+                    for (int i = gln; i < ns; i += gl) {
+                        const T x = vp[i], y = vq[i];
+                        vp[i] = Scalar<T>::sub(Scalar<T>::scale(x, c), Scalar<T>::mul(spc, y));
+                        vq[i] = Scalar<T>::add(Scalar<T>::mul(sp, x), Scalar<T>::scale(y, c));
+                    }
+                    if (gln == 0) s_rot = 1;
+                }
+            }
+            __syncthreads();
+        }
+        const int rot = s_rot;
+        __syncthreads();
+        if (!rot) break;
+    }
+
+    // singular values, descending order by rank sort
+    for (int j = tid; j < ns; j += kJacThreads) {
+        double a = 0.0;
+        const T* g = G + (size_t)j * pad;
+        for (int i = 0; i < ns; ++i) a += Scalar<T>::abs2(g[i]);
+        sig[j] = sqrt(a);
+    }
+    __syncthreads();
+    for (int j = tid; j < ns; j += kJacThreads) {
+        const double sj = sig[j];
+        int pos = 0;
+        for (int i = 0; i < ns; ++i) {
+            const double si = sig[i];
+            pos += (si > sj || (si == sj && i < j)) ? 1 : 0;
+        }
+        order[pos] = j;
+    }
+    __syncthreads();
+    // sorted sigma (permute through registers), then the sequential truncation rule
+    double mine[8];
+    int cnt = 0;
+    for (int j = tid; j < ns; j += kJacThreads) mine[cnt++] = sig[order[j]];
+    __syncthreads();
+    cnt = 0;
+    for (int j = tid; j < ns; j += kJacThreads) {
+        sig[j] = mine[cnt];
+        p.S[j] = mine[cnt++];
+    }
+    __syncthreads();
+    if (tid == 0) *p.rank = truncate_rank_dev(sig, ns, p.cutoff, p.maxdim, p.mindim);
+    // outputs: row-major with sorted columns
+    for (int idx = tid; idx < ns * ns; idx += kJacThreads) {
+        const int i = idx / ns, j = idx - i * ns;
+        const int src = order[j];
+        p.V[(long long)i * ns + j] = V[(size_t)src * pad + i];
+        p.W[(long long)i * ns + j] = G[(size_t)src * pad + i];
+    }
+}
+
+template <typename T>
+__global__ void sum_partials_kernel(long long count, int nsum, long long stride, const T* __restrict__ in,
+                                    T* __restrict__ out) {
+    for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < count;
+         i += (long long)gridDim.x * blockDim.x) {
+        T v = in[i];
+        for (int s = 1; s < nsum; ++s) v = Scalar<T>::add(v, in[i + (long long)s * stride]);
+        out[i] = v;
+    }
+}
+
+template <typename T>
+static size_t jac_smem(int ns) {
+    const int pad = ns | 1;
+    return (size_t)2 * ns * pad * sizeof(T) + (size_t)ns * (sizeof(double) + sizeof(int)) + 64;
+}
+
+// Jacobi on G = R^H for a square ns x ns R; returns V, W (ns x ns, sorted columns), S and the rank.
+template <typename T>
+static int jacobi_square(qil_ctx* ctx, int ns, const T* R, int64_t ld, double cutoff, int64_t maxdim, int64_t mindim,
+                         Mat<T>& V, Mat<T>& W, Mat<double>& S) {
+    QIL_REQUIRE(ns <= 8 * kJacThreads, QIL_ERR_UNSUPPORTED, "svd: %d columns exceed the Jacobi kernel", ns);
+    size_t smem = jac_smem<T>(ns);
+    const size_t budget = std::min<size_t>(ctx->smem_optin, 225 * 1024);
+    const bool use_global = smem > budget;
+    Mat<T> gscratch;
+    if (use_global) {
+        gscratch = Mat<T>(ctx, 2 * (int64_t)ns, ns | 1);
+        smem = (size_t)ns * (sizeof(double) + sizeof(int)) + 64;
+    }
+    V = Mat<T>(ctx, ns, ns);
+    W = Mat<T>(ctx, ns, ns);
+    S = Mat<double>(ctx, ns, 1);
+    int* d_rank = (int*)ctx->alloc(sizeof(int));
+    JacParams<T> p;
+    p.R = R; p.ld = ld; p.ns = ns; p.pad = ns | 1; p.V = V.p; p.W = W.p; p.S = S.p; p.rank = d_rank;
+    p.cutoff = cutoff; p.maxdim = maxdim; p.mindim = std::max<int64_t>(mindim, 1);
+    p.gl = ns <= 32 ? 8 : (ns <= 64 ? 16 : 32);
+    p.gscratch = use_global ? gscratch.p : nullptr;
+    auto kern = jacobi_kernel<T>;
+    QIL_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+    kern<<<1, use_global ? kJacThreadsGlobal : kJacThreads, smem, ctx->stream>>>(p);
+    QIL_LAUNCH_CHECK(ctx);
+    int rank = 0;
+    QIL_CUDA(cudaMemcpyAsync(&rank, d_rank, sizeof(int), cudaMemcpyDeviceToHost, ctx->stream));
+    ctx->sync();
+    ctx->free(d_rank);
+    return rank;
+}
+
+template <typename T>
+int svd_trunc(qil_ctx* ctx, int64_t m, int64_t n, const T* A, int64_t lda, double cutoff, int64_t maxdim,
+              int64_t mindim, Mat<T>* U, Mat<T>* US, Mat<T>* Vh, Mat<T>* SVh, Mat<double>* S, int nsum,
+              int64_t sum_stride) {
+    QIL_REQUIRE(m >= 1 && n >= 1, QIL_ERR_ARGUMENT, "svd: empty matrix");
+    if (maxdim < 1) maxdim = 1;
+    Mat<T> Q, R, V, W;
+    Mat<double> Sv;
+    const bool tall = m >= n;
+    const int ns = (int)std::min(m, n);
+    bool have_q = true;
+    Mat<T> At;
+    if (tall) {
+        if (m == n && nsum == 1) {
+            have_q = false;
+        } else {
+            qr_thin<T>(ctx, m, n, A, lda, false, Q, R, nsum, sum_stride, true);
+        }
+    } else {
+        Mat<T> Asum;
+        const T* src = A;
+        int64_t ld = lda;
+        if (nsum > 1) {
+            QIL_REQUIRE(lda == n, QIL_ERR_ARGUMENT, "svd: partial sums need a dense leading dimension");
+            Asum = Mat<T>(ctx, m, n);
+            int grid = (int)std::min<long long>((m * n + 255) / 256, (long long)ctx->sm_count * 16);
+            sum_partials_kernel<T><<<grid, 256, 0, ctx->stream>>>(m * n, nsum, sum_stride, A, Asum.p);
+            QIL_LAUNCH_CHECK(ctx);
+            src = Asum.p;
+            ld = n;
+        }
+        At = Mat<T>(ctx, n, m);
+        transpose_conj<T>(ctx, m, n, src, ld, At.p, m);
+        qr_thin<T>(ctx, n, m, At.p, m, false, Q, R, 1, 0, true);
+    }
+    const T* Rp = have_q ? R.p : A;
+    const int64_t ldr = have_q ? ns : lda;
+    const int r = jacobi_square<T>(ctx, ns, Rp, ldr, cutoff, maxdim, mindim, V, W, Sv);
+
+    if (tall) {
+        // U = Q V[:, :r] ; SVh = W[:, :r]^H
+        Mat<T> Uloc;
+        if (U || US) {
+            Uloc = Mat<T>(ctx, m, r);
+            if (have_q) gemm<T>(ctx, OP_N, OP_N, m, r, ns, 1.0, Q.p, ns, V.p, ns, 0.0, Uloc.p, r);
+            else QIL_CUDA(cudaMemcpy2DAsync(Uloc.p, r * sizeof(T), V.p, ns * sizeof(T), r * sizeof(T), m,
+                                            cudaMemcpyDeviceToDevice, ctx->stream));
+        }
+        if (US) {
+            *US = Mat<T>(ctx, m, r);
+            scale_rows_cols<T>(ctx, m, r, Uloc.p, r, Sv.p, false, false, US->p, r);
+        }
+        if (U) *U = std::move(Uloc);
+        if (SVh || Vh) {
+            Mat<T> sv(ctx, r, ns);
+            transpose_conj<T>(ctx, ns, r, W.p, ns, sv.p, ns);
+            if (Vh) {
+                *Vh = Mat<T>(ctx, r, ns);
+                scale_rows_cols<T>(ctx, r, ns, sv.p, ns, Sv.p, true, true, Vh->p, ns);
+            }
+            if (SVh) *SVh = std::move(sv);
+        }
+    } else {
+        // A = W (Q V)^H : US = W[:, :r], Vh = (Q V[:, :r])^H
+        if (US || U) {
+            Mat<T> us(ctx, m, r);
+            QIL_CUDA(cudaMemcpy2DAsync(us.p, r * sizeof(T), W.p, ns * sizeof(T), r * sizeof(T), m,
+                                       cudaMemcpyDeviceToDevice, ctx->stream));
+            if (U) {
+                *U = Mat<T>(ctx, m, r);
+                scale_rows_cols<T>(ctx, m, r, us.p, r, Sv.p, false, true, U->p, r);
+            }
+            if (US) *US = std::move(us);
+        }
+        if (Vh || SVh) {
+            Mat<T> qv(ctx, n, r);
+            gemm<T>(ctx, OP_N, OP_N, n, r, ns, 1.0, Q.p, ns, V.p, ns, 0.0, qv.p, r);
+            Mat<T> vh(ctx, r, n);
+            transpose_conj<T>(ctx, n, r, qv.p, r, vh.p, n);
+            if (SVh) {
+                *SVh = Mat<T>(ctx, r, n);
+                scale_rows_cols<T>(ctx, r, n, vh.p, n, Sv.p, true, false, SVh->p, n);
+            }
+            if (Vh) *Vh = std::move(vh);
+        }
+    }
+    if (S) {
+        *S = Mat<double>(ctx, r, 1);
+        QIL_CUDA(cudaMemcpyAsync(S->p, Sv.p, r * sizeof(double), cudaMemcpyDeviceToDevice, ctx->stream));
+    }
+    return r;
+}
+
+template int svd_trunc<double>(qil_ctx*, int64_t, int64_t, const double*, int64_t, double, int64_t, int64_t,
+                               Mat<double>*, Mat<double>*, Mat<double>*, Mat<double>*, Mat<double>*, int, int64_t);
+template int svd_trunc<cplx>(qil_ctx*, int64_t, int64_t, const cplx*, int64_t, double, int64_t, int64_t, Mat<cplx>*,
+                             Mat<cplx>*, Mat<cplx>*, Mat<cplx>*, Mat<double>*, int, int64_t);
+
+}  // namespace qil

@@ -99,7 +99,9 @@ def test_coefficient_all_bitstrings_reconstruct_signal(q):
     psi = q.SignalMPS.from_cores(cores, c)
     bits = np.array([O.bits_msb(i, n) for i in range(2**n)], dtype=np.uint8)
     got = q.coefficients(psi, bits)
-    assert np.abs(got - x).max() <= 1e-12 * np.abs(x).max()
+    want = O.coefficient_batch(cores, c, bits)
+    assert np.abs(got - want).max() <= 1e-13 * np.abs(x).max()
+    assert np.abs(got - x).max() <= 1e-6 * np.abs(x).max()   # cutoff 1e-15 on sigma^2
 
 
 # ------------------------------------------------------------------------------------------

@@ -1,0 +1,278 @@
+"""GPU parity for the MPS-level algorithms and the MPO builders, through the C ABI, against the CPU
+oracle and the reference's golden vectors (bond dimensions identical, amplitudes within 1e-10)."""
+import math
+
+import numpy as np
+import pytest
+
+import qil_oracle as O
+
+pytestmark = pytest.mark.gpu
+TOL = 1e-10
+
+
+def _all_bits(n):
+    idx = np.arange(2**n)
+    return ((idx[:, None] >> np.arange(n - 1, -1, -1)[None, :]) & 1).astype(np.uint8)
+
+
+# ---------------------------------------------------------------------------------------------
+# signal_mps(:svd), signal_ztmps
+# ---------------------------------------------------------------------------------------------
+def test_encode_svd_kats(q, goldens):
+    x = np.array(goldens["coefficient_kats"]["x"], dtype=float)
+    psi = q.signal_mps(x)
+    assert abs(psi.amplitude - np.linalg.norm(x)) < 1e-12
+    for i in range(8):
+        assert abs(q.coefficient(psi, i) - x[i]) < 1e-12
+    assert np.allclose(q.mps_to_vector(psi), x, atol=1e-12)
+    rev = np.array([x[O.bitrev(i, 3)] for i in range(8)])
+    assert np.allclose(q.mps_to_vector(psi, reverse=True), rev, atol=1e-12)
+    with pytest.raises(q.ArgumentError):
+        q.signal_mps(x, method="nope")
+    # N = 5 -> n = round(log2 5) = 2 -> length mismatch is an error, not padding (SignalConverters.jl:18-30)
+    with pytest.raises(AssertionError):
+        q.signal_mps(np.arange(5.0))
+    # N = 7 -> n = 3 -> zero padded
+    p7 = q.signal_mps(np.arange(1.0, 8.0))
+    assert np.allclose(q.mps_to_vector(p7), list(range(1, 8)) + [0], atol=1e-12)
+
+
+@pytest.mark.parametrize("cplx", [False, True])
+@pytest.mark.parametrize("n", [1, 2, 5, 6, 9])
+def test_encode_svd_random_roundtrip(q, n, cplx):
+    rng = np.random.default_rng(n * 3 + cplx)
+    x = rng.standard_normal(2**n) + (1j * rng.standard_normal(2**n) if cplx else 0)
+    psi = q.signal_mps(x)
+    co, c = O.tt_svd(x)
+    assert psi.bonds == O.bonds_of(co)
+    assert np.abs(q.mps_to_vector(psi) - x).max() <= 1e-12 * np.abs(x).max()
+
+
+def test_encode_svd_structured_matches_oracle(q, goldens):
+    g = goldens["signal_tutorial_n10"]
+    n = g["n"]
+    x = q.generate_signal(n, kind="sin_decay", dt=1.0 / 2**n, freq=[2 * math.pi * f for f in g["freq_over_2pi"]],
+                          decay_rate=g["decay_rate"], phase=g["phase"])
+    psi = q.signal_mps(x, method="svd", cutoff=g["cutoff"], maxdim=g["maxdim"])
+    co, c = O.tt_svd(x, cutoff=g["cutoff"], maxdim=g["maxdim"])
+    assert psi.bonds == O.bonds_of(co)
+    assert max(psi.bonds) == g["max_bond_svd"]
+    got = q.mps_to_vector(psi)
+    want = O.mps_to_vector(co, c)
+    assert np.abs(got - want).max() <= TOL * np.abs(want).max()
+    assert np.linalg.norm(got - x) / np.linalg.norm(x) == pytest.approx(g["rel_err_svd"], rel=0.01)
+    # quick-start signal (README.md:107-109), n = 10 and cutoff 1e-12: bonds [2,3,3,2,...]
+    x = q.generate_signal(10, kind="sin_decay", freq=[1.0, 2.5], decay_rate=[0.08, 0.03])
+    psi = q.signal_mps(x, cutoff=1e-12)
+    co, c = O.tt_svd(x, cutoff=1e-12)
+    assert psi.bonds == O.bonds_of(co) == [2, 3, 3, 2, 2, 2, 2, 2, 2]
+
+
+def test_signal_ztmps(q, goldens):
+    g = goldens["zt_tutorial_n2"]
+    n, N = 2, 4
+    x = np.array([g["a"] ** j * math.cos(g["omega0_over_pi"] * math.pi * j) for j in range(N)])
+    z = q.signal_ztmps(x, cutoff=1e-14, maxdim=64)
+    co, c = O.signal_ztmps(x, cutoff=1e-14, maxdim=64)
+    assert z.bonds == O.bonds_of(co) and len(z) == n
+    for j in range(N):
+        b = O.bits_msb(j, n)
+        assert abs(q.coefficient(z, O.interleave(b, b)) - x[j]) < 1e-13
+    assert abs(z[0, 1, 0, 0]) < 1e-13   # off-diagonal (main != copy) entries vanish
+    with pytest.raises(q.ArgumentError):
+        q.coefficient(z, [1, 0, 1])
+    # n = 14 structured complex signal: same paired bond structure as the oracle
+    n = 14
+    j = np.arange(2**n)
+    x = (1.0003 * np.exp(0.002j)) ** j * np.cos(0.0061 * j)
+    z = q.signal_ztmps(x, cutoff=1e-12, maxdim=128)
+    co, c = O.signal_ztmps(x, cutoff=1e-12, maxdim=128)
+    assert z.bonds == O.bonds_of(co)
+    bits = np.array([O.interleave(O.bits_msb(i, n), O.bits_msb(i, n)) for i in range(0, 2**n, 97)], dtype=np.uint8)
+    got = q.coefficients(z, bits)
+    assert np.abs(got - x[::97]).max() <= 1e-9 * np.abs(x).max()
+    assert np.abs(got - O.coefficient_batch(co, c, bits)).max() <= TOL * np.abs(x).max()
+
+
+# ---------------------------------------------------------------------------------------------
+# norm / canonicalize! / compress!
+# ---------------------------------------------------------------------------------------------
+@pytest.mark.parametrize("cplx", [False, True])
+def test_norm_canonicalize_compress(q, cplx):
+    rng = np.random.default_rng(5 + cplx)
+    bonds = [1, 2, 4, 6, 4, 2, 1]
+    cores = [rng.standard_normal((bonds[i], 2, bonds[i + 1])) + (1j * rng.standard_normal((bonds[i], 2, bonds[i + 1])) if cplx else 0)
+             for i in range(6)]
+    dense = O.mps_to_vector(cores)
+    psi = q.SignalMPS.from_cores(cores, 1.0)
+    assert abs(q.norm(psi) - np.linalg.norm(dense)) <= 1e-10 * np.linalg.norm(dense)
+    for d in ("right", "left"):
+        p2 = q.canonicalize(psi.copy(), d)
+        assert abs(q.norm(p2) - np.linalg.norm(dense)) <= 1e-10 * np.linalg.norm(dense)
+        assert np.abs(q.mps_to_vector(p2) - dense).max() <= 1e-10 * np.abs(dense).max()
+        assert p2.bonds == O.bonds_of(O.canonicalize(cores, d))
+    with pytest.raises(q.ArgumentError):
+        q.canonicalize(psi.copy(), "up")
+    with pytest.raises(q.DomainError):
+        q.canonicalize(psi.copy(), "left", center=9)
+    # compress!(maxdim=2, tol=1e-8, sweeps=2): bonds <= 2, unit norm (test/test_mps.jl:331-369)
+    p3 = q.compress(psi.copy(), maxdim=2, tol=1e-8, sweeps=2)
+    co, amp = O.compress(cores, 1.0, maxdim=2, tol=1e-8, sweeps=2)
+    assert max(p3.bonds) <= 2 and p3.bonds == O.bonds_of(co)
+    assert abs(q.norm(p3) - 1.0) < 1e-10
+    assert abs(p3.amplitude - amp) <= 1e-10 * amp
+    got = q.mps_to_vector(p3); want = O.mps_to_vector(co, amp)
+    assert np.abs(got - want).max() <= 1e-9 * np.abs(want).max()
+    # lossless at default tol
+    p4 = q.compress(psi.copy())
+    assert np.abs(q.mps_to_vector(p4) - dense).max() <= 1e-10 * np.abs(dense).max()
+    with pytest.raises(q.DomainError):
+        q.compress(q.SignalMPS.from_cores([rng.standard_normal((1, 2, 1))]))
+
+
+def test_compress_after_apply_reduces_product_bonds(q):
+    # README quick start: encode -> compress! -> QFT -> apply; then compress the product
+    n = 10
+    x = q.generate_signal(n, kind="sin_decay", freq=[1.0, 2.5], decay_rate=[0.08, 0.03])
+    psi = q.signal_mps(x, cutoff=1e-9, maxdim=64)
+    q.compress(psi, maxdim=64)
+    W = q.build_qft_mpo(psi, cutoff=1e-12, maxdim=128)
+    spec = W * psi
+    want = q.mps_to_vector(spec)
+    c2 = q.compress(spec.copy(), tol=1e-10)
+    assert max(c2.bonds) < max(spec.bonds)
+    # compress! starts with canonicalize!(cutoff=1e-12) (mps.jl:923), i.e. ~1e-6 relative truncation
+    assert np.abs(q.mps_to_vector(c2) - want).max() <= 5e-6 * np.linalg.norm(want)
+    # parity with the oracle's compress! on the very same cores
+    co, amp = O.compress(spec.cores(), spec.amplitude, tol=1e-10)
+    assert c2.bonds == O.bonds_of(co)
+    assert abs(c2.amplitude - amp) <= 1e-10 * amp
+    assert np.abs(q.mps_to_vector(c2) - O.mps_to_vector(co, amp)).max() <= 1e-9 * np.linalg.norm(want)
+
+
+# ---------------------------------------------------------------------------------------------
+# builders
+# ---------------------------------------------------------------------------------------------
+def test_qft_builder(q, goldens):
+    g = goldens["mpo_max_bond_series"]
+    for n in range(2, 13):
+        W = q.build_qft_mpo(n, cutoff=1e-15, maxdim=None)
+        assert max(W.bonds) == g["qft"][n - g["n_start"]], n
+        assert W.bonds == O.mpo_bonds(O.build_qft_mpo(n, cutoff=1e-15, maxdim=O.BIG))
+    assert q.build_qft_mpo(1).bonds == []
+    with pytest.raises(q.ArgumentError):
+        q.build_qft_mpo(0)
+    rng = np.random.default_rng(11)
+    for n in range(2, 6):   # test/test_qft_transformer.jl:331-464
+        N = 2**n
+        W = q.build_qft_mpo(n, cutoff=1e-14, maxdim=1000)
+        F = np.exp(-2j * math.pi * np.outer(np.arange(N), np.arange(N)) / N) / math.sqrt(N)
+        for j in list(range(N)) + ["rand"]:
+            if j == "rand":
+                x = rng.standard_normal(N) + 1j * rng.standard_normal(N)
+            else:
+                x = np.zeros(N); x[j] = 1.0
+            v = q.mps_to_vector(q.apply(W, q.signal_mps(x), cutoff=0.0, maxdim=1000))
+            fn = np.empty(N, dtype=complex)
+            for i in range(N):
+                fn[O.bitrev(i, n)] = v[i]
+            assert np.linalg.norm(fn - F @ x) < 1e-10
+
+
+def test_dft_tutorial_n4(q, goldens):
+    g = goldens["dft_tutorial_n4"]
+    x = q.generate_signal(g["n"], kind="sin", dt=g["dt"], freq=2 * math.pi)
+    psi = q.signal_mps(x)
+    assert psi.bonds == g["mps_bonds"]
+    W = q.build_qft_mpo(psi, cutoff=g["qft_cutoff"], maxdim=g["qft_maxdim"])
+    assert W.bonds == g["mpo_bonds"]
+    out = W * psi
+    assert out.bonds == g["product_bonds"]
+    v = q.mps_to_vector(out)
+    F = np.fft.fft(x) / 4.0
+    assert max(abs(v[i] - F[O.bitrev(i, 4)]) for i in range(16)) < 1e-13
+
+
+def test_dt_builder(q, goldens):
+    g = goldens["mpo_max_bond_series"]
+    for n in range(2, 8):
+        W = q.build_dt_mpo(n, 2 * math.pi, cutoff=1e-15, maxdim=None)
+        assert max(W.bonds) == g["dt"][n - g["n_start"]], n
+        assert not W.is_complex
+    for n in (1, 2, 3, 4):   # test/test_dt_transformer.jl:211-238
+        N = 2**n
+        for wr in (0.0, 0.75, 2.0, 5.0):
+            W = q.build_dt_mpo(n, wr)
+            for j in range(N):
+                x = np.zeros(N); x[j] = 1.0
+                out = W * q.signal_ztmps(x)
+                bits = np.array([O.interleave(O.bits_lsb(k, n), O.bits_msb(jj, n)) for k in range(N) for jj in range(N)],
+                                dtype=np.uint8)
+                got = q.coefficients(out, bits).reshape(N, N)
+                want = np.zeros((N, N)); want[:, j] = [math.exp(-wr * j * k / N) / math.sqrt(N) for k in range(N)]
+                assert np.abs(got - want).max() <= 1e-7
+
+
+def test_zt_builder(q, goldens):
+    g = goldens["mpo_max_bond_series"]
+    for n in range(2, 7):
+        W = q.build_zt_mpo(n, 2 * math.pi, cutoff=1e-15, maxdim=None)
+        assert max(W.bonds) == g["zt"][n - g["n_start"]], n
+        assert W.bonds == O.mpo_bonds(O.build_zt_mpo(n, 2 * math.pi, cutoff=1e-15, maxdim=O.BIG))
+    for n in (1, 2, 3, 4):   # test/test_zt_transformer.jl:68-110
+        N = 2**n
+        for wr in (0.0, 0.75, 5.0):
+            W = q.build_zt_mpo(n, wr)
+            for j in range(N):
+                x = np.zeros(N); x[j] = 1.0
+                out = W * q.signal_ztmps(x)
+                bits = np.array([O.interleave(O.bits_lsb(k, n), O.bits_lsb(l, n)) for k in range(N) for l in range(N)],
+                                dtype=np.uint8)
+                Z = q.coefficients(out, bits).reshape(N, N)
+                ref = np.array([[np.exp(-(wr * k + 2j * math.pi * l) / N * j) / N for l in range(N)] for k in range(N)])
+                assert np.linalg.norm(Z - ref) <= 2e-7
+
+
+def test_zt_tutorial_n2_end_to_end(q, goldens):
+    g = goldens["zt_tutorial_n2"]
+    n, N = 2, 4
+    x = np.array([g["a"] ** j * math.cos(g["omega0_over_pi"] * math.pi * j) for j in range(N)])
+    z = q.signal_ztmps(x, cutoff=g["encode_cutoff"], maxdim=g["encode_maxdim"])
+    W = q.build_zt_mpo(z, 2 * math.pi, cutoff=g["mpo_cutoff"], maxdim=g["mpo_maxdim"])
+    assert W.bonds == g["mpo_bonds"]
+    out = W * z
+    bits = np.array([O.interleave(O.bits_lsb(k, n), O.bits_lsb(l, n)) for k in range(N) for l in range(N)], dtype=np.uint8)
+    chi = q.coefficients(out, bits).reshape(N, N)
+    assert np.abs(chi.real - np.array(g["chi_5digits_re"])).max() < 6e-6
+    assert np.abs(chi.imag - np.array(g["chi_5digits_im"])).max() < 6e-6
+    ref = np.array([[sum(x[j] * np.exp(-(2 * math.pi * k + 2j * math.pi * l) / N * j) for j in range(N)) / N
+                     for l in range(N)] for k in range(N)])
+    assert (np.abs(chi - ref) / np.abs(ref)).max() < 1e-13
+
+
+def test_zt_medium_matches_oracle(q):
+    # n = 8 paired (16 sites): GPU-built zT MPO applied to a GPU-encoded ZTMPS vs the oracle pipeline
+    n = 8
+    j = np.arange(2**n)
+    x = (0.995 * np.exp(0.01j)) ** j * np.cos(0.07 * j)
+    z = q.signal_ztmps(x, cutoff=1e-12, maxdim=128)
+    W = q.build_zt_mpo(z, 2 * math.pi, cutoff=1e-12, maxdim=128)
+    co, c = O.signal_ztmps(x, cutoff=1e-12, maxdim=128)
+    Wo = O.build_zt_mpo(n, 2 * math.pi, cutoff=1e-12, maxdim=128)
+    assert z.bonds == O.bonds_of(co)
+    assert W.bonds == O.mpo_bonds(Wo)
+    out = W * z
+    oo = O.apply_mpo_mps(Wo, co)
+    rng = np.random.default_rng(0)
+    bits = rng.integers(0, 2, size=(4000, 2 * n)).astype(np.uint8)
+    got = q.coefficients(out, bits)
+    want = O.coefficient_batch(oo, c, bits)
+    # both MPOs carry a truncation error ~ sqrt(cutoff); gauge-invariant amplitudes agree to that level
+    assert np.abs(got - want).max() <= 5e-6 * np.abs(want).max()
+    ks = rng.integers(0, 2**n, 200); ls = rng.integers(0, 2**n, 200)
+    bits = np.array([O.interleave(O.bits_lsb(int(k), n), O.bits_lsb(int(l), n)) for k, l in zip(ks, ls)], dtype=np.uint8)
+    got = q.coefficients(out, bits)
+    ref = np.array([np.sum(x * np.exp(-(2 * math.pi * k + 2j * math.pi * l) / 2**n * j)) / 2**n for k, l in zip(ks, ls)])
+    # MPO truncated at cutoff 1e-12 on sigma^2: ~1e-6 of the operator norm
+    assert np.abs(got - ref).max() <= 5e-5 * np.abs(ref).max()
