@@ -96,6 +96,17 @@ int qil_encode_svd(qil_ctx* ctx, int is_complex, const void* x, int64_t N, doubl
                    qil_mps** out);
 int qil_encode_svd_dev(qil_ctx* ctx, int is_complex, const void* d_x, int64_t N, double cutoff,
                        int64_t maxdim, qil_mps** out);
+/* signal_mps(x; method=:rsvd, k, p, q, random_seed, cutoff, maxdim, mindim) -- divide-and-conquer TT with
+ * randomized SVD (SignalConverters.jl:107-196, rsvd.jl:38-121).  Every split uses the same normal stream:
+ * Omega[c][j] = stream[c + C*j] (the column-major `random_itensor` of the reference).  `normal_stream` may
+ * be NULL (device generator seeded with `seed`) or point at `stream_len` scalars of the signal's type drawn
+ * by the host (`Random.seed!(seed); randn(T, len)` in the Julia shim), len >= max over splits of C*l. */
+int qil_encode_rsvd(qil_ctx* ctx, int is_complex, const void* x, int64_t N, int k, int p, int q, int64_t seed,
+                    double cutoff, int64_t maxdim, int64_t mindim, const void* normal_stream, int64_t stream_len,
+                    int64_t reserved, qil_mps** out);
+int qil_encode_rsvd_dev(qil_ctx* ctx, int is_complex, const void* d_x, int64_t N, int k, int p, int q, int64_t seed,
+                        double cutoff, int64_t maxdim, int64_t mindim, const void* d_normal_stream,
+                        int64_t stream_len, int64_t reserved, qil_mps** out);
 /* Per-site copy-tensor split of signal_ztmps (SignalConverters.jl:258-277): n-site MPS -> 2n-site chain. */
 int qil_ztmps_split(qil_ctx* ctx, const qil_mps* psi, double cutoff, int64_t maxdim, qil_mps** out);
 
@@ -119,6 +130,12 @@ int qil_build_zt_mpo(qil_ctx* ctx, int n, double omega_r, double cutoff, int64_t
 int qil_qr(qil_ctx* ctx, int is_complex, int64_t m, int64_t n, const void* A, int positive, void* Q, void* R);
 int qil_svd_trunc(qil_ctx* ctx, int is_complex, int64_t m, int64_t n, const void* A, double cutoff,
                   int64_t maxdim, int64_t mindim, int64_t* rank, void* U, double* S, void* Vh);
+/* rsvd(A, Linds...; k=20, p=10, q=0, random_seed, cutoff=1e-15, maxdim=k, mindim=1) (src/linalg/rsvd.jl:38-121)
+ * on a host matrix; outputs as for qil_svd_trunc (room for min(k+p, m, n) columns/rows).  An empty index set
+ * (m == 0 or n == 0) is an ErrorException like the reference (rsvd.jl:56-60). */
+int qil_rsvd(qil_ctx* ctx, int is_complex, int64_t m, int64_t n, const void* A, int k, int p, int q, int64_t seed,
+             double cutoff, int64_t maxdim, int64_t mindim, const void* normal_stream, int64_t stream_len,
+             int64_t* rank, void* U, double* S, void* Vh);
 
 #ifdef __cplusplus
 }

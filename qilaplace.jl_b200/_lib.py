@@ -64,6 +64,10 @@ _SIGS = {
     "qil_apply_mpo_mpo": [c_ctx, c_mpo, c_mpo, C.c_int, C.c_int, C.POINTER(c_mpo)],
     "qil_encode_svd": [c_ctx, C.c_int, C.c_void_p, C.c_int64, C.c_double, C.c_int64, C.POINTER(c_mps)],
     "qil_encode_svd_dev": [c_ctx, C.c_int, C.c_void_p, C.c_int64, C.c_double, C.c_int64, C.POINTER(c_mps)],
+    "qil_encode_rsvd": [c_ctx, C.c_int, C.c_void_p, C.c_int64, C.c_int, C.c_int, C.c_int, C.c_int64, C.c_double,
+                        C.c_int64, C.c_int64, C.c_void_p, C.c_int64, C.c_int64, C.POINTER(c_mps)],
+    "qil_encode_rsvd_dev": [c_ctx, C.c_int, C.c_void_p, C.c_int64, C.c_int, C.c_int, C.c_int, C.c_int64, C.c_double,
+                            C.c_int64, C.c_int64, C.c_void_p, C.c_int64, C.c_int64, C.POINTER(c_mps)],
     "qil_ztmps_split": [c_ctx, c_mps, C.c_double, C.c_int64, C.POINTER(c_mps)],
     "qil_canonicalize": [c_ctx, c_mps, C.c_int, C.c_int, C.c_double, C.c_int64],
     "qil_compress": [c_ctx, c_mps, C.c_int64, C.c_double, C.c_int],
@@ -72,6 +76,8 @@ _SIGS = {
     "qil_build_dt_mpo": [c_ctx, C.c_int, C.c_double, C.c_double, C.c_int64, C.POINTER(c_mpo)],
     "qil_build_zt_mpo": [c_ctx, C.c_int, C.c_double, C.c_double, C.c_int64, C.POINTER(c_mpo)],
     "qil_qr": [c_ctx, C.c_int, C.c_int64, C.c_int64, C.c_void_p, C.c_int, C.c_void_p, C.c_void_p],
+    "qil_rsvd": [c_ctx, C.c_int, C.c_int64, C.c_int64, C.c_void_p, C.c_int, C.c_int, C.c_int, C.c_int64, C.c_double,
+                 C.c_int64, C.c_int64, C.c_void_p, C.c_int64, i64p, C.c_void_p, C.c_void_p, C.c_void_p],
     "qil_svd_trunc": [c_ctx, C.c_int, C.c_int64, C.c_int64, C.c_void_p, C.c_double, C.c_int64, C.c_int64,
                       i64p, C.c_void_p, C.c_void_p, C.c_void_p],
 }

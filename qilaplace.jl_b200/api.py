@@ -413,17 +413,17 @@ def signal_mps(x, method="svd", ctx=None, **kwargs):
         k = int(kwargs.pop("k", 20)); p = int(kwargs.pop("p", 10)); q = int(kwargs.pop("q", 0))
         seed = int(kwargs.pop("random_seed", 1234)); mindim = int(kwargs.pop("mindim", 1))
         kwargs.pop("verbose", None); kwargs.pop("bondtag", None)
-        omega = kwargs.pop("omega", None)
+        stream = kwargs.pop("normal_stream", None)
         if kwargs:
             raise TypeError(f"signal_mps(method=:rsvd): unexpected keyword(s) {sorted(kwargs)}")
-        if omega is not None:
-            om = np.ascontiguousarray(omega, dtype=_np_dtype(is_complex))
-            op, orows, ocols = C.c_void_p(om.ctypes.data), om.shape[0], om.shape[1]
+        if stream is not None:
+            st = np.ascontiguousarray(stream, dtype=_np_dtype(is_complex)).reshape(-1)
+            sp, slen = C.c_void_p(st.ctypes.data), st.size
         else:
-            op, orows, ocols = None, 0, 0
+            sp, slen = None, 0
         call("qil_encode_rsvd", ctx.handle, int(is_complex), C.c_void_p(xa.ctypes.data), C.c_int64(xa.size),
-             k, p, q, C.c_int64(seed), cutoff, C.c_int64(maxdim), C.c_int64(mindim), op, C.c_int64(orows),
-             C.c_int64(ocols), C.byref(h))
+             k, p, q, C.c_int64(seed), cutoff, C.c_int64(maxdim), C.c_int64(mindim), sp, C.c_int64(slen),
+             C.c_int64(0), C.byref(h))
     return SignalMPS(ctx, h)
 
 
@@ -545,5 +545,34 @@ def svd_trunc(A, cutoff=0.0, maxdim=None, mindim=1, ctx=None):
     call("qil_svd_trunc", ctx.handle, int(ic), C.c_int64(m), C.c_int64(n), C.c_void_p(A.ctypes.data), float(cutoff),
          C.c_int64(_maxdim_arg(maxdim)), C.c_int64(mindim), C.byref(r), C.c_void_p(U.ctypes.data),
          C.c_void_p(S.ctypes.data), C.c_void_p(Vh.ctypes.data))
+    r = int(r.value)
+    return U[: m * r].reshape(m, r), S[:r], Vh[: r * n].reshape(r, n)
+
+
+def rsvd(A, k=20, p=10, q=0, random_seed=1234, cutoff=1e-15, maxdim=None, mindim=1, normal_stream=None, ctx=None,
+         **_ignored):
+    """rsvd(A, Linds...; k=20, p=10, q=0, random_seed=1234, cutoff=1e-15, maxdim=k, mindim=1) on a matrix
+    (src/linalg/rsvd.jl:38-121) -> (U, S, Vh)."""
+    ctx = ctx or default_context()
+    A = np.asarray(A)
+    if A.ndim != 2 or A.shape[0] == 0 or A.shape[1] == 0:
+        raise ErrorException("In `rsvd`, left or right index set is empty.")
+    ic = np.iscomplexobj(A)
+    A = np.ascontiguousarray(A, dtype=_np_dtype(ic))
+    m, n = A.shape
+    l = min(k + p, m, n)
+    U = np.empty(m * l, dtype=A.dtype)
+    S = np.empty(l, dtype=np.float64)
+    Vh = np.empty(l * n, dtype=A.dtype)
+    r = C.c_int64(0)
+    if normal_stream is not None:
+        st = np.ascontiguousarray(normal_stream, dtype=A.dtype).reshape(-1)
+        sp, slen = C.c_void_p(st.ctypes.data), st.size
+    else:
+        sp, slen = None, 0
+    call("qil_rsvd", ctx.handle, int(ic), C.c_int64(m), C.c_int64(n), C.c_void_p(A.ctypes.data), int(k), int(p), int(q),
+         C.c_int64(random_seed), float(cutoff), C.c_int64(k if maxdim is None else _maxdim_arg(maxdim)),
+         C.c_int64(mindim), sp, C.c_int64(slen), C.byref(r), C.c_void_p(U.ctypes.data), C.c_void_p(S.ctypes.data),
+         C.c_void_p(Vh.ctypes.data))
     r = int(r.value)
     return U[: m * r].reshape(m, r), S[:r], Vh[: r * n].reshape(r, n)

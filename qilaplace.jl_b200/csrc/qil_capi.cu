@@ -54,6 +54,26 @@ static int svd_host(qil_ctx* ctx, int64_t m, int64_t n, const void* A, double cu
     return r;
 }
 
+template <typename T>
+static int rsvd_host(qil_ctx* ctx, int64_t m, int64_t n, const void* A, const RsvdOpts& oin, const void* stream,
+                     int64_t stream_len, void* Uh, double* Sh, void* Vhh) {
+    Mat<T> dA(ctx, m, n), U, Vh, dS;
+    Mat<double> S;
+    RsvdOpts o = oin;
+    QIL_CUDA(cudaMemcpyAsync(dA.p, A, (size_t)m * n * sizeof(T), cudaMemcpyHostToDevice, ctx->stream));
+    if (stream && stream_len > 0) {
+        dS = Mat<T>(ctx, stream_len, 1);
+        QIL_CUDA(cudaMemcpyAsync(dS.p, stream, (size_t)stream_len * sizeof(T), cudaMemcpyHostToDevice, ctx->stream));
+        o.omega = dS.p; o.omega_rows = stream_len; o.omega_cols = 1;
+    }
+    const int r = rsvd_matrix<T>(ctx, dA.p, m, n, o, U, S, Vh);
+    if (Uh) QIL_CUDA(cudaMemcpyAsync(Uh, U.p, (size_t)m * r * sizeof(T), cudaMemcpyDeviceToHost, ctx->stream));
+    if (Sh) QIL_CUDA(cudaMemcpyAsync(Sh, S.p, (size_t)r * sizeof(double), cudaMemcpyDeviceToHost, ctx->stream));
+    if (Vhh) QIL_CUDA(cudaMemcpyAsync(Vhh, Vh.p, (size_t)r * n * sizeof(T), cudaMemcpyDeviceToHost, ctx->stream));
+    ctx->sync();
+    return r;
+}
+
 extern "C" {
 
 const char* qil_last_error(void) { return g_last_error.c_str(); }
@@ -334,6 +354,45 @@ int qil_encode_svd(qil_ctx* ctx, int is_complex, const void* x, int64_t N, doubl
     QIL_API_END
 }
 
+int qil_encode_rsvd_dev(qil_ctx* ctx, int is_complex, const void* d_x, int64_t N, int k, int p, int q, int64_t seed,
+                        double cutoff, int64_t maxdim, int64_t mindim, const void* d_normal_stream,
+                        int64_t stream_len, int64_t reserved, qil_mps** out) {
+    QIL_API_BEGIN
+    (void)reserved;
+    QIL_NONNULL(ctx); QIL_NONNULL(d_x); QIL_NONNULL(out);
+    QIL_CUDA(cudaSetDevice(ctx->device));
+    RsvdOpts o;
+    o.k = k; o.p = p; o.q = q; o.seed = seed; o.cutoff = cutoff; o.maxdim = fix_maxdim(maxdim);
+    o.mindim = mindim < 1 ? 1 : mindim;
+    o.omega = d_normal_stream; o.omega_rows = d_normal_stream ? stream_len : 0; o.omega_cols = 1;
+    *out = is_complex ? encode_rsvd<cplx>(ctx, (const cplx*)d_x, N, o) : encode_rsvd<double>(ctx, (const double*)d_x, N, o);
+    QIL_API_END
+}
+
+int qil_encode_rsvd(qil_ctx* ctx, int is_complex, const void* x, int64_t N, int k, int p, int q, int64_t seed,
+                    double cutoff, int64_t maxdim, int64_t mindim, const void* normal_stream, int64_t stream_len,
+                    int64_t reserved, qil_mps** out) {
+    QIL_API_BEGIN
+    QIL_NONNULL(ctx); QIL_NONNULL(x); QIL_NONNULL(out);
+    QIL_REQUIRE(N >= 1, QIL_ERR_ARGUMENT, "signal_mps: empty signal");
+    QIL_CUDA(cudaSetDevice(ctx->device));
+    const size_t es = elem_size(is_complex);
+    void* d_x = ctx->alloc((size_t)N * es);
+    void* d_s = nullptr;
+    QIL_CUDA(cudaMemcpyAsync(d_x, x, (size_t)N * es, cudaMemcpyHostToDevice, ctx->stream));
+    if (normal_stream && stream_len > 0) {
+        d_s = ctx->alloc((size_t)stream_len * es);
+        QIL_CUDA(cudaMemcpyAsync(d_s, normal_stream, (size_t)stream_len * es, cudaMemcpyHostToDevice, ctx->stream));
+    }
+    int rc = qil_encode_rsvd_dev(ctx, is_complex, d_x, N, k, p, q, seed, cutoff, maxdim, mindim, d_s, stream_len,
+                                 reserved, out);
+    ctx->free(d_x);
+    if (d_s) ctx->free(d_s);
+    cudaStreamSynchronize(ctx->stream);
+    return rc;
+    QIL_API_END
+}
+
 int qil_ztmps_split(qil_ctx* ctx, const qil_mps* psi, double cutoff, int64_t maxdim, qil_mps** out) {
     QIL_API_BEGIN
     QIL_NONNULL(ctx); QIL_NONNULL(psi); QIL_NONNULL(out);
@@ -417,6 +476,24 @@ int qil_svd_trunc(qil_ctx* ctx, int is_complex, int64_t m, int64_t n, const void
     QIL_CUDA(cudaSetDevice(ctx->device));
     *rank = is_complex ? svd_host<cplx>(ctx, m, n, A, cutoff, fix_maxdim(maxdim), mindim, U, S, Vh)
                        : svd_host<double>(ctx, m, n, A, cutoff, fix_maxdim(maxdim), mindim, U, S, Vh);
+    QIL_API_END
+}
+
+int qil_rsvd(qil_ctx* ctx, int is_complex, int64_t m, int64_t n, const void* A, int k, int p, int q, int64_t seed,
+             double cutoff, int64_t maxdim, int64_t mindim, const void* normal_stream, int64_t stream_len,
+             int64_t* rank, void* U, double* S, void* Vh) {
+    QIL_API_BEGIN
+    QIL_NONNULL(ctx); QIL_NONNULL(rank);
+    QIL_REQUIRE(m >= 1 && n >= 1, QIL_ERR_RUNTIME, "In `rsvd`, left or right index set is empty.");
+    QIL_NONNULL(A);
+    QIL_REQUIRE(k >= 1 && p >= 0 && q >= 0, QIL_ERR_ARGUMENT, "rsvd: k >= 1, p >= 0, q >= 0 required");
+    QIL_CUDA(cudaSetDevice(ctx->device));
+    RsvdOpts o;
+    o.k = k; o.p = p; o.q = q; o.seed = seed; o.cutoff = cutoff;
+    o.maxdim = maxdim <= 0 ? k : maxdim;   // rsvd.jl:48: maxdim defaults to k
+    o.mindim = mindim < 1 ? 1 : mindim;
+    *rank = is_complex ? rsvd_host<cplx>(ctx, m, n, A, o, normal_stream, stream_len, U, S, Vh)
+                       : rsvd_host<double>(ctx, m, n, A, o, normal_stream, stream_len, U, S, Vh);
     QIL_API_END
 }
 

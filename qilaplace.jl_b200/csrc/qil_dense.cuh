@@ -88,4 +88,11 @@ int svd_trunc(qil_ctx* ctx, int64_t m, int64_t n, const T* A, int64_t lda, doubl
               int64_t mindim, Mat<T>* U, Mat<T>* US, Mat<T>* Vh, Mat<T>* SVh, Mat<double>* S,
               int nsum = 1, int64_t sum_stride = 0);
 
+
+// Same for a wide A (m <= n) whose adjoint At = A^H (n x m, row-major, pitch ldat) is what the caller holds
+// (the randomized SVD produces B^H = A^H Q directly).
+template <typename T>
+int svd_trunc_adj(qil_ctx* ctx, int64_t m, int64_t n, const T* At, int64_t ldat, double cutoff, int64_t maxdim,
+                  int64_t mindim, Mat<T>* U, Mat<T>* US, Mat<T>* Vh, Mat<T>* SVh, Mat<double>* S);
+
 }  // namespace qil

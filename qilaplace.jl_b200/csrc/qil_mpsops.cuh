@@ -22,6 +22,9 @@ struct RsvdOpts {
 // signal_mps(x; method=:rsvd, ...)
 template <typename T> qil_mps* encode_rsvd(qil_ctx* ctx, const T* d_x, int64_t N, const RsvdOpts& o);
 
+template <typename T>
+int rsvd_matrix(qil_ctx* ctx, const T* d_A, int64_t m, int64_t n, const RsvdOpts& o, Mat<T>& U, Mat<double>& S, Mat<T>& Vh);
+
 qil_mps* ztmps_split(qil_ctx* ctx, const qil_mps* psi, double cutoff, int64_t maxdim);
 void canonicalize(qil_ctx* ctx, qil_mps* psi, int dir_right, int center, double cutoff, int64_t maxdim);
 void compress(qil_ctx* ctx, qil_mps* psi, int64_t maxdim, double tol, int sweeps);
@@ -31,4 +34,14 @@ qil_mpo* build_qft_mpo(qil_ctx* ctx, int n, double cutoff, int64_t maxdim);
 qil_mpo* build_dt_mpo(qil_ctx* ctx, int n, double wr, double cutoff, int64_t maxdim);
 qil_mpo* build_zt_mpo(qil_ctx* ctx, int n, double wr, double cutoff, int64_t maxdim);
 
+}  // namespace qil
+
+namespace qil {
+// streaming DMMA/TMA GEMMs (qil_sketch.cu)
+int stream_nt_for(int cols);
+bool stream_supported(long long R, long long C, long long ld, int cols);
+void stream_plan(qil_ctx* ctx, long long Mtot, long long Kdim, int* ksplit, long long* kchunk);
+int stream_grid(qil_ctx* ctx, long long Mtot, int ksplit);
+void stream_gemm(qil_ctx* ctx, bool trans, const double* A, long long R, long long C, long long ld, const double* X,
+                 int lpp, int nt, double* out, int ksplit, long long kchunk, double* sumsq_partials);
 }  // namespace qil

@@ -245,15 +245,16 @@ static int jacobi_square(qil_ctx* ctx, int ns, const T* R, int64_t ld, double cu
     return rank;
 }
 
+// adj != nullptr: the caller already holds A^H (n x m row-major, pitch ldadj) for a wide A (m <= n)
 template <typename T>
-int svd_trunc(qil_ctx* ctx, int64_t m, int64_t n, const T* A, int64_t lda, double cutoff, int64_t maxdim,
-              int64_t mindim, Mat<T>* U, Mat<T>* US, Mat<T>* Vh, Mat<T>* SVh, Mat<double>* S, int nsum,
-              int64_t sum_stride) {
+static int svd_core(qil_ctx* ctx, int64_t m, int64_t n, const T* A, int64_t lda, const T* adj, int64_t ldadj,
+                    double cutoff, int64_t maxdim, int64_t mindim, Mat<T>* U, Mat<T>* US, Mat<T>* Vh, Mat<T>* SVh,
+                    Mat<double>* S, int nsum, int64_t sum_stride) {
     QIL_REQUIRE(m >= 1 && n >= 1, QIL_ERR_ARGUMENT, "svd: empty matrix");
     if (maxdim < 1) maxdim = 1;
     Mat<T> Q, R, V, W;
     Mat<double> Sv;
-    const bool tall = m >= n;
+    const bool tall = (adj == nullptr) && m >= n;
     const int ns = (int)std::min(m, n);
     bool have_q = true;
     Mat<T> At;
@@ -263,6 +264,9 @@ int svd_trunc(qil_ctx* ctx, int64_t m, int64_t n, const T* A, int64_t lda, doubl
         } else {
             qr_thin<T>(ctx, m, n, A, lda, false, Q, R, nsum, sum_stride, true);
         }
+    } else if (adj) {
+        QIL_REQUIRE(m <= n, QIL_ERR_ARGUMENT, "svd: adjoint input requires a wide matrix");
+        qr_thin<T>(ctx, n, m, adj, ldadj, false, Q, R, 1, 0, true);
     } else {
         Mat<T> Asum;
         const T* src = A;
@@ -337,6 +341,23 @@ int svd_trunc(qil_ctx* ctx, int64_t m, int64_t n, const T* A, int64_t lda, doubl
     }
     return r;
 }
+
+template <typename T>
+int svd_trunc(qil_ctx* ctx, int64_t m, int64_t n, const T* A, int64_t lda, double cutoff, int64_t maxdim,
+              int64_t mindim, Mat<T>* U, Mat<T>* US, Mat<T>* Vh, Mat<T>* SVh, Mat<double>* S, int nsum,
+              int64_t sum_stride) {
+    return svd_core<T>(ctx, m, n, A, lda, nullptr, 0, cutoff, maxdim, mindim, U, US, Vh, SVh, S, nsum, sum_stride);
+}
+
+template <typename T>
+int svd_trunc_adj(qil_ctx* ctx, int64_t m, int64_t n, const T* At, int64_t ldat, double cutoff, int64_t maxdim,
+                  int64_t mindim, Mat<T>* U, Mat<T>* US, Mat<T>* Vh, Mat<T>* SVh, Mat<double>* S) {
+    return svd_core<T>(ctx, m, n, nullptr, 0, At, ldat, cutoff, maxdim, mindim, U, US, Vh, SVh, S, 1, 0);
+}
+template int svd_trunc_adj<double>(qil_ctx*, int64_t, int64_t, const double*, int64_t, double, int64_t, int64_t,
+                                   Mat<double>*, Mat<double>*, Mat<double>*, Mat<double>*, Mat<double>*);
+template int svd_trunc_adj<cplx>(qil_ctx*, int64_t, int64_t, const cplx*, int64_t, double, int64_t, int64_t,
+                                 Mat<cplx>*, Mat<cplx>*, Mat<cplx>*, Mat<cplx>*, Mat<double>*);
 
 template int svd_trunc<double>(qil_ctx*, int64_t, int64_t, const double*, int64_t, double, int64_t, int64_t,
                                Mat<double>*, Mat<double>*, Mat<double>*, Mat<double>*, Mat<double>*, int, int64_t);
