@@ -1,0 +1,385 @@
+#!/usr/bin/env python
+"""bench.py -- headline measurement of the QILaplace hot path on B200.
+
+Workload (BASELINE.json configs[3] / SURVEY.md 8d "C4", the configuration the metric is quoted on and
+the largest that fits one GPU comfortably): one real n=28 `:sin_decay` signal (2^28 samples, 2 GiB)
+  step = signal_mps(:rsvd, k=15, p=5, q=2, cutoff=1e-12)      (scripts/benchmark/qft_vs_fftw.jl:18-28)
+       -> signal_ztmps copy-tensor split                       (SignalConverters.jl:258-277)
+       -> W_zT * psi                                            (apply.jl:201-218; MPO built in setup,
+                                                                 as in the reference's timed regions)
+       -> 10^6 `coefficient`s                                   (mps.jl:669-693)
+metric = encode+zT-apply(+coefficients) samples/s = 2^n * signals / step time (whole job, all ranks).
+`value` is measured with the signal resident in HBM, `e2e` through the host-buffer C-ABI path with the
+host->device copy of the signal/bitstrings and the device->host read of the coefficients inside the timed
+region.  N > 1: every rank encodes its own signal (independent units, no data-path collective): weak scaling.
+
+    python bench.py --gpus 1 --steps 5 --warmup 3
+    python bench.py --impl reference        # the CPU oracle (numpy/OpenBLAS) on the host cores
+"""
+from __future__ import annotations
+
+import argparse
+import json
+import math
+import os
+import subprocess
+import sys
+import threading
+import time
+
+ROOT = os.path.dirname(os.path.abspath(__file__))
+sys.path.insert(0, ROOT)
+
+ALGO = dict(k=15, p=5, q=2, cutoff=1e-12)
+OMEGA_R = 2 * math.pi
+MPO_CUTOFF, MPO_MAXDIM = 1e-12, 128
+
+
+def parse():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--gpus", type=int, default=1)
+    ap.add_argument("--steps", type=int, default=5)
+    ap.add_argument("--warmup", type=int, default=3)
+    ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
+    ap.add_argument("--n", type=int, default=28)
+    ap.add_argument("--coeffs", type=int, default=1_000_000)
+    ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--cpu-n", type=int, default=0, help="n of the bounded CPU sample (default: min(n, 26))")
+    return ap.parse_args()
+
+
+def hash_bits(B, n, seed=1234):
+    """Counter-based hash bits (reproducible on any machine)."""
+    import numpy as np
+    out = np.empty((B, n), dtype=np.uint8)
+    chunk = 1 << 18
+    for s in range(0, B, chunk):
+        e = min(B, s + chunk)
+        idx = (np.arange(s, e, dtype=np.uint64)[:, None] * np.uint64(n) + np.arange(n, dtype=np.uint64)[None, :])
+        z = idx * np.uint64(0x9E3779B97F4A7C15) + np.uint64(seed)
+        z ^= z >> np.uint64(30); z *= np.uint64(0xBF58476D1CE4E5B9)
+        z ^= z >> np.uint64(27); z *= np.uint64(0x94D049BB133111EB)
+        z ^= z >> np.uint64(31)
+        out[s:e] = (z & np.uint64(1)).astype(np.uint8)
+    return out
+
+
+def signal_numpy(n):
+    import numpy as np
+    N = 2**n
+    dt = 1.0 / (2.5 * N)
+    j = np.arange(N, dtype=np.float64)
+    t = dt * j
+    return np.sin(1.0 * t) * np.exp(-0.08 * t) + np.sin(2.5 * t) * np.exp(-0.03 * t)
+
+
+class ClockSampler(threading.Thread):
+    """nvidia-smi clocks / throttle reasons sampled during the timed region."""
+
+    def __init__(self, index):
+        super().__init__(daemon=True)
+        self.index = index
+        self.samples = []
+        self.stop_flag = False
+        self.proc = None
+
+    def run(self):
+        q = ("clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.hw_slowdown,"
+             "clocks_event_reasons.hw_thermal_slowdown,clocks_event_reasons.sw_thermal_slowdown,"
+             "clocks_event_reasons.sw_power_cap")
+        try:
+            self.proc = subprocess.Popen(["nvidia-smi", f"--id={self.index}", f"--query-gpu={q}",
+                                          "--format=csv,noheader,nounits", "-lms", "100"],
+                                         stdout=subprocess.PIPE, stderr=subprocess.DEVNULL, text=True)
+            for line in self.proc.stdout:
+                if self.stop_flag:
+                    break
+                self.samples.append([c.strip() for c in line.split(",")])
+        except Exception:
+            pass
+
+    def finish(self):
+        self.stop_flag = True
+        if self.proc:
+            try:
+                self.proc.terminate()
+            except Exception:
+                pass
+        sm, mx, reasons = [], [], set()
+        names = ["hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"]
+        for s in self.samples:
+            try:
+                sm.append(float(s[0])); mx.append(float(s[1]))
+                for nm, v in zip(names, s[3:7]):
+                    if v.lower().startswith("active"):
+                        reasons.add(nm)
+            except Exception:
+                continue
+        sm.sort()
+        return {"sm_mhz": sm[len(sm) // 2] if sm else None, "sm_max_mhz": max(mx) if mx else None,
+                "reasons": sorted(reasons), "samples": len(sm)}
+
+
+# --------------------------------------------------------------------------------------------------
+# CPU oracle arm (cpu_baseline leg and --impl reference)
+# --------------------------------------------------------------------------------------------------
+def cpu_pipeline(n, coeff_sample, coeffs_full, reps=1):
+    """Times the numpy/OpenBLAS oracle on the host cores.  Returns (step_seconds_extrapolated, detail)."""
+    sys.path.insert(0, os.path.join(ROOT, "oracle"))
+    import numpy as np
+    import qil_oracle as O
+    x = signal_numpy(n)
+    W = O.build_zt_mpo(n, OMEGA_R, cutoff=MPO_CUTOFF, maxdim=MPO_MAXDIM)      # setup, untimed
+    bits = hash_bits(coeff_sample, 2 * n)
+    best = None
+    for _ in range(reps):
+        t0 = time.perf_counter()
+        cores, c = O.signal_mps(x, method="rsvd", **ALGO)
+        t1 = time.perf_counter()
+        z = O.ztmps_split(cores, ALGO["cutoff"])
+        out = O.apply_mpo_mps(W, z)
+        t2 = time.perf_counter()
+        O.coefficient_batch(out, c, bits)
+        t3 = time.perf_counter()
+        d = {"encode_s": t1 - t0, "split_apply_s": t2 - t1, "coeff_s_sample": t3 - t2}
+        d["step_s"] = d["encode_s"] + d["split_apply_s"] + d["coeff_s_sample"] * (coeffs_full / coeff_sample)
+        if best is None or d["step_s"] < best["step_s"]:
+            best = d
+    return best["step_s"], best
+
+
+def run_reference(args):
+    rank = int(os.environ.get("RANK", "0"))
+    if rank != 0:
+        return
+    import numpy as np  # noqa: F401
+    n = args.cpu_n or min(args.n, 26)
+    cores = os.cpu_count() or 1
+    sample_B = 20000
+    times = []
+    detail = None
+    for i in range(args.warmup + args.steps):
+        if i >= 1 and i < args.warmup:
+            continue  # one warm-up pass is enough for numpy; keep the run bounded
+        t, detail = cpu_pipeline(n, sample_B, args.coeffs)
+        if i >= args.warmup:
+            times.append(t)
+    ms = 1e3 * sum(times) / len(times)
+    value = (2**n) / (ms / 1e3)
+    unit = "samples/s"
+    sample = (f"n={n} real sin_decay signal (2^{n} samples) encoded with the numpy/OpenBLAS oracle, zT split+apply, "
+              f"{sample_B} coefficients timed and extrapolated to {args.coeffs}")
+    line = {
+        "impl": "reference", "metric": "encode_zt_apply_coeff_samples_per_s", "value": value, "unit": unit,
+        "n_gpus": args.gpus, "steps": args.steps, "warmup": args.warmup, "ms_per_step": ms,
+        "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f64", "data": "synthetic",
+        "config": {"workload": f"C4 n={args.n} sin_decay RSVD(k=15,p=5,q=2,cutoff=1e-12) + zT apply + {args.coeffs} coefficients",
+                   "cpu_sample_n": n},
+        "cpu_baseline": {"value": value, "unit": unit, "cores": cores, "kind": "port", "sample": sample, "detail": detail},
+        "e2e": {"value": value, "unit": unit, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
+        "gpu_launches": 0,
+    }
+    print(json.dumps(line))
+
+
+# --------------------------------------------------------------------------------------------------
+# CUDA arm
+# --------------------------------------------------------------------------------------------------
+def run_ours(args):
+    import numpy as np
+    import torch
+    import torch.distributed as dist
+
+    world = int(os.environ.get("WORLD_SIZE", "1"))
+    rank = int(os.environ.get("RANK", "0"))
+    local = int(os.environ.get("LOCAL_RANK", "0"))
+    torch.cuda.set_device(local)
+    dev = torch.device("cuda", local)
+    if world > 1:
+        dist.init_process_group("nccl", device_id=dev)
+
+    import qilaplace_b200 as q
+
+    n, B = args.n, args.coeffs
+    N = 2**n
+    stream = torch.cuda.current_stream()
+    ctx = q.Context(local, stream=stream.cuda_stream)
+
+    # ---- synthetic input: generated on the device, mirrored into pinned host memory for the e2e leg
+    j = torch.arange(N, dtype=torch.float64, device=dev)
+    t = j * (1.0 / (2.5 * N))
+    x_dev = torch.sin(1.0 * t) * torch.exp(-0.08 * t) + torch.sin(2.5 * t) * torch.exp(-0.03 * t)
+    del j, t
+    x_pin = torch.empty(N, dtype=torch.float64, pin_memory=True)
+    x_pin.copy_(x_dev)
+    bits_np = hash_bits(B, 2 * n)
+    bits_pin = torch.from_numpy(bits_np).pin_memory()
+    bits_dev = bits_pin.to(dev)
+    out_dev = torch.empty(B, dtype=torch.complex128, device=dev)
+    out_pin = torch.empty(B, dtype=torch.complex128, pin_memory=True)
+    torch.cuda.synchronize()
+
+    # ---- setup (untimed, like the reference's benchmark protocol): the zT MPO
+    t0 = time.perf_counter()
+    W = q.build_zt_mpo(n, OMEGA_R, cutoff=MPO_CUTOFF, maxdim=MPO_MAXDIM, ctx=ctx)
+    ctx.sync()
+    build_s = time.perf_counter() - t0
+
+    state = {}
+
+    def step_device():
+        psi = q.signal_mps_dev(ctx, x_dev.data_ptr(), N, False, method="rsvd", **ALGO)
+        z = q.ztmps_from_mps(psi, cutoff=ALGO["cutoff"])
+        out = q.apply(W, z)
+        q.coefficients_dev(out, bits_dev.data_ptr(), B, out_dev.data_ptr())
+        state["psi"], state["z"], state["out"] = psi, z, out
+
+    def step_e2e():
+        x_dev.copy_(x_pin, non_blocking=True)
+        bits_dev.copy_(bits_pin, non_blocking=True)
+        step_device()
+        out_pin.copy_(out_dev, non_blocking=True)
+
+    def barrier():
+        if world > 1:
+            dist.barrier()
+        torch.cuda.synchronize()
+
+    def timed(fn, steps):
+        e0 = torch.cuda.Event(enable_timing=True)
+        e1 = torch.cuda.Event(enable_timing=True)
+        barrier()
+        e0.record()
+        for _ in range(steps):
+            fn()
+        e1.record()
+        barrier()
+        ms = e0.elapsed_time(e1)
+        if world > 1:
+            tt = torch.tensor([ms], dtype=torch.float64, device=dev)
+            dist.all_reduce(tt, op=dist.ReduceOp.MAX)
+            ms = float(tt.item())
+        return ms
+
+    for _ in range(max(args.warmup, 3)):
+        step_device()
+    torch.cuda.synchronize()
+
+    # ---- timed: device-resident (`value`), with per-kernel-class events for the roofline
+    sampler = ClockSampler(local)
+    sampler.start()
+    time.sleep(0.3)
+    ctx.profile_reset(); ctx.profile_enable(True)
+    l0 = ctx.launch_count()
+    ms_dev = timed(step_device, args.steps)
+    launches = ctx.launch_count() - l0
+    g_ms, g_cnt = ctx.profile_read(0)
+    c_ms, c_cnt = ctx.profile_read(1)
+    a_ms, a_cnt = ctx.profile_read(2)
+    ctx.profile_enable(False); ctx.profile_reset()
+    # ---- stage breakdown (separate pass, CUDA events between the stages of one step)
+    def stage_breakdown(reps=3):
+        names = ["encode_rsvd", "ztmps_split", "zt_apply", "coefficients"]
+        acc = [0.0] * 4
+        for _ in range(reps):
+            ev = [torch.cuda.Event(enable_timing=True) for _ in range(5)]
+            torch.cuda.synchronize()
+            ev[0].record()
+            psi = q.signal_mps_dev(ctx, x_dev.data_ptr(), N, False, method="rsvd", **ALGO)
+            ev[1].record()
+            z = q.ztmps_from_mps(psi, cutoff=ALGO["cutoff"])
+            ev[2].record()
+            out = q.apply(W, z)
+            ev[3].record()
+            q.coefficients_dev(out, bits_dev.data_ptr(), B, out_dev.data_ptr())
+            ev[4].record()
+            torch.cuda.synchronize()
+            for i in range(4):
+                acc[i] += ev[i].elapsed_time(ev[i + 1])
+        return {nm: a / reps for nm, a in zip(names, acc)}
+
+    stages_ms = stage_breakdown()
+
+    # ---- timed: end to end through host buffers
+    for _ in range(2):
+        step_e2e()
+    ms_e2e = timed(step_e2e, args.steps)
+    clocks = sampler.finish()
+
+    psi, z, out = state["psi"], state["z"], state["out"]
+    ms_step = ms_dev / args.steps
+    value = world * N / (ms_step / 1e3)
+    e2e_value = world * N / (ms_e2e / args.steps / 1e3)
+
+    # ---- roofline of the dominant kernel (streaming sketch/projection GEMM): algorithmic bytes = e*N per launch
+    peaks = {}
+    try:
+        peaks = json.load(open(os.path.join(ROOT, "MEASURED_PEAKS.json")))
+    except Exception:
+        pass
+    hbm_peak = float(peaks.get("hbm_gbs", 6650.0))
+    peak_src = "measured (MEASURED_PEAKS.json)" if "hbm_gbs" in peaks else "fallback (B200_PROFILING.md)"
+    l = min(ALGO["k"] + ALGO["p"], 2 ** (n // 2))
+    gemm_ms = g_ms / max(g_cnt, 1)
+    alg_bytes = 8.0 * N
+    achieved = alg_bytes / (gemm_ms / 1e3) / 1e9
+    flops = 2.0 * N * l
+    obonds = [1] + out.bonds + [1]
+    coeff_bytes = sum(16.0 * obonds[i] * obonds[i + 1] for i in range(2 * n))
+    coeff_ms = c_ms / max(c_cnt, 1)
+    roofline = {
+        "kernel": "stream_gemm_kernel (K1/K2, qil_sketch.cu)", "bound": "hbm", "achieved": achieved, "peak": hbm_peak,
+        "unit": "GB/s", "frac": achieved / hbm_peak, "traffic": None, "peak_source": peak_src,
+        "launches_per_step": g_cnt / args.steps, "avg_launch_ms": gemm_ms, "share_of_step": g_ms / ms_dev,
+        "fp64_tflops": flops / (gemm_ms / 1e3) / 1e12, "fp64_peak_tflops_measured_dmma": 37.1,
+        "fp64_frac": flops / (gemm_ms / 1e3) / 1e12 / 37.1,
+        "coefficient_kernel": {"avg_launch_ms": coeff_ms, "coefficients_per_s": B / (coeff_ms / 1e3) if coeff_ms else None,
+                               "algorithmic_GBps": coeff_bytes * B / (coeff_ms / 1e3) / 1e9 if coeff_ms else None,
+                               "share_of_step": c_ms / ms_dev},
+        "apply_kernel": {"avg_launch_ms": a_ms / max(a_cnt, 1), "share_of_step": a_ms / ms_dev},
+    }
+
+    line = {
+        "metric": "encode_zt_apply_coeff_samples_per_s", "value": value, "unit": "samples/s", "n_gpus": world,
+        "steps": args.steps, "warmup": max(args.warmup, 3), "ms_per_step": ms_step, "higher_is_better": True,
+        "scaling": "weak", "vs_baseline": None, "dtype": "f64", "data": "synthetic",
+        "config": {"workload": f"C4 n={n} sin_decay RSVD(k=15,p=5,q=2,cutoff=1e-12) + zT apply + {B} coefficients",
+                   "signals_per_rank": 1, "l2": "inputs (2 GiB signal) larger than L2", "zt_mpo_build_s": build_s,
+                   "mps_bonds_max": max(psi.bonds), "zt_mpo_bonds_max": max(W.bonds), "out_bonds_max": max(out.bonds)},
+        "e2e": {"value": e2e_value, "unit": "samples/s", "ms_per_step": ms_e2e / args.steps,
+                "h2d_bytes_per_step": int(8 * N + bits_np.nbytes), "d2h_bytes_per_step": int(16 * B)},
+        "gpu_launches": int(launches),
+        "clocks": clocks,
+        "roofline": roofline,
+        "coefficients_per_s": roofline["coefficient_kernel"]["coefficients_per_s"],
+        "stages_ms": stages_ms,
+        "encode_apply_samples_per_s": world * N / ((stages_ms["encode_rsvd"] + stages_ms["ztmps_split"] + stages_ms["zt_apply"]) / 1e3),
+    }
+
+    if rank == 0 and world == 1 and not args.no_cpu_baseline:
+        cn = args.cpu_n or min(n, 26)
+        try:
+            t, detail = cpu_pipeline(cn, 20000, B)
+            line["cpu_baseline"] = {
+                "value": (2**cn) / t, "unit": "samples/s", "cores": os.cpu_count() or 1, "kind": "port",
+                "sample": f"numpy/OpenBLAS oracle, n={cn} signal (2^{cn} samples), same algorithm; 20000 coefficients "
+                          f"timed and extrapolated to {B}", "detail": detail}
+        except Exception as e:  # the baseline is reported, never required
+            line["cpu_baseline"] = {"value": None, "unit": "samples/s", "cores": os.cpu_count() or 1, "kind": "port",
+                                    "sample": f"failed: {e}"}
+    if rank == 0:
+        print(json.dumps(line))
+    if world > 1:
+        dist.destroy_process_group()
+
+
+def main():
+    args = parse()
+    if args.impl == "reference":
+        run_reference(args)
+    else:
+        run_ours(args)
+
+
+if __name__ == "__main__":
+    main()

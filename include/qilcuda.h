@@ -55,6 +55,14 @@ int qil_sync(qil_ctx* ctx);
 /* Number of kernels this library has launched on the context since creation. */
 int qil_launch_count(qil_ctx* ctx, uint64_t* out);
 
+/* Per-kernel-class device timing with CUDA events on the context's stream (used by bench.py for the
+ * roofline numbers).  Classes: 0 = streaming sketch/projection GEMM (K1/K2), 1 = coefficient chain (K8),
+ * 2 = apply (K6/K7), 3 = QR/TSQR (K3/K5), 4 = Jacobi SVD (K4).  qil_profile_read synchronises, returns the
+ * summed milliseconds and launch count of one class since the last reset, and keeps the records. */
+int qil_profile_enable(qil_ctx* ctx, int on);
+int qil_profile_reset(qil_ctx* ctx);
+int qil_profile_read(qil_ctx* ctx, int kernel_class, double* total_ms, int64_t* launches);
+
 /* ---- MPS / MPO containers (replace Vector{ITensor} storage; src/mps.jl:70-130, src/mpo.jl:26-99) -- */
 /* bond has n+1 entries with bond[0] == bond[n] == 1; cores[i] points at bond[i]*2*bond[i+1] scalars */
 int qil_mps_from_host(qil_ctx* ctx, int n, int is_complex, const int64_t* bond,

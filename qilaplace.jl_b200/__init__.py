@@ -9,4 +9,5 @@ from .api import *  # noqa: F401,F403
 from .api import (Context, default_context, SignalMPS, ZTMPS, SingleSiteMPO, PairedSiteMPO,
                   coefficient, coefficients, apply, generate_signal, signal_mps, signal_ztmps,
                   canonicalize, canonicalize_, compress, compress_, norm, mps_to_vector,
-                  build_qft_mpo, build_dt_mpo, build_zt_mpo, qr, svd_trunc, rsvd)
+                  build_qft_mpo, build_dt_mpo, build_zt_mpo, qr, svd_trunc, rsvd,
+                  signal_mps_dev, ztmps_from_mps, coefficients_dev)

@@ -46,6 +46,9 @@ _SIGS = {
     "qil_destroy": [c_ctx],
     "qil_sync": [c_ctx],
     "qil_launch_count": [c_ctx, C.POINTER(C.c_uint64)],
+    "qil_profile_enable": [c_ctx, C.c_int],
+    "qil_profile_reset": [c_ctx],
+    "qil_profile_read": [c_ctx, C.c_int, C.POINTER(C.c_double), i64p],
     "qil_mps_from_host": [c_ctx, C.c_int, C.c_int, i64p, C.POINTER(C.c_void_p), C.c_double, C.POINTER(c_mps)],
     "qil_mps_info": [c_mps, C.POINTER(C.c_int), C.POINTER(C.c_int), C.POINTER(C.c_double)],
     "qil_mps_dims": [c_mps, i64p],

@@ -41,6 +41,18 @@ class Context:
         call("qil_launch_count", self.handle, C.byref(v))
         return int(v.value)
 
+    def profile_enable(self, on=True):
+        call("qil_profile_enable", self.handle, 1 if on else 0)
+
+    def profile_reset(self):
+        call("qil_profile_reset", self.handle)
+
+    def profile_read(self, kernel_class):
+        """(total_ms, launches) of one kernel class: 0 stream GEMM, 1 coefficient, 2 apply."""
+        t, c = C.c_double(), C.c_int64()
+        call("qil_profile_read", self.handle, int(kernel_class), C.byref(t), C.byref(c))
+        return float(t.value), int(c.value)
+
     def close(self):
         if self.handle:
             _lib.load().qil_destroy(self.handle)
@@ -576,3 +588,33 @@ def rsvd(A, k=20, p=10, q=0, random_seed=1234, cutoff=1e-15, maxdim=None, mindim
          C.c_void_p(Vh.ctypes.data))
     r = int(r.value)
     return U[: m * r].reshape(m, r), S[:r], Vh[: r * n].reshape(r, n)
+
+
+# ------------------------------------------------------------------------------------------
+# device-resident entry points (inputs already in HBM; pointers are raw CUDA device addresses)
+# ------------------------------------------------------------------------------------------
+def signal_mps_dev(ctx, d_x, N, is_complex, method="rsvd", cutoff=1e-15, maxdim=None, k=20, p=10, q=0,
+                   random_seed=1234, mindim=1):
+    """signal_mps on a signal that already lives on the device (stream-ordered, no host copies)."""
+    h = _lib.c_mps()
+    if method == "svd":
+        call("qil_encode_svd_dev", ctx.handle, int(is_complex), C.c_void_p(int(d_x)), C.c_int64(N), float(cutoff),
+             C.c_int64(_maxdim_arg(maxdim)), C.byref(h))
+    else:
+        call("qil_encode_rsvd_dev", ctx.handle, int(is_complex), C.c_void_p(int(d_x)), C.c_int64(N), int(k), int(p),
+             int(q), C.c_int64(random_seed), float(cutoff), C.c_int64(_maxdim_arg(maxdim)), C.c_int64(mindim), None,
+             C.c_int64(0), C.c_int64(0), C.byref(h))
+    return SignalMPS(ctx, h)
+
+
+def ztmps_from_mps(psi, cutoff=1e-10, maxdim=None):
+    """The copy-tensor split of signal_ztmps (SignalConverters.jl:258-277) applied to an encoded SignalMPS."""
+    h = _lib.c_mps()
+    call("qil_ztmps_split", psi.ctx.handle, psi.handle, float(cutoff), C.c_int64(_maxdim_arg(maxdim)), C.byref(h))
+    return ZTMPS(psi.ctx, h)
+
+
+def coefficients_dev(psi, d_bits, B, d_out):
+    """Batched coefficient with device-resident bits (uint8[B][n]) and output (B scalars)."""
+    call("qil_coefficient_batch_dev", psi.ctx.handle, psi.handle, C.c_void_p(int(d_bits)), C.c_int64(B),
+         C.c_void_p(int(d_out)))

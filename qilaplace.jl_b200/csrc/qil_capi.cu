@@ -146,6 +146,40 @@ int qil_launch_count(qil_ctx* ctx, uint64_t* out) {
     QIL_API_END
 }
 
+int qil_profile_enable(qil_ctx* ctx, int on) {
+    QIL_API_BEGIN
+    QIL_NONNULL(ctx);
+    ctx->prof_on = on != 0;
+    QIL_API_END
+}
+
+int qil_profile_reset(qil_ctx* ctx) {
+    QIL_API_BEGIN
+    QIL_NONNULL(ctx);
+    ctx->sync();
+    for (auto& r : ctx->prof) { cudaEventDestroy(r.e0); cudaEventDestroy(r.e1); }
+    ctx->prof.clear();
+    QIL_API_END
+}
+
+int qil_profile_read(qil_ctx* ctx, int kernel_class, double* total_ms, int64_t* launches) {
+    QIL_API_BEGIN
+    QIL_NONNULL(ctx); QIL_NONNULL(total_ms); QIL_NONNULL(launches);
+    ctx->sync();
+    double t = 0.0;
+    int64_t c = 0;
+    for (auto& r : ctx->prof) {
+        if (r.id != kernel_class) continue;
+        float ms = 0.f;
+        QIL_CUDA(cudaEventElapsedTime(&ms, r.e0, r.e1));
+        t += ms;
+        ++c;
+    }
+    *total_ms = t;
+    *launches = c;
+    QIL_API_END
+}
+
 // ---- containers ----------------------------------------------------------------------------
 int qil_mps_from_host(qil_ctx* ctx, int n, int is_complex, const int64_t* bond, const void* const* cores,
                       double amplitude, qil_mps** out) {

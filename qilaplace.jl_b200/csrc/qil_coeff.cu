@@ -133,12 +133,238 @@ static void launch_coeff(qil_ctx* ctx, const qil_mps* psi, const uint8_t* d_bits
     QIL_LAUNCH_CHECK(ctx);
 }
 
+// ------------------------------------------------------------------------------------------------
+// Large-bond variant (complex MPS, e.g. the output of a zT apply with chi ~ 100..600): per site the
+// update of a tile of S strings is a GEMM  V'[S x chi_r] = V[S x chi_l] * A_i[:, b, :]  whose B operand
+// depends on the bit of each string.  The strings of a CTA tile are regrouped by bit at every site
+// (row lists, 16-row DMMA tiles never mix bits), V lives in an L2-resident scratch, and the complex
+// product runs on the FP64 tensor path through the real 2x2 embedding
+//     [Vr Vi] * [[Br Bi], [-Bi Br]]     (8*S*chi_l*chi_r flop, same as the complex MAC count).
+// Operand tiles are staged with cp.async into an XOR-swizzled 3-stage ring.
+// ------------------------------------------------------------------------------------------------
+constexpr int kCgS = 112;        // strings per CTA tile: ceil(n0/16)+ceil(n1/16) <= 8 for any split
+constexpr int kCgRows = 128;     // 8 DMMA m-tiles
+constexpr int kCgKc = 16;        // complex k per chunk (32 real)
+constexpr int kCgNc = 64;        // complex n per pass (128 real, 16 n8 tiles)
+constexpr int kCgStages = 3;
+constexpr int kCgABytes = kCgRows * kCgKc * 16;        // 32 KB
+constexpr int kCgBBytes = 2 * kCgKc * kCgNc * 16;      // 32 KB (both bit slices)
+constexpr int kCgThreads = 256;
+
+__device__ __forceinline__ void cp_async16(void* dst, const void* src, bool valid) {
+    const unsigned d = (unsigned)__cvta_generic_to_shared(dst);
+    const int sz = valid ? 16 : 0;
+    asm volatile("cp.async.cg.shared.global [%0], [%1], 16, %2;" ::"r"(d), "l"(src), "r"(sz) : "memory");
+}
+__device__ __forceinline__ void cp_async_commit() { asm volatile("cp.async.commit_group;" ::: "memory"); }
+template <int N> __device__ __forceinline__ void cp_async_wait() {
+    asm volatile("cp.async.wait_group %0;" ::"n"(N) : "memory");
+}
+__device__ __forceinline__ void dmma16816c(double* c, const double* a, const double* b) {
+    asm volatile(
+        "mma.sync.aligned.m16n8k16.row.col.f64.f64.f64.f64 {%0,%1,%2,%3}, {%4,%5,%6,%7,%8,%9,%10,%11}, "
+        "{%12,%13,%14,%15}, {%0,%1,%2,%3};"
+        : "+d"(c[0]), "+d"(c[1]), "+d"(c[2]), "+d"(c[3])
+        : "d"(a[0]), "d"(a[1]), "d"(a[2]), "d"(a[3]), "d"(a[4]), "d"(a[5]), "d"(a[6]), "d"(a[7]), "d"(b[0]), "d"(b[1]),
+          "d"(b[2]), "d"(b[3]));
+}
+
+__global__ void __launch_bounds__(kCgThreads, 1)
+coeff_gemm_kernel(const ChainDesc d, const uint8_t* __restrict__ bits, long long B, cplx* __restrict__ out,
+                  double amplitude, cplx* __restrict__ vscratch, int chi_pad) {
+    extern __shared__ __align__(1024) unsigned char smem_raw[];
+    unsigned char* sA = smem_raw;                                        // stages x 32 KB
+    unsigned char* sB = sA + kCgStages * kCgABytes;                      // stages x 32 KB
+    uint8_t* sbits = sB + kCgStages * kCgBBytes;                         // [kCgS][n]
+    int* rowmap = reinterpret_cast<int*>(sbits + ((kCgS * d.n + 15) & ~15));  // [128] string of each tile row
+    int* tilebit = rowmap + kCgRows;                                     // [8]
+    __shared__ int s_cnt[2];
+
+    const int n = d.n;
+    const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
+    const int g = lane >> 2, t = lane & 3;
+    cplx* V0 = vscratch + (size_t)blockIdx.x * 2 * kCgS * chi_pad;
+    cplx* V1 = V0 + (size_t)kCgS * chi_pad;
+    const long long ntiles = (B + kCgS - 1) / kCgS;
+
+    for (long long tile = blockIdx.x; tile < ntiles; tile += gridDim.x) {
+        const long long s0 = tile * kCgS;
+        const int ns = (int)min((long long)kCgS, B - s0);
+        __syncthreads();
+        for (int idx = tid; idx < kCgS * n; idx += kCgThreads)
+            sbits[idx] = (idx < ns * n) ? bits[s0 * n + idx] : (uint8_t)0;
+        for (int s = tid; s < kCgS; s += kCgThreads) V0[(size_t)s * chi_pad] = make_double2(1.0, 0.0);
+        __syncthreads();
+
+        cplx* Vc = V0;
+        cplx* Vn = V1;
+        for (int i = 0; i < n; ++i) {
+            const int cl = d.bond[i], cr = d.bond[i + 1];
+            const cplx* __restrict__ M = reinterpret_cast<const cplx*>(d.core[i]);
+            // ---- regroup the strings of the tile by their bit at this site (tiles never mix bits)
+            if (tid < kCgRows) rowmap[tid] = -1;
+            if (tid == 0) { s_cnt[0] = 0; s_cnt[1] = 0; }
+            __syncthreads();
+            int enc = -1;   // position inside the bit group | bit << 16, for string `tid`
+            if (warp < 4) {
+                const int bit = (tid < kCgS) ? (sbits[tid * n + i] & 1) : -1;
+                const unsigned m0 = __ballot_sync(0xffffffffu, bit == 0);
+                const unsigned m1 = __ballot_sync(0xffffffffu, bit == 1);
+                int base0 = 0, base1 = 0;
+                if (lane == 0) {
+                    base0 = atomicAdd(&s_cnt[0], __popc(m0));
+                    base1 = atomicAdd(&s_cnt[1], __popc(m1));
+                }
+                base0 = __shfl_sync(0xffffffffu, base0, 0);
+                base1 = __shfl_sync(0xffffffffu, base1, 0);
+                const unsigned below = (1u << lane) - 1u;
+                if (bit == 0) enc = base0 + __popc(m0 & below);
+                if (bit == 1) enc = (base1 + __popc(m1 & below)) | (1 << 16);
+            }
+            __syncthreads();
+            {
+                const int t0 = (s_cnt[0] + 15) >> 4;           // DMMA tiles holding bit-0 strings
+                if (enc >= 0) {
+                    const int bit = enc >> 16, pos = enc & 0xffff;
+                    rowmap[bit == 0 ? pos : t0 * 16 + pos] = tid;
+                }
+                if (tid < 8) tilebit[tid] = (tid < t0) ? 0 : 1;
+            }
+            __syncthreads();
+
+            const int kchunks = (cl + kCgKc - 1) / kCgKc;
+            const int npass = (cr + kCgNc - 1) / kCgNc;
+            const int iters = kchunks * npass;
+            const int mybit = tilebit[warp];
+            const int R0 = warp * 16 + g, R1 = R0 + 8;
+            const int str0 = rowmap[R0], str1 = rowmap[R1];
+
+            auto issue = [&](int it) {
+                const int stage = it % kCgStages;
+                const int pass = it / kchunks, kc = it - pass * kchunks;
+                unsigned char* a = sA + stage * kCgABytes;
+                unsigned char* b = sB + stage * kCgBBytes;
+                // A: 128 rows x 16 complex
+#pragma unroll
+                for (int e = 0; e < (kCgRows * kCgKc) / kCgThreads; ++e) {
+                    const int idx = e * kCgThreads + tid;
+                    const int row = idx >> 4, j = idx & 15;
+                    const int sidx = rowmap[row];
+                    const int l = kc * kCgKc + j;
+                    const bool ok = (sidx >= 0) && (l < cl);
+                    const cplx* src = ok ? (Vc + (size_t)sidx * chi_pad + l) : Vc;
+                    cp_async16(a + row * 256 + ((j ^ (row & 7)) << 4), src, ok);
+                }
+                // B: (bit, 16 l) x 64 complex
+#pragma unroll
+                for (int e = 0; e < (2 * kCgKc * kCgNc) / kCgThreads; ++e) {
+                    const int idx = e * kCgThreads + tid;
+                    const int rowb = idx >> 6, c = idx & 63;        // rowb = bit*16 + lr
+                    const int bit = rowb >> 4, lr = rowb & 15;
+                    const int l = kc * kCgKc + lr, r = pass * kCgNc + c;
+                    const bool ok = (l < cl) && (r < cr);
+                    const cplx* src = ok ? (M + ((size_t)l * 2 + bit) * cr + r) : M;
+                    cp_async16(b + rowb * 1024 + ((c ^ (((lr >> 1) & 3) << 2)) << 4), src, ok);
+                }
+            };
+
+            // prologue
+            for (int it = 0; it < kCgStages - 1; ++it) {
+                if (it < iters) issue(it);
+                cp_async_commit();
+            }
+            double acc[16][4];
+            for (int it = 0; it < iters; ++it) {
+                const int pass = it / kchunks, kc = it - pass * kchunks;
+                if (kc == 0) {
+#pragma unroll
+                    for (int x = 0; x < 16; ++x) { acc[x][0] = acc[x][1] = acc[x][2] = acc[x][3] = 0.0; }
+                }
+                cp_async_wait<kCgStages - 2>();
+                __syncthreads();
+                if (it + kCgStages - 1 < iters) issue(it + kCgStages - 1);
+                cp_async_commit();
+                const int stage = it % kCgStages;
+                const unsigned char* a = sA + stage * kCgABytes;
+                const unsigned char* b = sB + stage * kCgBBytes + mybit * (kCgKc * 1024);
+#pragma unroll
+                for (int kb = 0; kb < 2; ++kb) {
+                    double af[8];
+                    const int j0 = kb * 8 + 2 * t;
+                    const double2 x00 = *reinterpret_cast<const double2*>(a + R0 * 256 + (((j0) ^ (R0 & 7)) << 4));
+                    const double2 x01 = *reinterpret_cast<const double2*>(a + R0 * 256 + (((j0 + 1) ^ (R0 & 7)) << 4));
+                    const double2 x10 = *reinterpret_cast<const double2*>(a + R1 * 256 + (((j0) ^ (R1 & 7)) << 4));
+                    const double2 x11 = *reinterpret_cast<const double2*>(a + R1 * 256 + (((j0 + 1) ^ (R1 & 7)) << 4));
+                    af[0] = x00.x; af[2] = x00.y; af[4] = x01.x; af[6] = x01.y;
+                    af[1] = x10.x; af[3] = x10.y; af[5] = x11.x; af[7] = x11.y;
+                    const int lr0 = kb * 8 + 2 * t, lr1 = lr0 + 1;
+                    const unsigned char* b0p = b + lr0 * 1024;
+                    const unsigned char* b1p = b + lr1 * 1024;
+                    const int sw0 = ((lr0 >> 1) & 3) << 2, sw1 = ((lr1 >> 1) & 3) << 2;
+#pragma unroll
+                    for (int nt = 0; nt < 16; ++nt) {
+                        const int c = nt * 4 + (g >> 1);
+                        const double2 e0 = *reinterpret_cast<const double2*>(b0p + ((c ^ sw0) << 4));
+                        const double2 e1 = *reinterpret_cast<const double2*>(b1p + ((c ^ sw1) << 4));
+                        double bf[4];
+                        if (g & 1) { bf[0] = e0.y; bf[1] = e0.x; bf[2] = e1.y; bf[3] = e1.x; }
+                        else       { bf[0] = e0.x; bf[1] = -e0.y; bf[2] = e1.x; bf[3] = -e1.y; }
+                        dmma16816c(acc[nt], af, bf);
+                    }
+                }
+                if (kc == kchunks - 1) {
+                    // epilogue of this pass: complex column = pass*64 + nt*4 + t
+#pragma unroll
+                    for (int nt = 0; nt < 16; ++nt) {
+                        const int r = pass * kCgNc + nt * 4 + t;
+                        if (r < cr) {
+                            if (str0 >= 0) Vn[(size_t)str0 * chi_pad + r] = make_double2(acc[nt][0], acc[nt][1]);
+                            if (str1 >= 0) Vn[(size_t)str1 * chi_pad + r] = make_double2(acc[nt][2], acc[nt][3]);
+                        }
+                    }
+                }
+            }
+            cp_async_wait<0>();
+            __syncthreads();
+            cplx* tmp = Vc; Vc = Vn; Vn = tmp;
+        }
+        for (int s = tid; s < ns; s += kCgThreads) {
+            const cplx v = Vc[(size_t)s * chi_pad];
+            out[s0 + s] = make_double2(v.x * amplitude, v.y * amplitude);
+        }
+    }
+}
+
+static void launch_coeff_gemm(qil_ctx* ctx, const qil_mps* psi, const uint8_t* d_bits, int64_t B, void* d_out) {
+    int chimax = 1;
+    for (int i = 0; i <= psi->n; ++i) chimax = max(chimax, (int)psi->bond[i]);
+    const int chi_pad = (chimax + 3) & ~3;
+    const long long ntiles = (B + kCgS - 1) / kCgS;
+    const int grid = (int)std::min<long long>(ntiles, ctx->sm_count);
+    const size_t smem = (size_t)kCgStages * (kCgABytes + kCgBBytes) + (((size_t)kCgS * psi->n + 15) & ~(size_t)15) +
+                        (kCgRows + 8) * sizeof(int) + 64;
+    QIL_REQUIRE(smem <= ctx->smem_optin, QIL_ERR_UNSUPPORTED, "coefficient: chain of %d sites does not fit", psi->n);
+    cplx* scratch = (cplx*)ctx->alloc((size_t)grid * 2 * kCgS * chi_pad * sizeof(cplx));
+    auto kern = coeff_gemm_kernel;
+    QIL_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+    kern<<<grid, kCgThreads, smem, ctx->stream>>>(make_desc(psi), d_bits, (long long)B, reinterpret_cast<cplx*>(d_out),
+                                                  psi->amplitude, scratch, chi_pad);
+    QIL_LAUNCH_CHECK(ctx);
+    ctx->free(scratch);
+}
+
 void coefficient_batch_dev(qil_ctx* ctx, const qil_mps* psi, const uint8_t* d_bits, int64_t B, void* d_out) {
     if (B <= 0) return;
-    if (psi->is_complex)
+    int chimax = 1;
+    for (int i = 0; i <= psi->n; ++i) chimax = max(chimax, (int)psi->bond[i]);
+    ctx->prof_begin(PROF_COEFF);
+    if (psi->is_complex && chimax >= 48 && B >= 64)
+        launch_coeff_gemm(ctx, psi, d_bits, B, d_out);
+    else if (psi->is_complex)
         launch_coeff<cplx>(ctx, psi, d_bits, B, d_out);
     else
         launch_coeff<double>(ctx, psi, d_bits, B, d_out);
+    ctx->prof_end();
 }
 
 }  // namespace qil

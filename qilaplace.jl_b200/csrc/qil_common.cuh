@@ -109,6 +109,13 @@ struct qil_ctx {
     void* scratch = nullptr;
     size_t scratch_bytes = 0;
 
+    // optional per-kernel-class timing (CUDA events on `stream`), enabled by qil_profile_enable
+    struct ProfRegion { int id; cudaEvent_t e0, e1; };
+    bool prof_on = false;
+    std::vector<ProfRegion> prof;
+    void prof_begin(int id);
+    void prof_end();
+
     void* alloc(size_t bytes);           // stream-ordered device allocation
     void free(void* p);                  // stream-ordered free
     void* get_scratch(size_t bytes);     // grow-only scratch (valid until next get_scratch)
@@ -150,6 +157,8 @@ qil_mps* new_mps(qil_ctx* ctx, int n, int is_complex, const int64_t* bond /* n+1
 qil_mpo* new_mpo(qil_ctx* ctx, int n, int is_complex, const int64_t* bond /* n+1 */, bool allocate);
 void destroy(qil_mps* m);
 void destroy(qil_mpo* m);
+
+enum ProfId { PROF_STREAM_GEMM = 0, PROF_COEFF = 1, PROF_APPLY = 2, PROF_QR = 3, PROF_SVD = 4, PROF_COUNT = 5 };
 
 #define QIL_LAUNCH_CHECK(ctx)            \
     do {                                 \

@@ -25,6 +25,21 @@ void* qil_ctx::get_scratch(size_t bytes) {
     return scratch;
 }
 
+void qil_ctx::prof_begin(int id) {
+    if (!prof_on) return;
+    ProfRegion r;
+    r.id = id;
+    QIL_CUDA(cudaEventCreate(&r.e0));
+    QIL_CUDA(cudaEventCreate(&r.e1));
+    QIL_CUDA(cudaEventRecord(r.e0, stream));
+    prof.push_back(r);
+}
+
+void qil_ctx::prof_end() {
+    if (!prof_on || prof.empty()) return;
+    QIL_CUDA(cudaEventRecord(prof.back().e1, stream));
+}
+
 void qil_ctx::sync() { QIL_CUDA(cudaStreamSynchronize(stream)); }
 
 namespace qil {

@@ -309,13 +309,11 @@ void stream_gemm(qil_ctx* ctx, bool trans, const double* A, long long R, long lo
     p.out = out;
     p.X = X;
     p.sumsq = sumsq_partials;
-    if (!trans) {
-        CUtensorMap tm = make_tmap(A, R, C, ld, 16, kBM);
-        dispatch_stream<false>(ctx, nt, tm, p);
-    } else {
-        CUtensorMap tm = make_tmap(A, R, C, ld, 16, kBK);
-        dispatch_stream<true>(ctx, nt, tm, p);
-    }
+    const CUtensorMap tm = trans ? make_tmap(A, R, C, ld, 16, kBK) : make_tmap(A, R, C, ld, 16, kBM);
+    ctx->prof_begin(PROF_STREAM_GEMM);
+    if (!trans) dispatch_stream<false>(ctx, nt, tm, p);
+    else dispatch_stream<true>(ctx, nt, tm, p);
+    ctx->prof_end();
 }
 
 void stream_plan(qil_ctx* ctx, long long Mtot, long long Kdim, int* ksplit, long long* kchunk) {

@@ -61,6 +61,29 @@ __global__ void dmma_kernel(double* out, int iters) {
     out[blockIdx.x * blockDim.x + threadIdx.x] = s;
 }
 
+// mixed: every warp issues DMMA and independent DFMA chains -- do the two FP64 paths add up?
+template <int NF>
+__global__ void mixed_kernel(double* out, int iters) {
+    double c[4][4];
+    double a[8], b[4], f[NF > 0 ? NF : 1];
+    double x = 1.0000001 + threadIdx.x * 1e-9, y = 0.999999;
+    for (int i = 0; i < 8; ++i) a[i] = 1.0 + 1e-9 * (threadIdx.x + i);
+    for (int i = 0; i < 4; ++i) b[i] = 1.0 - 1e-9 * (threadIdx.x + i);
+    for (int j = 0; j < 4; ++j) for (int i = 0; i < 4; ++i) c[j][i] = 0;
+    for (int i = 0; i < NF; ++i) f[i] = i;
+    for (int it = 0; it < iters; ++it) {
+#pragma unroll
+        for (int j = 0; j < 4; ++j) {
+            mma16816(c[j], a, b);
+#pragma unroll
+            for (int i = 0; i < NF; ++i) f[i] = fma(f[i], x, y);
+        }
+    }
+    double s = 0; for (int j = 0; j < 4; ++j) for (int i = 0; i < 4; ++i) s += c[j][i];
+    for (int i = 0; i < NF; ++i) s += f[i];
+    out[blockIdx.x * blockDim.x + threadIdx.x] = s;
+}
+
 // layout check: C[16x8] = A[16x16] * B[16x8] with the assumed fragment layout
 __global__ void layout_kernel(const double* A, const double* B, double* C) {
     int lane = threadIdx.x, g = lane >> 2, t = lane & 3;
@@ -124,6 +147,19 @@ int main() {
             double fl = fl_per[kind] * 4 * it * (double)blocks * wpb;
             printf("DMMA %-9s warps/blk=%2d : %.2f TFLOP/s\n", names[kind], wpb, fl / ms / 1e9);
         }
+    {
+        int blocks = sms * 2, wpb = 8, it = 4000;
+        auto report = [&](const char* nm, int nf, float ms) {
+            double fl_mma = fl_per[3] * 4 * it * (double)blocks * wpb;
+            double fl_fma = 2.0 * nf * 4 * it * (double)blocks * wpb * 32;
+            printf("MIXED %-22s : DMMA %.2f + DFMA %.2f = %.2f TFLOP/s\n", nm, fl_mma / ms / 1e9, fl_fma / ms / 1e9, (fl_mma + fl_fma) / ms / 1e9);
+        };
+        report("dmma only", 0, time_ms([&] { mixed_kernel<0><<<blocks, wpb * 32>>>(out, it); }, 3));
+        report("dmma + 8 dfma/mma", 8, time_ms([&] { mixed_kernel<8><<<blocks, wpb * 32>>>(out, it); }, 3));
+        report("dmma + 16 dfma/mma", 16, time_ms([&] { mixed_kernel<16><<<blocks, wpb * 32>>>(out, it); }, 3));
+        report("dmma + 32 dfma/mma", 32, time_ms([&] { mixed_kernel<32><<<blocks, wpb * 32>>>(out, it); }, 3));
+        report("dmma + 64 dfma/mma", 64, time_ms([&] { mixed_kernel<64><<<blocks, wpb * 32>>>(out, it); }, 3));
+    }
     // layout check
     {
         std::vector<double> A(256), B(128), Cw(128, 0), Cg(128);
