@@ -95,4 +95,11 @@ template <typename T>
 int svd_trunc_adj(qil_ctx* ctx, int64_t m, int64_t n, const T* At, int64_t ldat, double cutoff, int64_t maxdim,
                   int64_t mindim, Mat<T>* U, Mat<T>* US, Mat<T>* Vh, Mat<T>* SVh, Mat<double>* S);
 
+
+// Fused single-launch variant for matrices that fit one CTA's shared memory (qil_svd_small.cu)
+template <typename T> bool svd_small_fits(qil_ctx* ctx, int64_t m, int64_t n);
+template <typename T>
+int svd_small(qil_ctx* ctx, int64_t m, int64_t n, const T* A, int64_t lda, double cutoff, int64_t maxdim,
+              int64_t mindim, Mat<T>* U, Mat<T>* US, Mat<T>* Vh, Mat<T>* SVh, Mat<double>* S);
+
 }  // namespace qil

@@ -261,6 +261,22 @@ static int rsvd_split(SplitCtx<T>& sc, const T* A, int64_t R, int64_t C, bool to
     const RsvdOpts& o = *sc.o;
     const int l = (int)std::min<int64_t>((int64_t)o.k + o.p, std::min(R, C));
     QIL_REQUIRE(l >= 1, QIL_ERR_RUNTIME, "In `rsvd`, left or right index set is empty.");
+    if (std::min(R, C) <= (int64_t)o.k + o.p) {
+        // l == min(R, C): the sketch spans the whole row/column space, so the randomized SVD IS the truncated
+        // SVD of A (to rounding, for any Omega).  Skip the sketch/QR/projection chain.
+        if (top && !sc.nrm_ready) {
+            const double c = device_norm2<T>(ctx, A, R * C);
+            set_norm_kernel<<<1, 32, 0, ctx->stream>>>(c, sc.d_nrm);
+            QIL_LAUNCH_CHECK(ctx);
+            sc.nrm_ready = true;
+        }
+        const int r = svd_trunc<T>(ctx, R, C, A, C, o.cutoff, o.maxdim, o.mindim, &U, nullptr, Vh, SVh, S);
+        if (top) {
+            if (SVh) { scale_by_dev_kernel<T><<<grid_for(ctx, r * C), 256, 0, ctx->stream>>>(r * C, sc.d_nrm + 1, SVh->p); QIL_LAUNCH_CHECK(ctx); }
+            if (S) { scale_by_dev_kernel<double><<<1, 256, 0, ctx->stream>>>(r, sc.d_nrm + 1, S->p); QIL_LAUNCH_CHECK(ctx); }
+        }
+        return r;
+    }
     if (sc.stream) QIL_REQUIRE(C * (int64_t)l <= sc.stream_len, QIL_ERR_ARGUMENT,
                                "rsvd: the supplied normal stream is shorter than %lld", (long long)(C * l));
     Mat<T> Y = mul_A<T>(sc, A, R, C, l, nullptr, top && !sc.nrm_ready);

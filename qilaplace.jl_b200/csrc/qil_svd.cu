@@ -252,6 +252,8 @@ static int svd_core(qil_ctx* ctx, int64_t m, int64_t n, const T* A, int64_t lda,
                     Mat<double>* S, int nsum, int64_t sum_stride) {
     QIL_REQUIRE(m >= 1 && n >= 1, QIL_ERR_ARGUMENT, "svd: empty matrix");
     if (maxdim < 1) maxdim = 1;
+    if (adj == nullptr && nsum == 1 && svd_small_fits<T>(ctx, m, n))
+        return svd_small<T>(ctx, m, n, A, lda, cutoff, maxdim, mindim, U, US, Vh, SVh, S);
     Mat<T> Q, R, V, W;
     Mat<double> Sv;
     const bool tall = (adj == nullptr) && m >= n;

@@ -1,0 +1,370 @@
+// qil_svd_small.cu -- fused truncated SVD for bond matrices that fit one CTA's shared memory.
+//
+// One launch does what qil_svd.cu does in ~8: load (optionally transposed), Householder QR, in-place
+// explicit Q, one-sided Jacobi on G = R^H, sort, NDTensors truncation and the requested factors written
+// compactly (leading dimension = kept rank).  This is the latency path of the divide-and-conquer encoder's
+// lower levels, signal_ztmps, canonicalize!/compress! and the QFT/DT builders, where the matrices are a few
+// dozen rows/columns and launch + sync overhead used to dominate.
+#include "qil_dense.cuh"
+
+namespace qil {
+
+constexpr int kSsThreads = 256;
+constexpr int kSsWarps = kSsThreads / 32;
+
+template <typename T>
+struct SmallSvdParams {
+    const T* A;      // m x n row-major (lda)
+    long long lda;
+    int m, n;
+    int mt, nt;      // tall orientation: mt >= nt; M = A (m >= n) or A^H (m < n)
+    int mpad, npad;
+    double cutoff;
+    long long maxdim, mindim;
+    T* U;            // m x r   (ld r) or null
+    T* US;           // m x r   or null
+    T* Vh;           // r x n   or null
+    T* SVh;          // r x n   or null
+    double* S;       // min(m,n) values (first r meaningful) or null
+    int* rank;
+};
+
+template <typename T> __device__ __forceinline__ T wsum(T v);
+template <> __device__ __forceinline__ double wsum<double>(double v) {
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) v += __shfl_xor_sync(0xffffffffu, v, o);
+    return v;
+}
+template <> __device__ __forceinline__ cplx wsum<cplx>(cplx v) {
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) {
+        v.x += __shfl_xor_sync(0xffffffffu, v.x, o);
+        v.y += __shfl_xor_sync(0xffffffffu, v.y, o);
+    }
+    return v;
+}
+template <typename T> __device__ __forceinline__ T gsum(T v, int gl, unsigned mask);
+template <> __device__ __forceinline__ double gsum<double>(double v, int gl, unsigned mask) {
+    for (int o = gl >> 1; o > 0; o >>= 1) v += __shfl_xor_sync(mask, v, o);
+    return v;
+}
+template <> __device__ __forceinline__ cplx gsum<cplx>(cplx v, int gl, unsigned mask) {
+    for (int o = gl >> 1; o > 0; o >>= 1) {
+        v.x += __shfl_xor_sync(mask, v.x, o);
+        v.y += __shfl_xor_sync(mask, v.y, o);
+    }
+    return v;
+}
+
+__device__ inline int trunc_rank_small(const double* sig, int n, double cutoff, long long maxdim, long long mindim) {
+    if (n <= 1) return n;
+    int r = n;
+    double err = 0.0;
+    while ((long long)r > maxdim) { err += sig[r - 1] * sig[r - 1]; --r; }
+    double scale = 0.0;
+    for (int i = 0; i < n; ++i) scale += sig[i] * sig[i];
+    if (scale == 0.0) scale = 1.0;
+    while ((long long)r > mindim && err + sig[r - 1] * sig[r - 1] <= cutoff * scale) {
+        err += sig[r - 1] * sig[r - 1];
+        --r;
+    }
+    return r < 1 ? 1 : r;
+}
+
+template <typename T>
+__global__ void __launch_bounds__(kSsThreads) svd_small_kernel(const SmallSvdParams<T> p) {
+    extern __shared__ __align__(16) unsigned char smem_raw[];
+    const int mt = p.mt, nt = p.nt, mpad = p.mpad, npad = p.npad;
+    T* As = reinterpret_cast<T*>(smem_raw);              // [nt][mpad]  reflectors, later Q (column-major)
+    T* qb = As + (size_t)nt * mpad;                      // [kSsWarps][mpad]
+    T* G = qb + (size_t)kSsWarps * mpad;                 // [nt][npad]  G = R^H, later W = G V
+    T* V = G + (size_t)nt * npad;                        // [nt][npad]
+    T* sbeta = V + (size_t)nt * npad;                    // [nt]
+    double* ss = reinterpret_cast<double*>(sbeta + nt);  // [nt]
+    double* sig = ss + nt;                               // [nt]
+    int* order = reinterpret_cast<int*>(sig + nt);       // [nt]
+    __shared__ int s_rot, s_rank;
+
+    const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
+    const bool tall = p.m >= p.n;
+
+    // ---- load M (tall orientation) column-major: M[i][j] = A[i][j] or conj(A[j][i])
+    for (int idx = tid; idx < p.m * p.n; idx += kSsThreads) {
+        const int ia = idx / p.n, ja = idx - ia * p.n;
+        const T v = p.A[(long long)ia * p.lda + ja];
+        if (tall) As[(size_t)ja * mpad + ia] = v;
+        else As[(size_t)ia * mpad + ja] = Scalar<T>::conj(v);
+    }
+    __syncthreads();
+
+    // ---- Householder factorisation (see qil_qr.cu)
+    for (int j = 0; j < nt; ++j) {
+        T* col = As + (size_t)j * mpad;
+        if (warp == 0) {
+            double xn2 = 0.0;
+            for (int i = j + 1 + lane; i < mt; i += 32) xn2 += Scalar<T>::abs2(col[i]);
+            xn2 = wsum<double>(xn2);
+            if (lane == 0) {
+                const T x0 = col[j];
+                const double a0 = sqrt(Scalar<T>::abs2(x0));
+                const double nx = sqrt(a0 * a0 + xn2);
+                if (nx == 0.0) {
+                    sbeta[j] = Scalar<T>::zero();
+                    ss[j] = 0.0;
+                } else {
+                    const T ph = (a0 > 0.0) ? Scalar<T>::scale(x0, 1.0 / a0) : Scalar<T>::one();
+                    const T beta = Scalar<T>::scale(ph, -nx);
+                    sbeta[j] = beta;
+                    col[j] = Scalar<T>::sub(x0, beta);
+                    ss[j] = 1.0 / (nx * (nx + a0));
+                }
+            }
+        }
+        __syncthreads();
+        const double s = ss[j];
+        if (s != 0.0) {
+            for (int c = j + 1 + warp; c < nt; c += kSsWarps) {
+                T* cc = As + (size_t)c * mpad;
+                T w = Scalar<T>::zero();
+                for (int i = j + lane; i < mt; i += 32) w = Scalar<T>::fma(Scalar<T>::conj(col[i]), cc[i], w);
+                w = wsum<T>(w);
+                w = Scalar<T>::scale(w, -s);
+                for (int i = j + lane; i < mt; i += 32) cc[i] = Scalar<T>::fma(w, col[i], cc[i]);
+            }
+        }
+        __syncthreads();
+    }
+
+    // ---- G = R^H (column-major G[col j][row i] = conj(R[j][i])), V = I
+    for (int idx = tid; idx < nt * nt; idx += kSsThreads) {
+        const int j = idx / nt, i = idx - j * nt;
+        T r = Scalar<T>::zero();
+        if (i == j) r = sbeta[j];
+        else if (i > j) r = As[(size_t)i * mpad + j];     // R[j][i], stored in column i, row j
+        G[(size_t)j * npad + i] = Scalar<T>::conj(r);
+        V[(size_t)j * npad + i] = (i == j) ? Scalar<T>::one() : Scalar<T>::zero();
+    }
+    __syncthreads();
+
+    // ---- explicit Q in place, columns from the last group to the first
+    {
+        T* q = qb + (size_t)warp * mpad;
+        const int ngroups = (nt + kSsWarps - 1) / kSsWarps;
+        for (int gi = ngroups - 1; gi >= 0; --gi) {
+            const int c = gi * kSsWarps + warp;
+            if (c < nt) {
+                for (int i = lane; i < mt; i += 32) q[i] = (i == c) ? Scalar<T>::one() : Scalar<T>::zero();
+                __syncwarp();
+                for (int j = c; j >= 0; --j) {
+                    const double s = ss[j];
+                    if (s == 0.0) continue;
+                    const T* col = As + (size_t)j * mpad;
+                    T w = Scalar<T>::zero();
+                    for (int i = j + lane; i < mt; i += 32) w = Scalar<T>::fma(Scalar<T>::conj(col[i]), q[i], w);
+                    w = wsum<T>(w);
+                    w = Scalar<T>::scale(w, -s);
+                    for (int i = j + lane; i < mt; i += 32) q[i] = Scalar<T>::fma(w, col[i], q[i]);
+                    __syncwarp();
+                }
+            }
+            __syncthreads();
+            if (c < nt) {
+                T* dst = As + (size_t)c * mpad;
+                for (int i = lane; i < mt; i += 32) dst[i] = q[i];
+            }
+            __syncthreads();
+        }
+    }
+
+    // ---- one-sided Jacobi on the columns of G (see qil_svd.cu)
+    {
+        const int ns = nt;
+        const int gl = ns <= 32 ? 8 : (ns <= 64 ? 16 : 32);
+        const int grp = tid / gl, gln = tid % gl;
+        const unsigned gmask = (gl == 32) ? 0xffffffffu : (((1u << gl) - 1u) << ((tid & 31) / gl * gl));
+        const int ngr = kSsThreads / gl;
+        const int ne = ns + (ns & 1);
+        const int npairs = ne / 2;
+        const double tol = sqrt((double)ns) * 2.220446049250313e-16;
+        for (int sweep = 0; sweep < 60 && ns > 1; ++sweep) {
+            if (tid == 0) s_rot = 0;
+            __syncthreads();
+            for (int r = 0; r < ne - 1; ++r) {
+                for (int pi = grp; pi < npairs; pi += ngr) {
+                    int a, b;
+                    if (pi == 0) { a = ne - 1; b = r; }
+                    else { a = (r + pi) % (ne - 1); b = (r - pi + (ne - 1)) % (ne - 1); }
+                    if (a >= ns || b >= ns) continue;
+                    const int cp = min(a, b), cq = max(a, b);
+                    T* gp = G + (size_t)cp * npad;
+                    T* gq = G + (size_t)cq * npad;
+                    double al = 0.0, be = 0.0;
+                    T ga = Scalar<T>::zero();
+                    for (int i = gln; i < ns; i += gl) {
+                        const T x = gp[i], y = gq[i];
+                        al += Scalar<T>::abs2(x);
+                        be += Scalar<T>::abs2(y);
+                        ga = Scalar<T>::fma(Scalar<T>::conj(x), y, ga);
+                    }
+                    al = gsum<double>(al, gl, gmask);
+                    be = gsum<double>(be, gl, gmask);
+                    ga = gsum<T>(ga, gl, gmask);
+                    const double g2 = Scalar<T>::abs2(ga);
+                    if (g2 > tol * tol * al * be && g2 > 0.0) {
+                        const double ag = sqrt(g2);
+                        const T ph = Scalar<T>::scale(ga, 1.0 / ag);
+                        const double zeta = (be - al) / (2.0 * ag);
+                        const double tt = (zeta >= 0.0 ? 1.0 : -1.0) / (fabs(zeta) + sqrt(1.0 + zeta * zeta));
+                        const double c = 1.0 / sqrt(1.0 + tt * tt);
+                        const double s = c * tt;
+                        const T sp = Scalar<T>::scale(ph, s);
+                        const T spc = Scalar<T>::conj(sp);
+                        T* vp = V + (size_t)cp * npad;
+                        T* vq = V + (size_t)cq * npad;
+                        for (int i = gln; i < ns; i += gl) {
+                            const T x = gp[i], y = gq[i];
+                            gp[i] = Scalar<T>::sub(Scalar<T>::scale(x, c), Scalar<T>::mul(spc, y));
+                            gq[i] = Scalar<T>::add(Scalar<T>::mul(sp, x), Scalar<T>::scale(y, c));
+                            const T vx = vp[i], vy = vq[i];
+                            vp[i] = Scalar<T>::sub(Scalar<T>::scale(vx, c), Scalar<T>::mul(spc, vy));
+                            vq[i] = Scalar<T>::add(Scalar<T>::mul(sp, vx), Scalar<T>::scale(vy, c));
+                        }
+                        if (gln == 0) s_rot = 1;
+                    }
+                }
+                __syncthreads();
+            }
+            const int rot = s_rot;
+            __syncthreads();
+            if (!rot) break;
+        }
+    }
+
+    // ---- singular values, order, rank
+    for (int j = tid; j < nt; j += kSsThreads) {
+        double a = 0.0;
+        const T* g = G + (size_t)j * npad;
+        for (int i = 0; i < nt; ++i) a += Scalar<T>::abs2(g[i]);
+        sig[j] = sqrt(a);
+    }
+    __syncthreads();
+    double mysig = 0.0;
+    int mypos = 0;
+    if (tid < nt) {
+        mysig = sig[tid];
+        for (int i = 0; i < nt; ++i) {
+            const double si = sig[i];
+            mypos += (si > mysig || (si == mysig && i < tid)) ? 1 : 0;
+        }
+    }
+    __syncthreads();
+    if (tid < nt) { order[mypos] = tid; sig[mypos] = mysig; }
+    __syncthreads();
+    if (tid == 0) {
+        s_rank = trunc_rank_small(sig, nt, p.cutoff, p.maxdim, p.mindim);
+        *p.rank = s_rank;
+    }
+    __syncthreads();
+    const int r = s_rank;
+    if (p.S) for (int j = tid; j < nt; j += kSsThreads) p.S[j] = sig[j];
+
+    // ---- outputs.  M = Q R, G = R^H, G V = W  =>  M = (Q V) W^H
+    //   tall (A = M):    U = Q V_r,            S Vh = W_r^H
+    //   wide (A = M^H):  U S = W_r,            Vh   = (Q V_r)^H
+    // QV[i][j] = sum_c Q[i][c] V[c][j]  with Q = As (column-major), V column-major, j -> order[j]
+    const bool need_qv = tall ? (p.U || p.US) : (p.Vh || p.SVh);
+    if (need_qv) {
+        for (int idx = tid; idx < mt * r; idx += kSsThreads) {
+            const int i = idx / r, j = idx - i * r;
+            const T* vc = V + (size_t)order[j] * npad;
+            T acc = Scalar<T>::zero();
+            for (int c = 0; c < nt; ++c) acc = Scalar<T>::fma(As[(size_t)c * mpad + i], vc[c], acc);
+            const double sj = sig[j];
+            if (tall) {
+                if (p.U) p.U[(long long)i * r + j] = acc;
+                if (p.US) p.US[(long long)i * r + j] = Scalar<T>::scale(acc, sj);
+            } else {
+                const T cj = Scalar<T>::conj(acc);          // Vh[j][i]
+                if (p.Vh) p.Vh[(long long)j * mt + i] = cj;
+                if (p.SVh) p.SVh[(long long)j * mt + i] = Scalar<T>::scale(cj, sj);
+            }
+        }
+    }
+    const bool need_w = tall ? (p.Vh || p.SVh) : (p.U || p.US);
+    if (need_w) {
+        for (int idx = tid; idx < nt * r; idx += kSsThreads) {
+            const int i = idx / r, j = idx - i * r;         // W[i][j], i < nt
+            const T w = G[(size_t)order[j] * npad + i];
+            const double sj = sig[j];
+            const double inv = sj != 0.0 ? 1.0 / sj : 0.0;
+            if (tall) {
+                const T wc = Scalar<T>::conj(w);            // (W^H)[j][i]
+                if (p.SVh) p.SVh[(long long)j * nt + i] = wc;
+                if (p.Vh) p.Vh[(long long)j * nt + i] = Scalar<T>::scale(wc, inv);
+            } else {
+                if (p.US) p.US[(long long)i * r + j] = w;
+                if (p.U) p.U[(long long)i * r + j] = Scalar<T>::scale(w, inv);
+            }
+        }
+    }
+}
+
+template <typename T>
+static size_t ss_smem(int mt, int nt) {
+    const int mpad = mt | 1, npad = nt | 1;
+    return ((size_t)(nt + kSsWarps) * mpad + 2 * (size_t)nt * npad + nt) * sizeof(T) + (size_t)nt * (2 * sizeof(double) + sizeof(int)) + 64;
+}
+
+template <typename T>
+bool svd_small_fits(qil_ctx* ctx, int64_t m, int64_t n) {
+    const int64_t mt = std::max(m, n), nt = std::min(m, n);
+    if (nt > 96 || mt > 4096) return false;
+    return ss_smem<T>((int)mt, (int)nt) <= std::min<size_t>(ctx->smem_optin, 200 * 1024);
+}
+
+// Fused path of svd_trunc for small matrices; same contract (returns the rank after a host sync).
+template <typename T>
+int svd_small(qil_ctx* ctx, int64_t m, int64_t n, const T* A, int64_t lda, double cutoff, int64_t maxdim,
+              int64_t mindim, Mat<T>* U, Mat<T>* US, Mat<T>* Vh, Mat<T>* SVh, Mat<double>* S) {
+    const int k = (int)std::min(m, n);
+    SmallSvdParams<T> p;
+    p.A = A; p.lda = lda; p.m = (int)m; p.n = (int)n;
+    p.mt = (int)std::max(m, n); p.nt = k;
+    p.mpad = p.mt | 1; p.npad = p.nt | 1;
+    p.cutoff = cutoff; p.maxdim = maxdim < 1 ? 1 : maxdim; p.mindim = std::max<int64_t>(mindim, 1);
+    Mat<T> bu, bus, bvh, bsvh;
+    Mat<double> bs;
+    if (U) bu = Mat<T>(ctx, m, k);
+    if (US) bus = Mat<T>(ctx, m, k);
+    if (Vh) bvh = Mat<T>(ctx, k, n);
+    if (SVh) bsvh = Mat<T>(ctx, k, n);
+    if (S) bs = Mat<double>(ctx, k, 1);
+    int* d_rank = (int*)ctx->alloc(sizeof(int));
+    p.U = U ? bu.p : nullptr; p.US = US ? bus.p : nullptr; p.Vh = Vh ? bvh.p : nullptr;
+    p.SVh = SVh ? bsvh.p : nullptr; p.S = S ? bs.p : nullptr; p.rank = d_rank;
+    const size_t smem = ss_smem<T>(p.mt, p.nt);
+    auto kern = svd_small_kernel<T>;
+    QIL_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+    kern<<<1, kSsThreads, smem, ctx->stream>>>(p);
+    QIL_LAUNCH_CHECK(ctx);
+    int r = 0;
+    QIL_CUDA(cudaMemcpyAsync(&r, d_rank, sizeof(int), cudaMemcpyDeviceToHost, ctx->stream));
+    ctx->sync();
+    ctx->free(d_rank);
+    // the kernel wrote compactly with leading dimension r: shrink the logical shapes
+    if (U) { bu.cols = r; *U = std::move(bu); }
+    if (US) { bus.cols = r; *US = std::move(bus); }
+    if (Vh) { bvh.rows = r; *Vh = std::move(bvh); }
+    if (SVh) { bsvh.rows = r; *SVh = std::move(bsvh); }
+    if (S) { bs.rows = r; *S = std::move(bs); }
+    return r;
+}
+
+template bool svd_small_fits<double>(qil_ctx*, int64_t, int64_t);
+template bool svd_small_fits<cplx>(qil_ctx*, int64_t, int64_t);
+template int svd_small<double>(qil_ctx*, int64_t, int64_t, const double*, int64_t, double, int64_t, int64_t,
+                               Mat<double>*, Mat<double>*, Mat<double>*, Mat<double>*, Mat<double>*);
+template int svd_small<cplx>(qil_ctx*, int64_t, int64_t, const cplx*, int64_t, double, int64_t, int64_t, Mat<cplx>*,
+                             Mat<cplx>*, Mat<cplx>*, Mat<cplx>*, Mat<double>*);
+
+}  // namespace qil

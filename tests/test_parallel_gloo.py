@@ -1,0 +1,58 @@
+"""world_size-2 gloo tests (CPU) of the N>1 host logic: unit sharding, MPS broadcast, result gather, peak search.
+The compute callable is the CPU oracle here (no GPU in this suite); on the GPU box the default is the CUDA path."""
+import os
+import sys
+
+import numpy as np
+import pytest
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+
+
+def test_shard_range_covers_everything(q):
+    from qilaplace_b200 import parallel
+    for total in (0, 1, 7, 8, 1000003):
+        for world in (1, 2, 3, 8):
+            spans = [parallel.shard_range(total, world, r) for r in range(world)]
+            assert spans[0][0] == 0 and spans[-1][1] == total
+            assert all(spans[i][1] == spans[i + 1][0] for i in range(world - 1))
+            sizes = [h - l for l, h in spans]
+            assert max(sizes) - min(sizes) <= 1
+
+
+def _worker(rank, world, port, ret):
+    sys.path.insert(0, ROOT)
+    sys.path.insert(0, os.path.join(ROOT, "oracle"))
+    os.environ["MASTER_ADDR"] = "127.0.0.1"
+    os.environ["MASTER_PORT"] = str(port)
+    import torch.distributed as dist
+    import qil_oracle as O
+    from qilaplace_b200 import parallel
+    dist.init_process_group("gloo", rank=rank, world_size=world)
+    try:
+        rng = np.random.default_rng(0)          # same stream on both ranks
+        bonds = [1, 2, 4, 3, 2, 1]
+        cores = [rng.standard_normal((bonds[i], 2, bonds[i + 1])) + 1j * rng.standard_normal((bonds[i], 2, bonds[i + 1]))
+                 for i in range(5)]
+        bits = rng.integers(0, 2, size=(37, 5)).astype(np.uint8)
+        c2, amp = parallel.broadcast_cores(cores if rank == 0 else None, 1.5 if rank == 0 else None)
+        assert amp == 1.5 and all(np.array_equal(a, b) for a, b in zip(c2, cores))
+        got = parallel.coefficients_sharded(c2, amp, bits, compute=O.coefficient_batch)
+        want = O.coefficient_batch(cores, 1.5, bits)
+        assert np.allclose(got, want, atol=1e-14)
+        lo, hi = parallel.shard_range(len(bits), world, rank)
+        v, idx = parallel.argmax_abs_sharded(want[lo:hi], lo)
+        assert idx == int(np.abs(want).argmax()) and abs(v - np.abs(want).max()) < 1e-15
+        ret[rank] = "ok"
+    finally:
+        dist.destroy_process_group()
+
+
+def test_coefficient_grid_sharded_over_gloo():
+    import torch.multiprocessing as mp
+    world = 2
+    port = 29500 + (os.getpid() % 2000)
+    mgr = mp.Manager()
+    ret = mgr.dict()
+    mp.spawn(_worker, args=(world, port, ret), nprocs=world, join=True)
+    assert dict(ret) == {0: "ok", 1: "ok"}
