@@ -102,4 +102,19 @@ template <typename T>
 int svd_small(qil_ctx* ctx, int64_t m, int64_t n, const T* A, int64_t lda, double cutoff, int64_t maxdim,
               int64_t mindim, Mat<T>* U, Mat<T>* US, Mat<T>* Vh, Mat<T>* SVh, Mat<double>* S);
 
+// Batch of independent small SVDs (one launch, one sync).  `copy_tensor`: A points at an MPS core [cl][2][cr]
+// and the decomposed matrix is T[(l,s),(s',r)] = delta(s,s') core[l,s,r] (m = 2 cl, n = 2 cr).
+template <typename T>
+struct SmallSvdItem {
+    const T* A = nullptr;
+    int64_t lda = 0, m = 0, n = 0;
+    bool copy_tensor = false;
+    int cl = 0, cr = 0;
+    bool want_U = false, want_US = false, want_Vh = false, want_SVh = false;
+    Mat<T> U, US, Vh, SVh;
+    int rank = 0;
+};
+template <typename T>
+void svd_small_batch(qil_ctx* ctx, std::vector<SmallSvdItem<T>>& items, double cutoff, int64_t maxdim, int64_t mindim);
+
 }  // namespace qil

@@ -316,29 +316,82 @@ int rsvd_matrix(qil_ctx* ctx, const T* d_A, int64_t m, int64_t n, const RsvdOpts
 template int rsvd_matrix<double>(qil_ctx*, const double*, int64_t, int64_t, const RsvdOpts&, Mat<double>&, Mat<double>&, Mat<double>&);
 template int rsvd_matrix<cplx>(qil_ctx*, const cplx*, int64_t, int64_t, const RsvdOpts&, Mat<cplx>&, Mat<double>&, Mat<cplx>&);
 
+// Level-synchronous divide and conquer (SignalConverters.jl:145-186).  The nodes of one level are independent:
+// those whose split is an exact small SVD (min(R,C) <= k+p and the matrix fits one CTA) are decomposed by ONE
+// batched launch; the rest (the streaming top split, mid-size randomized splits) go one by one.
 template <typename T>
-static void rec_split(SplitCtx<T>& sc, const T* Tp, Mat<T>* owner, int64_t lb, int first, int last, int64_t rb, bool top,
-                      std::vector<void*>& cores, std::vector<int64_t>& bond) {
+struct DcNode {
+    const T* ptr;
+    Mat<T> owner;
+    int64_t lb, rb;
+    int first, last;
+    bool top;
+};
+
+template <typename T>
+static void dc_encode(SplitCtx<T>& sc, const T* x, int n, std::vector<void*>& cores, std::vector<int64_t>& bond) {
     qil_ctx* ctx = sc.ctx;
-    if (first == last) {
-        if (owner && owner->p == Tp) {
-            cores[first] = owner->take();
-        } else {
-            T* c = (T*)ctx->alloc((size_t)lb * 2 * rb * sizeof(T));
-            QIL_CUDA(cudaMemcpyAsync(c, Tp, (size_t)lb * 2 * rb * sizeof(T), cudaMemcpyDeviceToDevice, ctx->stream));
-            cores[first] = c;
-        }
-        return;
+    const RsvdOpts& o = *sc.o;
+    std::vector<DcNode<T>> level;
+    {
+        DcNode<T> root;
+        root.ptr = x; root.lb = 1; root.rb = 1; root.first = 0; root.last = n - 1; root.top = true;
+        level.push_back(std::move(root));
     }
-    const int mid = (first + last + 1) / 2 - 1;        // 0-based form of (first+last-1) / 2 (SignalConverters.jl:161)
-    const int nl = mid - first + 1, nr = last - mid;
-    const int64_t R = lb << nl, C = ((int64_t)1 << nr) * rb;
-    Mat<T> U, SVh;
-    const int r = rsvd_split<T>(sc, Tp, R, C, top, U, &SVh);
-    if (owner) owner->release();
-    bond[mid + 1] = r;
-    rec_split<T>(sc, U.p, &U, lb, first, mid, r, false, cores, bond);
-    rec_split<T>(sc, SVh.p, &SVh, r, mid + 1, last, rb, false, cores, bond);
+    while (!level.empty()) {
+        std::vector<DcNode<T>> next;
+        std::vector<SmallSvdItem<T>> batch;
+        std::vector<size_t> batch_node;
+        std::vector<Mat<T>> Us(level.size()), SVs(level.size());
+        std::vector<int> ranks(level.size(), 0);
+        for (size_t i = 0; i < level.size(); ++i) {
+            DcNode<T>& nd = level[i];
+            if (nd.first == nd.last) {
+                if (nd.owner.p == nd.ptr && nd.ptr != nullptr) {
+                    cores[nd.first] = nd.owner.take();
+                } else {
+                    T* c = (T*)ctx->alloc((size_t)nd.lb * 2 * nd.rb * sizeof(T));
+                    QIL_CUDA(cudaMemcpyAsync(c, nd.ptr, (size_t)nd.lb * 2 * nd.rb * sizeof(T), cudaMemcpyDeviceToDevice,
+                                             ctx->stream));
+                    cores[nd.first] = c;
+                }
+                continue;
+            }
+            const int mid = (nd.first + nd.last + 1) / 2 - 1;   // 0-based (first+last-1) / 2 (SignalConverters.jl:161)
+            const int nl = mid - nd.first + 1, nr = nd.last - mid;
+            const int64_t R = nd.lb << nl, C = ((int64_t)1 << nr) * nd.rb;
+            if (!nd.top && std::min(R, C) <= (int64_t)o.k + o.p && svd_small_fits<T>(ctx, R, C)) {
+                SmallSvdItem<T> it;
+                it.A = nd.ptr; it.m = R; it.n = C; it.lda = C;
+                it.want_U = true; it.want_SVh = true;
+                batch.push_back(std::move(it));
+                batch_node.push_back(i);
+            } else {
+                ranks[i] = rsvd_split<T>(sc, nd.ptr, R, C, nd.top, Us[i], &SVs[i]);
+            }
+        }
+        svd_small_batch<T>(ctx, batch, o.cutoff, o.maxdim, o.mindim);
+        for (size_t b = 0; b < batch.size(); ++b) {
+            const size_t i = batch_node[b];
+            ranks[i] = batch[b].rank;
+            Us[i] = std::move(batch[b].U);
+            SVs[i] = std::move(batch[b].SVh);
+        }
+        for (size_t i = 0; i < level.size(); ++i) {
+            DcNode<T>& nd = level[i];
+            if (nd.first == nd.last) continue;
+            const int mid = (nd.first + nd.last + 1) / 2 - 1;
+            const int r = ranks[i];
+            bond[mid + 1] = r;
+            nd.owner.release();
+            DcNode<T> a, b;
+            a.ptr = Us[i].p; a.owner = std::move(Us[i]); a.lb = nd.lb; a.rb = r; a.first = nd.first; a.last = mid; a.top = false;
+            b.ptr = SVs[i].p; b.owner = std::move(SVs[i]); b.lb = r; b.rb = nd.rb; b.first = mid + 1; b.last = nd.last; b.top = false;
+            next.push_back(std::move(a));
+            next.push_back(std::move(b));
+        }
+        level = std::move(next);
+    }
 }
 
 template <typename T>
@@ -372,7 +425,7 @@ qil_mps* encode_rsvd(qil_ctx* ctx, const T* d_x, int64_t N, const RsvdOpts& o) {
         m->amplitude = c;
         return m;
     }
-    rec_split<T>(sc, x, nullptr, 1, 0, n - 1, 1, true, cores, bond);
+    dc_encode<T>(sc, x, n, cores, bond);
     double h_nrm[2];
     QIL_CUDA(cudaMemcpyAsync(h_nrm, nrm.p, 2 * sizeof(double), cudaMemcpyDeviceToHost, ctx->stream));
     ctx->sync();

@@ -110,20 +110,41 @@ static qil_mps* ztmps_split_t(qil_ctx* ctx, const qil_mps* psi, double cutoff, i
     QIL_REQUIRE(2 * n <= kMaxSites, QIL_ERR_UNSUPPORTED, "signal_ztmps: too many sites");
     std::vector<int64_t> bond(2 * n + 1, 1);
     std::vector<void*> cores(2 * n, nullptr);
+    // sites whose (2 chi_l) x (2 chi_r) copy tensor fits one CTA go into ONE batched launch (the sites are
+    // independent); larger bonds take the general path
+    std::vector<SmallSvdItem<T>> batch;
+    std::vector<int> batch_site;
     for (int i = 0; i < n; ++i) {
         const int l = (int)psi->bond[i], r = (int)psi->bond[i + 1];
-        Mat<T> Tm(ctx, 2 * l, 2 * r);
-        const long long total = 4ll * l * r;
-        copy_tensor_kernel<T><<<(int)std::min<long long>((total + 255) / 256, 1024), 256, 0, ctx->stream>>>(
-            (const T*)psi->core[i], l, r, Tm.p);
-        QIL_LAUNCH_CHECK(ctx);
-        Mat<T> U, SVh;
-        const int c = svd_trunc<T>(ctx, 2 * l, 2 * r, Tm.p, 2 * r, cutoff, maxdim, 1, &U, nullptr, nullptr, &SVh, nullptr);
         bond[2 * i] = l;
-        bond[2 * i + 1] = c;
         bond[2 * i + 2] = r;
-        cores[2 * i] = U.take();
-        cores[2 * i + 1] = SVh.take();
+        if (svd_small_fits<T>(ctx, 2 * l, 2 * r)) {
+            SmallSvdItem<T> it;
+            it.A = (const T*)psi->core[i];
+            it.m = 2 * l; it.n = 2 * r; it.lda = 2 * r;
+            it.copy_tensor = true; it.cl = l; it.cr = r;
+            it.want_U = true; it.want_SVh = true;
+            batch.push_back(std::move(it));
+            batch_site.push_back(i);
+        } else {
+            Mat<T> Tm(ctx, 2 * l, 2 * r);
+            const long long total = 4ll * l * r;
+            copy_tensor_kernel<T><<<(int)std::min<long long>((total + 255) / 256, 1024), 256, 0, ctx->stream>>>(
+                (const T*)psi->core[i], l, r, Tm.p);
+            QIL_LAUNCH_CHECK(ctx);
+            Mat<T> U, SVh;
+            const int c = svd_trunc<T>(ctx, 2 * l, 2 * r, Tm.p, 2 * r, cutoff, maxdim, 1, &U, nullptr, nullptr, &SVh, nullptr);
+            bond[2 * i + 1] = c;
+            cores[2 * i] = U.take();
+            cores[2 * i + 1] = SVh.take();
+        }
+    }
+    svd_small_batch<T>(ctx, batch, cutoff, maxdim, 1);
+    for (size_t b = 0; b < batch.size(); ++b) {
+        const int i = batch_site[b];
+        bond[2 * i + 1] = batch[b].rank;
+        cores[2 * i] = batch[b].U.take();
+        cores[2 * i + 1] = batch[b].SVh.take();
     }
     qil_mps* m = new_mps(ctx, 2 * n, psi->is_complex, bond.data(), false);
     m->core = cores;

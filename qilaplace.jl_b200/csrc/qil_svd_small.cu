@@ -27,6 +27,8 @@ struct SmallSvdParams {
     T* SVh;          // r x n   or null
     double* S;       // min(m,n) values (first r meaningful) or null
     int* rank;
+    int mode;        // 0: A is the matrix; 1: A is an MPS core [cl][2][cr] and the matrix is the copy tensor
+    int cl, cr;      //    T[(l,s),(s',r)] = delta(s,s') core[l,s,r]  (signal_ztmps, SignalConverters.jl:263)
 };
 
 template <typename T> __device__ __forceinline__ T wsum(T v);
@@ -72,8 +74,7 @@ __device__ inline int trunc_rank_small(const double* sig, int n, double cutoff, 
 }
 
 template <typename T>
-__global__ void __launch_bounds__(kSsThreads) svd_small_kernel(const SmallSvdParams<T> p) {
-    extern __shared__ __align__(16) unsigned char smem_raw[];
+__device__ __forceinline__ void svd_small_body(const SmallSvdParams<T>& p, unsigned char* smem_raw) {
     const int mt = p.mt, nt = p.nt, mpad = p.mpad, npad = p.npad;
     T* As = reinterpret_cast<T*>(smem_raw);              // [nt][mpad]  reflectors, later Q (column-major)
     T* qb = As + (size_t)nt * mpad;                      // [kSsWarps][mpad]
@@ -91,7 +92,13 @@ __global__ void __launch_bounds__(kSsThreads) svd_small_kernel(const SmallSvdPar
     // ---- load M (tall orientation) column-major: M[i][j] = A[i][j] or conj(A[j][i])
     for (int idx = tid; idx < p.m * p.n; idx += kSsThreads) {
         const int ia = idx / p.n, ja = idx - ia * p.n;
-        const T v = p.A[(long long)ia * p.lda + ja];
+        T v;
+        if (p.mode == 0) {
+            v = p.A[(long long)ia * p.lda + ja];
+        } else {
+            const int ll = ia >> 1, s1 = ia & 1, s2 = ja / p.cr, rr = ja - s2 * p.cr;
+            v = (s1 == s2) ? p.A[((long long)ll * 2 + s1) * p.cr + rr] : Scalar<T>::zero();
+        }
         if (tall) As[(size_t)ja * mpad + ia] = v;
         else As[(size_t)ia * mpad + ja] = Scalar<T>::conj(v);
     }
@@ -310,6 +317,22 @@ __global__ void __launch_bounds__(kSsThreads) svd_small_kernel(const SmallSvdPar
 }
 
 template <typename T>
+__global__ void __launch_bounds__(kSsThreads) svd_small_kernel(const SmallSvdParams<T> p) {
+    extern __shared__ __align__(16) unsigned char smem_dyn[];
+    svd_small_body<T>(p, smem_dyn);
+}
+
+// one CTA per problem; descriptors live in device memory
+template <typename T>
+__global__ void __launch_bounds__(kSsThreads) svd_small_batched_kernel(const SmallSvdParams<T>* __restrict__ probs) {
+    extern __shared__ __align__(16) unsigned char smem_dyn[];
+    __shared__ SmallSvdParams<T> sp;
+    if (threadIdx.x == 0) sp = probs[blockIdx.x];
+    __syncthreads();
+    svd_small_body<T>(sp, smem_dyn);
+}
+
+template <typename T>
 static size_t ss_smem(int mt, int nt) {
     const int mpad = mt | 1, npad = nt | 1;
     return ((size_t)(nt + kSsWarps) * mpad + 2 * (size_t)nt * npad + nt) * sizeof(T) + (size_t)nt * (2 * sizeof(double) + sizeof(int)) + 64;
@@ -342,6 +365,7 @@ int svd_small(qil_ctx* ctx, int64_t m, int64_t n, const T* A, int64_t lda, doubl
     int* d_rank = (int*)ctx->alloc(sizeof(int));
     p.U = U ? bu.p : nullptr; p.US = US ? bus.p : nullptr; p.Vh = Vh ? bvh.p : nullptr;
     p.SVh = SVh ? bsvh.p : nullptr; p.S = S ? bs.p : nullptr; p.rank = d_rank;
+    p.mode = 0; p.cl = 0; p.cr = 0;
     const size_t smem = ss_smem<T>(p.mt, p.nt);
     auto kern = svd_small_kernel<T>;
     QIL_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
@@ -359,6 +383,56 @@ int svd_small(qil_ctx* ctx, int64_t m, int64_t n, const T* A, int64_t lda, doubl
     if (S) { bs.rows = r; *S = std::move(bs); }
     return r;
 }
+
+// Batched variant: every item is an independent small SVD (one CTA each, one launch, one host sync).
+template <typename T>
+void svd_small_batch(qil_ctx* ctx, std::vector<SmallSvdItem<T>>& items, double cutoff, int64_t maxdim, int64_t mindim) {
+    const int nb = (int)items.size();
+    if (nb == 0) return;
+    std::vector<SmallSvdParams<T>> h(nb);
+    int* d_rank = (int*)ctx->alloc(sizeof(int) * nb);
+    size_t smem = 0;
+    for (int i = 0; i < nb; ++i) {
+        SmallSvdItem<T>& it = items[i];
+        const int64_t m = it.m, n = it.n;
+        const int k = (int)std::min(m, n);
+        SmallSvdParams<T>& p = h[i];
+        p.A = it.A; p.lda = it.lda; p.m = (int)m; p.n = (int)n;
+        p.mt = (int)std::max(m, n); p.nt = k; p.mpad = p.mt | 1; p.npad = p.nt | 1;
+        p.cutoff = cutoff; p.maxdim = maxdim < 1 ? 1 : maxdim; p.mindim = std::max<int64_t>(mindim, 1);
+        if (it.want_U) it.U = Mat<T>(ctx, m, k);
+        if (it.want_US) it.US = Mat<T>(ctx, m, k);
+        if (it.want_Vh) it.Vh = Mat<T>(ctx, k, n);
+        if (it.want_SVh) it.SVh = Mat<T>(ctx, k, n);
+        p.U = it.want_U ? it.U.p : nullptr; p.US = it.want_US ? it.US.p : nullptr;
+        p.Vh = it.want_Vh ? it.Vh.p : nullptr; p.SVh = it.want_SVh ? it.SVh.p : nullptr;
+        p.S = nullptr; p.rank = d_rank + i;
+        p.mode = it.copy_tensor ? 1 : 0; p.cl = it.cl; p.cr = it.cr;
+        smem = std::max(smem, ss_smem<T>(p.mt, p.nt));
+    }
+    SmallSvdParams<T>* d_p = (SmallSvdParams<T>*)ctx->alloc(sizeof(SmallSvdParams<T>) * nb);
+    QIL_CUDA(cudaMemcpyAsync(d_p, h.data(), sizeof(SmallSvdParams<T>) * nb, cudaMemcpyHostToDevice, ctx->stream));
+    auto kern = svd_small_batched_kernel<T>;
+    QIL_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+    kern<<<nb, kSsThreads, smem, ctx->stream>>>(d_p);
+    QIL_LAUNCH_CHECK(ctx);
+    std::vector<int> ranks(nb);
+    QIL_CUDA(cudaMemcpyAsync(ranks.data(), d_rank, sizeof(int) * nb, cudaMemcpyDeviceToHost, ctx->stream));
+    ctx->sync();
+    ctx->free(d_rank);
+    ctx->free(d_p);
+    for (int i = 0; i < nb; ++i) {
+        SmallSvdItem<T>& it = items[i];
+        const int r = ranks[i];
+        it.rank = r;
+        if (it.want_U) it.U.cols = r;
+        if (it.want_US) it.US.cols = r;
+        if (it.want_Vh) it.Vh.rows = r;
+        if (it.want_SVh) it.SVh.rows = r;
+    }
+}
+template void svd_small_batch<double>(qil_ctx*, std::vector<SmallSvdItem<double>>&, double, int64_t, int64_t);
+template void svd_small_batch<cplx>(qil_ctx*, std::vector<SmallSvdItem<cplx>>&, double, int64_t, int64_t);
 
 template bool svd_small_fits<double>(qil_ctx*, int64_t, int64_t);
 template bool svd_small_fits<cplx>(qil_ctx*, int64_t, int64_t);
