@@ -5,6 +5,7 @@
 // rounding even when the matrix is numerically rank deficient (the usual case for Y = A*Omega of a
 // structured signal), which Gram/Cholesky shortcuts do not.
 #include "qil_dense.cuh"
+#include "qil_hh.cuh"
 
 namespace qil {
 
@@ -48,21 +49,23 @@ __device__ __forceinline__ cplx warp_sum<cplx>(cplx v) {
     return v;
 }
 
-template <typename T>
-__global__ void __launch_bounds__(kQrThreadsGlobal) hhqr_kernel(const QrParams<T> p) {
+// GLOBAL = false: the work area is shared memory (the compiler then emits LDS/STS with 32-bit addressing);
+// GLOBAL = true : single CTA working on an L2-resident scratch (wide bond matrices that do not fit).
+template <typename T, bool GLOBAL>
+__global__ void __launch_bounds__(GLOBAL ? kQrThreadsGlobal : kQrThreads) hhqr_kernel(const QrParams<T> p) {
     extern __shared__ __align__(16) unsigned char smem_raw[];
     const int n = p.n, mpad = p.mpad;
     const int kQrThreads = blockDim.x, kQrWarps = blockDim.x >> 5;
     T* As;                                                 // [n][mpad] column-major
     T* sbeta;                                              // [n]
-    if (p.gscratch) {
+    if (GLOBAL) {
         As = p.gscratch;
         sbeta = reinterpret_cast<T*>(smem_raw);
     } else {
         As = reinterpret_cast<T*>(smem_raw);
-        sbeta = As + (size_t)(n + kQrWarps) * mpad;
+        sbeta = As + (n + kHhIlp * kQrWarps) * mpad;
     }
-    T* qb = As + (size_t)n * mpad;                         // [kQrWarps][mpad]
+    T* qb = As + n * mpad;                                 // [kHhIlp * kQrWarps][mpad]
     T* su0 = sbeta + n;                                    // [n]
     double* ss = reinterpret_cast<double*>(su0 + n);       // [n]
 
@@ -74,55 +77,17 @@ __global__ void __launch_bounds__(kQrThreadsGlobal) hhqr_kernel(const QrParams<T
     const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
 
     // ---- load (sum of partials), transposing into column-major smem
-    for (long long idx = tid; idx < (long long)mloc * n; idx += kQrThreads) {
-        const int i = (int)(idx / n), j = (int)(idx - (long long)i * n);
+    for (int idx = tid; idx < mloc * n; idx += kQrThreads) {
+        const int i = idx / n, j = idx - i * n;
         const T* src = p.A + (r0 + i) * p.lda + j;
         T v = src[0];
         for (int s = 1; s < p.nsum; ++s) v = Scalar<T>::add(v, src[(long long)s * p.sum_stride]);
-        As[(size_t)j * mpad + i] = v;
+        As[j * mpad + i] = v;
     }
     __syncthreads();
 
-    // ---- factorisation: H_j = I - s_j u_j u_j^H,  H_j x = beta_j e_1
-    for (int j = 0; j < k; ++j) {
-        T* col = As + (size_t)j * mpad;
-        if (warp == 0) {
-            double xn2 = 0.0;
-            for (int i = j + 1 + lane; i < mloc; i += 32) xn2 += Scalar<T>::abs2(col[i]);
-            xn2 = warp_sum<double>(xn2);
-            if (lane == 0) {
-                const T x0 = col[j];
-                const double a0 = sqrt(Scalar<T>::abs2(x0));
-                const double nx = sqrt(a0 * a0 + xn2);
-                if (nx == 0.0) {
-                    sbeta[j] = Scalar<T>::zero();
-                    su0[j] = Scalar<T>::zero();
-                    ss[j] = 0.0;
-                } else {
-                    const T ph = (a0 > 0.0) ? Scalar<T>::scale(x0, 1.0 / a0) : Scalar<T>::one();
-                    const T beta = Scalar<T>::scale(ph, -nx);
-                    sbeta[j] = beta;
-                    const T u0 = Scalar<T>::sub(x0, beta);
-                    su0[j] = u0;
-                    col[j] = u0;
-                    ss[j] = 1.0 / (nx * (nx + a0));
-                }
-            }
-        }
-        __syncthreads();
-        const double s = ss[j];
-        if (s != 0.0) {
-            for (int c = j + 1 + warp; c < n; c += kQrWarps) {
-                T* cc = As + (size_t)c * mpad;
-                T w = Scalar<T>::zero();
-                for (int i = j + lane; i < mloc; i += 32) w = Scalar<T>::fma(Scalar<T>::conj(col[i]), cc[i], w);
-                w = warp_sum<T>(w);
-                w = Scalar<T>::scale(w, -s);
-                for (int i = j + lane; i < mloc; i += 32) cc[i] = Scalar<T>::fma(w, col[i], cc[i]);
-            }
-        }
-        __syncthreads();
-    }
+    // ---- factorisation: H_j = I - s_j u_j u_j^H,  H_j x = beta_j e_1  (qil_hh.cuh)
+    hh_factor<T>(As, mpad, mloc, n, k, sbeta, ss);
 
     // ---- R (k x n), optional positive diagonal
     if (p.R) {
@@ -130,7 +95,7 @@ __global__ void __launch_bounds__(kQrThreadsGlobal) hhqr_kernel(const QrParams<T
             const int j = idx / n, c = idx - j * n;
             T v = Scalar<T>::zero();
             if (c == j) v = sbeta[j];
-            else if (c > j) v = As[(size_t)c * mpad + j];
+            else if (c > j) v = As[c * mpad + j];
             if (p.positive) {
                 const T bj = sbeta[j];
                 const double ab = sqrt(Scalar<T>::abs2(bj));
@@ -140,42 +105,17 @@ __global__ void __launch_bounds__(kQrThreadsGlobal) hhqr_kernel(const QrParams<T
         }
     }
 
-    // ---- explicit Q (mloc x k): column c = H_0 ... H_c e_c, groups of kQrWarps columns
+    // ---- explicit Q (mloc x k)
     if (p.Q) {
-        T* q = qb + (size_t)warp * mpad;
-        for (int c0 = 0; c0 < k; c0 += kQrWarps) {
-            const int c = c0 + warp;
-            if (c < k) {
-                for (int i = lane; i < mloc; i += 32) q[i] = (i == c) ? Scalar<T>::one() : Scalar<T>::zero();
-                __syncwarp();
-                for (int j = c; j >= 0; --j) {
-                    const double s = ss[j];
-                    if (s == 0.0) continue;
-                    const T* col = As + (size_t)j * mpad;
-                    T w = Scalar<T>::zero();
-                    for (int i = j + lane; i < mloc; i += 32) w = Scalar<T>::fma(Scalar<T>::conj(col[i]), q[i], w);
-                    w = warp_sum<T>(w);
-                    w = Scalar<T>::scale(w, -s);
-                    for (int i = j + lane; i < mloc; i += 32) q[i] = Scalar<T>::fma(w, col[i], q[i]);
-                    __syncwarp();
-                }
-                if (p.positive) {
-                    const T bj = sbeta[c];
-                    const double ab = sqrt(Scalar<T>::abs2(bj));
-                    if (ab > 0.0) {
-                        const T ph = Scalar<T>::scale(bj, 1.0 / ab);
-                        for (int i = lane; i < mloc; i += 32) q[i] = Scalar<T>::mul(q[i], ph);
-                    }
-                }
+        hh_form_q<T>(As, mpad, mloc, k, ss, qb, [&](int c, const T* q) {
+            T ph = Scalar<T>::one();
+            if (p.positive) {
+                const T bj = sbeta[c];
+                const double ab = sqrt(Scalar<T>::abs2(bj));
+                if (ab > 0.0) ph = Scalar<T>::scale(bj, 1.0 / ab);
             }
-            __syncthreads();
-            const int nc = min(kQrWarps, k - c0);
-            for (int idx = tid; idx < mloc * nc; idx += kQrThreads) {
-                const int i = idx / nc, w = idx - i * nc;
-                p.Q[(r0 + i) * p.ldq + c0 + w] = qb[(size_t)w * mpad + i];
-            }
-            __syncthreads();
-        }
+            for (int i = lane; i < mloc; i += 32) p.Q[(r0 + i) * p.ldq + c] = Scalar<T>::mul(q[i], ph);
+        });
     }
 }
 
@@ -204,7 +144,7 @@ __global__ void __launch_bounds__(256) tsqr_combine_kernel(const T* __restrict__
 template <typename T>
 static size_t qr_smem(int n, int mloc) {
     const int mpad = mloc | 1;
-    return ((size_t)n * mpad + (size_t)kQrWarps * mpad + 2 * (size_t)n) * sizeof(T) + (size_t)n * sizeof(double) + 32;
+    return ((size_t)n * mpad + (size_t)kHhIlp * kQrWarps * mpad + 2 * (size_t)n) * sizeof(T) + (size_t)n * sizeof(double) + 32;
 }
 
 template <typename T>
@@ -212,7 +152,7 @@ static int qr_capacity(qil_ctx* ctx, int n) {
     const size_t budget = std::min<size_t>(ctx->smem_optin, 220 * 1024);
     // rows that fit: (n + warps) * mpad * sizeof(T) <= budget - small
     long long fixed = (2ll * n) * sizeof(T) + (long long)n * 8 + 64;
-    long long rows = ((long long)budget - fixed) / ((long long)(n + kQrWarps) * sizeof(T));
+    long long rows = ((long long)budget - fixed) / ((long long)(n + kHhIlp * kQrWarps) * sizeof(T));
     rows -= 2;
     return (int)std::max<long long>(rows, 0);
 }
@@ -221,8 +161,8 @@ template <typename T>
 static void launch_hhqr(qil_ctx* ctx, const QrParams<T>& p, int max_mloc, bool use_global = false) {
     QrParams<T> q = p;
     q.mpad = max_mloc | 1;
-    auto kern = hhqr_kernel<T>;
     if (!use_global) {
+        auto kern = hhqr_kernel<T, false>;
         const size_t smem = qr_smem<T>(p.n, max_mloc);
         q.gscratch = nullptr;
         QIL_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
@@ -233,9 +173,10 @@ static void launch_hhqr(qil_ctx* ctx, const QrParams<T>& p, int max_mloc, bool u
     // one CTA, 32 warps, work area in global memory (stays in L2): slow but shape-agnostic
     QIL_REQUIRE(p.nblk == 1, QIL_ERR_RUNTIME, "qr: global-scratch variant handles a single block");
     const int nw = kQrThreadsGlobal / 32;
-    Mat<T> scratch(ctx, (int64_t)p.n + nw, q.mpad);
+    Mat<T> scratch(ctx, (int64_t)p.n + kHhIlp * nw, q.mpad);
     q.gscratch = scratch.p;
     const size_t smem = 2 * (size_t)p.n * sizeof(T) + (size_t)p.n * sizeof(double) + 32;
+    auto kern = hhqr_kernel<T, true>;
     QIL_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
     kern<<<1, kQrThreadsGlobal, smem, ctx->stream>>>(q);
     QIL_LAUNCH_CHECK(ctx);

@@ -292,7 +292,7 @@ int stream_nt_for(int cols) {
 
 bool stream_supported(long long R, long long C, long long ld, int cols) {
     // TMA needs a 16-byte aligned row pitch; small problems go to the generic GEMM
-    return (ld % 2 == 0) && R >= 256 && C >= 256 && (R * C) >= (1ll << 20) && stream_nt_for(cols) <= 14;
+    return (ld % 2 == 0) && R >= 64 && C >= 64 && (R * C) >= (1ll << 13) && stream_nt_for(cols) <= 14;
 }
 
 // out[ksplit][Mtot][8*nt] partials of A*X (trans=false) or A^T*X (trans=true); A is a REAL R x C view.

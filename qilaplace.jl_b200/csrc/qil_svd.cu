@@ -67,29 +67,29 @@ __device__ __forceinline__ cplx group_sum<cplx>(cplx v, int gl, unsigned mask) {
     return v;
 }
 
-template <typename T>
-__global__ void __launch_bounds__(kJacThreadsGlobal) jacobi_kernel(const JacParams<T> p) {
+template <typename T, bool GLOBAL>
+__global__ void __launch_bounds__(GLOBAL ? kJacThreadsGlobal : kJacThreads) jacobi_kernel(const JacParams<T> p) {
     extern __shared__ __align__(16) unsigned char smem_raw[];
     const int ns = p.ns, pad = p.pad;
     const int kJacThreads = blockDim.x;
     T* G;                                         // [ns][pad] column-major
     double* sig;                                  // [ns]
-    if (p.gscratch) {
+    if (GLOBAL) {
         G = p.gscratch;
         sig = reinterpret_cast<double*>(smem_raw);
     } else {
         G = reinterpret_cast<T*>(smem_raw);
-        sig = reinterpret_cast<double*>(G + (size_t)2 * ns * pad);
+        sig = reinterpret_cast<double*>(G + 2 * ns * pad);
     }
-    T* V = G + (size_t)ns * pad;                  // [ns][pad]
+    T* V = G + ns * pad;                          // [ns][pad]
     int* order = reinterpret_cast<int*>(sig + ns);                  // [ns]
     __shared__ int s_rot;
 
     const int tid = threadIdx.x;
     for (int idx = tid; idx < ns * ns; idx += kJacThreads) {
         const int j = idx / ns, i = idx - j * ns;
-        G[(size_t)j * pad + i] = Scalar<T>::conj(p.R[(long long)j * p.ld + i]);
-        V[(size_t)j * pad + i] = (i == j) ? Scalar<T>::one() : Scalar<T>::zero();
+        G[j * pad + i] = Scalar<T>::conj(p.R[(long long)j * p.ld + i]);
+        V[j * pad + i] = (i == j) ? Scalar<T>::one() : Scalar<T>::zero();
     }
     __syncthreads();
 
@@ -111,8 +111,8 @@ __global__ void __launch_bounds__(kJacThreadsGlobal) jacobi_kernel(const JacPara
                 else { a = (r + pi) % (ne - 1); b = (r - pi + (ne - 1)) % (ne - 1); }
                 if (a >= ns || b >= ns) continue;   // group-uniform
                 const int cp = min(a, b), cq = max(a, b);
-                T* gp = G + (size_t)cp * pad;
-                T* gq = G + (size_t)cq * pad;
+                T* gp = G + cp * pad;
+                T* gq = G + cq * pad;
                 double al = 0.0, be = 0.0;
                 T ga = Scalar<T>::zero();
                 for (int i = gln; i < ns; i += gl) {
@@ -126,11 +126,17 @@ __global__ void __launch_bounds__(kJacThreadsGlobal) jacobi_kernel(const JacPara
                 ga = group_sum<T>(ga, gl, gmask);
                 const double g2 = Scalar<T>::abs2(ga);
                 if (g2 > tol * tol * al * be && g2 > 0.0) {
-                    const double ag = sqrt(g2);
-                    const T ph = Scalar<T>::scale(ga, 1.0 / ag);          // e^{i phi}
-                    const double zeta = (be - al) / (2.0 * ag);
-                    const double t = (zeta >= 0.0 ? 1.0 : -1.0) / (fabs(zeta) + sqrt(1.0 + zeta * zeta));
-                    const double c = 1.0 / sqrt(1.0 + t * t);
+                    // t = 2|g| sgn(d) / (|d| + sqrt(d^2 + 4|g|^2)), d = beta - alpha; c = rsqrt(1 + t^2), s = c t.
+                    // rsqrt-based: the rotation only has to be orthogonal to rounding (c^2 + s^2 = 1), its angle
+                    // may carry a few ulps of error (fixed by the next sweep) -- 3 sqrt + 4 div become 3 rsqrt + 1 div.
+                    const double rg = rsqrt(g2);
+                    const double ag = g2 * rg;
+                    const T ph = Scalar<T>::scale(ga, rg);                // e^{i phi}
+                    const double dd = be - al;
+                    const double hh = dd * dd + 4.0 * g2;
+                    const double sq = hh * rsqrt(hh);
+                    const double t = (dd >= 0.0 ? 2.0 : -2.0) * ag / (fabs(dd) + sq);
+                    const double c = rsqrt(1.0 + t * t);
                     const double s = c * t;
                     const T sp = Scalar<T>::scale(ph, s);                 // s e^{i phi}
                     const T spc = Scalar<T>::conj(sp);                    // s e^{-i phi}
@@ -139,8 +145,8 @@ __global__ void __launch_bounds__(kJacThreadsGlobal) jacobi_kernel(const JacPara
                         gp[i] = Scalar<T>::sub(Scalar<T>::scale(x, c), Scalar<T>::mul(spc, y));
                         gq[i] = Scalar<T>::add(Scalar<T>::mul(sp, x), Scalar<T>::scale(y, c));
                     }
-                    T* vp = V + (size_t)cp * pad;
-                    T* vq = V + (size_t)cq * pad;
+                    T* vp = V + cp * pad;
+                    T* vq = V + cq * pad;
                     for (int i = gln; i < ns; i += gl) {
                         const T x = vp[i], y = vq[i];
                         vp[i] = Scalar<T>::sub(Scalar<T>::scale(x, c), Scalar<T>::mul(spc, y));
@@ -159,7 +165,7 @@ __global__ void __launch_bounds__(kJacThreadsGlobal) jacobi_kernel(const JacPara
     // singular values, descending order by rank sort
     for (int j = tid; j < ns; j += kJacThreads) {
         double a = 0.0;
-        const T* g = G + (size_t)j * pad;
+        const T* g = G + j * pad;
         for (int i = 0; i < ns; ++i) a += Scalar<T>::abs2(g[i]);
         sig[j] = sqrt(a);
     }
@@ -190,8 +196,8 @@ __global__ void __launch_bounds__(kJacThreadsGlobal) jacobi_kernel(const JacPara
     for (int idx = tid; idx < ns * ns; idx += kJacThreads) {
         const int i = idx / ns, j = idx - i * ns;
         const int src = order[j];
-        p.V[(long long)i * ns + j] = V[(size_t)src * pad + i];
-        p.W[(long long)i * ns + j] = G[(size_t)src * pad + i];
+        p.V[(long long)i * ns + j] = V[src * pad + i];
+        p.W[(long long)i * ns + j] = G[src * pad + i];
     }
 }
 
@@ -234,9 +240,15 @@ static int jacobi_square(qil_ctx* ctx, int ns, const T* R, int64_t ld, double cu
     p.cutoff = cutoff; p.maxdim = maxdim; p.mindim = std::max<int64_t>(mindim, 1);
     p.gl = ns <= 32 ? 8 : (ns <= 64 ? 16 : 32);
     p.gscratch = use_global ? gscratch.p : nullptr;
-    auto kern = jacobi_kernel<T>;
-    QIL_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-    kern<<<1, use_global ? kJacThreadsGlobal : kJacThreads, smem, ctx->stream>>>(p);
+    if (use_global) {
+        auto kern = jacobi_kernel<T, true>;
+        QIL_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+        kern<<<1, kJacThreadsGlobal, smem, ctx->stream>>>(p);
+    } else {
+        auto kern = jacobi_kernel<T, false>;
+        QIL_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+        kern<<<1, kJacThreads, smem, ctx->stream>>>(p);
+    }
     QIL_LAUNCH_CHECK(ctx);
     int rank = 0;
     QIL_CUDA(cudaMemcpyAsync(&rank, d_rank, sizeof(int), cudaMemcpyDeviceToHost, ctx->stream));

@@ -6,6 +6,7 @@
 // lower levels, signal_ztmps, canonicalize!/compress! and the QFT/DT builders, where the matrices are a few
 // dozen rows/columns and launch + sync overhead used to dominate.
 #include "qil_dense.cuh"
+#include "qil_hh.cuh"
 
 namespace qil {
 
@@ -77,10 +78,10 @@ template <typename T>
 __device__ __forceinline__ void svd_small_body(const SmallSvdParams<T>& p, unsigned char* smem_raw) {
     const int mt = p.mt, nt = p.nt, mpad = p.mpad, npad = p.npad;
     T* As = reinterpret_cast<T*>(smem_raw);              // [nt][mpad]  reflectors, later Q (column-major)
-    T* qb = As + (size_t)nt * mpad;                      // [kSsWarps][mpad]
-    T* G = qb + (size_t)kSsWarps * mpad;                 // [nt][npad]  G = R^H, later W = G V
-    T* V = G + (size_t)nt * npad;                        // [nt][npad]
-    T* sbeta = V + (size_t)nt * npad;                    // [nt]
+    T* qb = As + nt * mpad;                      // [kHhIlp * kSsWarps][mpad]
+    T* G = qb + kHhIlp * kSsWarps * mpad;        // [nt][npad]  G = R^H, later W = G V
+    T* V = G + nt * npad;                        // [nt][npad]
+    T* sbeta = V + nt * npad;                    // [nt]
     double* ss = reinterpret_cast<double*>(sbeta + nt);  // [nt]
     double* sig = ss + nt;                               // [nt]
     int* order = reinterpret_cast<int*>(sig + nt);       // [nt]
@@ -99,89 +100,30 @@ __device__ __forceinline__ void svd_small_body(const SmallSvdParams<T>& p, unsig
             const int ll = ia >> 1, s1 = ia & 1, s2 = ja / p.cr, rr = ja - s2 * p.cr;
             v = (s1 == s2) ? p.A[((long long)ll * 2 + s1) * p.cr + rr] : Scalar<T>::zero();
         }
-        if (tall) As[(size_t)ja * mpad + ia] = v;
-        else As[(size_t)ia * mpad + ja] = Scalar<T>::conj(v);
+        if (tall) As[ja * mpad + ia] = v;
+        else As[ia * mpad + ja] = Scalar<T>::conj(v);
     }
     __syncthreads();
 
-    // ---- Householder factorisation (see qil_qr.cu)
-    for (int j = 0; j < nt; ++j) {
-        T* col = As + (size_t)j * mpad;
-        if (warp == 0) {
-            double xn2 = 0.0;
-            for (int i = j + 1 + lane; i < mt; i += 32) xn2 += Scalar<T>::abs2(col[i]);
-            xn2 = wsum<double>(xn2);
-            if (lane == 0) {
-                const T x0 = col[j];
-                const double a0 = sqrt(Scalar<T>::abs2(x0));
-                const double nx = sqrt(a0 * a0 + xn2);
-                if (nx == 0.0) {
-                    sbeta[j] = Scalar<T>::zero();
-                    ss[j] = 0.0;
-                } else {
-                    const T ph = (a0 > 0.0) ? Scalar<T>::scale(x0, 1.0 / a0) : Scalar<T>::one();
-                    const T beta = Scalar<T>::scale(ph, -nx);
-                    sbeta[j] = beta;
-                    col[j] = Scalar<T>::sub(x0, beta);
-                    ss[j] = 1.0 / (nx * (nx + a0));
-                }
-            }
-        }
-        __syncthreads();
-        const double s = ss[j];
-        if (s != 0.0) {
-            for (int c = j + 1 + warp; c < nt; c += kSsWarps) {
-                T* cc = As + (size_t)c * mpad;
-                T w = Scalar<T>::zero();
-                for (int i = j + lane; i < mt; i += 32) w = Scalar<T>::fma(Scalar<T>::conj(col[i]), cc[i], w);
-                w = wsum<T>(w);
-                w = Scalar<T>::scale(w, -s);
-                for (int i = j + lane; i < mt; i += 32) cc[i] = Scalar<T>::fma(w, col[i], cc[i]);
-            }
-        }
-        __syncthreads();
-    }
+    // ---- Householder factorisation (qil_hh.cuh)
+    hh_factor<T>(As, mpad, mt, nt, nt, sbeta, ss);
 
     // ---- G = R^H (column-major G[col j][row i] = conj(R[j][i])), V = I
     for (int idx = tid; idx < nt * nt; idx += kSsThreads) {
         const int j = idx / nt, i = idx - j * nt;
         T r = Scalar<T>::zero();
         if (i == j) r = sbeta[j];
-        else if (i > j) r = As[(size_t)i * mpad + j];     // R[j][i], stored in column i, row j
-        G[(size_t)j * npad + i] = Scalar<T>::conj(r);
-        V[(size_t)j * npad + i] = (i == j) ? Scalar<T>::one() : Scalar<T>::zero();
+        else if (i > j) r = As[i * mpad + j];     // R[j][i], stored in column i, row j
+        G[j * npad + i] = Scalar<T>::conj(r);
+        V[j * npad + i] = (i == j) ? Scalar<T>::one() : Scalar<T>::zero();
     }
     __syncthreads();
 
-    // ---- explicit Q in place, columns from the last group to the first
-    {
-        T* q = qb + (size_t)warp * mpad;
-        const int ngroups = (nt + kSsWarps - 1) / kSsWarps;
-        for (int gi = ngroups - 1; gi >= 0; --gi) {
-            const int c = gi * kSsWarps + warp;
-            if (c < nt) {
-                for (int i = lane; i < mt; i += 32) q[i] = (i == c) ? Scalar<T>::one() : Scalar<T>::zero();
-                __syncwarp();
-                for (int j = c; j >= 0; --j) {
-                    const double s = ss[j];
-                    if (s == 0.0) continue;
-                    const T* col = As + (size_t)j * mpad;
-                    T w = Scalar<T>::zero();
-                    for (int i = j + lane; i < mt; i += 32) w = Scalar<T>::fma(Scalar<T>::conj(col[i]), q[i], w);
-                    w = wsum<T>(w);
-                    w = Scalar<T>::scale(w, -s);
-                    for (int i = j + lane; i < mt; i += 32) q[i] = Scalar<T>::fma(w, col[i], q[i]);
-                    __syncwarp();
-                }
-            }
-            __syncthreads();
-            if (c < nt) {
-                T* dst = As + (size_t)c * mpad;
-                for (int i = lane; i < mt; i += 32) dst[i] = q[i];
-            }
-            __syncthreads();
-        }
-    }
+    // ---- explicit Q in place (groups from the highest columns down, so reflectors still needed stay intact)
+    hh_form_q<T>(As, mpad, mt, nt, ss, qb, [&](int c, const T* q) {
+        T* dst = As + c * mpad;
+        for (int i = lane; i < mt; i += 32) dst[i] = q[i];
+    });
 
     // ---- one-sided Jacobi on the columns of G (see qil_svd.cu)
     {
@@ -203,8 +145,8 @@ __device__ __forceinline__ void svd_small_body(const SmallSvdParams<T>& p, unsig
                     else { a = (r + pi) % (ne - 1); b = (r - pi + (ne - 1)) % (ne - 1); }
                     if (a >= ns || b >= ns) continue;
                     const int cp = min(a, b), cq = max(a, b);
-                    T* gp = G + (size_t)cp * npad;
-                    T* gq = G + (size_t)cq * npad;
+                    T* gp = G + cp * npad;
+                    T* gq = G + cq * npad;
                     double al = 0.0, be = 0.0;
                     T ga = Scalar<T>::zero();
                     for (int i = gln; i < ns; i += gl) {
@@ -218,16 +160,20 @@ __device__ __forceinline__ void svd_small_body(const SmallSvdParams<T>& p, unsig
                     ga = gsum<T>(ga, gl, gmask);
                     const double g2 = Scalar<T>::abs2(ga);
                     if (g2 > tol * tol * al * be && g2 > 0.0) {
-                        const double ag = sqrt(g2);
-                        const T ph = Scalar<T>::scale(ga, 1.0 / ag);
-                        const double zeta = (be - al) / (2.0 * ag);
-                        const double tt = (zeta >= 0.0 ? 1.0 : -1.0) / (fabs(zeta) + sqrt(1.0 + zeta * zeta));
-                        const double c = 1.0 / sqrt(1.0 + tt * tt);
+                        // rsqrt-based rotation (see qil_svd.cu)
+                        const double rg = rsqrt(g2);
+                        const double ag = g2 * rg;
+                        const T ph = Scalar<T>::scale(ga, rg);
+                        const double dd = be - al;
+                        const double hh = dd * dd + 4.0 * g2;
+                        const double sq = hh * rsqrt(hh);
+                        const double tt = (dd >= 0.0 ? 2.0 : -2.0) * ag / (fabs(dd) + sq);
+                        const double c = rsqrt(1.0 + tt * tt);
                         const double s = c * tt;
                         const T sp = Scalar<T>::scale(ph, s);
                         const T spc = Scalar<T>::conj(sp);
-                        T* vp = V + (size_t)cp * npad;
-                        T* vq = V + (size_t)cq * npad;
+                        T* vp = V + cp * npad;
+                        T* vq = V + cq * npad;
                         for (int i = gln; i < ns; i += gl) {
                             const T x = gp[i], y = gq[i];
                             gp[i] = Scalar<T>::sub(Scalar<T>::scale(x, c), Scalar<T>::mul(spc, y));
@@ -250,7 +196,7 @@ __device__ __forceinline__ void svd_small_body(const SmallSvdParams<T>& p, unsig
     // ---- singular values, order, rank
     for (int j = tid; j < nt; j += kSsThreads) {
         double a = 0.0;
-        const T* g = G + (size_t)j * npad;
+        const T* g = G + j * npad;
         for (int i = 0; i < nt; ++i) a += Scalar<T>::abs2(g[i]);
         sig[j] = sqrt(a);
     }
@@ -283,9 +229,9 @@ __device__ __forceinline__ void svd_small_body(const SmallSvdParams<T>& p, unsig
     if (need_qv) {
         for (int idx = tid; idx < mt * r; idx += kSsThreads) {
             const int i = idx / r, j = idx - i * r;
-            const T* vc = V + (size_t)order[j] * npad;
+            const T* vc = V + order[j] * npad;
             T acc = Scalar<T>::zero();
-            for (int c = 0; c < nt; ++c) acc = Scalar<T>::fma(As[(size_t)c * mpad + i], vc[c], acc);
+            for (int c = 0; c < nt; ++c) acc = Scalar<T>::fma(As[c * mpad + i], vc[c], acc);
             const double sj = sig[j];
             if (tall) {
                 if (p.U) p.U[(long long)i * r + j] = acc;
@@ -301,7 +247,7 @@ __device__ __forceinline__ void svd_small_body(const SmallSvdParams<T>& p, unsig
     if (need_w) {
         for (int idx = tid; idx < nt * r; idx += kSsThreads) {
             const int i = idx / r, j = idx - i * r;         // W[i][j], i < nt
-            const T w = G[(size_t)order[j] * npad + i];
+            const T w = G[order[j] * npad + i];
             const double sj = sig[j];
             const double inv = sj != 0.0 ? 1.0 / sj : 0.0;
             if (tall) {
@@ -335,7 +281,7 @@ __global__ void __launch_bounds__(kSsThreads) svd_small_batched_kernel(const Sma
 template <typename T>
 static size_t ss_smem(int mt, int nt) {
     const int mpad = mt | 1, npad = nt | 1;
-    return ((size_t)(nt + kSsWarps) * mpad + 2 * (size_t)nt * npad + nt) * sizeof(T) + (size_t)nt * (2 * sizeof(double) + sizeof(int)) + 64;
+    return ((size_t)(nt + kHhIlp * kSsWarps) * mpad + 2 * (size_t)nt * npad + nt) * sizeof(T) + (size_t)nt * (2 * sizeof(double) + sizeof(int)) + 64;
 }
 
 template <typename T>
