@@ -74,7 +74,9 @@ static int rsvd_host(qil_ctx* ctx, int64_t m, int64_t n, const void* A, const Rs
     return r;
 }
 
+
 extern "C" {
+
 
 const char* qil_last_error(void) { return g_last_error.c_str(); }
 const char* qil_version(void) { return "qilcuda 0.1 (sm_100a)"; }

@@ -71,7 +71,24 @@ __device__ __forceinline__ void hh_factor(T* As, int mpad, int mloc, int n, int 
 #pragma unroll
             for (int q = 0; q < kHhIlp; ++q) w[q] = Scalar<T>::zero();
             if (s != 0.0) {
-                for (int i = j + lane; i < mloc; i += 32) {
+                int i = j + lane;
+                for (; i + 96 < mloc; i += 128) {       // 4 row chunks in flight: loads first, then the FMAs
+                    T uc[4];
+#pragma unroll
+                    for (int r = 0; r < 4; ++r) uc[r] = Scalar<T>::conj(col[i + 32 * r]);
+#pragma unroll
+                    for (int q = 0; q < kHhIlp; ++q) {
+                        const int c = cb + q * nwarps;
+                        if (c < n) {
+                            T a[4];
+#pragma unroll
+                            for (int r = 0; r < 4; ++r) a[r] = As[c * mpad + i + 32 * r];
+#pragma unroll
+                            for (int r = 0; r < 4; ++r) w[q] = Scalar<T>::fma(uc[r], a[r], w[q]);
+                        }
+                    }
+                }
+                for (; i < mloc; i += 32) {
                     const T uc = Scalar<T>::conj(col[i]);
 #pragma unroll
                     for (int q = 0; q < kHhIlp; ++q) {
@@ -85,16 +102,40 @@ __device__ __forceinline__ void hh_factor(T* As, int mpad, int mloc, int n, int 
             // update; the owner of column j+1 (q == 0, cb == j+1) also accumulates its sub-diagonal norm
             double xn2 = 0.0;
             const bool owner = (cb == j + 1) && (j + 1 < k);
-            for (int i = j + lane; i < mloc; i += 32) {
-                const T u = col[i];
+            int i2 = j + lane;
+            for (; i2 + 96 < mloc; i2 += 128) {
+                T u[4];
+#pragma unroll
+                for (int r = 0; r < 4; ++r) u[r] = col[i2 + 32 * r];
 #pragma unroll
                 for (int q = 0; q < kHhIlp; ++q) {
                     const int c = cb + q * nwarps;
                     if (c < n) {
-                        T* dst = As + c * mpad + i;
+                        T* dst = As + c * mpad + i2;
+                        T v[4];
+#pragma unroll
+                        for (int r = 0; r < 4; ++r) v[r] = dst[32 * r];
+                        if (s != 0.0) {
+#pragma unroll
+                            for (int r = 0; r < 4; ++r) { v[r] = Scalar<T>::fma(w[q], u[r], v[r]); dst[32 * r] = v[r]; }
+                        }
+                        if (q == 0 && owner) {
+#pragma unroll
+                            for (int r = 0; r < 4; ++r) if (i2 + 32 * r > j + 1) xn2 += Scalar<T>::abs2(v[r]);
+                        }
+                    }
+                }
+            }
+            for (; i2 < mloc; i2 += 32) {
+                const T u = col[i2];
+#pragma unroll
+                for (int q = 0; q < kHhIlp; ++q) {
+                    const int c = cb + q * nwarps;
+                    if (c < n) {
+                        T* dst = As + c * mpad + i2;
                         T v = *dst;
                         if (s != 0.0) { v = Scalar<T>::fma(w[q], u, v); *dst = v; }
-                        if (q == 0 && owner && i > j + 1) xn2 += Scalar<T>::abs2(v);
+                        if (q == 0 && owner && i2 > j + 1) xn2 += Scalar<T>::abs2(v);
                     }
                 }
             }
@@ -140,20 +181,53 @@ __device__ __forceinline__ void hh_form_q(const T* As, int mpad, int mloc, int k
             T w[kHhIlp];
 #pragma unroll
             for (int q = 0; q < kHhIlp; ++q) w[q] = Scalar<T>::zero();
-            for (int i = j + lane; i < mloc; i += 32) {
+            bool act[kHhIlp];
+#pragma unroll
+            for (int q = 0; q < kHhIlp; ++q) act[q] = (c0 + q * nwarps >= j) && (c0 + q * nwarps < k);
+            int i = j + lane;
+            for (; i + 96 < mloc; i += 128) {
+                T uc[4];
+#pragma unroll
+                for (int r = 0; r < 4; ++r) uc[r] = Scalar<T>::conj(col[i + 32 * r]);
+#pragma unroll
+                for (int q = 0; q < kHhIlp; ++q)
+                    if (act[q]) {
+                        T a[4];
+#pragma unroll
+                        for (int r = 0; r < 4; ++r) a[r] = qb[q * mpad + i + 32 * r];
+#pragma unroll
+                        for (int r = 0; r < 4; ++r) w[q] = Scalar<T>::fma(uc[r], a[r], w[q]);
+                    }
+            }
+            for (; i < mloc; i += 32) {
                 const T uc = Scalar<T>::conj(col[i]);
 #pragma unroll
                 for (int q = 0; q < kHhIlp; ++q)
-                    if (c0 + q * nwarps >= j && c0 + q * nwarps < k) w[q] = Scalar<T>::fma(uc, qb[q * mpad + i], w[q]);
+                    if (act[q]) w[q] = Scalar<T>::fma(uc, qb[q * mpad + i], w[q]);
             }
 #pragma unroll
             for (int q = 0; q < kHhIlp; ++q) w[q] = Scalar<T>::scale(hh_wsum<T>(w[q]), -s);
-            for (int i = j + lane; i < mloc; i += 32) {
+            i = j + lane;
+            for (; i + 96 < mloc; i += 128) {
+                T u[4];
+#pragma unroll
+                for (int r = 0; r < 4; ++r) u[r] = col[i + 32 * r];
+#pragma unroll
+                for (int q = 0; q < kHhIlp; ++q)
+                    if (act[q]) {
+                        T* dst = qb + q * mpad + i;
+                        T v[4];
+#pragma unroll
+                        for (int r = 0; r < 4; ++r) v[r] = dst[32 * r];
+#pragma unroll
+                        for (int r = 0; r < 4; ++r) dst[32 * r] = Scalar<T>::fma(w[q], u[r], v[r]);
+                    }
+            }
+            for (; i < mloc; i += 32) {
                 const T u = col[i];
 #pragma unroll
                 for (int q = 0; q < kHhIlp; ++q)
-                    if (c0 + q * nwarps >= j && c0 + q * nwarps < k)
-                        qb[q * mpad + i] = Scalar<T>::fma(w[q], u, qb[q * mpad + i]);
+                    if (act[q]) qb[q * mpad + i] = Scalar<T>::fma(w[q], u, qb[q * mpad + i]);
             }
             __syncwarp();
         }

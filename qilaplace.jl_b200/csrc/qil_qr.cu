@@ -9,6 +9,7 @@
 
 namespace qil {
 
+
 constexpr int kQrThreads = 256;        // shared-memory variant
 constexpr int kQrWarps = kQrThreads / 32;
 constexpr int kQrThreadsGlobal = 1024; // single-CTA variant on an L2-resident scratch copy (large bond matrices)
