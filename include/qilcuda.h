@@ -62,6 +62,10 @@ int qil_launch_count(qil_ctx* ctx, uint64_t* out);
 int qil_profile_enable(qil_ctx* ctx, int on);
 int qil_profile_reset(qil_ctx* ctx);
 int qil_profile_read(qil_ctx* ctx, int kernel_class, double* total_ms, int64_t* launches);
+/* Same, plus the summed ALGORITHMIC bytes and flops the launches of that class declared (class 0: one read of the
+ * streamed matrix view and 2 flops per element and sketch column; 0 for classes that do not state their work). */
+int qil_profile_read_work(qil_ctx* ctx, int kernel_class, double* total_ms, int64_t* launches, double* bytes,
+                          double* flops);
 
 /* ---- MPS / MPO containers (replace Vector{ITensor} storage; src/mps.jl:70-130, src/mpo.jl:26-99) -- */
 /* bond has n+1 entries with bond[0] == bond[n] == 1; cores[i] points at bond[i]*2*bond[i+1] scalars */
@@ -88,6 +92,18 @@ int qil_mpo_free(qil_mpo* m);
 int qil_coefficient_batch(qil_ctx* ctx, const qil_mps* psi, const uint8_t* bits, int64_t B, void* out);
 int qil_coefficient_batch_dev(qil_ctx* ctx, const qil_mps* psi, const uint8_t* d_bits, int64_t B,
                               void* d_out);
+
+/* Dense grid of coefficients: every combination of the "free" sites at once.  Replaces the loops over
+ * `coefficient` of the pole scans (docs/src/tutorials/zt.jl:152-157, 283-287, 330-411), of the full read-out
+ * (docs/src/tutorials/signal.jl:149-150) and `mps_to_vector` (src/mps.jl:716-743; all sites free).
+ * site_mode[i] (HOST array, n entries): 0 / 1 = site i fixed to that bit, 2 = free.  With F free sites the
+ * result has 2^F scalars of the MPS element type, multiplied by the stored amplitude.  out_bit (HOST array,
+ * F entries, or NULL): bit position, inside the linear output index, of the j-th free site in site order;
+ * NULL = big-endian (first free site most significant -- the reference's Integer convention, mps.jl:633-645;
+ * `mps_to_vector(reverse=false)`); out_bit[j] = j is `mps_to_vector(reverse=true)`. */
+int qil_coefficient_grid(qil_ctx* ctx, const qil_mps* psi, const uint8_t* site_mode, const int32_t* out_bit, void* out);
+int qil_coefficient_grid_dev(qil_ctx* ctx, const qil_mps* psi, const uint8_t* site_mode, const int32_t* out_bit,
+                             void* d_out);
 
 /* ---- apply (src/linalg/apply.jl:75-122, 124-199, 201-236) ----------------------------------
  * Exact MPO x MPS: out core = [D_l*chi_l][2][D_r*chi_r] with the MPO bond fastest; never truncates;

@@ -339,6 +339,24 @@ def mps_to_vector(cores, amplitude=1.0, reverse=False):
     return v * amplitude
 
 
+def coefficient_grid(cores, amplitude, site_mode, out_bit=None):
+    """Every combination of the free sites (site_mode == 2), each evaluated by the reference's chain
+    (mps.jl:669-678), i.e. the loops of docs/src/tutorials/zt.jl:152-157.  Entry j of out_bit is the output-index
+    bit of the j-th free site; default big-endian (mps.jl:633-645)."""
+    mode = [int(m) for m in site_mode]
+    free = [i for i, m in enumerate(mode) if m == 2]
+    F = len(free)
+    ob = list(range(F - 1, -1, -1)) if out_bit is None else [int(b) for b in out_bit]
+    idx = np.arange(2**F, dtype=np.int64)
+    bits = np.empty((2**F, len(cores)), dtype=np.uint8)
+    for i, m in enumerate(mode):
+        if m != 2:
+            bits[:, i] = m
+    for j, site in enumerate(free):
+        bits[:, site] = (idx >> ob[j]) & 1
+    return coefficient_batch(cores, amplitude, bits)
+
+
 def mps_norm(cores):
     """norm (mps.jl:754-765): sqrt(|<psi|psi>|) by a transfer-matrix chain; ignores amplitude."""
     E = np.ones((1, 1), dtype=np.complex128)

@@ -49,6 +49,8 @@ _SIGS = {
     "qil_profile_enable": [c_ctx, C.c_int],
     "qil_profile_reset": [c_ctx],
     "qil_profile_read": [c_ctx, C.c_int, C.POINTER(C.c_double), i64p],
+    "qil_profile_read_work": [c_ctx, C.c_int, C.POINTER(C.c_double), i64p, C.POINTER(C.c_double),
+                              C.POINTER(C.c_double)],
     "qil_mps_from_host": [c_ctx, C.c_int, C.c_int, i64p, C.POINTER(C.c_void_p), C.c_double, C.POINTER(c_mps)],
     "qil_mps_info": [c_mps, C.POINTER(C.c_int), C.POINTER(C.c_int), C.POINTER(C.c_double)],
     "qil_mps_dims": [c_mps, i64p],
@@ -63,6 +65,8 @@ _SIGS = {
     "qil_mpo_free": [c_mpo],
     "qil_coefficient_batch": [c_ctx, c_mps, C.c_void_p, C.c_int64, C.c_void_p],
     "qil_coefficient_batch_dev": [c_ctx, c_mps, C.c_void_p, C.c_int64, C.c_void_p],
+    "qil_coefficient_grid": [c_ctx, c_mps, C.c_void_p, C.c_void_p, C.c_void_p],
+    "qil_coefficient_grid_dev": [c_ctx, c_mps, C.c_void_p, C.c_void_p, C.c_void_p],
     "qil_apply_mpo_mps": [c_ctx, c_mpo, c_mps, C.POINTER(c_mps)],
     "qil_apply_mpo_mpo": [c_ctx, c_mpo, c_mpo, C.c_int, C.c_int, C.POINTER(c_mpo)],
     "qil_encode_svd": [c_ctx, C.c_int, C.c_void_p, C.c_int64, C.c_double, C.c_int64, C.POINTER(c_mps)],

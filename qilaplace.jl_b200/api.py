@@ -53,6 +53,12 @@ class Context:
         call("qil_profile_read", self.handle, int(kernel_class), C.byref(t), C.byref(c))
         return float(t.value), int(c.value)
 
+    def profile_read_work(self, kernel_class):
+        """(total_ms, launches, algorithmic bytes, algorithmic flops) of one kernel class."""
+        t, c, b, f = C.c_double(), C.c_int64(), C.c_double(), C.c_double()
+        call("qil_profile_read_work", self.handle, int(kernel_class), C.byref(t), C.byref(c), C.byref(b), C.byref(f))
+        return float(t.value), int(c.value), float(b.value), float(f.value)
+
     def close(self):
         if self.handle:
             _lib.load().qil_destroy(self.handle)
@@ -481,16 +487,79 @@ def norm(psi):
     return float(v.value)
 
 
+def _grid_args(psi, site_mode, out_bit):
+    n = psi.nsites_flat
+    mode = np.ascontiguousarray(site_mode, dtype=np.int64)
+    if mode.ndim != 1 or mode.shape[0] != n:
+        raise ArgumentError(f"coefficient_grid: expected {n} site modes, got {mode.shape}")
+    if mode.size and (mode.min() < 0 or mode.max() > 2):
+        raise ArgumentError("coefficient_grid: site modes must be 0, 1 (fixed bit) or 2 (free)")
+    mode8 = mode.astype(np.uint8)
+    F = int((mode8 == 2).sum())
+    ob = None
+    if out_bit is not None:
+        ob = np.ascontiguousarray(out_bit, dtype=np.int32)
+        if ob.shape != (F,) or sorted(ob.tolist()) != list(range(F)):
+            raise ArgumentError(f"coefficient_grid: out_bit must be a permutation of 0..{F - 1}")
+    return mode8, F, ob
+
+
+def coefficient_grid(psi, site_mode, out_bit=None):
+    """All 2^F coefficients over the free sites (site_mode[i] == 2; 0/1 = fixed bit) in one call -- the grids the
+    reference evaluates by looping `coefficient` (docs/src/tutorials/zt.jl:152-157, 283-411).  The j-th free
+    site (in site order) lands on bit out_bit[j] of the output index; default big-endian (mps.jl:633-645)."""
+    mode8, F, ob = _grid_args(psi, site_mode, out_bit)
+    if F > 30:
+        raise UnsupportedError("coefficient_grid: refusing to materialise more than 2^30 amplitudes on the host")
+    out = np.empty(2**F, dtype=_np_dtype(psi.is_complex))
+    call("qil_coefficient_grid", psi.ctx.handle, psi.handle, C.c_void_p(mode8.ctypes.data),
+         C.c_void_p(ob.ctypes.data) if ob is not None else None, C.c_void_p(out.ctypes.data))
+    return out
+
+
+def coefficient_grid_dev(psi, site_mode, d_out, out_bit=None):
+    """Same with a device output buffer (2^F scalars); stream-ordered on the context's stream."""
+    mode8, F, ob = _grid_args(psi, site_mode, out_bit)
+    call("qil_coefficient_grid_dev", psi.ctx.handle, psi.handle, C.c_void_p(mode8.ctypes.data),
+         C.c_void_p(ob.ctypes.data) if ob is not None else None, C.c_void_p(int(d_out)))
+    return F
+
+
 def mps_to_vector(psi, reverse=False):
     """mps_to_vector(psi; reverse=false) (mps.jl:716-743): every coefficient, MSB-first by default,
-    bit-reversed ordering with reverse=true.  Runs the batched coefficient kernel over all 2^n strings."""
+    bit-reversed ordering with reverse=true.  One dense-grid evaluation with all sites free."""
     n = psi.nsites_flat
-    if n > 26:
-        raise UnsupportedError("mps_to_vector: refusing to materialise more than 2^26 amplitudes")
-    idx = np.arange(2**n, dtype=np.int64)
-    shifts = np.arange(n - 1, -1, -1) if not reverse else np.arange(n)
-    bits = ((idx[:, None] >> shifts[None, :]) & 1).astype(np.uint8)
-    return coefficients(psi, bits)
+    return coefficient_grid(psi, np.full(n, 2), out_bit=np.arange(n) if reverse else None)
+
+
+def pole_scan_modes(n, k0, l0, log2_k, log2_l, stride_log2_k=0, stride_log2_l=0):
+    """Site modes / output bits of a (k, l) block on a paired-register chain of 2n sites (main_j = bit j-1 of k,
+    copy_j = bit j-1 of l, LSB first; test/test_zt_transformer.jl:20-62, docs/src/tutorials/zt.jl:152-157):
+    k = k0 + a * 2^stride_log2_k, a in [0, 2^log2_k); l likewise.  k0 / l0 must have zero bits on the free range.
+    The output index is a * 2^log2_l + b, i.e. a row-major (k, l) table."""
+    mode = np.zeros(2 * n, dtype=np.uint8)
+    out_bit = []
+    for j in range(n):
+        for reg, (base, lg, st) in enumerate(((k0, log2_k, stride_log2_k), (l0, log2_l, stride_log2_l))):
+            site = 2 * j + reg
+            if st <= j < st + lg:
+                if (base >> j) & 1:
+                    raise ArgumentError("pole_scan: the block origin must be aligned to the block size")
+                mode[site] = 2
+                out_bit.append((j - st) + (log2_l if reg == 0 else 0))
+            else:
+                mode[site] = (base >> j) & 1
+    return mode, np.asarray(out_bit, dtype=np.int32)
+
+
+def pole_scan(psi, k0=0, l0=0, log2_k=None, log2_l=None, stride_log2_k=0, stride_log2_l=0):
+    """chi[a, b] = coefficient(psi, interleave(lsb(k), lsb(l))) on the block k = k0 + a * 2^stride_log2_k,
+    l = l0 + b * 2^stride_log2_l (the coarse / fine / superfine scans of docs/src/tutorials/zt.jl:283-411)."""
+    n = psi.nsites_flat // 2
+    log2_k = n - stride_log2_k if log2_k is None else log2_k
+    log2_l = n - stride_log2_l if log2_l is None else log2_l
+    mode, ob = pole_scan_modes(n, k0, l0, log2_k, log2_l, stride_log2_k, stride_log2_l)
+    return coefficient_grid(psi, mode, ob).reshape(2**log2_k, 2**log2_l)
 
 
 # ------------------------------------------------------------------------------------------

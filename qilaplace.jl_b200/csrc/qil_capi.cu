@@ -164,21 +164,38 @@ int qil_profile_reset(qil_ctx* ctx) {
     QIL_API_END
 }
 
-int qil_profile_read(qil_ctx* ctx, int kernel_class, double* total_ms, int64_t* launches) {
-    QIL_API_BEGIN
-    QIL_NONNULL(ctx); QIL_NONNULL(total_ms); QIL_NONNULL(launches);
+static void profile_sum(qil_ctx* ctx, int kernel_class, double* total_ms, int64_t* launches, double* bytes,
+                        double* flops) {
     ctx->sync();
-    double t = 0.0;
+    double t = 0.0, b = 0.0, f = 0.0;
     int64_t c = 0;
     for (auto& r : ctx->prof) {
         if (r.id != kernel_class) continue;
         float ms = 0.f;
         QIL_CUDA(cudaEventElapsedTime(&ms, r.e0, r.e1));
         t += ms;
+        b += r.bytes;
+        f += r.flops;
         ++c;
     }
     *total_ms = t;
     *launches = c;
+    if (bytes) *bytes = b;
+    if (flops) *flops = f;
+}
+
+int qil_profile_read(qil_ctx* ctx, int kernel_class, double* total_ms, int64_t* launches) {
+    QIL_API_BEGIN
+    QIL_NONNULL(ctx); QIL_NONNULL(total_ms); QIL_NONNULL(launches);
+    profile_sum(ctx, kernel_class, total_ms, launches, nullptr, nullptr);
+    QIL_API_END
+}
+
+int qil_profile_read_work(qil_ctx* ctx, int kernel_class, double* total_ms, int64_t* launches, double* bytes,
+                          double* flops) {
+    QIL_API_BEGIN
+    QIL_NONNULL(ctx); QIL_NONNULL(total_ms); QIL_NONNULL(launches); QIL_NONNULL(bytes); QIL_NONNULL(flops);
+    profile_sum(ctx, kernel_class, total_ms, launches, bytes, flops);
     QIL_API_END
 }
 
@@ -333,6 +350,40 @@ int qil_coefficient_batch(qil_ctx* ctx, const qil_mps* psi, const uint8_t* bits,
     QIL_CUDA(cudaMemcpyAsync(out, d_out, ob, cudaMemcpyDeviceToHost, ctx->stream));
     ctx->sync();
     ctx->free(d_bits);
+    ctx->free(d_out);
+    QIL_API_END
+}
+
+static int grid_free_sites(const qil_mps* psi, const uint8_t* site_mode) {
+    int F = 0;
+    for (int i = 0; i < psi->n; ++i) {
+        QIL_REQUIRE(site_mode[i] <= 2, QIL_ERR_ARGUMENT, "coefficient grid: site mode %d outside {0,1,2}", (int)site_mode[i]);
+        F += (site_mode[i] == 2);
+    }
+    return F;
+}
+
+int qil_coefficient_grid_dev(qil_ctx* ctx, const qil_mps* psi, const uint8_t* site_mode, const int32_t* out_bit,
+                             void* d_out) {
+    QIL_API_BEGIN
+    QIL_NONNULL(ctx); QIL_NONNULL(psi); QIL_NONNULL(site_mode); QIL_NONNULL(d_out);
+    QIL_CUDA(cudaSetDevice(ctx->device));
+    grid_free_sites(psi, site_mode);
+    coefficient_grid_dev(ctx, psi, site_mode, out_bit, d_out);
+    QIL_API_END
+}
+
+int qil_coefficient_grid(qil_ctx* ctx, const qil_mps* psi, const uint8_t* site_mode, const int32_t* out_bit, void* out) {
+    QIL_API_BEGIN
+    QIL_NONNULL(ctx); QIL_NONNULL(psi); QIL_NONNULL(site_mode); QIL_NONNULL(out);
+    QIL_CUDA(cudaSetDevice(ctx->device));
+    const int F = grid_free_sites(psi, site_mode);
+    QIL_REQUIRE(F <= 34, QIL_ERR_UNSUPPORTED, "coefficient grid: 2^%d results do not fit a host buffer here", F);
+    const size_t ob = ((size_t)1 << F) * elem_size(psi->is_complex);
+    void* d_out = ctx->alloc(ob);
+    coefficient_grid_dev(ctx, psi, site_mode, out_bit, d_out);
+    QIL_CUDA(cudaMemcpyAsync(out, d_out, ob, cudaMemcpyDeviceToHost, ctx->stream));
+    ctx->sync();
     ctx->free(d_out);
     QIL_API_END
 }

@@ -110,10 +110,11 @@ struct qil_ctx {
     size_t scratch_bytes = 0;
 
     // optional per-kernel-class timing (CUDA events on `stream`), enabled by qil_profile_enable
-    struct ProfRegion { int id; cudaEvent_t e0, e1; };
+    struct ProfRegion { int id; cudaEvent_t e0, e1; double bytes, flops; };
     bool prof_on = false;
     std::vector<ProfRegion> prof;
-    void prof_begin(int id);
+    // bytes / flops: ALGORITHMIC work of the region (what the roofline is computed from), 0 if not stated
+    void prof_begin(int id, double bytes = 0.0, double flops = 0.0);
     void prof_end();
 
     void* alloc(size_t bytes);           // stream-ordered device allocation
@@ -170,6 +171,9 @@ enum ProfId { PROF_STREAM_GEMM = 0, PROF_COEFF = 1, PROF_APPLY = 2, PROF_QR = 3,
 // K8: batched coefficient extraction (mps.jl:669-678)
 void coefficient_batch_dev(qil_ctx* ctx, const qil_mps* psi, const uint8_t* d_bits, int64_t B,
                            void* d_out /* B scalars of psi's type */);
+// Dense grid of coefficients over the free sites (mode[i] == 2; 0/1 = fixed bit), meet-in-the-middle GEMMs
+// (qil_grid.cu).  mode / out_bit are HOST arrays; d_out receives 2^F scalars of psi's type.
+void coefficient_grid_dev(qil_ctx* ctx, const qil_mps* psi, const uint8_t* mode, const int32_t* out_bit, void* d_out);
 // K6: exact MPO x MPS (apply.jl:75-122)
 qil_mps* apply_mpo_mps(qil_ctx* ctx, const qil_mpo* W, const qil_mps* psi);
 // K7: MPO o MPO (apply.jl:124-199), W1 acts first, equal lengths or windowed

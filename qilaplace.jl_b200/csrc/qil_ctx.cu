@@ -25,10 +25,12 @@ void* qil_ctx::get_scratch(size_t bytes) {
     return scratch;
 }
 
-void qil_ctx::prof_begin(int id) {
+void qil_ctx::prof_begin(int id, double bytes, double flops) {
     if (!prof_on) return;
     ProfRegion r;
     r.id = id;
+    r.bytes = bytes;
+    r.flops = flops;
     QIL_CUDA(cudaEventCreate(&r.e0));
     QIL_CUDA(cudaEventCreate(&r.e1));
     QIL_CUDA(cudaEventRecord(r.e0, stream));

@@ -57,6 +57,11 @@ template <typename T>
 void gemm(qil_ctx* ctx, Op opa, Op opb, int64_t M, int64_t N, int64_t K, double alpha, const T* A, int64_t lda,
           const T* B, int64_t ldb, double beta, T* C, int64_t ldc);
 
+// C(MxN) = alpha * A * B on the FP64 tensor path (DMMA m16n8k16, cp.async ring; qil_grid.cu); no transposes
+template <typename T>
+void gemm_tc(qil_ctx* ctx, int64_t M, int64_t N, int64_t K, double alpha, const T* A, int64_t lda, const T* B,
+             int64_t ldb, T* C, int64_t ldc);
+
 // y[i] = alpha * x[i]  (n elements); row/col scaling helpers
 template <typename T> void scale_copy(qil_ctx* ctx, int64_t n, double alpha, const T* x, T* y);
 // B[i][j] = A[i][j] * s[j] (col) or * s[i] (row); inv => divide (0 -> 0)

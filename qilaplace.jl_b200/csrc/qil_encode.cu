@@ -200,7 +200,7 @@ static Mat<T> mul_A(SplitCtx<T>& sc, const T* A, int64_t R, int64_t C, int l, co
         const int grid = stream_grid(ctx, R, ks);
         if (want_sumsq) ssq = Mat<double>(ctx, grid, 1);
         stream_gemm(ctx, false, reinterpret_cast<const double*>(A), R, C * F, C * F, X.p, lpp, nt, part.p, ks, kc,
-                    want_sumsq ? ssq.p : nullptr);
+                    want_sumsq ? ssq.p : nullptr, l * F);
         reduce_k1_kernel<T><<<grid_for(ctx, R * l * F), 256, 0, ctx->stream>>>(part.p, ks, R, nt * 8, l, Y.p);
         QIL_LAUNCH_CHECK(ctx);
         if (want_sumsq) {
@@ -239,7 +239,7 @@ static Mat<T> mul_AH(SplitCtx<T>& sc, const T* A, int64_t R, int64_t C, int l, c
         int ks; long long kc;
         stream_plan(ctx, C * F, R, &ks, &kc);
         Mat<double> part(ctx, (int64_t)ks * C * F, nt * 8);
-        stream_gemm(ctx, true, reinterpret_cast<const double*>(A), R, C * F, C * F, X.p, lpp, nt, part.p, ks, kc, nullptr);
+        stream_gemm(ctx, true, reinterpret_cast<const double*>(A), R, C * F, C * F, X.p, lpp, nt, part.p, ks, kc, nullptr, l * F);
         reduce_k2_kernel<T><<<grid_for(ctx, C * l), 256, 0, ctx->stream>>>(part.p, ks, C, nt * 8, l, scale, Z.p);
         QIL_LAUNCH_CHECK(ctx);
     } else {

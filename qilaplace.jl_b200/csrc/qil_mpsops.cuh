@@ -43,5 +43,6 @@ bool stream_supported(long long R, long long C, long long ld, int cols);
 void stream_plan(qil_ctx* ctx, long long Mtot, long long Kdim, int* ksplit, long long* kchunk);
 int stream_grid(qil_ctx* ctx, long long Mtot, int ksplit);
 void stream_gemm(qil_ctx* ctx, bool trans, const double* A, long long R, long long C, long long ld, const double* X,
-                 int lpp, int nt, double* out, int ksplit, long long kchunk, double* sumsq_partials);
+                 int lpp, int nt, double* out, int ksplit, long long kchunk, double* sumsq_partials,
+                 int ncols /* real sketch columns, for the profiler's algorithmic flops */);
 }  // namespace qil

@@ -297,7 +297,7 @@ bool stream_supported(long long R, long long C, long long ld, int cols) {
 
 // out[ksplit][Mtot][8*nt] partials of A*X (trans=false) or A^T*X (trans=true); A is a REAL R x C view.
 void stream_gemm(qil_ctx* ctx, bool trans, const double* A, long long R, long long C, long long ld, const double* X,
-                 int lpp, int nt, double* out, int ksplit, long long kchunk, double* sumsq_partials) {
+                 int lpp, int nt, double* out, int ksplit, long long kchunk, double* sumsq_partials, int ncols) {
     StreamParams p;
     p.Mtot = trans ? C : R;
     p.Kdim = trans ? R : C;
@@ -310,7 +310,8 @@ void stream_gemm(qil_ctx* ctx, bool trans, const double* A, long long R, long lo
     p.X = X;
     p.sumsq = sumsq_partials;
     const CUtensorMap tm = trans ? make_tmap(A, R, C, ld, 16, kBK) : make_tmap(A, R, C, ld, 16, kBM);
-    ctx->prof_begin(PROF_STREAM_GEMM);
+    // algorithmic work: one read of the R x C view, 2 flops per element and sketch column
+    ctx->prof_begin(PROF_STREAM_GEMM, 8.0 * (double)R * (double)C, 2.0 * (double)R * (double)C * (double)ncols);
     if (!trans) dispatch_stream<false>(ctx, nt, tm, p);
     else dispatch_stream<true>(ctx, nt, tm, p);
     ctx->prof_end();

@@ -1,0 +1,141 @@
+"""GPU parity tests of the dense coefficient-grid path (qil_coefficient_grid: pole scans, mps_to_vector,
+the DMMA GEMM underneath) against the CPU oracle, which evaluates every grid point by the reference's
+`coefficient` chain (src/mps.jl:669-678).  Tolerance 1e-10 relative to the largest amplitude."""
+import math
+
+import numpy as np
+import pytest
+
+import qil_oracle as O
+
+pytestmark = pytest.mark.gpu
+
+TOL = 1e-10
+
+
+def _rand_mps(rng, bonds, cplx):
+    cores = []
+    for i in range(len(bonds) - 1):
+        c = rng.standard_normal((bonds[i], 2, bonds[i + 1]))
+        if cplx:
+            c = c + 1j * rng.standard_normal(c.shape)
+        cores.append(c / math.sqrt(bonds[i] * 2))
+    return cores
+
+
+def _relerr(got, want):
+    return np.abs(np.asarray(got) - np.asarray(want)).max() / max(np.abs(want).max(), 1e-300)
+
+
+@pytest.mark.parametrize("cplx", [False, True])
+@pytest.mark.parametrize("bonds", [
+    [1, 2, 3, 5, 7, 5, 3, 2, 1],                 # odd bonds: unaligned rows for the 8-byte copies
+    [1, 2, 4, 8, 16, 32, 33, 17, 40, 20, 8, 4, 1],
+    [1, 2, 4, 8, 16, 32, 64, 128, 150, 131, 70, 40, 20, 10, 5, 2, 1],
+])
+def test_grid_all_free_is_mps_to_vector(q, bonds, cplx):
+    rng = np.random.default_rng(len(bonds) * 2 + cplx)
+    cores = _rand_mps(rng, bonds, cplx)
+    amp = 1.7
+    psi = q.SignalMPS.from_cores(cores, amp)
+    want = O.mps_to_vector(cores, amp)
+    got = q.mps_to_vector(psi)
+    assert got.dtype == want.dtype
+    assert _relerr(got, want) < TOL
+    got_r = q.mps_to_vector(psi, reverse=True)
+    assert _relerr(got_r, O.mps_to_vector(cores, amp, reverse=True)) < TOL
+
+
+@pytest.mark.parametrize("cplx", [False, True])
+def test_grid_mixed_modes_and_output_bits(q, cplx):
+    rng = np.random.default_rng(77 + cplx)
+    bonds = [1, 2, 4, 8, 13, 21, 34, 55, 34, 21, 13, 8, 4, 2, 1]
+    n = len(bonds) - 1
+    cores = _rand_mps(rng, bonds, cplx)
+    psi = q.SignalMPS.from_cores(cores, 0.3)
+    for trial in range(6):
+        mode = rng.integers(0, 3, size=n)
+        F = int((mode == 2).sum())
+        out_bit = rng.permutation(F) if trial % 2 else None
+        want = O.coefficient_grid(cores, 0.3, mode, out_bit)
+        got = q.coefficient_grid(psi, mode, out_bit)
+        assert got.shape == (2**F,)
+        assert _relerr(got, want) < TOL
+    # no free site at all: one coefficient
+    mode = rng.integers(0, 2, size=n)
+    got = q.coefficient_grid(psi, mode)
+    assert got.shape == (1,)
+    assert abs(got[0] - O.coefficient(cores, 0.3, mode)) < TOL * abs(got[0]) + 1e-300
+
+
+def test_grid_matches_batched_coefficient_kernel(q):
+    """Two independent CUDA paths (chain/GEMM coefficient kernel and the grid) agree on a large-bond chain."""
+    rng = np.random.default_rng(5)
+    bonds = [1, 2, 4, 8, 16, 32, 64, 128, 200, 128, 64, 32, 16, 8, 4, 2, 1]
+    n = len(bonds) - 1
+    cores = _rand_mps(rng, bonds, True)
+    psi = q.SignalMPS.from_cores(cores, 1.0)
+    vec = q.mps_to_vector(psi)
+    idx = rng.integers(0, 2**n, size=4096)
+    bits = ((idx[:, None] >> np.arange(n - 1, -1, -1)[None, :]) & 1).astype(np.uint8)
+    assert _relerr(vec[idx], q.coefficients(psi, bits)) < TOL
+    assert _relerr(vec[idx], O.coefficient_batch(cores, 1.0, bits)) < TOL
+
+
+def test_grid_errors(q):
+    rng = np.random.default_rng(1)
+    cores = _rand_mps(rng, [1, 2, 2, 1], False)
+    psi = q.SignalMPS.from_cores(cores, 1.0)
+    with pytest.raises(q.ArgumentError):
+        q.coefficient_grid(psi, [2, 2])                    # wrong length
+    with pytest.raises(q.ArgumentError):
+        q.coefficient_grid(psi, [2, 3, 0])                 # bad mode
+    with pytest.raises(q.ArgumentError):
+        q.coefficient_grid(psi, [2, 2, 0], out_bit=[0, 0])  # not a permutation
+
+
+@pytest.mark.parametrize("n", [3, 5])
+def test_pole_scan_on_zt_output_matches_analytic(q, n):
+    """chi(k, l) = (1/N) sum_j x_j exp(-(wr k + 2 pi i l) j / N) (test/test_zt_transformer.jl:20-62)."""
+    wr = 0.75
+    N = 2**n
+    rng = np.random.default_rng(n)
+    x = rng.standard_normal(N) + 1j * rng.standard_normal(N)
+    z = q.signal_ztmps(x, cutoff=1e-14)
+    W = q.build_zt_mpo(n, wr, cutoff=1e-15, maxdim=1000)
+    out = W * z
+    chi = q.pole_scan(out)                                   # full N x N table
+    j = np.arange(N)
+    k = np.arange(N)[:, None, None]
+    l = np.arange(N)[None, :, None]
+    want = (x[None, None, :] * np.exp(-(wr * k + 2j * np.pi * l) * j[None, None, :] / N)).sum(-1) / N
+    assert np.abs(chi - want).max() < 2e-7 * np.abs(want).max()   # the reference's own zT tolerance
+    # the oracle evaluates the same chain point by point: tight agreement
+    cores = out.cores()
+    ks, ls = [1, N - 1, N // 2], [0, 3, N - 2]
+    for kk in ks:
+        for ll in ls:
+            bits = O.interleave(O.bits_lsb(kk, n), O.bits_lsb(ll, n))
+            assert abs(chi[kk, ll] - O.coefficient(cores, out.amplitude, bits)) < TOL * np.abs(want).max()
+    # a strided sub-block (coarse scan) and an aligned contiguous block (fine scan)
+    sub = q.pole_scan(out, log2_k=n - 1, log2_l=n - 2, stride_log2_k=1, stride_log2_l=2)
+    assert _relerr(sub, chi[::2, ::4]) < TOL
+    blk = q.pole_scan(out, k0=N // 2, l0=N // 4, log2_k=n - 1, log2_l=n - 2)
+    assert _relerr(blk, chi[N // 2:, N // 4: N // 2]) < TOL
+
+
+@pytest.mark.parametrize("n,cplx", [(22, False), (20, True)])
+def test_encode_decode_roundtrip_full_size(q, n, cplx):
+    """Size-independent property: decode(encode(x)) == x to the truncation level (streaming RSVD encoder +
+    dense grid decode), on a structured signal whose ranks stay below k+p."""
+    N = 2**n
+    t = np.arange(N) / (2.5 * N)
+    x = np.sin(1.0 * t) * np.exp(-0.08 * t) + np.sin(2.5 * t) * np.exp(-0.03 * t)
+    if cplx:
+        x = x * np.exp(0.3j * t)
+    psi = q.signal_mps(x, method="rsvd", k=15, p=5, q=2, cutoff=1e-14)
+    back = q.mps_to_vector(psi)
+    assert np.linalg.norm(back - x) / np.linalg.norm(x) < 1e-6      # sqrt(cutoff * sites) scale
+    # and the decode agrees with the oracle's decode of the very same cores to rounding
+    want = O.mps_to_vector(psi.cores(), psi.amplitude)
+    assert _relerr(back, want) < TOL

@@ -258,3 +258,18 @@ def test_apply_vs_dense():
     W2 = [rng.standard_normal((wb[i], 2, 2, wb[i + 1])) for i in range(n)]
     W12 = O.apply_mpo_mpo(W, W2)  # W acts first
     assert np.allclose(O.mpo_to_dense(W12), O.mpo_to_dense(W2) @ O.mpo_to_dense(W), atol=1e-12)
+
+
+def test_coefficient_grid_oracle_consistency():
+    """The grid helper is nothing but the reference's chain looped over the free sites: all-free == mps_to_vector
+    (mps.jl:716-729, both orders), and x = 1..8 reads back through it (test/test_signal_converters.jl:146-191)."""
+    x = np.arange(1.0, 9.0)
+    cores, c = O.tt_svd(x)
+    assert np.allclose(O.coefficient_grid(cores, c, [2, 2, 2]), x, atol=1e-12)
+    assert np.allclose(O.coefficient_grid(cores, c, [1, 2, 2]), x[4:], atol=1e-12)
+    assert np.allclose(O.coefficient_grid(cores, c, [2, 0, 2]), x[[0, 1, 4, 5]], atol=1e-12)
+    assert np.allclose(O.coefficient_grid(cores, c, [2, 2, 2], out_bit=[0, 1, 2]),
+                       O.mps_to_vector(cores, c, reverse=True), atol=1e-12)
+    rng = np.random.default_rng(3)
+    cores = [rng.standard_normal(s) for s in [(1, 2, 3), (3, 2, 4), (4, 2, 2), (2, 2, 1)]]
+    assert np.allclose(O.coefficient_grid(cores, 2.0, [2] * 4), O.mps_to_vector(cores, 2.0), atol=1e-13)
