@@ -218,6 +218,14 @@ def run_ours(args):
     bits_dev = bits_pin.to(dev)
     out_dev = torch.empty(B, dtype=torch.complex128, device=dev)
     out_pin = torch.empty(B, dtype=torch.complex128, pin_memory=True)
+    # pole scan (BASELINE configs[2], docs/src/tutorials/zt.jl:330-411): an aligned 2^a x 2^a block of (k, l) with
+    # 2^(2a) >= B points, around k = 0 / the top of the l range like the tutorial's fine scan
+    scan_a = max(1, (int(math.ceil(math.log2(max(B, 2)))) + 1) // 2)
+    scan_a = min(scan_a, n)
+    scan_pts = 4 ** scan_a
+    scan_mode, scan_bits = q.pole_scan_modes(n, 0, (2**n - 2**scan_a), scan_a, scan_a)
+    scan_dev = torch.empty(scan_pts, dtype=torch.complex128, device=dev)
+    scan_pin = torch.empty(scan_pts, dtype=torch.complex128, pin_memory=True)
     torch.cuda.synchronize()
 
     # ---- setup (untimed, like the reference's benchmark protocol): the zT MPO
@@ -236,6 +244,13 @@ def run_ours(args):
 
     def step_coeff():
         q.coefficients_dev(state["out"], bits_dev.data_ptr(), B, out_dev.data_ptr())
+
+    def step_scan():
+        q.coefficient_grid_dev(state["out"], scan_mode, scan_dev.data_ptr(), out_bit=scan_bits)
+
+    def step_scan_e2e():
+        step_scan()
+        scan_pin.copy_(scan_dev, non_blocking=True)
 
     x_host = x_pin.numpy()
 
@@ -274,7 +289,21 @@ def run_ours(args):
     for _ in range(max(args.warmup, 3)):
         step_device()
     step_coeff()
+    step_scan()
     torch.cuda.synchronize()
+    # the two coefficient paths must agree on the scan block (sanity, untimed): sample 4096 grid points
+    import numpy as _np
+    _rng = _np.random.default_rng(0)
+    _a = _rng.integers(0, 2**scan_a, size=4096); _b = _rng.integers(0, 2**scan_a, size=4096)
+    _k = _a; _l = (2**n - 2**scan_a) + _b
+    _bits = _np.zeros((4096, 2 * n), dtype=_np.uint8)
+    for _j in range(n):
+        _bits[:, 2 * _j] = (_k >> _j) & 1
+        _bits[:, 2 * _j + 1] = (_l >> _j) & 1
+    _chk = q.coefficients(state["out"], _bits)
+    _got = scan_dev.cpu().numpy().reshape(2**scan_a, 2**scan_a)[_a, _b]
+    scan_check = float(_np.abs(_got - _chk).max() / max(_np.abs(_chk).max(), 1e-300))
+    assert scan_check < 1e-9, f"pole scan disagrees with the chain kernel: {scan_check}"
 
     # ---- timed: device-resident (`value`), with per-kernel-class events for the roofline
     sampler = ClockSampler(local)
@@ -291,6 +320,7 @@ def run_ours(args):
     ms_coeff = timed(step_coeff, csteps)
     c_ms, c_cnt = ctx.profile_read(1)
     ctx.profile_enable(False); ctx.profile_reset()
+    ms_scan = timed(step_scan, max(csteps, 3)) / max(csteps, 3)
     # ---- stage breakdown (separate pass, CUDA events between the stages of one step)
     def stage_breakdown(reps=3):
         names = ["encode_rsvd", "ztmps_split", "zt_apply", "coefficients"]
@@ -320,6 +350,8 @@ def run_ours(args):
     ms_e2e = timed(step_e2e, args.steps)
     step_coeff_e2e()
     ms_coeff_e2e = timed(step_coeff_e2e, csteps)
+    step_scan_e2e()
+    ms_scan_e2e = timed(step_scan_e2e, max(csteps, 3)) / max(csteps, 3)
     clocks = sampler.finish()
 
     psi, z, out = state["psi"], state["z"], state["out"]
@@ -383,6 +415,11 @@ def run_ours(args):
         "coefficients_per_s": world * B / (ms_coeff / csteps / 1e3),
         "coefficients_e2e": {"value": world * B / (ms_coeff_e2e / csteps / 1e3), "unit": "coefficients/s",
                              "h2d_bytes_per_step": int(bits_np.nbytes), "d2h_bytes_per_step": int(16 * B)},
+        "pole_scan": {"what": f"2^{scan_a} x 2^{scan_a} aligned (k, l) block of the zT output through qil_coefficient_grid "
+                              f"(meet-in-the-middle DMMA GEMMs); same chain arithmetic per point",
+                      "points": scan_pts, "ms": ms_scan, "coefficients_per_s": world * scan_pts / (ms_scan / 1e3),
+                      "e2e_ms": ms_scan_e2e, "e2e_coefficients_per_s": world * scan_pts / (ms_scan_e2e / 1e3),
+                      "d2h_bytes_per_step": int(16 * scan_pts), "max_rel_dev_vs_chain_kernel": scan_check},
         "full_step": {"what": f"encode + split + apply + {B} coefficients", "ms": full_ms,
                       "samples_per_s": world * N / (full_ms / 1e3)},
         "stages_ms": stages_ms,

@@ -131,6 +131,29 @@ int qil_encode_rsvd(qil_ctx* ctx, int is_complex, const void* x, int64_t N, int 
 int qil_encode_rsvd_dev(qil_ctx* ctx, int is_complex, const void* d_x, int64_t N, int k, int p, int q, int64_t seed,
                         double cutoff, int64_t maxdim, int64_t mindim, const void* d_normal_stream,
                         int64_t stream_len, int64_t reserved, qil_mps** out);
+/* ---- one signal row-sharded over several devices (one process per device) ---------------------
+ * The length-N signal is split in rank order into world contiguous chunks of N/world samples, i.e. into
+ * leading-qubit (row) blocks of the top-level matrix of the divide and conquer (SignalConverters.jl:161).  The
+ * sketch and projection GEMMs stream each rank's own block; the exchange steps are: an 8-byte all-reduce of the
+ * sum of squares, an all-gather of the per-rank l x l R factors of the tall-skinny QR (once per QR), an all-reduce
+ * of the partial l x 2^ceil(n/2) projections (once per power iteration and for B = Q^H A), and an all-gather of the
+ * row blocks of U.  The library stays free of any communication dependency: the host supplies the two
+ * collectives (torch.distributed / NCCL in the Python host, NCCL.jl or MPI.jl in a Julia host).  Both callbacks
+ * receive DEVICE pointers to float64 data (complex = interleaved pairs), must be ordered on the context's stream
+ * (see qil_get_stream) and return 0 on success.  Every rank must make the same call; every rank receives the
+ * same MPS. */
+typedef struct qil_comm {
+    int rank;
+    int world;
+    void* user;
+    int (*allreduce_sum_f64)(void* user, void* d_buf, int64_t count);                          /* in place */
+    int (*allgather_f64)(void* user, const void* d_send, void* d_recv, int64_t count_per_rank); /* rank order */
+} qil_comm;
+int qil_get_stream(qil_ctx* ctx, void** cuda_stream);
+int qil_encode_rsvd_sharded_dev(qil_ctx* ctx, const qil_comm* comm, int is_complex, const void* d_x_local,
+                                int64_t N_total, int k, int p, int q, int64_t seed, double cutoff, int64_t maxdim,
+                                int64_t mindim, const void* d_normal_stream, int64_t stream_len, qil_mps** out);
+
 /* Per-site copy-tensor split of signal_ztmps (SignalConverters.jl:258-277): n-site MPS -> 2n-site chain. */
 int qil_ztmps_split(qil_ctx* ctx, const qil_mps* psi, double cutoff, int64_t maxdim, qil_mps** out);
 

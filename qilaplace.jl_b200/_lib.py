@@ -75,6 +75,10 @@ _SIGS = {
                         C.c_int64, C.c_int64, C.c_void_p, C.c_int64, C.c_int64, C.POINTER(c_mps)],
     "qil_encode_rsvd_dev": [c_ctx, C.c_int, C.c_void_p, C.c_int64, C.c_int, C.c_int, C.c_int, C.c_int64, C.c_double,
                             C.c_int64, C.c_int64, C.c_void_p, C.c_int64, C.c_int64, C.POINTER(c_mps)],
+    "qil_get_stream": [c_ctx, C.POINTER(C.c_void_p)],
+    "qil_encode_rsvd_sharded_dev": [c_ctx, C.c_void_p, C.c_int, C.c_void_p, C.c_int64, C.c_int, C.c_int, C.c_int,
+                                    C.c_int64, C.c_double, C.c_int64, C.c_int64, C.c_void_p, C.c_int64,
+                                    C.POINTER(c_mps)],
     "qil_ztmps_split": [c_ctx, c_mps, C.c_double, C.c_int64, C.POINTER(c_mps)],
     "qil_canonicalize": [c_ctx, c_mps, C.c_int, C.c_int, C.c_double, C.c_int64],
     "qil_compress": [c_ctx, c_mps, C.c_int64, C.c_double, C.c_int],
@@ -88,6 +92,14 @@ _SIGS = {
     "qil_svd_trunc": [c_ctx, C.c_int, C.c_int64, C.c_int64, C.c_void_p, C.c_double, C.c_int64, C.c_int64,
                       i64p, C.c_void_p, C.c_void_p, C.c_void_p],
 }
+
+
+class QilComm(C.Structure):
+    """struct qil_comm (include/qilcuda.h): the two collectives of a row-sharded encode."""
+    ALLREDUCE = C.CFUNCTYPE(C.c_int, C.c_void_p, C.c_void_p, C.c_int64)
+    ALLGATHER = C.CFUNCTYPE(C.c_int, C.c_void_p, C.c_void_p, C.c_void_p, C.c_int64)
+    _fields_ = [("rank", C.c_int), ("world", C.c_int), ("user", C.c_void_p),
+                ("allreduce_sum_f64", ALLREDUCE), ("allgather_f64", ALLGATHER)]
 
 
 def declared_symbols():

@@ -480,6 +480,29 @@ int qil_encode_rsvd(qil_ctx* ctx, int is_complex, const void* x, int64_t N, int 
     QIL_API_END
 }
 
+int qil_get_stream(qil_ctx* ctx, void** cuda_stream) {
+    QIL_API_BEGIN
+    QIL_NONNULL(ctx); QIL_NONNULL(cuda_stream);
+    *cuda_stream = (void*)ctx->stream;
+    QIL_API_END
+}
+
+int qil_encode_rsvd_sharded_dev(qil_ctx* ctx, const qil_comm* comm, int is_complex, const void* d_x_local,
+                                int64_t N_total, int k, int p, int q, int64_t seed, double cutoff, int64_t maxdim,
+                                int64_t mindim, const void* d_normal_stream, int64_t stream_len, qil_mps** out) {
+    QIL_API_BEGIN
+    QIL_NONNULL(ctx); QIL_NONNULL(comm); QIL_NONNULL(d_x_local); QIL_NONNULL(out);
+    QIL_NONNULL(comm->allreduce_sum_f64); QIL_NONNULL(comm->allgather_f64);
+    QIL_CUDA(cudaSetDevice(ctx->device));
+    RsvdOpts o;
+    o.k = k; o.p = p; o.q = q; o.seed = seed; o.cutoff = cutoff; o.maxdim = fix_maxdim(maxdim);
+    o.mindim = mindim < 1 ? 1 : mindim;
+    o.omega = d_normal_stream; o.omega_rows = d_normal_stream ? stream_len : 0; o.omega_cols = 1;
+    *out = is_complex ? encode_rsvd_sharded<cplx>(ctx, comm, (const cplx*)d_x_local, N_total, o)
+                      : encode_rsvd_sharded<double>(ctx, comm, (const double*)d_x_local, N_total, o);
+    QIL_API_END
+}
+
 int qil_ztmps_split(qil_ctx* ctx, const qil_mps* psi, double cutoff, int64_t maxdim, qil_mps** out) {
     QIL_API_BEGIN
     QIL_NONNULL(ctx); QIL_NONNULL(psi); QIL_NONNULL(out);

@@ -177,7 +177,33 @@ struct SplitCtx {
     int64_t stream_len;
     double* d_nrm;          // [0] = ||x||, [1] = 1/||x||  (device)
     bool nrm_ready;
+    const qil_comm* comm = nullptr;   // row-sharded top split: collectives of the host (nullptr = single device)
 };
+
+// ---- collectives of a row-sharded encode (callbacks supplied by the host, ordered on ctx->stream) ----
+static void comm_allreduce(const qil_comm* c, void* d_buf, int64_t count_f64) {
+    QIL_REQUIRE(c->allreduce_sum_f64(c->user, d_buf, count_f64) == 0, QIL_ERR_RUNTIME,
+                "sharded encode: the all-reduce callback failed");
+}
+static void comm_allgather(const qil_comm* c, const void* d_send, void* d_recv, int64_t count_f64) {
+    QIL_REQUIRE(c->allgather_f64(c->user, d_send, d_recv, count_f64) == 0, QIL_ERR_RUNTIME,
+                "sharded encode: the all-gather callback failed");
+}
+// nrm[0] = sum of the per-CTA partial sums of squares (before the cross-rank reduction)
+__global__ void sum_partials_kernel(const double* partials, int n, double* nrm) {
+    if (threadIdx.x == 0 && blockIdx.x == 0) {
+        double s = 0.0;
+        for (int i = 0; i < n; ++i) s += partials[i];
+        nrm[0] = s;
+    }
+}
+__global__ void norm_from_sumsq_kernel(double* nrm) {
+    if (threadIdx.x == 0 && blockIdx.x == 0) {
+        const double c = sqrt(nrm[0]);
+        nrm[0] = c;
+        nrm[1] = 1.0 / c;
+    }
+}
 
 // A*X for X = Omega (Xsrc == nullptr) or a dense C x l matrix.  Returns Y (R x l).
 template <typename T>
@@ -203,7 +229,15 @@ static Mat<T> mul_A(SplitCtx<T>& sc, const T* A, int64_t R, int64_t C, int l, co
                     want_sumsq ? ssq.p : nullptr, l * F);
         reduce_k1_kernel<T><<<grid_for(ctx, R * l * F), 256, 0, ctx->stream>>>(part.p, ks, R, nt * 8, l, Y.p);
         QIL_LAUNCH_CHECK(ctx);
-        if (want_sumsq) {
+        if (want_sumsq && sc.comm) {
+            // ||x||^2 = sum over ranks of the local sums (8-byte all-reduce)
+            sum_partials_kernel<<<1, 32, 0, ctx->stream>>>(ssq.p, grid, sc.d_nrm);
+            QIL_LAUNCH_CHECK(ctx);
+            comm_allreduce(sc.comm, sc.d_nrm, 1);
+            norm_from_sumsq_kernel<<<1, 32, 0, ctx->stream>>>(sc.d_nrm);
+            QIL_LAUNCH_CHECK(ctx);
+            sc.nrm_ready = true;
+        } else if (want_sumsq) {
             finalize_norm_kernel<<<1, 32, 0, ctx->stream>>>(ssq.p, grid, sc.d_nrm);
             QIL_LAUNCH_CHECK(ctx);
             sc.nrm_ready = true;
@@ -305,6 +339,62 @@ static int rsvd_split(SplitCtx<T>& sc, const T* A, int64_t R, int64_t C, bool to
     return r;
 }
 
+// ---- row-sharded top split -------------------------------------------------------------
+// The signal matrix X (R x C, row-major) is split into G contiguous row blocks = leading-qubit blocks, one per
+// rank.  Y = X Omega, U = Q U_s are row-local; the QR of the tall sketch is a TSQR whose per-rank l x l R factors
+// are all-gathered; the l x C projections B = Q^H X (and Z = X^H Q of a power iteration) are sums of per-rank
+// partials (all-reduce).  Everything below the top split is small and runs replicated on every rank.
+template <typename T>
+static void tsqr_sharded(SplitCtx<T>& sc, const Mat<T>& Y, int64_t Rg, int l, Mat<T>& Q) {
+    qil_ctx* ctx = sc.ctx;
+    constexpr int F = Scalar<T>::is_complex ? 2 : 1;
+    const int G = sc.comm->world, g = sc.comm->rank;
+    Mat<T> Qg, Rloc;
+    qr_thin<T>(ctx, Rg, l, Y.p, l, true, Qg, Rloc);
+    Mat<T> Rall(ctx, (int64_t)G * l, l);
+    comm_allgather(sc.comm, Rloc.p, Rall.p, (int64_t)l * l * F);
+    Mat<T> Q2, R2;
+    qr_thin<T>(ctx, (int64_t)G * l, l, Rall.p, l, true, Q2, R2);
+    Q = Mat<T>(ctx, Rg, l);
+    gemm<T>(ctx, OP_N, OP_N, Rg, l, l, 1.0, Qg.p, l, Q2.p + (size_t)g * l * l, l, 0.0, Q.p, l);
+}
+
+// A = this rank's Rg x C row block.  Returns the rank r; U is the FULL (G*Rg) x r factor, SVh is r x C (both replicated).
+template <typename T>
+static int rsvd_split_sharded(SplitCtx<T>& sc, const T* A, int64_t Rg, int64_t C, Mat<T>& U, Mat<T>& SVh) {
+    qil_ctx* ctx = sc.ctx;
+    const RsvdOpts& o = *sc.o;
+    constexpr int F = Scalar<T>::is_complex ? 2 : 1;
+    const int G = sc.comm->world;
+    const int64_t R = Rg * G;
+    const int l = (int)std::min<int64_t>((int64_t)o.k + o.p, std::min(R, C));
+    QIL_REQUIRE(Rg >= l && stream_supported(Rg, C * F, C * F, l * F), QIL_ERR_UNSUPPORTED,
+                "sharded encode: a %lld x %lld row block per rank is too small for k+p = %d; encode on one device",
+                (long long)Rg, (long long)C, l);
+    if (sc.stream) QIL_REQUIRE(C * (int64_t)l <= sc.stream_len, QIL_ERR_ARGUMENT,
+                               "rsvd: the supplied normal stream is shorter than %lld", (long long)(C * l));
+    Mat<T> Y = mul_A<T>(sc, A, Rg, C, l, nullptr, true);
+    Mat<T> Q;
+    tsqr_sharded<T>(sc, Y, Rg, l, Q);
+    for (int it = 0; it < o.q; ++it) {
+        Mat<T> Z = mul_AH<T>(sc, A, Rg, C, l, Q.p, nullptr);
+        comm_allreduce(sc.comm, Z.p, C * l * F);
+        Mat<T> Qz, Rz;
+        qr_thin<T>(ctx, C, l, Z.p, l, true, Qz, Rz);
+        Mat<T> Y2 = mul_A<T>(sc, A, Rg, C, l, Qz.p, false);
+        tsqr_sharded<T>(sc, Y2, Rg, l, Q);
+    }
+    Mat<T> Bh = mul_AH<T>(sc, A, Rg, C, l, Q.p, sc.d_nrm + 1);
+    comm_allreduce(sc.comm, Bh.p, C * l * F);
+    Mat<T> Us;
+    const int r = svd_trunc_adj<T>(ctx, l, C, Bh.p, l, o.cutoff, o.maxdim, o.mindim, &Us, nullptr, nullptr, &SVh, nullptr);
+    Mat<T> Ug(ctx, Rg, r);
+    gemm<T>(ctx, OP_N, OP_N, Rg, r, l, 1.0, Q.p, l, Us.p, r, 0.0, Ug.p, r);
+    U = Mat<T>(ctx, R, r);
+    comm_allgather(sc.comm, Ug.p, U.p, Rg * r * F);
+    return r;
+}
+
 // rsvd(A, Linds...; k, p, q, ...) on a dense device matrix (rsvd.jl:38-121) -> U (m x r), S (r), Vh (r x n)
 template <typename T>
 int rsvd_matrix(qil_ctx* ctx, const T* d_A, int64_t m, int64_t n, const RsvdOpts& o, Mat<T>& U, Mat<double>& S, Mat<T>& Vh) {
@@ -329,15 +419,10 @@ struct DcNode {
 };
 
 template <typename T>
-static void dc_encode(SplitCtx<T>& sc, const T* x, int n, std::vector<void*>& cores, std::vector<int64_t>& bond) {
+static void dc_encode(SplitCtx<T>& sc, std::vector<DcNode<T>> level, std::vector<void*>& cores,
+                      std::vector<int64_t>& bond) {
     qil_ctx* ctx = sc.ctx;
     const RsvdOpts& o = *sc.o;
-    std::vector<DcNode<T>> level;
-    {
-        DcNode<T> root;
-        root.ptr = x; root.lb = 1; root.rb = 1; root.first = 0; root.last = n - 1; root.top = true;
-        level.push_back(std::move(root));
-    }
     while (!level.empty()) {
         std::vector<DcNode<T>> next;
         std::vector<SmallSvdItem<T>> batch;
@@ -425,7 +510,12 @@ qil_mps* encode_rsvd(qil_ctx* ctx, const T* d_x, int64_t N, const RsvdOpts& o) {
         m->amplitude = c;
         return m;
     }
-    dc_encode<T>(sc, x, n, cores, bond);
+    {
+        std::vector<DcNode<T>> level(1);
+        DcNode<T>& root = level[0];
+        root.ptr = x; root.lb = 1; root.rb = 1; root.first = 0; root.last = n - 1; root.top = true;
+        dc_encode<T>(sc, std::move(level), cores, bond);
+    }
     double h_nrm[2];
     QIL_CUDA(cudaMemcpyAsync(h_nrm, nrm.p, 2 * sizeof(double), cudaMemcpyDeviceToHost, ctx->stream));
     ctx->sync();
@@ -434,6 +524,49 @@ qil_mps* encode_rsvd(qil_ctx* ctx, const T* d_x, int64_t N, const RsvdOpts& o) {
     m->amplitude = h_nrm[0];
     return m;
 }
+// signal_mps(x; method=:rsvd) with x split over comm->world ranks in contiguous chunks (rank order); every rank
+// returns the same MPS.  N is the TOTAL length and must be a power of two divisible by the world size.
+template <typename T>
+qil_mps* encode_rsvd_sharded(qil_ctx* ctx, const qil_comm* comm, const T* d_x_local, int64_t N, const RsvdOpts& o) {
+    QIL_REQUIRE(comm->world >= 1 && comm->rank >= 0 && comm->rank < comm->world, QIL_ERR_ARGUMENT,
+                "sharded encode: invalid rank %d of %d", comm->rank, comm->world);
+    QIL_REQUIRE(o.k >= 1 && o.p >= 0 && o.q >= 0, QIL_ERR_ARGUMENT, "rsvd: k >= 1, p >= 0, q >= 0 required");
+    const int n = ilog2_round(N);
+    QIL_REQUIRE(n >= 2 && N == ((int64_t)1 << n), QIL_ERR_ARGUMENT,
+                "sharded encode: the total length must be a power of two (pad on the host)");
+    QIL_REQUIRE(n <= kMaxSites, QIL_ERR_UNSUPPORTED, "signal too long");
+    const int G = comm->world;
+    QIL_REQUIRE((G & (G - 1)) == 0, QIL_ERR_ARGUMENT, "sharded encode: the world size must be a power of two");
+    const int mid = n / 2 - 1;                               // top split, 0-based (SignalConverters.jl:161)
+    const int64_t R = (int64_t)1 << (mid + 1), C = (int64_t)1 << (n - 1 - mid);
+    QIL_REQUIRE(R % G == 0, QIL_ERR_UNSUPPORTED, "sharded encode: %d ranks do not divide the %lld rows", G, (long long)R);
+    Mat<double> nrm(ctx, 2, 1);
+    SplitCtx<T> sc{ctx, &o, (const T*)o.omega, o.omega_rows * std::max<int64_t>(o.omega_cols, 1), nrm.p, false, comm};
+    std::vector<int64_t> bond(n + 1, 1);
+    std::vector<void*> cores(n, nullptr);
+    Mat<T> U, SVh;
+    const int r = rsvd_split_sharded<T>(sc, d_x_local, R / G, C, U, SVh);
+    bond[mid + 1] = r;
+    sc.comm = nullptr;                                       // the lower levels are replicated, no collectives
+    {
+        std::vector<DcNode<T>> level(2);
+        DcNode<T>& a = level[0];
+        DcNode<T>& b = level[1];
+        a.ptr = U.p; a.owner = std::move(U); a.lb = 1; a.rb = r; a.first = 0; a.last = mid; a.top = false;
+        b.ptr = SVh.p; b.owner = std::move(SVh); b.lb = r; b.rb = 1; b.first = mid + 1; b.last = n - 1; b.top = false;
+        dc_encode<T>(sc, std::move(level), cores, bond);
+    }
+    double h_nrm[2];
+    QIL_CUDA(cudaMemcpyAsync(h_nrm, nrm.p, 2 * sizeof(double), cudaMemcpyDeviceToHost, ctx->stream));
+    ctx->sync();
+    qil_mps* m = new_mps(ctx, n, Scalar<T>::is_complex ? 1 : 0, bond.data(), false);
+    m->core = cores;
+    m->amplitude = h_nrm[0];
+    return m;
+}
+template qil_mps* encode_rsvd_sharded<double>(qil_ctx*, const qil_comm*, const double*, int64_t, const RsvdOpts&);
+template qil_mps* encode_rsvd_sharded<cplx>(qil_ctx*, const qil_comm*, const cplx*, int64_t, const RsvdOpts&);
+
 template qil_mps* encode_rsvd<double>(qil_ctx*, const double*, int64_t, const RsvdOpts&);
 template qil_mps* encode_rsvd<cplx>(qil_ctx*, const cplx*, int64_t, const RsvdOpts&);
 

@@ -22,6 +22,10 @@ struct RsvdOpts {
 // signal_mps(x; method=:rsvd, ...)
 template <typename T> qil_mps* encode_rsvd(qil_ctx* ctx, const T* d_x, int64_t N, const RsvdOpts& o);
 
+// same with the signal row-sharded over the ranks of `comm` (host-supplied collectives, include/qilcuda.h)
+template <typename T>
+qil_mps* encode_rsvd_sharded(qil_ctx* ctx, const qil_comm* comm, const T* d_x_local, int64_t N, const RsvdOpts& o);
+
 template <typename T>
 int rsvd_matrix(qil_ctx* ctx, const T* d_A, int64_t m, int64_t n, const RsvdOpts& o, Mat<T>& U, Mat<double>& S, Mat<T>& Vh);
 

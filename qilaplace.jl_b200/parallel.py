@@ -67,3 +67,99 @@ def argmax_abs_sharded(values_local, offset, group=None):
     vals = [(float(b[0]), int(b[1])) for b in allb]
     v, idx = max(vals, key=lambda t: (t[0], -t[1]))
     return v, idx
+
+
+# --------------------------------------------------------------------------------------------------
+# One signal row-sharded over the ranks: the exchange steps of the divide-and-conquer top split
+# (all-gather of the TSQR R factors, all-reduce of the partial projections) run through torch.distributed;
+# the library calls back into the two collectives below with device pointers.
+# --------------------------------------------------------------------------------------------------
+class _DevBuf:
+    """A raw device allocation exposed through __cuda_array_interface__ so torch can wrap it without a copy."""
+
+    def __init__(self, ptr, count):
+        self.__cuda_array_interface__ = {"shape": (int(count),), "typestr": "<f8", "data": (int(ptr), False),
+                                         "version": 3, "strides": None}
+
+
+class TorchComm:
+    """struct qil_comm backed by a torch.distributed process group (NCCL over NVLink on the GPU box).
+
+    With the NCCL backend the collectives are enqueued relative to the context's stream (made torch's current
+    stream for the duration of the callback), so no host synchronisation happens inside the encode.  Any other
+    backend (gloo) is served through a host staging copy; it exists for functional tests only."""
+
+    def __init__(self, ctx, group=None):
+        import ctypes as C
+        import torch
+        from . import _lib
+        dist = _dist()
+        self.ctx, self.group = ctx, group
+        self.rank, self.world = dist.get_rank(group), dist.get_world_size(group)
+        self.device = torch.device("cuda", ctx.device)
+        self.nccl = dist.get_backend(group) == "nccl"
+        sp = C.c_void_p()
+        _lib.call("qil_get_stream", ctx.handle, C.byref(sp))
+        self.stream = torch.cuda.ExternalStream(sp.value or 0, device=self.device)
+        self.calls = {"allreduce": 0, "allgather": 0, "bytes": 0}
+        self.error = None
+
+        def wrap(ptr, count):
+            return torch.as_tensor(_DevBuf(ptr, count), device=self.device)
+
+        def allreduce(_user, d_buf, count):
+            try:
+                with torch.cuda.stream(self.stream):
+                    t = wrap(d_buf, count)
+                    if self.nccl:
+                        dist.all_reduce(t, group=group)
+                    else:
+                        h = t.cpu()
+                        dist.all_reduce(h, group=group)
+                        t.copy_(h)
+                self.calls["allreduce"] += 1
+                self.calls["bytes"] += 8 * int(count)
+                return 0
+            except Exception as e:   # never let an exception cross the C boundary
+                self.error = e
+                return 1
+
+        def allgather(_user, d_send, d_recv, count):
+            try:
+                with torch.cuda.stream(self.stream):
+                    s = wrap(d_send, count)
+                    r = wrap(d_recv, count * self.world)
+                    if self.nccl:
+                        dist.all_gather_into_tensor(r, s, group=group)
+                    else:
+                        hs = s.cpu()
+                        parts = [torch.empty_like(hs) for _ in range(self.world)]
+                        dist.all_gather(parts, hs, group=group)
+                        r.copy_(torch.cat(parts))
+                self.calls["allgather"] += 1
+                self.calls["bytes"] += 8 * int(count) * self.world
+                return 0
+            except Exception as e:
+                self.error = e
+                return 1
+
+        self._cb = (_lib.QilComm.ALLREDUCE(allreduce), _lib.QilComm.ALLGATHER(allgather))   # keep alive
+        self.struct = _lib.QilComm(self.rank, self.world, None, self._cb[0], self._cb[1])
+
+
+def signal_mps_sharded_dev(comm, d_x_local, N_total, is_complex, cutoff=1e-15, maxdim=None, k=20, p=10, q=0,
+                           random_seed=1234, mindim=1):
+    """signal_mps(x; method=:rsvd) for ONE signal whose rank-th contiguous chunk of N_total / world samples lives at
+    device pointer d_x_local on this rank.  Every rank makes the call and receives the same SignalMPS."""
+    import ctypes as C
+    from . import _lib, api
+    h = _lib.c_mps()
+    try:
+        _lib.call("qil_encode_rsvd_sharded_dev", comm.ctx.handle, C.byref(comm.struct), int(is_complex),
+                  C.c_void_p(int(d_x_local)), C.c_int64(N_total), int(k), int(p), int(q), C.c_int64(random_seed),
+                  float(cutoff), C.c_int64(api._maxdim_arg(maxdim)), C.c_int64(mindim), None, C.c_int64(0), C.byref(h))
+    except Exception:
+        if comm.error is not None:
+            raise comm.error
+        raise
+    return api.SignalMPS(comm.ctx, h)

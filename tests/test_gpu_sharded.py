@@ -1,0 +1,77 @@
+"""Row-sharded encode of ONE signal (qil_encode_rsvd_sharded_dev + the torch.distributed collectives of
+qilaplace_b200.parallel.TorchComm) against the single-device CUDA encode and the CPU oracle.
+
+On a one-GPU box the ranks share cuda:0 and the process group is gloo (NCCL refuses two ranks on one device), which
+drives the identical library code through the host-staged variant of the two callbacks; with >= 2 GPUs the group
+is NCCL, one device per rank."""
+import os
+import sys
+
+import numpy as np
+import pytest
+
+pytestmark = pytest.mark.gpu
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+
+
+def _signal(n, cplx):
+    N = 2**n
+    t = np.arange(N) / (2.5 * N)
+    x = np.sin(1.0 * t) * np.exp(-0.08 * t) + np.sin(2.5 * t) * np.exp(-0.03 * t)
+    return x * np.exp(0.3j * t) if cplx else x
+
+
+def _worker(rank, world, port, ret):
+    sys.path.insert(0, ROOT)
+    sys.path.insert(0, os.path.join(ROOT, "oracle"))
+    os.environ["MASTER_ADDR"] = "127.0.0.1"
+    os.environ["MASTER_PORT"] = str(port)
+    import torch
+    import torch.distributed as dist
+    import qil_oracle as O
+    import qilaplace_b200 as q
+    from qilaplace_b200 import parallel
+    ngpu = torch.cuda.device_count()
+    nccl = ngpu >= world
+    dev = rank if nccl else 0
+    torch.cuda.set_device(dev)
+    dist.init_process_group("nccl" if nccl else "gloo", rank=rank, world_size=world)
+    try:
+        ctx = q.Context(dev)
+        comm = parallel.TorchComm(ctx)
+        for n, cplx, qit in ((20, False, 2), (21, True, 1), (22, False, 0)):
+            N = 2**n
+            x = _signal(n, cplx)
+            lo, hi = rank * N // world, (rank + 1) * N // world
+            xl = torch.from_numpy(np.ascontiguousarray(x[lo:hi])).to(f"cuda:{dev}")
+            torch.cuda.synchronize()
+            psi = parallel.signal_mps_sharded_dev(comm, xl.data_ptr(), N, cplx, k=15, p=5, q=qit, cutoff=1e-12)
+            # single-device CUDA encode of the whole signal on this rank's device
+            xf = torch.from_numpy(np.ascontiguousarray(x)).to(f"cuda:{dev}")
+            torch.cuda.synchronize()
+            one = q.signal_mps_dev(ctx, xf.data_ptr(), N, cplx, method="rsvd", k=15, p=5, q=qit, cutoff=1e-12)
+            assert psi.bonds == one.bonds, (psi.bonds, one.bonds)
+            assert abs(psi.amplitude - one.amplitude) < 1e-12 * one.amplitude
+            v, v1 = q.mps_to_vector(psi), q.mps_to_vector(one)
+            assert np.abs(v - v1).max() < 1e-10 * np.abs(v1).max()
+            # CPU oracle (single process, reference algorithm)
+            ref, cref = O.tt_rsvd(x, k=15, p=5, q=qit, cutoff=1e-12)
+            assert psi.bonds == O.bonds_of(ref)
+            vref = O.mps_to_vector(ref, cref)
+            assert np.abs(v - vref).max() < 1e-10 * np.abs(vref).max()
+            assert np.linalg.norm(v - x) < 1e-5 * np.linalg.norm(x)
+        assert comm.calls["allreduce"] > 0 and comm.calls["allgather"] > 0
+        ret[rank] = "ok"
+    finally:
+        dist.destroy_process_group()
+
+
+@pytest.mark.parametrize("world", [1, 2])
+def test_row_sharded_encode_matches_single_device_and_oracle(world):
+    import torch.multiprocessing as mp
+    port = 33500 + (os.getpid() % 2000) + world
+    mgr = mp.Manager()
+    ret = mgr.dict()
+    mp.spawn(_worker, args=(world, port, ret), nprocs=world, join=True)
+    assert dict(ret) == {r: "ok" for r in range(world)}

@@ -56,3 +56,44 @@ def test_coefficient_grid_sharded_over_gloo():
     ret = mgr.dict()
     mp.spawn(_worker, args=(world, port, ret), nprocs=world, join=True)
     assert dict(ret) == {0: "ok", 1: "ok"}
+
+
+def _worker_sharded(rank, world, port, ret):
+    sys.path.insert(0, ROOT)
+    sys.path.insert(0, os.path.join(ROOT, "oracle"))
+    sys.path.insert(0, os.path.join(ROOT, "tests"))
+    os.environ["MASTER_ADDR"] = "127.0.0.1"
+    os.environ["MASTER_PORT"] = str(port)
+    import torch.distributed as dist
+    import qil_oracle as O
+    import sharded_ref
+    dist.init_process_group("gloo", rank=rank, world_size=world)
+    try:
+        for n, cplx, qit in ((12, False, 2), (13, True, 1)):
+            N = 2**n
+            t = np.arange(N) / (2.5 * N)
+            x = np.sin(1.0 * t) * np.exp(-0.08 * t) + np.sin(2.5 * t) * np.exp(-0.03 * t)
+            if cplx:
+                x = x * np.exp(0.3j * t)
+            lo, hi = rank * N // world, (rank + 1) * N // world
+            cores, c = sharded_ref.tt_rsvd_sharded(x[lo:hi], n, k=15, p=5, q=qit, cutoff=1e-12)
+            ref, cref = O.tt_rsvd(x, k=15, p=5, q=qit, cutoff=1e-12)
+            assert abs(c - cref) < 1e-12 * cref
+            assert O.bonds_of(cores) == O.bonds_of(ref)
+            v, vref = O.mps_to_vector(cores, c), O.mps_to_vector(ref, cref)
+            assert np.abs(v - vref).max() < 1e-10 * np.abs(vref).max()
+        ret[rank] = "ok"
+    finally:
+        dist.destroy_process_group()
+
+
+def test_row_sharded_encode_formulation_over_gloo():
+    """The exchange steps of the row-sharded top split (TSQR all-gather of R factors, all-reduce of the partial
+    projections, all-gather of U) reproduce the single-process oracle: identical bonds, amplitudes to 1e-10."""
+    import torch.multiprocessing as mp
+    world = 2
+    port = 31500 + (os.getpid() % 2000)
+    mgr = mp.Manager()
+    ret = mgr.dict()
+    mp.spawn(_worker_sharded, args=(world, port, ret), nprocs=world, join=True)
+    assert dict(ret) == {0: "ok", 1: "ok"}
