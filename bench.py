@@ -44,9 +44,12 @@ def parse():
     ap.add_argument("--steps", type=int, default=5)
     ap.add_argument("--warmup", type=int, default=3)
     ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
-    ap.add_argument("--n", type=int, default=28)
+    ap.add_argument("--log2n", dest="n", type=int, default=28, help="qubits n (signal length 2^n)")
     ap.add_argument("--coeffs", type=int, default=1_000_000)
     ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--shard-signal", action="store_true",
+                    help="N > 1: ONE signal row-sharded over the ranks (strong scaling, SURVEY.md 8e) instead of one "
+                         "signal per rank (weak scaling, the default)")
     ap.add_argument("--cpu-n", type=int, default=0, help="n of the bounded CPU sample (default: n)")
     return ap.parse_args()
 
@@ -186,6 +189,14 @@ def run_reference(args):
 # --------------------------------------------------------------------------------------------------
 # CUDA arm
 # --------------------------------------------------------------------------------------------------
+def log(msg):
+    """Progress on stderr (stdout carries only the JSON line)."""
+    if os.environ.get("QIL_BENCH_QUIET"):
+        return
+    sys.stderr.write(f"[bench r{os.environ.get('RANK', '0')} {time.strftime('%H:%M:%S')}] {msg}\n")
+    sys.stderr.flush()
+
+
 def run_ours(args):
     import numpy as np
     import torch
@@ -197,21 +208,31 @@ def run_ours(args):
     torch.cuda.set_device(local)
     dev = torch.device("cuda", local)
     if world > 1:
+        os.environ.setdefault("NCCL_DEBUG_FILE", "/dev/stderr")      # stdout carries only the JSON line
         dist.init_process_group("nccl", device_id=dev)
 
     import qilaplace_b200 as q
+    log(f"process group up: world {world}, device {local}")
 
     n, B = args.n, args.coeffs
     N = 2**n
     stream = torch.cuda.current_stream()
     ctx = q.Context(local, stream=stream.cuda_stream)
 
+    shard = bool(args.shard_signal and world > 1)
+    NL = N // world if shard else N            # samples resident on this rank
+    off = rank * NL if shard else 0
+    comm = None
+    if shard:
+        from qilaplace_b200 import parallel
+        comm = parallel.TorchComm(ctx)
+
     # ---- synthetic input: generated on the device, mirrored into pinned host memory for the e2e leg
-    j = torch.arange(N, dtype=torch.float64, device=dev)
+    j = torch.arange(off, off + NL, dtype=torch.float64, device=dev)
     t = j * (1.0 / (2.5 * N))
     x_dev = torch.sin(1.0 * t) * torch.exp(-0.08 * t) + torch.sin(2.5 * t) * torch.exp(-0.03 * t)
     del j, t
-    x_pin = torch.empty(N, dtype=torch.float64, pin_memory=True)
+    x_pin = torch.empty(NL, dtype=torch.float64, pin_memory=True)
     x_pin.copy_(x_dev)
     bits_np = hash_bits(B, 2 * n)
     bits_pin = torch.from_numpy(bits_np).pin_memory()
@@ -233,11 +254,17 @@ def run_ours(args):
     W = q.build_zt_mpo(n, OMEGA_R, cutoff=MPO_CUTOFF, maxdim=MPO_MAXDIM, ctx=ctx)
     ctx.sync()
     build_s = time.perf_counter() - t0
+    log(f"inputs resident, zT MPO built in {build_s:.1f} s")
 
     state = {}
 
+    def encode_dev(ptr):
+        if shard:
+            return parallel.signal_mps_sharded_dev(comm, ptr, N, False, **ALGO)
+        return q.signal_mps_dev(ctx, ptr, N, False, method="rsvd", **ALGO)
+
     def step_device():
-        psi = q.signal_mps_dev(ctx, x_dev.data_ptr(), N, False, method="rsvd", **ALGO)
+        psi = encode_dev(x_dev.data_ptr())
         z = q.ztmps_from_mps(psi, cutoff=ALGO["cutoff"])
         out = q.apply(W, z)
         state["psi"], state["z"], state["out"] = psi, z, out
@@ -254,9 +281,15 @@ def run_ours(args):
 
     x_host = x_pin.numpy()
 
+    x_stage = torch.empty(NL, dtype=torch.float64, device=dev) if shard else None
+
     def step_e2e():
         # the call a user makes: host signal in, host cores out, through the host-buffer C-ABI entry points
-        z = q.signal_ztmps(x_host, ctx=ctx, method="rsvd", **ALGO)       # H2D of the 2 GiB signal inside
+        if shard:
+            x_stage.copy_(x_pin, non_blocking=True)                       # H2D of this rank's chunk
+            z = q.ztmps_from_mps(encode_dev(x_stage.data_ptr()), cutoff=ALGO["cutoff"])
+        else:
+            z = q.signal_ztmps(x_host, ctx=ctx, method="rsvd", **ALGO)   # H2D of the 2 GiB signal inside
         out = W * z
         state["host_cores"] = out.cores()                                 # D2H read of the step's result
 
@@ -305,6 +338,7 @@ def run_ours(args):
     scan_check = float(_np.abs(_got - _chk).max() / max(_np.abs(_chk).max(), 1e-300))
     assert scan_check < 1e-9, f"pole scan disagrees with the chain kernel: {scan_check}"
 
+    log(f"warm-up done: MPS bonds {state['psi'].bonds}, zT output max bond {max(state['out'].bonds)}")
     # ---- timed: device-resident (`value`), with per-kernel-class events for the roofline
     sampler = ClockSampler(local)
     sampler.start()
@@ -329,7 +363,7 @@ def run_ours(args):
             ev = [torch.cuda.Event(enable_timing=True) for _ in range(5)]
             torch.cuda.synchronize()
             ev[0].record()
-            psi = q.signal_mps_dev(ctx, x_dev.data_ptr(), N, False, method="rsvd", **ALGO)
+            psi = encode_dev(x_dev.data_ptr())
             ev[1].record()
             z = q.ztmps_from_mps(psi, cutoff=ALGO["cutoff"])
             ev[2].record()
@@ -342,22 +376,28 @@ def run_ours(args):
                 acc[i] += ev[i].elapsed_time(ev[i + 1])
         return {nm: a / reps for nm, a in zip(names, acc)}
 
+    log(f"device-resident legs timed: {ms_dev / args.steps:.3f} ms/step, scan {ms_scan:.3f} ms")
     stages_ms = stage_breakdown()
+    log(f"stage breakdown: {stages_ms}")
 
     # ---- timed: end to end through host buffers
     for _ in range(2):
         step_e2e()
+    log("e2e warm-up done")
     ms_e2e = timed(step_e2e, args.steps)
+    log(f"e2e encode leg timed: {ms_e2e / args.steps:.3f} ms/step")
     step_coeff_e2e()
     ms_coeff_e2e = timed(step_coeff_e2e, csteps)
     step_scan_e2e()
     ms_scan_e2e = timed(step_scan_e2e, max(csteps, 3)) / max(csteps, 3)
     clocks = sampler.finish()
+    log(f"e2e legs timed: {ms_e2e / args.steps:.3f} ms/step")
 
     psi, z, out = state["psi"], state["z"], state["out"]
     ms_step = ms_dev / args.steps
-    value = world * N / (ms_step / 1e3)
-    e2e_value = world * N / (ms_e2e / args.steps / 1e3)
+    units = 1 if shard else world              # signals processed per step by the whole job
+    value = units * N / (ms_step / 1e3)
+    e2e_value = units * N / (ms_e2e / args.steps / 1e3)
 
     # ---- roofline of the dominant kernel (streaming sketch/projection GEMM): algorithmic bytes = e*N per launch
     peaks = {}
@@ -402,13 +442,15 @@ def run_ours(args):
     line = {
         "metric": "encode_zt_apply_samples_per_s", "value": value, "unit": "samples/s", "n_gpus": world,
         "steps": args.steps, "warmup": max(args.warmup, 3), "ms_per_step": ms_step, "higher_is_better": True,
-        "scaling": "weak", "vs_baseline": None, "dtype": "f64", "data": "synthetic",
+        "scaling": "strong" if shard else "weak", "vs_baseline": None, "dtype": "f64", "data": "synthetic",
         "config": {"workload": f"C4 n={n} real sin_decay: signal_ztmps(:rsvd k=15 p=5 q=2 cutoff=1e-12) + zT apply "
                                f"(omega_r=2pi, MPO cutoff 1e-12 maxdim 128, built in setup); then {B} coefficients",
-                   "signals_per_rank": 1, "l2": "inputs (2 GiB signal) larger than L2", "zt_mpo_build_s": build_s,
+                   "signals_per_rank": (1.0 / world) if shard else 1,
+                   "sharding": ("one signal row-sharded over the ranks: TSQR all-gather + projection all-reduce over NCCL"
+                                if shard else "one signal per rank, no data-path collective"), "l2": "inputs (2 GiB signal) larger than L2", "zt_mpo_build_s": build_s,
                    "mps_bonds_max": max(psi.bonds), "zt_mpo_bonds_max": max(W.bonds), "out_bonds_max": max(out.bonds)},
         "e2e": {"value": e2e_value, "unit": "samples/s", "ms_per_step": ms_e2e / args.steps,
-                "h2d_bytes_per_step": int(8 * N), "d2h_bytes_per_step": host_bytes},
+                "h2d_bytes_per_step": int(8 * NL), "d2h_bytes_per_step": host_bytes},
         "gpu_launches": int(launches),
         "clocks": clocks,
         "roofline": roofline,
@@ -421,10 +463,12 @@ def run_ours(args):
                       "e2e_ms": ms_scan_e2e, "e2e_coefficients_per_s": world * scan_pts / (ms_scan_e2e / 1e3),
                       "d2h_bytes_per_step": int(16 * scan_pts), "max_rel_dev_vs_chain_kernel": scan_check},
         "full_step": {"what": f"encode + split + apply + {B} coefficients", "ms": full_ms,
-                      "samples_per_s": world * N / (full_ms / 1e3)},
+                      "samples_per_s": units * N / (full_ms / 1e3)},
         "stages_ms": stages_ms,
     }
 
+    if shard:
+        line["config"]["collectives_total"] = dict(comm.calls)
     if rank == 0 and world == 1 and not args.no_cpu_baseline:
         cn = args.cpu_n or n
         try:

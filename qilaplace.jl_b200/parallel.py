@@ -100,7 +100,10 @@ class TorchComm:
         self.nccl = dist.get_backend(group) == "nccl"
         sp = C.c_void_p()
         _lib.call("qil_get_stream", ctx.handle, C.byref(sp))
-        self.stream = torch.cuda.ExternalStream(sp.value or 0, device=self.device)
+        # a NULL handle is the legacy default stream, which is torch's default stream; ExternalStream(0) would
+        # silently hand out a pool stream with no ordering against the library's work
+        self.stream = (torch.cuda.ExternalStream(sp.value, device=self.device) if sp.value
+                       else torch.cuda.default_stream(self.device))
         self.calls = {"allreduce": 0, "allgather": 0, "bytes": 0}
         self.error = None
 

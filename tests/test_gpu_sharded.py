@@ -22,7 +22,7 @@ def _signal(n, cplx):
     return x * np.exp(0.3j * t) if cplx else x
 
 
-def _worker(rank, world, port, ret):
+def _worker(rank, world, port, ret, default_stream=False):
     sys.path.insert(0, ROOT)
     sys.path.insert(0, os.path.join(ROOT, "oracle"))
     os.environ["MASTER_ADDR"] = "127.0.0.1"
@@ -38,7 +38,8 @@ def _worker(rank, world, port, ret):
     torch.cuda.set_device(dev)
     dist.init_process_group("nccl" if nccl else "gloo", rank=rank, world_size=world)
     try:
-        ctx = q.Context(dev)
+        # own stream, or torch's (legacy default) stream like bench.py
+        ctx = q.Context(dev, stream=torch.cuda.current_stream().cuda_stream) if default_stream else q.Context(dev)
         comm = parallel.TorchComm(ctx)
         for n, cplx, qit in ((20, False, 2), (21, True, 1), (22, False, 0)):
             N = 2**n
@@ -67,11 +68,11 @@ def _worker(rank, world, port, ret):
         dist.destroy_process_group()
 
 
-@pytest.mark.parametrize("world", [1, 2])
-def test_row_sharded_encode_matches_single_device_and_oracle(world):
+@pytest.mark.parametrize("world,default_stream", [(1, False), (2, False), (2, True)])
+def test_row_sharded_encode_matches_single_device_and_oracle(world, default_stream):
     import torch.multiprocessing as mp
-    port = 33500 + (os.getpid() % 2000) + world
+    port = 33500 + (os.getpid() % 2000) + 2 * world + int(default_stream)
     mgr = mp.Manager()
     ret = mgr.dict()
-    mp.spawn(_worker, args=(world, port, ret), nprocs=world, join=True)
+    mp.spawn(_worker, args=(world, port, ret, default_stream), nprocs=world, join=True)
     assert dict(ret) == {r: "ok" for r in range(world)}
