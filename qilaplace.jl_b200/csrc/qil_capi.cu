@@ -152,6 +152,7 @@ int qil_profile_enable(qil_ctx* ctx, int on) {
     QIL_API_BEGIN
     QIL_NONNULL(ctx);
     ctx->prof_on = on != 0;
+    ctx->prof_depth = 0;
     QIL_API_END
 }
 

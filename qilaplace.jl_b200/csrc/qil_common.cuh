@@ -112,6 +112,7 @@ struct qil_ctx {
     // optional per-kernel-class timing (CUDA events on `stream`), enabled by qil_profile_enable
     struct ProfRegion { int id; cudaEvent_t e0, e1; double bytes, flops; };
     bool prof_on = false;
+    int prof_depth = 0;               // regions nest: only the outermost one is recorded
     std::vector<ProfRegion> prof;
     // bytes / flops: ALGORITHMIC work of the region (what the roofline is computed from), 0 if not stated
     void prof_begin(int id, double bytes = 0.0, double flops = 0.0);

@@ -27,6 +27,7 @@ void* qil_ctx::get_scratch(size_t bytes) {
 
 void qil_ctx::prof_begin(int id, double bytes, double flops) {
     if (!prof_on) return;
+    if (prof_depth++ > 0) return;
     ProfRegion r;
     r.id = id;
     r.bytes = bytes;
@@ -38,7 +39,8 @@ void qil_ctx::prof_begin(int id, double bytes, double flops) {
 }
 
 void qil_ctx::prof_end() {
-    if (!prof_on || prof.empty()) return;
+    if (!prof_on || prof.empty() || prof_depth == 0) return;
+    if (--prof_depth > 0) return;
     QIL_CUDA(cudaEventRecord(prof.back().e1, stream));
 }
 

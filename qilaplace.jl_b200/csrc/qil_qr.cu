@@ -186,6 +186,11 @@ static void launch_hhqr(qil_ctx* ctx, const QrParams<T>& p, int max_mloc, bool u
 template <typename T>
 void qr_thin(qil_ctx* ctx, int64_t m, int64_t n64, const T* A, int64_t lda, bool positive, Mat<T>& Q, Mat<T>& R,
              int nsum, int64_t sum_stride, bool want_q) {
+    struct Region {   // profiler class 3 (outermost region only; TSQR recursion and SVD callers nest)
+        qil_ctx* c;
+        explicit Region(qil_ctx* cc) : c(cc) { c->prof_begin(PROF_QR); }
+        ~Region() { c->prof_end(); }
+    } region(ctx);
     QIL_REQUIRE(m >= 1 && n64 >= 1, QIL_ERR_ARGUMENT, "qr: empty matrix");
     QIL_REQUIRE(n64 < (1 << 20), QIL_ERR_UNSUPPORTED, "qr: too many columns");
     const int n = (int)n64;

@@ -263,6 +263,11 @@ static int svd_core(qil_ctx* ctx, int64_t m, int64_t n, const T* A, int64_t lda,
                     double cutoff, int64_t maxdim, int64_t mindim, Mat<T>* U, Mat<T>* US, Mat<T>* Vh, Mat<T>* SVh,
                     Mat<double>* S, int nsum, int64_t sum_stride) {
     QIL_REQUIRE(m >= 1 && n >= 1, QIL_ERR_ARGUMENT, "svd: empty matrix");
+    struct Region {   // profiler class 4 (contains its QR)
+        qil_ctx* c;
+        explicit Region(qil_ctx* cc) : c(cc) { c->prof_begin(PROF_SVD); }
+        ~Region() { c->prof_end(); }
+    } region(ctx);
     if (maxdim < 1) maxdim = 1;
     if (adj == nullptr && nsum == 1 && svd_small_fits<T>(ctx, m, n))
         return svd_small<T>(ctx, m, n, A, lda, cutoff, maxdim, mindim, U, US, Vh, SVh, S);

@@ -333,6 +333,11 @@ int svd_small(qil_ctx* ctx, int64_t m, int64_t n, const T* A, int64_t lda, doubl
 // Batched variant: every item is an independent small SVD (one CTA each, one launch, one host sync).
 template <typename T>
 void svd_small_batch(qil_ctx* ctx, std::vector<SmallSvdItem<T>>& items, double cutoff, int64_t maxdim, int64_t mindim) {
+    struct Region {
+        qil_ctx* c;
+        explicit Region(qil_ctx* cc) : c(cc) { c->prof_begin(PROF_SVD); }
+        ~Region() { c->prof_end(); }
+    } region(ctx);
     const int nb = (int)items.size();
     if (nb == 0) return;
     std::vector<SmallSvdParams<T>> h(nb);

@@ -14,7 +14,9 @@ j = torch.arange(N, dtype=torch.float64, device=dev)
 t = j * (1.0 / (2.5 * N))
 x = torch.sin(1.0 * t) * torch.exp(-0.08 * t) + torch.sin(2.5 * t) * torch.exp(-0.03 * t)
 del j, t
+ctx.profile_enable(True)
 for it in range(reps):
+    ctx.profile_reset()
     torch.cuda.synchronize()
     t0 = time.perf_counter()
     psi = q.signal_mps_dev(ctx, x.data_ptr(), N, False, method="rsvd", **bench.ALGO)
@@ -24,4 +26,7 @@ for it in range(reps):
     torch.cuda.synchronize()
     t2 = time.perf_counter()
     print("iter", it, "encode ms", (t1 - t0) * 1e3, "split ms", (t2 - t1) * 1e3, "launches", ctx.launch_count())
+    for cls, nm in ((0, "stream_gemm"), (3, "qr (outside svd)"), (4, "svd (incl. its qr)")):
+        ms, cnt = ctx.profile_read(cls)
+        print("   class %-20s %8.3f ms in %d regions" % (nm, ms, cnt))
 print("ok", psi.bonds)
