@@ -139,3 +139,68 @@ def test_encode_decode_roundtrip_full_size(q, n, cplx):
     # and the decode agrees with the oracle's decode of the very same cores to rounding
     want = O.mps_to_vector(psi.cores(), psi.amplitude)
     assert _relerr(back, want) < TOL
+
+
+def test_c3_pole_scan_n20_tutorial_peaks(q, goldens):
+    """BASELINE configs[2] at full size: n = 20 paired-register signal of docs/src/tutorials/zt.jl:257-267,
+    signal_ztmps(:rsvd), build_zt_mpo + apply, coarse (stride 2^12, zt.jl:296-310) and superfine (stride 1 around the
+    pole, zt.jl:378-398) scans.  Golden peaks (executed tutorial, zt.md:473-475, 562-564): coarse (0, 0),
+    superfine (320, 1047872).  Values are checked against the closed form chi(z) of zt.jl:276-280 and, point by
+    point, against the independent chain kernel."""
+    g = goldens["zt_tutorial_n20"]
+    n = g["n"]
+    N = 2**n
+    a = g["a_abs"] * np.exp(1j * g["a_arg"])
+    w0 = g["omega0"]
+    j = np.arange(N)
+    x = a**j * np.cos(w0 * j)
+    z = q.signal_ztmps(x, method="rsvd", k=g["k"], p=g["p"], q=g["q"], cutoff=g["cutoff"], maxdim=g["maxdim"])
+    gp, gm = a * np.exp(1j * w0), a * np.exp(-1j * w0)
+
+    def closed_form(k, l, wr):
+        w = np.exp(-(wr * k + 2j * np.pi * l) / N)
+        return (0.5 / N) * ((1 - (gp * w) ** N) / (1 - gp * w) + (1 - (gm * w) ** N) / (1 - gm * w))
+
+    # ---- coarse scan, omega_r = 2 pi
+    W = q.build_zt_mpo(z, 2 * math.pi, cutoff=1e-12, maxdim=128)
+    out = W * z
+    chi = q.pole_scan(out, log2_k=8, log2_l=8, stride_log2_k=12, stride_log2_l=12)
+    assert chi.shape == (256, 256)
+    assert np.unravel_index(np.abs(chi).argmax(), chi.shape) == (0, 0)
+    ks = (np.arange(256) * 4096)[:, None]
+    ls = (np.arange(256) * 4096)[None, :]
+    ref = closed_form(ks, ls, 2 * math.pi)
+    assert np.abs(chi - ref).max() < 1e-4 * np.abs(ref).max()        # MPO + MPS truncated at 1e-12 on sigma^2 per bond
+    # ---- superfine scan, omega_r = 0.5: the 49 x 49 block of the tutorial inside an aligned 128 x 128 block
+    wr = 0.5
+    W = q.build_zt_mpo(z, wr, cutoff=1e-12, maxdim=128)
+    out = W * z
+    zt = (1 / a) * np.exp(1j * w0)
+    kc = int(np.clip(round((-N / wr) * math.log(abs(zt))), 0, N - 1))
+    lc = int(round((N / (2 * math.pi)) * ((-np.angle(zt)) % (2 * math.pi)))) % N
+    k0, l0 = (kc - 24) & ~127, (lc - 24) & ~127
+    assert kc + 24 < k0 + 128 and lc + 24 < l0 + 128
+    blk = q.pole_scan(out, k0=k0, l0=l0, log2_k=7, log2_l=7)
+    sub = blk[kc - 24 - k0: kc + 25 - k0, lc - 24 - l0: lc + 25 - l0]
+    pk = np.unravel_index(np.abs(sub).argmax(), sub.shape)
+    assert (kc - 24 + pk[0], lc - 24 + pk[1]) == (320, 1047872)
+    kk, ll = np.meshgrid(np.arange(kc - 24, kc + 25), np.arange(lc - 24, lc + 25), indexing="ij")
+    bits = np.array([O.interleave(O.bits_lsb(int(k), n), O.bits_lsb(int(l), n)) for k, l in zip(kk.ravel(), ll.ravel())],
+                    dtype=np.uint8)
+    chain = q.coefficients(out, bits).reshape(49, 49)
+    # This chain is badly conditioned in fp64 (bond ~ 400, |chi| spans 1e45 .. 1e59 inside the block): the two
+    # summation orders differ by a few 1e-10 of the block maximum.  Referee: the reference's left-to-right chain
+    # (mps.jl:669-678) in 80-bit extended precision on the same cores, for a sample of points.
+    cores = [c.astype(np.clongdouble) for c in out.cores()]
+    rng = np.random.default_rng(0)
+    pick = rng.choice(49 * 49, size=24, replace=False)
+    exact = np.array([O.coefficient(cores, np.longdouble(out.amplitude), bits[i]) for i in pick])
+    scale = float(np.abs(chain).max())
+    err_grid = float(np.abs(sub.ravel()[pick] - exact).max()) / scale
+    err_chain = float(np.abs(chain.ravel()[pick] - exact).max()) / scale
+    assert err_grid < 2e-9 and err_chain < 2e-9, (err_grid, err_chain)
+    assert err_grid <= 3 * err_chain + TOL, (err_grid, err_chain)    # as accurate as the reference's own order
+    assert np.abs(sub - chain).max() < 4e-9 * scale
+    # (no closed-form check here: at omega_r = 0.5 the exact chi near k ~ 320 is ~1e-54 of the state's largest
+    #  entries, so what the reference's tutorial -- and this test -- read off the MPS at these points is the
+    #  deterministic truncation-error field of the cutoff-1e-12 MPO; reproducing its golden peak is the parity check)
