@@ -208,8 +208,20 @@ def run_ours(args):
     torch.cuda.set_device(local)
     dev = torch.device("cuda", local)
     if world > 1:
-        os.environ.setdefault("NCCL_DEBUG_FILE", "/dev/stderr")      # stdout carries only the JSON line
-        dist.init_process_group("nccl", device_id=dev)
+        # stdout carries only the JSON line: NCCL prints its version banner with a C-level printf while the
+        # communicator comes up, so fd 1 points at stderr until the first collective is through
+        import ctypes
+        sys.stdout.flush()
+        saved = os.dup(1)
+        os.dup2(2, 1)
+        try:
+            dist.init_process_group("nccl", device_id=dev)
+            dist.barrier()
+            torch.cuda.synchronize()
+            ctypes.CDLL(None).fflush(None)
+        finally:
+            os.dup2(saved, 1)
+            os.close(saved)
 
     import qilaplace_b200 as q
     log(f"process group up: world {world}, device {local}")

@@ -131,6 +131,14 @@ int qil_encode_rsvd(qil_ctx* ctx, int is_complex, const void* x, int64_t N, int 
 int qil_encode_rsvd_dev(qil_ctx* ctx, int is_complex, const void* d_x, int64_t N, int k, int p, int q, int64_t seed,
                         double cutoff, int64_t maxdim, int64_t mindim, const void* d_normal_stream,
                         int64_t stream_len, int64_t reserved, qil_mps** out);
+/* A batch of `count` independent signals of N samples each, stored back to back on the device (BASELINE configs[1]:
+ * 256 signals of n = 20).  Same result per signal as qil_encode_rsvd_dev with the device generator; the signals are
+ * encoded concurrently by `workers` host threads, each on its own stream (<= 0: default 16).  out[count] receives
+ * the handles.  Synchronous. */
+int qil_encode_rsvd_batch_dev(qil_ctx* ctx, int is_complex, const void* d_x, int64_t N, int64_t count, int k, int p,
+                              int q, int64_t seed, double cutoff, int64_t maxdim, int64_t mindim, int workers,
+                              qil_mps** out);
+
 /* ---- one signal row-sharded over several devices (one process per device) ---------------------
  * The length-N signal is split in rank order into world contiguous chunks of N/world samples, i.e. into
  * leading-qubit (row) blocks of the top-level matrix of the divide and conquer (SignalConverters.jl:161).  The

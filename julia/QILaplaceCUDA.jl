@@ -130,6 +130,33 @@ end
 coefficient(ψ::SignalMPS, config::AbstractVector{<:Integer}) = coefficients(ψ, reshape(collect(config), 1, :))[1]
 coefficient(ψ::ZTMPS, config) = coefficient(_as_signal_2n(ψ), config)
 
+# ---- dense coefficient grids (pole scans docs/src/tutorials/zt.jl:152-157, 283-411; mps_to_vector mps.jl:716-743) --
+# site_mode[i] in (0, 1) fixes site i, 2 frees it; out_bit[j] = output-index bit of the j-th free site (nothing = big-endian)
+function coefficient_grid(ψ::SignalMPS, site_mode::AbstractVector{<:Integer}; out_bit=nothing)
+    length(site_mode) == length(ψ.data) ||
+        throw(ArgumentError("coefficient_grid: expected $(length(ψ.data)) site modes, got $(length(site_mode))"))
+    h = _upload(ψ)
+    mode = Vector{UInt8}(site_mode)
+    F = count(==(2), mode)
+    T = any(t -> eltype(t) <: Complex, ψ.data) ? ComplexF64 : Float64
+    out = Vector{T}(undef, 2^F)
+    ob = out_bit === nothing ? C_NULL : Vector{Int32}(out_bit)
+    rc = GC.@preserve mode ob out ccall((:qil_coefficient_grid, LIB), Cint,
+               (Ptr{Cvoid}, Ptr{Cvoid}, Ptr{UInt8}, Ptr{Int32}, Ptr{Cvoid}), ctx(), h, mode, ob, out)
+    ccall((:qil_mps_free, LIB), Cint, (Ptr{Cvoid},), h)
+    _check(rc)
+    return out
+end
+mps_to_vector(ψ::SignalMPS; reverse::Bool=false) =
+    coefficient_grid(ψ, fill(2, length(ψ.data)); out_bit=reverse ? collect(0:length(ψ.data)-1) : nothing)
+mps_to_vector(ψ::ZTMPS; reverse::Bool=false) = mps_to_vector(_as_signal_2n(ψ); reverse=reverse)
+
+# ---- one signal row-sharded over several GPUs (one Julia process per GPU, e.g. MPI.jl + NCCL.jl) ---------------
+# struct qil_comm { Cint rank; Cint world; Ptr{Cvoid} user; allreduce_sum_f64; allgather_f64 }: build it with
+#   @cfunction((user, buf, n) -> (NCCL.Allreduce!(unsafe_wrap(CuArray, Ptr{Float64}(buf), n), +, comm); Cint(0)), ...)
+# and call qil_encode_rsvd_sharded_dev(ctx, Ref(comm), is_complex, d_x_local, N_total, k, p, q, seed, cutoff,
+# maxdim, mindim, C_NULL, 0, out) on every rank; all ranks receive the same MPS handle contents.
+
 # ---- apply (src/linalg/apply.jl:75-122, 201-218) ---------------------------------------------------
 # W is uploaded with qil_mpo_from_host exactly like _upload (cores Array(T, r, s, s', l)), then
 #   qil_apply_mpo_mps(ctx, hW, hψ, out) ; _download_mps(out[], ψ.sites)

@@ -10,5 +10,5 @@ from .api import (Context, default_context, SignalMPS, ZTMPS, SingleSiteMPO, Pai
                   coefficient, coefficients, apply, generate_signal, signal_mps, signal_ztmps,
                   canonicalize, canonicalize_, compress, compress_, norm, mps_to_vector,
                   build_qft_mpo, build_dt_mpo, build_zt_mpo, qr, svd_trunc, rsvd,
-                  signal_mps_dev, ztmps_from_mps, coefficients_dev,
+                  signal_mps_dev, signal_mps_batch_dev, ztmps_from_mps, coefficients_dev,
                   coefficient_grid, coefficient_grid_dev, pole_scan, pole_scan_modes)

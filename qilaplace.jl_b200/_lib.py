@@ -75,6 +75,8 @@ _SIGS = {
                         C.c_int64, C.c_int64, C.c_void_p, C.c_int64, C.c_int64, C.POINTER(c_mps)],
     "qil_encode_rsvd_dev": [c_ctx, C.c_int, C.c_void_p, C.c_int64, C.c_int, C.c_int, C.c_int, C.c_int64, C.c_double,
                             C.c_int64, C.c_int64, C.c_void_p, C.c_int64, C.c_int64, C.POINTER(c_mps)],
+    "qil_encode_rsvd_batch_dev": [c_ctx, C.c_int, C.c_void_p, C.c_int64, C.c_int64, C.c_int, C.c_int, C.c_int, C.c_int64,
+                                  C.c_double, C.c_int64, C.c_int64, C.c_int, C.POINTER(c_mps)],
     "qil_get_stream": [c_ctx, C.POINTER(C.c_void_p)],
     "qil_encode_rsvd_sharded_dev": [c_ctx, C.c_void_p, C.c_int, C.c_void_p, C.c_int64, C.c_int, C.c_int, C.c_int,
                                     C.c_int64, C.c_double, C.c_int64, C.c_int64, C.c_void_p, C.c_int64,

@@ -676,6 +676,17 @@ def signal_mps_dev(ctx, d_x, N, is_complex, method="rsvd", cutoff=1e-15, maxdim=
     return SignalMPS(ctx, h)
 
 
+def signal_mps_batch_dev(ctx, d_x, N, count, is_complex, cutoff=1e-15, maxdim=None, k=20, p=10, q=0, random_seed=1234,
+                         mindim=1, workers=16):
+    """signal_mps(x_b; method=:rsvd) for `count` signals of N samples stored back to back on the device; the
+    independent encodes run concurrently on `workers` streams.  Returns a list of SignalMPS."""
+    hs = (_lib.c_mps * int(count))()
+    call("qil_encode_rsvd_batch_dev", ctx.handle, int(is_complex), C.c_void_p(int(d_x)), C.c_int64(N), C.c_int64(count),
+         int(k), int(p), int(q), C.c_int64(random_seed), float(cutoff), C.c_int64(_maxdim_arg(maxdim)),
+         C.c_int64(mindim), int(workers), hs)
+    return [SignalMPS(ctx, _lib.c_mps(h)) for h in hs]
+
+
 def ztmps_from_mps(psi, cutoff=1e-10, maxdim=None):
     """The copy-tensor split of signal_ztmps (SignalConverters.jl:258-277) applied to an encoded SignalMPS."""
     h = _lib.c_mps()

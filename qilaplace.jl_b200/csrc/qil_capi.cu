@@ -481,6 +481,24 @@ int qil_encode_rsvd(qil_ctx* ctx, int is_complex, const void* x, int64_t N, int 
     QIL_API_END
 }
 
+int qil_encode_rsvd_batch_dev(qil_ctx* ctx, int is_complex, const void* d_x, int64_t N, int64_t count, int k, int p,
+                              int q, int64_t seed, double cutoff, int64_t maxdim, int64_t mindim, int workers,
+                              qil_mps** out) {
+    QIL_API_BEGIN
+    QIL_NONNULL(ctx); QIL_NONNULL(out);
+    QIL_REQUIRE(count >= 0, QIL_ERR_ARGUMENT, "signal batch: negative count");
+    if (count == 0) return QIL_OK;
+    QIL_NONNULL(d_x);
+    QIL_REQUIRE(N >= 1, QIL_ERR_ARGUMENT, "signal_mps: empty signal");
+    QIL_CUDA(cudaSetDevice(ctx->device));
+    RsvdOpts o;
+    o.k = k; o.p = p; o.q = q; o.seed = seed; o.cutoff = cutoff; o.maxdim = fix_maxdim(maxdim);
+    o.mindim = mindim < 1 ? 1 : mindim;
+    if (is_complex) encode_rsvd_batch<cplx>(ctx, (const cplx*)d_x, N, count, o, workers, out);
+    else encode_rsvd_batch<double>(ctx, (const double*)d_x, N, count, o, workers, out);
+    QIL_API_END
+}
+
 int qil_get_stream(qil_ctx* ctx, void** cuda_stream) {
     QIL_API_BEGIN
     QIL_NONNULL(ctx); QIL_NONNULL(cuda_stream);

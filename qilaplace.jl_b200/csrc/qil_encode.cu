@@ -12,6 +12,9 @@
 // generate it on the device with a counter-based generator.
 #include "qil_mpsops.cuh"
 
+#include <atomic>
+#include <thread>
+
 namespace qil {
 
 // ---- counter-based N(0,1) stream -------------------------------------------------------------------
@@ -566,6 +569,68 @@ qil_mps* encode_rsvd_sharded(qil_ctx* ctx, const qil_comm* comm, const T* d_x_lo
 }
 template qil_mps* encode_rsvd_sharded<double>(qil_ctx*, const qil_comm*, const double*, int64_t, const RsvdOpts&);
 template qil_mps* encode_rsvd_sharded<cplx>(qil_ctx*, const qil_comm*, const cplx*, int64_t, const RsvdOpts&);
+
+// ---- batch of independent signals (BASELINE configs[1]: 256 signals of n = 20) ---------------------------------
+// One encode is a chain of ~150 small dependent launches with a handful of host read-backs (the data-dependent
+// ranks), i.e. latency bound; independent signals overlap perfectly.  `workers` host threads, each with its own
+// stream forked from the context's stream, pull signals from a shared counter and run the ordinary encoder.
+template <typename T>
+void encode_rsvd_batch(qil_ctx* ctx, const T* d_x, int64_t N, int64_t count, const RsvdOpts& o, int workers,
+                       qil_mps** out) {
+    QIL_REQUIRE(count >= 0, QIL_ERR_ARGUMENT, "signal batch: negative count");
+    if (count == 0) return;
+    workers = (int)std::max<int64_t>(1, std::min<int64_t>(workers <= 0 ? 16 : workers, count));
+    for (int64_t i = 0; i < count; ++i) out[i] = nullptr;
+    cudaEvent_t ready;
+    QIL_CUDA(cudaEventCreateWithFlags(&ready, cudaEventDisableTiming));
+    QIL_CUDA(cudaEventRecord(ready, ctx->stream));
+    std::vector<qil_ctx> sub(workers);
+    std::vector<std::string> err(workers);
+    std::vector<int> code(workers, QIL_OK);
+    std::atomic<int64_t> next(0);
+    for (int w = 0; w < workers; ++w) {
+        sub[w].device = ctx->device;
+        sub[w].sm_count = ctx->sm_count;
+        sub[w].smem_optin = ctx->smem_optin;
+        sub[w].own_stream = true;
+        QIL_CUDA(cudaStreamCreateWithFlags(&sub[w].stream, cudaStreamNonBlocking));
+        QIL_CUDA(cudaStreamWaitEvent(sub[w].stream, ready, 0));
+    }
+    auto body = [&](int w) {
+        try {
+            QIL_CUDA(cudaSetDevice(ctx->device));
+            for (;;) {
+                const int64_t i = next.fetch_add(1);
+                if (i >= count) break;
+                out[i] = encode_rsvd<T>(&sub[w], d_x + (size_t)i * N, N, o);   // ends synchronised on its stream
+                out[i]->ctx = ctx;                                             // the handle lives on the parent context
+            }
+        } catch (const Error& e) {
+            code[w] = e.code; err[w] = e.msg;
+        } catch (const std::exception& e) {
+            code[w] = QIL_ERR_RUNTIME; err[w] = e.what();
+        }
+    };
+    std::vector<std::thread> th;
+    for (int w = 1; w < workers; ++w) th.emplace_back(body, w);
+    body(0);
+    for (auto& t : th) t.join();
+    for (int w = 0; w < workers; ++w) {
+        cudaStreamSynchronize(sub[w].stream);
+        if (sub[w].scratch) cudaFreeAsync(sub[w].scratch, sub[w].stream);
+        cudaStreamSynchronize(sub[w].stream);
+        cudaStreamDestroy(sub[w].stream);
+        ctx->launches += sub[w].launches;
+    }
+    cudaEventDestroy(ready);
+    for (int w = 0; w < workers; ++w)
+        if (code[w] != QIL_OK) {
+            for (int64_t i = 0; i < count; ++i) { if (out[i]) { destroy(out[i]); out[i] = nullptr; } }
+            throw Error(code[w], err[w]);
+        }
+}
+template void encode_rsvd_batch<double>(qil_ctx*, const double*, int64_t, int64_t, const RsvdOpts&, int, qil_mps**);
+template void encode_rsvd_batch<cplx>(qil_ctx*, const cplx*, int64_t, int64_t, const RsvdOpts&, int, qil_mps**);
 
 template qil_mps* encode_rsvd<double>(qil_ctx*, const double*, int64_t, const RsvdOpts&);
 template qil_mps* encode_rsvd<cplx>(qil_ctx*, const cplx*, int64_t, const RsvdOpts&);

@@ -22,6 +22,11 @@ struct RsvdOpts {
 // signal_mps(x; method=:rsvd, ...)
 template <typename T> qil_mps* encode_rsvd(qil_ctx* ctx, const T* d_x, int64_t N, const RsvdOpts& o);
 
+// `count` independent signals of N samples each, stored back to back; `workers` host threads / streams
+template <typename T>
+void encode_rsvd_batch(qil_ctx* ctx, const T* d_x, int64_t N, int64_t count, const RsvdOpts& o, int workers,
+                       qil_mps** out);
+
 // same with the signal row-sharded over the ranks of `comm` (host-supplied collectives, include/qilcuda.h)
 template <typename T>
 qil_mps* encode_rsvd_sharded(qil_ctx* ctx, const qil_comm* comm, const T* d_x_local, int64_t N, const RsvdOpts& o);
