@@ -120,7 +120,7 @@ static void launch_coeff(qil_ctx* ctx, const qil_mps* psi, const uint8_t* d_bits
     S = std::min<long long>(S, std::max<long long>(1, B));
     const size_t smem = smem_for(S);
     auto kern = coeff_chain_kernel<T>;
-    QIL_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+    ensure_dynamic_smem(kern, smem);
     int occ = 1;
     QIL_CUDA(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ, kern, kCoeffThreads, smem));
     occ = std::max(occ, 1);
@@ -346,7 +346,7 @@ static void launch_coeff_gemm(qil_ctx* ctx, const qil_mps* psi, const uint8_t* d
     QIL_REQUIRE(smem <= ctx->smem_optin, QIL_ERR_UNSUPPORTED, "coefficient: chain of %d sites does not fit", psi->n);
     cplx* scratch = (cplx*)ctx->alloc((size_t)grid * 2 * kCgS * chi_pad * sizeof(cplx));
     auto kern = coeff_gemm_kernel;
-    QIL_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+    ensure_dynamic_smem(kern, smem);
     kern<<<grid, kCgThreads, smem, ctx->stream>>>(make_desc(psi), d_bits, (long long)B, reinterpret_cast<cplx*>(d_out),
                                                   psi->amplitude, scratch, chi_pad);
     QIL_LAUNCH_CHECK(ctx);

@@ -10,6 +10,8 @@
 #include <cstdint>
 #include <cstdio>
 #include <exception>
+#include <map>
+#include <mutex>
 #include <string>
 #include <vector>
 
@@ -161,6 +163,13 @@ void destroy(qil_mps* m);
 void destroy(qil_mpo* m);
 
 enum ProfId { PROF_STREAM_GEMM = 0, PROF_COEFF = 1, PROF_APPLY = 2, PROF_QR = 3, PROF_SVD = 4, PROF_COUNT = 5 };
+
+// Raise (never lower) a kernel's dynamic shared-memory limit.  The attribute is process-wide per function, so
+// concurrent host threads (batched encode) must not shrink what another thread is about to launch with; keeping
+// the running maximum also removes a driver call from every launch after the first.
+void ensure_dynamic_smem_impl(const void* func, size_t bytes);
+template <typename F>
+inline void ensure_dynamic_smem(F kern, size_t bytes) { ensure_dynamic_smem_impl(reinterpret_cast<const void*>(kern), bytes); }
 
 #define QIL_LAUNCH_CHECK(ctx)            \
     do {                                 \

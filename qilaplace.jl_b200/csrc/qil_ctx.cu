@@ -48,6 +48,17 @@ void qil_ctx::sync() { QIL_CUDA(cudaStreamSynchronize(stream)); }
 
 namespace qil {
 
+void ensure_dynamic_smem_impl(const void* func, size_t bytes) {
+    static std::mutex mu;
+    static std::map<const void*, size_t> current;
+    std::lock_guard<std::mutex> lock(mu);
+    size_t& cur = current[func];
+    if (bytes > cur) {
+        QIL_CUDA(cudaFuncSetAttribute(func, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)bytes));
+        cur = bytes;
+    }
+}
+
 static void check_bonds(int n, const int64_t* bond) {
     QIL_REQUIRE(n >= 1 && n <= kMaxSites, QIL_ERR_ARGUMENT, "number of sites %d outside [1,%d]", n, kMaxSites);
     QIL_REQUIRE(bond[0] == 1 && bond[n] == 1, QIL_ERR_ARGUMENT, "boundary bonds must have dimension 1");

@@ -193,11 +193,7 @@ void gemm_tc(qil_ctx* ctx, int64_t M, int64_t N, int64_t K, double alpha, const 
     TcParams p{A, B, C, M, N, K, lda, ldb, ldc, alpha};
     const size_t smem = (size_t)kTcStages * (kTcABytes + kTcBBytes);
     auto kern = gemm_tc_kernel<CP>;
-    static bool configured = false;   // per instantiation
-    if (!configured) {
-        QIL_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-        configured = true;
-    }
+    ensure_dynamic_smem(kern, smem);
     const long long gx = (N + NC - 1) / NC, gy = (M + kTcBM - 1) / kTcBM;
     QIL_REQUIRE(gy <= 65535, QIL_ERR_UNSUPPORTED, "gemm_tc: %lld row tiles exceed the grid limit", gy);
     dim3 grid((unsigned)gx, (unsigned)gy);

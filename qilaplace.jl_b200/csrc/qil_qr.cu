@@ -166,7 +166,7 @@ static void launch_hhqr(qil_ctx* ctx, const QrParams<T>& p, int max_mloc, bool u
         auto kern = hhqr_kernel<T, false>;
         const size_t smem = qr_smem<T>(p.n, max_mloc);
         q.gscratch = nullptr;
-        QIL_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+        ensure_dynamic_smem(kern, smem);
         kern<<<p.nblk, kQrThreads, smem, ctx->stream>>>(q);
         QIL_LAUNCH_CHECK(ctx);
         return;
@@ -178,7 +178,7 @@ static void launch_hhqr(qil_ctx* ctx, const QrParams<T>& p, int max_mloc, bool u
     q.gscratch = scratch.p;
     const size_t smem = 2 * (size_t)p.n * sizeof(T) + (size_t)p.n * sizeof(double) + 32;
     auto kern = hhqr_kernel<T, true>;
-    QIL_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+    ensure_dynamic_smem(kern, smem);
     kern<<<1, kQrThreadsGlobal, smem, ctx->stream>>>(q);
     QIL_LAUNCH_CHECK(ctx);
 }
@@ -230,7 +230,7 @@ void qr_thin(qil_ctx* ctx, int64_t m, int64_t n64, const T* A, int64_t lda, bool
         Q = Mat<T>(ctx, m, n);
         const size_t smem = (size_t)n * n * sizeof(T);
         auto kern = tsqr_combine_kernel<T>;
-        QIL_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+        ensure_dynamic_smem(kern, smem);
         int gy = (int)std::max<int64_t>(1, std::min<int64_t>(8, ((int64_t)max_mloc * n + 255) / 256));
         dim3 grid((unsigned)nblk, gy);
         kern<<<grid, 256, smem, ctx->stream>>>(Q0.p, Q1.p, Q.p, (long long)m, n, (int)nblk);

@@ -259,7 +259,7 @@ static void launch_stream(qil_ctx* ctx, const CUtensorMap& tm, const StreamParam
     const int xstride = (xbytes + 127) & ~127;
     const size_t smem = (size_t)STAGES * (kStageABytes + xstride) + 2 * STAGES * 8 + kConsumerWarps * 8 + 1024;
     auto kern = stream_gemm_kernel<NT, TRANS, STAGES>;
-    QIL_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+    ensure_dynamic_smem(kern, smem);
     const long long ntiles = (long long)p.tilesM * p.ksplit;
     const int grid = (int)std::min<long long>(ntiles, ctx->sm_count);
     kern<<<grid, kStreamThreads, smem, ctx->stream>>>(tm, p);

@@ -242,11 +242,11 @@ static int jacobi_square(qil_ctx* ctx, int ns, const T* R, int64_t ld, double cu
     p.gscratch = use_global ? gscratch.p : nullptr;
     if (use_global) {
         auto kern = jacobi_kernel<T, true>;
-        QIL_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+        ensure_dynamic_smem(kern, smem);
         kern<<<1, kJacThreadsGlobal, smem, ctx->stream>>>(p);
     } else {
         auto kern = jacobi_kernel<T, false>;
-        QIL_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+        ensure_dynamic_smem(kern, smem);
         kern<<<1, kJacThreads, smem, ctx->stream>>>(p);
     }
     QIL_LAUNCH_CHECK(ctx);

@@ -314,7 +314,7 @@ int svd_small(qil_ctx* ctx, int64_t m, int64_t n, const T* A, int64_t lda, doubl
     p.mode = 0; p.cl = 0; p.cr = 0;
     const size_t smem = ss_smem<T>(p.mt, p.nt);
     auto kern = svd_small_kernel<T>;
-    QIL_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+    ensure_dynamic_smem(kern, smem);
     kern<<<1, kSsThreads, smem, ctx->stream>>>(p);
     QIL_LAUNCH_CHECK(ctx);
     int r = 0;
@@ -364,7 +364,7 @@ void svd_small_batch(qil_ctx* ctx, std::vector<SmallSvdItem<T>>& items, double c
     SmallSvdParams<T>* d_p = (SmallSvdParams<T>*)ctx->alloc(sizeof(SmallSvdParams<T>) * nb);
     QIL_CUDA(cudaMemcpyAsync(d_p, h.data(), sizeof(SmallSvdParams<T>) * nb, cudaMemcpyHostToDevice, ctx->stream));
     auto kern = svd_small_batched_kernel<T>;
-    QIL_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+    ensure_dynamic_smem(kern, smem);
     kern<<<nb, kSsThreads, smem, ctx->stream>>>(d_p);
     QIL_LAUNCH_CHECK(ctx);
     std::vector<int> ranks(nb);

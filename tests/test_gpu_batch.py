@@ -1,0 +1,58 @@
+"""Batched encode of independent signals (BASELINE configs[1] family: sin_decay signals with shifted frequencies,
+signal_mps(:rsvd, maxdim=64), QFT apply) -- qil_encode_rsvd_batch_dev against the one-signal entry point and the
+CPU oracle."""
+import numpy as np
+import pytest
+
+import qil_oracle as O
+
+pytestmark = pytest.mark.gpu
+
+
+def _family(n, count):
+    N = 2**n
+    t = np.arange(N) / (2.5 * N)
+    return np.stack([np.sin((1 + 0.01 * b) * t) * np.exp(-0.08 * t) + np.sin((2.5 + 0.01 * b) * t) * np.exp(-0.03 * t)
+                     for b in range(count)])
+
+
+@pytest.mark.parametrize("n,count,workers", [(14, 9, 4), (20, 6, 16)])
+def test_batch_encode_matches_single_and_oracle(q, n, count, workers):
+    import torch
+    N = 2**n
+    xs = _family(n, count)
+    ctx = q.default_context()
+    d = torch.from_numpy(xs).cuda()
+    torch.cuda.synchronize()
+    kw = dict(k=20, p=10, q=0, cutoff=1e-14, maxdim=64)
+    batch = q.signal_mps_batch_dev(ctx, d.data_ptr(), N, count, False, workers=workers, **kw)
+    assert len(batch) == count
+    W = q.build_qft_mpo(n, cutoff=1e-14, maxdim=128, ctx=ctx)
+    rng = np.random.default_rng(0)
+    idx = rng.integers(0, N, 512)
+    bits = ((idx[:, None] >> np.arange(n - 1, -1, -1)[None, :]) & 1).astype(np.uint8)
+    for b in range(count):
+        one = q.signal_mps_dev(ctx, d[b].data_ptr(), N, False, method="rsvd", **kw)
+        assert batch[b].bonds == one.bonds
+        assert abs(batch[b].amplitude - one.amplitude) <= 1e-13 * one.amplitude
+        got = q.coefficients(batch[b], bits)
+        assert np.abs(got - q.coefficients(one, bits)).max() <= 1e-12 * np.abs(xs[b]).max()
+        assert np.abs(got - xs[b][idx]).max() <= 1e-6 * np.abs(xs[b]).max()
+        if b in (0, count - 1):
+            co, c = O.tt_rsvd(xs[b], **kw)
+            assert batch[b].bonds == O.bonds_of(co)
+            assert np.abs(got - O.coefficient_batch(co, c, bits)).max() <= 1e-10 * np.abs(xs[b]).max()
+            # QFT apply on the batched result == FFT with bit-reversed output (test_qft_transformer.jl:427-463)
+            out = W * batch[b]
+            f = np.fft.fft(xs[b]) / np.sqrt(N)
+            rev = np.array([O.bitrev(int(i), n) for i in idx])
+            assert np.abs(q.coefficients(out, bits) - f[rev]).max() <= 1e-6 * np.abs(f).max()
+
+
+def test_batch_encode_empty_and_errors(q):
+    import torch
+    ctx = q.default_context()
+    assert q.signal_mps_batch_dev(ctx, 0, 16, 0, False) == []
+    d = torch.zeros(64, dtype=torch.float64, device="cuda")
+    with pytest.raises(q.ArgumentError):
+        q.signal_mps_batch_dev(ctx, d.data_ptr(), 16, 4, False, k=0)
