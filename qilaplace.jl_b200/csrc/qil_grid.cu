@@ -21,11 +21,10 @@
 
 namespace qil {
 
-constexpr int kTcBM = 128;                  // rows per CTA tile (8 warps x 16)
-constexpr int kTcThreads = 256;
+constexpr int kTcThreads = 256;             // 8 warps: (BM / 16) row tiles x (128 / BM) column groups
 constexpr int kTcStages = 3;
-constexpr int kTcABytes = kTcBM * 32 * 8;   // 128 rows x 32 doubles (= 16 complex) per k-chunk
 constexpr int kTcBBytes = 32 * 128 * 8;     // real: 32 k x 128 cols; complex: 16 k x 64 complex cols (half used)
+constexpr int tc_a_bytes(int bm) { return bm * 32 * 8; }   // BM rows x 32 doubles (= 16 complex) per k-chunk
 
 struct TcParams {
     const void* A;
@@ -56,10 +55,15 @@ __device__ __forceinline__ void tc_dmma(double* c, const double* a, const double
 }
 
 // C (M x N) = alpha * A (M x K) * B (K x N), row-major with leading dimensions, T = double or cplx.
-// CTA tile 128 x (128 real | 64 complex) columns; warp w owns rows 16w..16w+15 and all columns of the tile.
-template <bool CPLX>
+// CTA tile BM x (128 real | 64 complex) columns, BM in {16, 32, 64, 128}: the 8 warps form BM/16 row tiles times
+// 128/BM column groups, so a skinny left operand (few grid rows) neither pads to 128 rows nor leaves SMs idle.
+template <bool CPLX, int BM>
 __global__ void __launch_bounds__(kTcThreads, 1) gemm_tc_kernel(const TcParams p) {
     extern __shared__ __align__(1024) unsigned char smem_raw[];
+    constexpr int kTcABytes = tc_a_bytes(BM);
+    constexpr int WM = BM / 16;            // warps along the rows
+    constexpr int WN = 8 / WM;             // warps along the columns
+    constexpr int NT = 16 / WN;            // n8 tiles per warp
     unsigned char* sA = smem_raw;
     unsigned char* sB = sA + kTcStages * kTcABytes;
     constexpr int KC = CPLX ? 16 : 32;     // elements along k per chunk
@@ -68,7 +72,8 @@ __global__ void __launch_bounds__(kTcThreads, 1) gemm_tc_kernel(const TcParams p
 
     const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
     const int g = lane >> 2, t = lane & 3;
-    const long long m0 = (long long)blockIdx.y * kTcBM, n0 = (long long)blockIdx.x * NC;
+    const long long m0 = (long long)blockIdx.y * BM, n0 = (long long)blockIdx.x * NC;
+    const int wm = warp % WM, wn = warp / WM;
     const unsigned char* Ab = reinterpret_cast<const unsigned char*>(p.A);
     const unsigned char* Bb = reinterpret_cast<const unsigned char*>(p.B);
     const int iters = (int)((p.K + KC - 1) / KC);
@@ -79,7 +84,7 @@ __global__ void __launch_bounds__(kTcThreads, 1) gemm_tc_kernel(const TcParams p
         unsigned char* a = sA + stage * kTcABytes;
         unsigned char* b = sB + stage * kTcBBytes;
 #pragma unroll
-        for (int e = 0; e < (kTcBM * KC) / kTcThreads; ++e) {
+        for (int e = 0; e < (BM * KC) / kTcThreads; ++e) {
             const int idx = e * kTcThreads + tid;
             const int row = idx / KC, j = idx % KC;
             const bool ok = (m0 + row < p.M) && (k0 + j < p.K);
@@ -102,10 +107,11 @@ __global__ void __launch_bounds__(kTcThreads, 1) gemm_tc_kernel(const TcParams p
         if (it < iters) issue(it);
         tc_commit();
     }
-    double acc[16][4];
+    double acc[NT][4];
 #pragma unroll
-    for (int x = 0; x < 16; ++x) { acc[x][0] = acc[x][1] = acc[x][2] = acc[x][3] = 0.0; }
-    const int R0 = warp * 16 + g, R1 = R0 + 8;
+    for (int x = 0; x < NT; ++x) { acc[x][0] = acc[x][1] = acc[x][2] = acc[x][3] = 0.0; }
+    const int R0 = wm * 16 + g, R1 = R0 + 8;
+    const int nt0 = wn * NT;               // first n8 tile of this warp
 
     for (int it = 0; it < iters; ++it) {
         tc_wait<kTcStages - 2>();
@@ -131,26 +137,28 @@ __global__ void __launch_bounds__(kTcThreads, 1) gemm_tc_kernel(const TcParams p
                 const unsigned char* b1p = b + lr1 * 1024;
                 const int sw = (lr0 >> 1) & 7;      // == (lr1 >> 1) & 7
 #pragma unroll
-                for (int nt = 0; nt < 16; ++nt) {
+                for (int x = 0; x < NT; ++x) {
+                    const int nt = nt0 + x;
                     const int c = nt * 4 + (g >> 1);
                     const double2 e0 = *reinterpret_cast<const double2*>(b0p + ((c ^ sw) << 4));
                     const double2 e1 = *reinterpret_cast<const double2*>(b1p + ((c ^ sw) << 4));
                     double bf[4];
                     if (g & 1) { bf[0] = e0.y; bf[1] = e0.x; bf[2] = e1.y; bf[3] = e1.x; }
                     else       { bf[0] = e0.x; bf[1] = -e0.y; bf[2] = e1.x; bf[3] = -e1.y; }
-                    tc_dmma(acc[nt], af, bf);
+                    tc_dmma(acc[x], af, bf);
                 }
             } else {
                 const int r0 = kb * 16 + 4 * t;
                 const int sw = ((r0 >> 2) & 3) << 2;   // same for r0 .. r0+3
                 const unsigned char* bp = b + r0 * 1024;
 #pragma unroll
-                for (int nt = 0; nt < 16; ++nt) {
+                for (int x = 0; x < NT; ++x) {
+                    const int nt = nt0 + x;
                     const int c = ((nt * 8 + g) ^ sw) << 3;
                     double bf[4];
 #pragma unroll
                     for (int i = 0; i < 4; ++i) bf[i] = *reinterpret_cast<const double*>(bp + i * 1024 + c);
-                    tc_dmma(acc[nt], af, bf);
+                    tc_dmma(acc[x], af, bf);
                 }
             }
         }
@@ -162,26 +170,39 @@ __global__ void __launch_bounds__(kTcThreads, 1) gemm_tc_kernel(const TcParams p
     if (CPLX) {
         cplx* C = reinterpret_cast<cplx*>(p.C);
 #pragma unroll
-        for (int nt = 0; nt < 16; ++nt) {
-            const long long c = n0 + nt * 4 + t;
+        for (int x = 0; x < NT; ++x) {
+            const long long c = n0 + (nt0 + x) * 4 + t;
             if (c < p.N) {
-                if (gr0 < p.M) C[gr0 * p.ldc + c] = make_double2(acc[nt][0] * p.alpha, acc[nt][1] * p.alpha);
-                if (gr1 < p.M) C[gr1 * p.ldc + c] = make_double2(acc[nt][2] * p.alpha, acc[nt][3] * p.alpha);
+                if (gr0 < p.M) C[gr0 * p.ldc + c] = make_double2(acc[x][0] * p.alpha, acc[x][1] * p.alpha);
+                if (gr1 < p.M) C[gr1 * p.ldc + c] = make_double2(acc[x][2] * p.alpha, acc[x][3] * p.alpha);
             }
         }
     } else {
         double* C = reinterpret_cast<double*>(p.C);
 #pragma unroll
-        for (int nt = 0; nt < 16; ++nt) {
-            const long long c = n0 + nt * 8 + 2 * t;
+        for (int x = 0; x < NT; ++x) {
+            const long long c = n0 + (nt0 + x) * 8 + 2 * t;
 #pragma unroll
             for (int h = 0; h < 2; ++h)
                 if (c + h < p.N) {
-                    if (gr0 < p.M) C[gr0 * p.ldc + c + h] = acc[nt][h] * p.alpha;
-                    if (gr1 < p.M) C[gr1 * p.ldc + c + h] = acc[nt][2 + h] * p.alpha;
+                    if (gr0 < p.M) C[gr0 * p.ldc + c + h] = acc[x][h] * p.alpha;
+                    if (gr1 < p.M) C[gr1 * p.ldc + c + h] = acc[x][2 + h] * p.alpha;
                 }
         }
     }
+}
+
+template <bool CP, int BM>
+static void launch_gemm_tc(qil_ctx* ctx, const TcParams& p) {
+    constexpr int NC = CP ? 64 : 128;
+    const size_t smem = (size_t)kTcStages * (tc_a_bytes(BM) + kTcBBytes);
+    auto kern = gemm_tc_kernel<CP, BM>;
+    ensure_dynamic_smem(kern, smem);
+    const long long gx = (p.N + NC - 1) / NC, gy = (p.M + BM - 1) / BM;
+    QIL_REQUIRE(gy <= 65535, QIL_ERR_UNSUPPORTED, "gemm_tc: %lld row tiles exceed the grid limit", gy);
+    dim3 grid((unsigned)gx, (unsigned)gy);
+    kern<<<grid, kTcThreads, smem, ctx->stream>>>(p);
+    QIL_LAUNCH_CHECK(ctx);
 }
 
 template <typename T>
@@ -191,19 +212,71 @@ void gemm_tc(qil_ctx* ctx, int64_t M, int64_t N, int64_t K, double alpha, const 
     constexpr bool CP = Scalar<T>::is_complex;
     constexpr int NC = CP ? 64 : 128;
     TcParams p{A, B, C, M, N, K, lda, ldb, ldc, alpha};
-    const size_t smem = (size_t)kTcStages * (kTcABytes + kTcBBytes);
-    auto kern = gemm_tc_kernel<CP>;
-    ensure_dynamic_smem(kern, smem);
-    const long long gx = (N + NC - 1) / NC, gy = (M + kTcBM - 1) / kTcBM;
-    QIL_REQUIRE(gy <= 65535, QIL_ERR_UNSUPPORTED, "gemm_tc: %lld row tiles exceed the grid limit", gy);
-    dim3 grid((unsigned)gx, (unsigned)gy);
-    kern<<<grid, kTcThreads, smem, ctx->stream>>>(p);
-    QIL_LAUNCH_CHECK(ctx);
+    // tallest row tile that still gives every SM a CTA (B operand re-reads grow as the tile shrinks)
+    const long long gx = (N + NC - 1) / NC;
+    int bm = 128;
+    while (bm > 16 && (bm / 2 >= M || gx * ((M + bm - 1) / bm) < ctx->sm_count)) bm >>= 1;
+    switch (bm) {
+        case 128: launch_gemm_tc<CP, 128>(ctx, p); break;
+        case 64: launch_gemm_tc<CP, 64>(ctx, p); break;
+        case 32: launch_gemm_tc<CP, 32>(ctx, p); break;
+        default: launch_gemm_tc<CP, 16>(ctx, p); break;
+    }
 }
 template void gemm_tc<double>(qil_ctx*, int64_t, int64_t, int64_t, double, const double*, int64_t, const double*,
                               int64_t, double*, int64_t);
 template void gemm_tc<cplx>(qil_ctx*, int64_t, int64_t, int64_t, double, const cplx*, int64_t, const cplx*, int64_t,
                             cplx*, int64_t);
+
+// ------------------------------------------------------------------------------------------------
+// single-vector steps of a fixed-site chain (no grid row / column yet): bandwidth-bound GEMVs
+// ------------------------------------------------------------------------------------------------
+// y[i] = sum_j A[i * lda + j] * x[j],  i < rows, j < cols : one warp per row, lanes along the row
+template <typename T>
+__global__ void __launch_bounds__(256) gemv_rows_kernel(const T* __restrict__ A, long long lda, int rows, int cols,
+                                                        const T* __restrict__ x, T* __restrict__ y) {
+    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+    const int i = blockIdx.x * 8 + warp;
+    if (i >= rows) return;
+    const T* a = A + (long long)i * lda;
+    T acc = Scalar<T>::zero();
+    for (int j = lane; j < cols; j += 32) acc = Scalar<T>::fma(a[j], x[j], acc);
+    double* av = reinterpret_cast<double*>(&acc);
+#pragma unroll
+    for (int off = 16; off > 0; off >>= 1)
+#pragma unroll
+        for (int c = 0; c < (int)(sizeof(T) / sizeof(double)); ++c) av[c] += __shfl_xor_sync(0xffffffffu, av[c], off);
+    if (lane == 0) y[i] = acc;
+}
+// y[j] = sum_i x[i] * A[i * lda + j],  i < rows, j < cols : 32 columns per CTA, the 8 warps split the rows
+template <typename T>
+__global__ void __launch_bounds__(256) gemv_cols_kernel(const T* __restrict__ A, long long lda, int rows, int cols,
+                                                        const T* __restrict__ x, T* __restrict__ y) {
+    __shared__ T part[8][33];
+    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+    const int j = blockIdx.x * 32 + lane;
+    T acc = Scalar<T>::zero();
+    if (j < cols)
+        for (int i = warp; i < rows; i += 8) acc = Scalar<T>::fma(x[i], A[(long long)i * lda + j], acc);
+    part[warp][lane] = acc;
+    __syncthreads();
+    if (warp == 0 && j < cols) {
+        T s = part[0][lane];
+#pragma unroll
+        for (int w = 1; w < 8; ++w) s = Scalar<T>::add(s, part[w][lane]);
+        y[j] = s;
+    }
+}
+template <typename T>
+static void gemv_rows(qil_ctx* ctx, const T* A, int64_t lda, int64_t rows, int64_t cols, const T* x, T* y) {
+    gemv_rows_kernel<T><<<(unsigned)((rows + 7) / 8), 256, 0, ctx->stream>>>(A, lda, (int)rows, (int)cols, x, y);
+    QIL_LAUNCH_CHECK(ctx);
+}
+template <typename T>
+static void gemv_cols(qil_ctx* ctx, const T* A, int64_t lda, int64_t rows, int64_t cols, const T* x, T* y) {
+    gemv_cols_kernel<T><<<(unsigned)((cols + 31) / 32), 256, 0, ctx->stream>>>(A, lda, (int)rows, (int)cols, x, y);
+    QIL_LAUNCH_CHECK(ctx);
+}
 
 // ------------------------------------------------------------------------------------------------
 // helpers
@@ -268,12 +341,14 @@ static void coefficient_grid_impl(qil_ctx* ctx, const qil_mps* psi, const uint8_
         const T* core = reinterpret_cast<const T*>(psi->core[i]);
         if (mode[i] == 2) {
             Mat<T> Ln(ctx, cntL, 2 * cr);
-            gemm_tc<T>(ctx, cntL, 2 * cr, cl, 1.0, L.p, cl, core, 2 * cr, Ln.p, 2 * cr);
+            if (cntL == 1) gemv_cols<T>(ctx, core, 2 * cr, cl, 2 * cr, L.p, Ln.p);
+            else gemm_tc<T>(ctx, cntL, 2 * cr, cl, 1.0, L.p, cl, core, 2 * cr, Ln.p, 2 * cr);
             L = std::move(Ln);
             cntL *= 2;
         } else {
             Mat<T> Ln(ctx, cntL, cr);
-            gemm_tc<T>(ctx, cntL, cr, cl, 1.0, L.p, cl, core + (size_t)mode[i] * cr, 2 * cr, Ln.p, cr);
+            if (cntL == 1) gemv_cols<T>(ctx, core + (size_t)mode[i] * cr, 2 * cr, cl, cr, L.p, Ln.p);
+            else gemm_tc<T>(ctx, cntL, cr, cl, 1.0, L.p, cl, core + (size_t)mode[i] * cr, 2 * cr, Ln.p, cr);
             L = std::move(Ln);
         }
     }
@@ -287,12 +362,14 @@ static void coefficient_grid_impl(qil_ctx* ctx, const qil_mps* psi, const uint8_
         const T* core = reinterpret_cast<const T*>(psi->core[i]);
         if (mode[i] == 2) {
             Mat<T> Rn(ctx, 2 * cl, cntR);
-            gemm_tc<T>(ctx, 2 * cl, cntR, cr, 1.0, core, cr, R.p, cntR, Rn.p, cntR);
+            if (cntR == 1) gemv_rows<T>(ctx, core, cr, 2 * cl, cr, R.p, Rn.p);
+            else gemm_tc<T>(ctx, 2 * cl, cntR, cr, 1.0, core, cr, R.p, cntR, Rn.p, cntR);
             R = std::move(Rn);
             cntR *= 2;
         } else {
             Mat<T> Rn(ctx, cl, cntR);
-            gemm_tc<T>(ctx, cl, cntR, cr, 1.0, core + (size_t)mode[i] * cr, 2 * cr, R.p, cntR, Rn.p, cntR);
+            if (cntR == 1) gemv_rows<T>(ctx, core + (size_t)mode[i] * cr, 2 * cr, cl, cr, R.p, Rn.p);
+            else gemm_tc<T>(ctx, cl, cntR, cr, 1.0, core + (size_t)mode[i] * cr, 2 * cr, R.p, cntR, Rn.p, cntR);
             R = std::move(Rn);
         }
     }

@@ -21,6 +21,9 @@ x = torch.sin(1.0 * t) * torch.exp(-0.08 * t) + torch.sin(2.5 * t) * torch.exp(-
 del j, t
 bits = torch.from_numpy(bench.hash_bits(B, 2 * n)).to(dev)
 out_dev = torch.empty(B, dtype=torch.complex128, device=dev)
+scan_a = 10
+scan_mode, scan_bits = q.pole_scan_modes(n, 0, 2**n - 2**scan_a, scan_a, scan_a)
+scan_dev = torch.empty(4**scan_a, dtype=torch.complex128, device=dev)
 W = q.build_zt_mpo(n, bench.OMEGA_R, cutoff=bench.MPO_CUTOFF, maxdim=bench.MPO_MAXDIM, ctx=ctx)
 for it in range(2):
     torch.cuda.synchronize()
@@ -29,6 +32,7 @@ for it in range(2):
     z = q.ztmps_from_mps(psi, cutoff=bench.ALGO["cutoff"])
     o = q.apply(W, z)
     q.coefficients_dev(o, bits.data_ptr(), B, out_dev.data_ptr())
+    q.coefficient_grid_dev(o, scan_mode, scan_dev.data_ptr(), out_bit=scan_bits)
     torch.cuda.synchronize()
     torch.cuda.nvtx.range_pop()
 print("ok", psi.bonds, max(o.bonds))
