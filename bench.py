@@ -49,6 +49,9 @@ def parse():
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--batch", type=int, default=4,
                     help="signals of the pipelined-batch leg (independent signals overlap on worker streams); 0 = skip")
+    ap.add_argument("--comm", default="peer", choices=["peer", "nccl"],
+                    help="--shard-signal exchange steps: the library's own peer-memory kernels over NVLink (default) or "
+                         "NCCL through torch.distributed callbacks")
     ap.add_argument("--shard-signal", action="store_true",
                     help="N > 1: ONE signal row-sharded over the ranks (strong scaling, SURVEY.md 8e) instead of one "
                          "signal per rank (weak scaling, the default)")
@@ -239,7 +242,10 @@ def run_ours(args):
     comm = None
     if shard:
         from qilaplace_b200 import parallel
-        comm = parallel.TorchComm(ctx)
+        if args.comm == "peer":
+            comm = parallel.PeerComm(ctx, parallel.encode_exchange_bytes(N, ALGO["k"], ALGO["p"], False))
+        else:
+            comm = parallel.TorchComm(ctx)
 
     # ---- synthetic input: generated on the device, mirrored into pinned host memory for the e2e leg
     j = torch.arange(off, off + NL, dtype=torch.float64, device=dev)
@@ -480,7 +486,9 @@ def run_ours(args):
         "config": {"workload": f"C4 n={n} real sin_decay: signal_ztmps(:rsvd k=15 p=5 q=2 cutoff=1e-12) + zT apply "
                                f"(omega_r=2pi, MPO cutoff 1e-12 maxdim 128, built in setup); then {B} coefficients",
                    "signals_per_rank": (1.0 / world) if shard else 1,
-                   "sharding": ("one signal row-sharded over the ranks: TSQR all-gather + projection all-reduce over NCCL"
+                   "sharding": (("one signal row-sharded over the ranks: TSQR all-gather + projection all-reduce, "
+                                 + ("library kernels over NVLink peer memory (CUDA IPC)" if args.comm == "peer"
+                                    else "NCCL through torch.distributed callbacks"))
                                 if shard else "one signal per rank, no data-path collective"), "l2": "inputs (2 GiB signal) larger than L2", "zt_mpo_build_s": build_s,
                    "mps_bonds_max": max(psi.bonds), "zt_mpo_bonds_max": max(W.bonds), "out_bonds_max": max(out.bonds)},
         "e2e": {"value": e2e_value, "unit": "samples/s", "ms_per_step": ms_e2e / args.steps,
@@ -518,6 +526,8 @@ def run_ours(args):
                                     "sample": f"failed: {e}"}
     if rank == 0:
         print(json.dumps(line))
+    if shard and args.comm == "peer":
+        comm.close()
     if world > 1:
         dist.destroy_process_group()
 

@@ -43,6 +43,7 @@ extern "C" {
 typedef struct qil_ctx qil_ctx;
 typedef struct qil_mps qil_mps;
 typedef struct qil_mpo qil_mpo;
+typedef struct qil_peer qil_peer;
 
 /* ---- context ------------------------------------------------------------------------------- */
 const char* qil_last_error(void);
@@ -161,6 +162,17 @@ int qil_get_stream(qil_ctx* ctx, void** cuda_stream);
 int qil_encode_rsvd_sharded_dev(qil_ctx* ctx, const qil_comm* comm, int is_complex, const void* d_x_local,
                                 int64_t N_total, int k, int p, int q, int64_t seed, double cutoff, int64_t maxdim,
                                 int64_t mindim, const void* d_normal_stream, int64_t stream_len, qil_mps** out);
+
+/* Native implementation of the two collectives over NVLink peer memory (qil_peer.cu): every rank allocates a
+ * symmetric exchange buffer of `bytes` payload (>= the largest message: 16 * l * 2^ceil(n/2) bytes covers every
+ * exchange of an encode) and publishes its 64-byte CUDA-IPC handle; the host gathers the handles of all ranks in
+ * rank order (any transport) and passes them to qil_peer_connect.  qil_peer_comm then fills a qil_comm whose
+ * callbacks launch the library's own exchange kernels on the context's stream: the reduction runs inside the
+ * exchange kernel over the peers' memory, with flag-based arrival through the same mapping.  No NCCL involved. */
+int qil_peer_create(qil_ctx* ctx, int rank, int world, int64_t bytes, qil_peer** out, unsigned char* handle64);
+int qil_peer_connect(qil_peer* peer, const unsigned char* all_handles /* world * 64 bytes, rank order */);
+int qil_peer_comm(qil_peer* peer, qil_comm* out);
+int qil_peer_destroy(qil_peer* peer);
 
 /* Per-site copy-tensor split of signal_ztmps (SignalConverters.jl:258-277): n-site MPS -> 2n-site chain. */
 int qil_ztmps_split(qil_ctx* ctx, const qil_mps* psi, double cutoff, int64_t maxdim, qil_mps** out);

@@ -522,6 +522,34 @@ int qil_encode_rsvd_sharded_dev(qil_ctx* ctx, const qil_comm* comm, int is_compl
     QIL_API_END
 }
 
+int qil_peer_create(qil_ctx* ctx, int rank, int world, int64_t bytes, qil_peer** out, unsigned char* handle64) {
+    QIL_API_BEGIN
+    QIL_NONNULL(ctx); QIL_NONNULL(out); QIL_NONNULL(handle64);
+    QIL_CUDA(cudaSetDevice(ctx->device));
+    *out = peer_create(ctx, rank, world, bytes, handle64);
+    QIL_API_END
+}
+
+int qil_peer_connect(qil_peer* peer, const unsigned char* all_handles) {
+    QIL_API_BEGIN
+    QIL_NONNULL(peer); QIL_NONNULL(all_handles);
+    peer_connect(peer, all_handles);
+    QIL_API_END
+}
+
+int qil_peer_comm(qil_peer* peer, qil_comm* out) {
+    QIL_API_BEGIN
+    QIL_NONNULL(peer); QIL_NONNULL(out);
+    peer_fill_comm(peer, out);
+    QIL_API_END
+}
+
+int qil_peer_destroy(qil_peer* peer) {
+    QIL_API_BEGIN
+    peer_destroy(peer);
+    QIL_API_END
+}
+
 int qil_ztmps_split(qil_ctx* ctx, const qil_mps* psi, double cutoff, int64_t maxdim, qil_mps** out) {
     QIL_API_BEGIN
     QIL_NONNULL(ctx); QIL_NONNULL(psi); QIL_NONNULL(out);

@@ -162,6 +162,12 @@ qil_mpo* new_mpo(qil_ctx* ctx, int n, int is_complex, const int64_t* bond /* n+1
 void destroy(qil_mps* m);
 void destroy(qil_mpo* m);
 
+// native collectives over peer memory (qil_peer.cu)
+qil_peer* peer_create(qil_ctx* ctx, int rank, int world, int64_t bytes, unsigned char* handle64);
+void peer_connect(qil_peer* p, const unsigned char* all_handles);
+void peer_fill_comm(qil_peer* p, qil_comm* out);
+void peer_destroy(qil_peer* p);
+
 enum ProfId { PROF_STREAM_GEMM = 0, PROF_COEFF = 1, PROF_APPLY = 2, PROF_QR = 3, PROF_SVD = 4, PROF_COUNT = 5 };
 
 // Raise (never lower) a kernel's dynamic shared-memory limit.  The attribute is process-wide per function, so

@@ -150,6 +150,47 @@ class TorchComm:
         self.struct = _lib.QilComm(self.rank, self.world, None, self._cb[0], self._cb[1])
 
 
+class PeerComm:
+    """struct qil_comm implemented by the library itself over NVLink peer memory (qil_peer.cu): exchange buffers are
+    shared between the ranks through CUDA IPC, the all-reduce / all-gather are the library's own kernels (the
+    reduction runs inside the exchange kernel).  torch.distributed is used ONCE, to swap the 64-byte IPC handles."""
+
+    def __init__(self, ctx, payload_bytes, group=None):
+        import ctypes as C
+        from . import _lib
+        dist = _dist()
+        self.ctx, self.group = ctx, group
+        self.rank, self.world = dist.get_rank(group), dist.get_world_size(group)
+        self.error = None
+        self.handle = C.c_void_p()
+        mine = (C.c_ubyte * 64)()
+        _lib.call("qil_peer_create", ctx.handle, self.rank, self.world, C.c_int64(int(payload_bytes)),
+                  C.byref(self.handle), mine)
+        handles = [None] * self.world
+        dist.all_gather_object(handles, bytes(mine), group=group)
+        blob = (C.c_ubyte * (64 * self.world)).from_buffer_copy(b"".join(handles))
+        _lib.call("qil_peer_connect", self.handle, blob)
+        self.struct = _lib.QilComm()
+        _lib.call("qil_peer_comm", self.handle, C.byref(self.struct))
+        dist.barrier(group=group)          # every rank is mapped before the first kernel raises a flag
+        self.calls = {"native": True}
+
+    def close(self):
+        from . import _lib
+        if self.handle:
+            _dist().barrier(group=self.group)   # nobody unmaps while a peer may still read
+            _lib.load().qil_peer_destroy(self.handle)
+            self.handle = None
+
+
+def encode_exchange_bytes(N_total, k, p, is_complex):
+    """Payload a PeerComm needs for signal_mps_sharded_dev: the largest message is the C x l partial projection
+    (or the R x r block of U, which is smaller)."""
+    n = int(round(np.log2(N_total)))
+    C = 2 ** (n - n // 2)
+    return 16 * (2 if is_complex else 1) * (k + p) * C
+
+
 def signal_mps_sharded_dev(comm, d_x_local, N_total, is_complex, cutoff=1e-15, maxdim=None, k=20, p=10, q=0,
                            random_seed=1234, mindim=1):
     """signal_mps(x; method=:rsvd) for ONE signal whose rank-th contiguous chunk of N_total / world samples lives at

@@ -22,7 +22,7 @@ def _signal(n, cplx):
     return x * np.exp(0.3j * t) if cplx else x
 
 
-def _worker(rank, world, port, ret, default_stream=False):
+def _worker(rank, world, port, ret, default_stream=False, peer=False):
     sys.path.insert(0, ROOT)
     sys.path.insert(0, os.path.join(ROOT, "oracle"))
     os.environ["MASTER_ADDR"] = "127.0.0.1"
@@ -40,7 +40,10 @@ def _worker(rank, world, port, ret, default_stream=False):
     try:
         # own stream, or torch's (legacy default) stream like bench.py
         ctx = q.Context(dev, stream=torch.cuda.current_stream().cuda_stream) if default_stream else q.Context(dev)
-        comm = parallel.TorchComm(ctx)
+        if peer:      # the library's own exchange kernels over CUDA-IPC peer memory
+            comm = parallel.PeerComm(ctx, parallel.encode_exchange_bytes(2**22, 15, 5, True))
+        else:
+            comm = parallel.TorchComm(ctx)
         for n, cplx, qit in ((20, False, 2), (21, True, 1), (22, False, 0)):
             N = 2**n
             x = _signal(n, cplx)
@@ -62,17 +65,21 @@ def _worker(rank, world, port, ret, default_stream=False):
             vref = O.mps_to_vector(ref, cref)
             assert np.abs(v - vref).max() < 1e-10 * np.abs(vref).max()
             assert np.linalg.norm(v - x) < 1e-5 * np.linalg.norm(x)
-        assert comm.calls["allreduce"] > 0 and comm.calls["allgather"] > 0
+        if peer:
+            comm.close()
+        else:
+            assert comm.calls["allreduce"] > 0 and comm.calls["allgather"] > 0
         ret[rank] = "ok"
     finally:
         dist.destroy_process_group()
 
 
-@pytest.mark.parametrize("world,default_stream", [(1, False), (2, False), (2, True)])
-def test_row_sharded_encode_matches_single_device_and_oracle(world, default_stream):
+@pytest.mark.parametrize("world,default_stream,peer", [(1, False, False), (2, False, False), (2, True, False),
+                                                       (1, False, True), (2, False, True), (2, True, True)])
+def test_row_sharded_encode_matches_single_device_and_oracle(world, default_stream, peer):
     import torch.multiprocessing as mp
-    port = 33500 + (os.getpid() % 2000) + 2 * world + int(default_stream)
+    port = 33500 + (os.getpid() % 2000) + 4 * world + 2 * int(default_stream) + int(peer)
     mgr = mp.Manager()
     ret = mgr.dict()
-    mp.spawn(_worker, args=(world, port, ret, default_stream), nprocs=world, join=True)
+    mp.spawn(_worker, args=(world, port, ret, default_stream, peer), nprocs=world, join=True)
     assert dict(ret) == {r: "ok" for r in range(world)}
