@@ -13,6 +13,7 @@
 #include "qil_mpsops.cuh"
 
 #include <atomic>
+#include <cstdlib>
 #include <thread>
 
 namespace qil {
@@ -289,6 +290,51 @@ static Mat<T> mul_AH(SplitCtx<T>& sc, const T* A, int64_t R, int64_t C, int l, c
     return Z;
 }
 
+// ---- rank-adaptive sketch width ------------------------------------------------------------------------
+// After the first QR of Y = A Omega the diagonal of R tells how many sketch directions carry anything: for a
+// Gaussian Omega every column beyond the numerical rank rho of A lies in the span of the first rho up to rounding,
+// so |R_jj| <= ~eps * max|R_ii| there.  Such directions give rows of B = Q^H A at the rounding level, i.e. singular
+// values whose squares are <= ~1e-26 of the total and are removed by ANY positive cutoff; dropping them right away
+// leaves the kept singular triplets unchanged to rounding while every later pass over A, QR and SVD works on
+// l' = (last significant column) + 1 columns instead of k + p.  Only done when the truncation rule is guaranteed to
+// discard them anyway (cutoff >= 1e-18, and never below mindim); full-rank inputs keep all k + p columns.
+constexpr double kSketchNoise = 1e-13;
+template <typename T>
+__global__ void sketch_width_kernel(const T* __restrict__ R, int l, long long ld, double thr, int* out) {
+    if (threadIdx.x == 0 && blockIdx.x == 0) {
+        double mx = 0.0;
+        for (int j = 0; j < l; ++j) mx = fmax(mx, sqrt(Scalar<T>::abs2(R[(long long)j * ld + j])));
+        int keep = 1;
+        for (int j = 0; j < l; ++j)
+            if (sqrt(Scalar<T>::abs2(R[(long long)j * ld + j])) > thr * mx) keep = j + 1;
+        out[0] = keep;
+    }
+}
+// l' for the R factor of the first sketch (host read-back); Q (rows x l) is compacted to its first l' columns
+template <typename T>
+static int shrink_sketch(qil_ctx* ctx, const RsvdOpts& o, int l, int64_t rows, Mat<T>& Q, const Mat<T>& Rr) {
+    static const bool disabled = [] { const char* e = getenv("QIL_RSVD_ADAPTIVE"); return e && e[0] == '0'; }();
+    if (disabled || !(o.cutoff >= 1e-18) || l <= 1) return l;
+    int* d_keep = (int*)ctx->alloc(sizeof(int));
+    sketch_width_kernel<T><<<1, 32, 0, ctx->stream>>>(Rr.p, l, Rr.cols, kSketchNoise, d_keep);
+    QIL_LAUNCH_CHECK(ctx);
+    int keep = l;
+    QIL_CUDA(cudaMemcpyAsync(&keep, d_keep, sizeof(int), cudaMemcpyDeviceToHost, ctx->stream));
+    ctx->sync();
+    ctx->free(d_keep);
+    // a few of the noise-level columns stay as oversampling: the conditioning of the first QR (kappa(Y) ~ sigma_1 /
+    // sigma_rho) otherwise shows up at the 1e-10 level when there is no power iteration to clean the basis
+    static const int margin = [] { const char* e = getenv("QIL_RSVD_MARGIN"); return e ? atoi(e) : 3; }();
+    keep = std::min(l, keep + margin);
+    keep = (int)std::max<int64_t>(keep, std::min<int64_t>(o.mindim, l));
+    if (keep >= l) return l;
+    Mat<T> Qc(ctx, rows, keep);
+    QIL_CUDA(cudaMemcpy2DAsync(Qc.p, (size_t)keep * sizeof(T), Q.p, (size_t)l * sizeof(T), (size_t)keep * sizeof(T),
+                               (size_t)rows, cudaMemcpyDeviceToDevice, ctx->stream));
+    Q = std::move(Qc);
+    return keep;
+}
+
 // rsvd of A (R x C contiguous): U (R x r), SVh (r x C).  `top` => A is the raw signal (scale by 1/||x||,
 // sum of squares fused into the first pass when the streaming kernel is used).
 template <typename T>
@@ -296,8 +342,8 @@ static int rsvd_split(SplitCtx<T>& sc, const T* A, int64_t R, int64_t C, bool to
                       Mat<T>* Vh = nullptr, Mat<double>* S = nullptr) {
     qil_ctx* ctx = sc.ctx;
     const RsvdOpts& o = *sc.o;
-    const int l = (int)std::min<int64_t>((int64_t)o.k + o.p, std::min(R, C));
-    QIL_REQUIRE(l >= 1, QIL_ERR_RUNTIME, "In `rsvd`, left or right index set is empty.");
+    const int l0 = (int)std::min<int64_t>((int64_t)o.k + o.p, std::min(R, C));
+    QIL_REQUIRE(l0 >= 1, QIL_ERR_RUNTIME, "In `rsvd`, left or right index set is empty.");
     if (std::min(R, C) <= (int64_t)o.k + o.p) {
         // l == min(R, C): the sketch spans the whole row/column space, so the randomized SVD IS the truncated
         // SVD of A (to rounding, for any Omega).  Skip the sketch/QR/projection chain.
@@ -314,9 +360,9 @@ static int rsvd_split(SplitCtx<T>& sc, const T* A, int64_t R, int64_t C, bool to
         }
         return r;
     }
-    if (sc.stream) QIL_REQUIRE(C * (int64_t)l <= sc.stream_len, QIL_ERR_ARGUMENT,
-                               "rsvd: the supplied normal stream is shorter than %lld", (long long)(C * l));
-    Mat<T> Y = mul_A<T>(sc, A, R, C, l, nullptr, top && !sc.nrm_ready);
+    if (sc.stream) QIL_REQUIRE(C * (int64_t)l0 <= sc.stream_len, QIL_ERR_ARGUMENT,
+                               "rsvd: the supplied normal stream is shorter than %lld", (long long)(C * l0));
+    Mat<T> Y = mul_A<T>(sc, A, R, C, l0, nullptr, top && !sc.nrm_ready);
     if (top && !sc.nrm_ready) {
         // generic path: the norm needs its own pass
         const double c = device_norm2<T>(ctx, A, R * C);
@@ -325,7 +371,8 @@ static int rsvd_split(SplitCtx<T>& sc, const T* A, int64_t R, int64_t C, bool to
         sc.nrm_ready = true;
     }
     Mat<T> Q, Rr;
-    qr_thin<T>(ctx, R, l, Y.p, l, true, Q, Rr);
+    qr_thin<T>(ctx, R, l0, Y.p, l0, true, Q, Rr);
+    const int l = shrink_sketch<T>(ctx, o, l0, R, Q, Rr);
     for (int it = 0; it < o.q; ++it) {
         Mat<T> Z = mul_AH<T>(sc, A, R, C, l, Q.p, nullptr);
         Mat<T> Qz, Rz;
@@ -348,7 +395,7 @@ static int rsvd_split(SplitCtx<T>& sc, const T* A, int64_t R, int64_t C, bool to
 // are all-gathered; the l x C projections B = Q^H X (and Z = X^H Q of a power iteration) are sums of per-rank
 // partials (all-reduce).  Everything below the top split is small and runs replicated on every rank.
 template <typename T>
-static void tsqr_sharded(SplitCtx<T>& sc, const Mat<T>& Y, int64_t Rg, int l, Mat<T>& Q) {
+static void tsqr_sharded(SplitCtx<T>& sc, const Mat<T>& Y, int64_t Rg, int l, Mat<T>& Q, Mat<T>* Rout = nullptr) {
     qil_ctx* ctx = sc.ctx;
     constexpr int F = Scalar<T>::is_complex ? 2 : 1;
     const int G = sc.comm->world, g = sc.comm->rank;
@@ -360,6 +407,7 @@ static void tsqr_sharded(SplitCtx<T>& sc, const Mat<T>& Y, int64_t Rg, int l, Ma
     qr_thin<T>(ctx, (int64_t)G * l, l, Rall.p, l, true, Q2, R2);
     Q = Mat<T>(ctx, Rg, l);
     gemm<T>(ctx, OP_N, OP_N, Rg, l, l, 1.0, Qg.p, l, Q2.p + (size_t)g * l * l, l, 0.0, Q.p, l);
+    if (Rout) *Rout = std::move(R2);
 }
 
 // A = this rank's Rg x C row block.  Returns the rank r; U is the FULL (G*Rg) x r factor, SVh is r x C (both replicated).
@@ -370,15 +418,16 @@ static int rsvd_split_sharded(SplitCtx<T>& sc, const T* A, int64_t Rg, int64_t C
     constexpr int F = Scalar<T>::is_complex ? 2 : 1;
     const int G = sc.comm->world;
     const int64_t R = Rg * G;
-    const int l = (int)std::min<int64_t>((int64_t)o.k + o.p, std::min(R, C));
-    QIL_REQUIRE(Rg >= l && stream_supported(Rg, C * F, C * F, l * F), QIL_ERR_UNSUPPORTED,
+    const int l0 = (int)std::min<int64_t>((int64_t)o.k + o.p, std::min(R, C));
+    QIL_REQUIRE(Rg >= l0 && stream_supported(Rg, C * F, C * F, l0 * F), QIL_ERR_UNSUPPORTED,
                 "sharded encode: a %lld x %lld row block per rank is too small for k+p = %d; encode on one device",
-                (long long)Rg, (long long)C, l);
-    if (sc.stream) QIL_REQUIRE(C * (int64_t)l <= sc.stream_len, QIL_ERR_ARGUMENT,
-                               "rsvd: the supplied normal stream is shorter than %lld", (long long)(C * l));
-    Mat<T> Y = mul_A<T>(sc, A, Rg, C, l, nullptr, true);
-    Mat<T> Q;
-    tsqr_sharded<T>(sc, Y, Rg, l, Q);
+                (long long)Rg, (long long)C, l0);
+    if (sc.stream) QIL_REQUIRE(C * (int64_t)l0 <= sc.stream_len, QIL_ERR_ARGUMENT,
+                               "rsvd: the supplied normal stream is shorter than %lld", (long long)(C * l0));
+    Mat<T> Y = mul_A<T>(sc, A, Rg, C, l0, nullptr, true);
+    Mat<T> Q, Rtop;
+    tsqr_sharded<T>(sc, Y, Rg, l0, Q, &Rtop);
+    const int l = shrink_sketch<T>(ctx, o, l0, Rg, Q, Rtop);      // Rtop is replicated: every rank picks the same l'
     for (int it = 0; it < o.q; ++it) {
         Mat<T> Z = mul_AH<T>(sc, A, Rg, C, l, Q.p, nullptr);
         comm_allreduce(sc.comm, Z.p, C * l * F);
