@@ -358,6 +358,10 @@ def run_ours(args):
     scan_check = float(_np.abs(_got - _chk).max() / max(_np.abs(_chk).max(), 1e-300))
     assert scan_check < 1e-9, f"pole scan disagrees with the chain kernel: {scan_check}"
 
+    ctx.truncation_margin(reset=True)
+    step_device()
+    ctx.sync()
+    trunc_margin = ctx.truncation_margin(reset=True)     # closest cutoff decision of one encode + split
     log(f"warm-up done: MPS bonds {state['psi'].bonds}, zT output max bond {max(state['out'].bonds)}")
     # ---- timed: device-resident (`value`), with per-kernel-class events for the roofline
     sampler = ClockSampler(local)
@@ -490,7 +494,7 @@ def run_ours(args):
                                  + ("library kernels over NVLink peer memory (CUDA IPC)" if args.comm == "peer"
                                     else "NCCL through torch.distributed callbacks"))
                                 if shard else "one signal per rank, no data-path collective"), "l2": "inputs (2 GiB signal) larger than L2", "zt_mpo_build_s": build_s,
-                   "mps_bonds_max": max(psi.bonds), "zt_mpo_bonds_max": max(W.bonds), "out_bonds_max": max(out.bonds)},
+                   "mps_bonds": psi.bonds, "truncation_margin": trunc_margin, "mps_bonds_max": max(psi.bonds), "zt_mpo_bonds_max": max(W.bonds), "out_bonds_max": max(out.bonds)},
         "e2e": {"value": e2e_value, "unit": "samples/s", "ms_per_step": ms_e2e / args.steps,
                 "h2d_bytes_per_step": int(8 * NL), "d2h_bytes_per_step": host_bytes},
         "gpu_launches": int(launches),

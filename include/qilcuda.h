@@ -68,6 +68,13 @@ int qil_profile_read(qil_ctx* ctx, int kernel_class, double* total_ms, int64_t* 
 int qil_profile_read_work(qil_ctx* ctx, int kernel_class, double* total_ms, int64_t* launches, double* bytes,
                           double* flops);
 
+/* Closest truncation decision since the last reset, over every cutoff-ruled SVD the context has run (encoders, split,
+ * compress, builders): min |w / (cutoff * sum sigma^2) - 1| where w is the discarded weight with and without the last
+ * kept value.  Two correct implementations whose sigma^2 agree to better than this relative amount choose the same
+ * bond dimensions; a value near rounding level flags a knife-edge rank ("rank parity").
+ * 1e300 = no decision taken.  reset != 0 clears it after reading. */
+int qil_truncation_margin(qil_ctx* ctx, int reset, double* out);
+
 /* ---- MPS / MPO containers (replace Vector{ITensor} storage; src/mps.jl:70-130, src/mpo.jl:26-99) -- */
 /* bond has n+1 entries with bond[0] == bond[n] == 1; cores[i] points at bond[i]*2*bond[i+1] scalars */
 int qil_mps_from_host(qil_ctx* ctx, int n, int is_complex, const int64_t* bond,

@@ -46,6 +46,7 @@ _SIGS = {
     "qil_destroy": [c_ctx],
     "qil_sync": [c_ctx],
     "qil_launch_count": [c_ctx, C.POINTER(C.c_uint64)],
+    "qil_truncation_margin": [c_ctx, C.c_int, C.POINTER(C.c_double)],
     "qil_profile_enable": [c_ctx, C.c_int],
     "qil_profile_reset": [c_ctx],
     "qil_profile_read": [c_ctx, C.c_int, C.POINTER(C.c_double), i64p],

@@ -41,6 +41,12 @@ class Context:
         call("qil_launch_count", self.handle, C.byref(v))
         return int(v.value)
 
+    def truncation_margin(self, reset=True):
+        """Closest cutoff decision since the last reset (qil_truncation_margin); inf if none was taken."""
+        v = C.c_double()
+        call("qil_truncation_margin", self.handle, 1 if reset else 0, C.byref(v))
+        return float("inf") if v.value >= 1e299 else float(v.value)
+
     def profile_enable(self, on=True):
         call("qil_profile_enable", self.handle, 1 if on else 0)
 

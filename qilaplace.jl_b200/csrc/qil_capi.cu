@@ -106,6 +106,11 @@ static int create_impl(int device, void* stream, bool have_stream, qil_ctx** out
         QIL_CUDA(cudaStreamCreateWithFlags(&ctx->stream, cudaStreamNonBlocking));
         ctx->own_stream = true;
     }
+    {
+        const double inf = 1e300;
+        QIL_CUDA(cudaMalloc(&ctx->d_margin, sizeof(double)));
+        QIL_CUDA(cudaMemcpy(ctx->d_margin, &inf, sizeof(double), cudaMemcpyHostToDevice));
+    }
     // keep freed blocks in the pool instead of returning them to the driver at every sync
     cudaMemPool_t pool;
     if (cudaDeviceGetDefaultMemPool(&pool, device) == cudaSuccess) {
@@ -126,6 +131,8 @@ int qil_destroy(qil_ctx* ctx) {
     if (!ctx) return QIL_OK;
     cudaSetDevice(ctx->device);
     cudaStreamSynchronize(ctx->stream);
+    ctx->release_aux();
+    if (ctx->d_margin) cudaFree(ctx->d_margin);
     if (ctx->scratch) cudaFreeAsync(ctx->scratch, ctx->stream);
     cudaStreamSynchronize(ctx->stream);
     if (ctx->own_stream) cudaStreamDestroy(ctx->stream);
@@ -145,6 +152,20 @@ int qil_launch_count(qil_ctx* ctx, uint64_t* out) {
     QIL_NONNULL(ctx);
     QIL_NONNULL(out);
     *out = ctx->launches;
+    QIL_API_END
+}
+
+int qil_truncation_margin(qil_ctx* ctx, int reset, double* out) {
+    QIL_API_BEGIN
+    QIL_NONNULL(ctx); QIL_NONNULL(out);
+    QIL_CUDA(cudaSetDevice(ctx->device));
+    ctx->sync();
+    for (qil_ctx* a : ctx->aux) a->sync();
+    QIL_CUDA(cudaMemcpy(out, ctx->d_margin, sizeof(double), cudaMemcpyDeviceToHost));
+    if (reset) {
+        const double inf = 1e300;
+        QIL_CUDA(cudaMemcpy(ctx->d_margin, &inf, sizeof(double), cudaMemcpyHostToDevice));
+    }
     QIL_API_END
 }
 

@@ -120,6 +120,16 @@ struct qil_ctx {
     void prof_begin(int id, double bytes = 0.0, double flops = 0.0);
     void prof_end();
 
+    // closest truncation decision since the last reset (device scalar, shared with the auxiliary contexts):
+    // min over all cutoff decisions of |discarded-or-kept weight / (cutoff * total) - 1|  -- see truncation_margin
+    double* d_margin = nullptr;
+
+    // auxiliary contexts (own non-blocking stream each) for independent sub-problems run by worker threads
+    bool is_aux = false;
+    std::vector<qil_ctx*> aux;
+    qil_ctx* aux_ctx(int w);             // created on first use, destroyed with the context
+    void release_aux();
+
     void* alloc(size_t bytes);           // stream-ordered device allocation
     void free(void* p);                  // stream-ordered free
     void* get_scratch(size_t bytes);     // grow-only scratch (valid until next get_scratch)
@@ -169,6 +179,37 @@ void peer_fill_comm(qil_peer* p, qil_comm* out);
 void peer_destroy(qil_peer* p);
 
 enum ProfId { PROF_STREAM_GEMM = 0, PROF_COEFF = 1, PROF_APPLY = 2, PROF_QR = 3, PROF_SVD = 4, PROF_COUNT = 5 };
+
+// NDTensors truncate!! on P = sigma^2 (descending): drop while n > maxdim, then while the discarded weight stays
+// <= cutoff * sum(P) and n > mindim (relative, cumulative).  `margin` (optional device scalar) receives, by atomic
+// min, how close the cutoff rule came to deciding otherwise: min(|w_keep / t - 1|, |w_drop / t - 1|) with
+// t = cutoff * sum(P), w_keep = discarded weight if the last kept value were dropped too, w_drop = discarded weight.
+// Two implementations whose sigma^2 differ by less than that relative amount pick the same rank.
+__device__ inline int truncate_rank_dev(const double* sig, int n, double cutoff, long long maxdim, long long mindim,
+                                        double* margin = nullptr) {
+    if (n <= 1) return n;
+    int r = n;
+    double err = 0.0;
+    while ((long long)r > maxdim) { err += sig[r - 1] * sig[r - 1]; --r; }
+    double scale = 0.0;
+    for (int i = 0; i < n; ++i) scale += sig[i] * sig[i];
+    if (scale == 0.0) scale = 1.0;
+    const double t = cutoff * scale;
+    bool dropped = false;
+    while ((long long)r > mindim && err + sig[r - 1] * sig[r - 1] <= t) {
+        err += sig[r - 1] * sig[r - 1];
+        --r;
+        dropped = true;
+    }
+    if (r < 1) r = 1;
+    if (margin && t > 0.0) {
+        double m = 1e300;
+        if ((long long)r > mindim) m = fmin(m, fabs((err + sig[r - 1] * sig[r - 1]) / t - 1.0));   // kept by the cutoff
+        if (dropped) m = fmin(m, fabs(err / t - 1.0));                                            // dropped by it
+        if (m < 1e300) atomicMin(reinterpret_cast<unsigned long long*>(margin), (unsigned long long)__double_as_longlong(m));
+    }
+    return r;
+}
 
 // Raise (never lower) a kernel's dynamic shared-memory limit.  The attribute is process-wide per function, so
 // concurrent host threads (batched encode) must not shrink what another thread is about to launch with; keeping

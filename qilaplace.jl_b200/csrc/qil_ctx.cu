@@ -44,6 +44,32 @@ void qil_ctx::prof_end() {
     QIL_CUDA(cudaEventRecord(prof.back().e1, stream));
 }
 
+qil_ctx* qil_ctx::aux_ctx(int w) {
+    while ((int)aux.size() <= w) {
+        qil_ctx* a = new qil_ctx();
+        a->device = device;
+        a->sm_count = sm_count;
+        a->smem_optin = smem_optin;
+        a->own_stream = true;
+        a->is_aux = true;
+        a->d_margin = d_margin;
+        QIL_CUDA(cudaStreamCreateWithFlags(&a->stream, cudaStreamNonBlocking));
+        aux.push_back(a);
+    }
+    return aux[w];
+}
+
+void qil_ctx::release_aux() {
+    for (qil_ctx* a : aux) {
+        cudaStreamSynchronize(a->stream);
+        if (a->scratch) cudaFreeAsync(a->scratch, a->stream);
+        cudaStreamSynchronize(a->stream);
+        cudaStreamDestroy(a->stream);
+        delete a;
+    }
+    aux.clear();
+}
+
 void qil_ctx::sync() { QIL_CUDA(cudaStreamSynchronize(stream)); }
 
 namespace qil {

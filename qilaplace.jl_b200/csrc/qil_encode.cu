@@ -481,6 +481,7 @@ static void dc_encode(SplitCtx<T>& sc, std::vector<DcNode<T>> level, std::vector
         std::vector<size_t> batch_node;
         std::vector<Mat<T>> Us(level.size()), SVs(level.size());
         std::vector<int> ranks(level.size(), 0);
+        std::vector<size_t> heavy;
         for (size_t i = 0; i < level.size(); ++i) {
             DcNode<T>& nd = level[i];
             if (nd.first == nd.last) {
@@ -504,8 +505,59 @@ static void dc_encode(SplitCtx<T>& sc, std::vector<DcNode<T>> level, std::vector
                 batch.push_back(std::move(it));
                 batch_node.push_back(i);
             } else {
-                ranks[i] = rsvd_split<T>(sc, nd.ptr, R, C, nd.top, Us[i], &SVs[i]);
+                heavy.push_back(i);
             }
+        }
+        // randomized splits of one level are independent: run them on worker threads, one auxiliary stream each
+        // (each split is a chain of small dependent launches with a host read-back of its rank)
+        auto split_node = [&](SplitCtx<T>& s, size_t i) {
+            DcNode<T>& nd = level[i];
+            const int mid = (nd.first + nd.last + 1) / 2 - 1;
+            const int nl = mid - nd.first + 1, nr = nd.last - mid;
+            const int64_t R = nd.lb << nl, C = ((int64_t)1 << nr) * nd.rb;
+            ranks[i] = rsvd_split<T>(s, nd.ptr, R, C, nd.top, Us[i], &SVs[i]);
+        };
+        const int nworkers = (int)std::min<size_t>(heavy.size(), 4);
+        if (nworkers >= 2 && !ctx->is_aux && !sc.comm) {
+            cudaEvent_t ready;
+            QIL_CUDA(cudaEventCreateWithFlags(&ready, cudaEventDisableTiming));
+            QIL_CUDA(cudaEventRecord(ready, ctx->stream));
+            std::vector<int> code(nworkers, QIL_OK);
+            std::vector<std::string> err(nworkers);
+            std::vector<qil_ctx*> sub(nworkers);
+            for (int w = 0; w < nworkers; ++w) {
+                sub[w] = ctx->aux_ctx(w);
+                QIL_CUDA(cudaStreamWaitEvent(sub[w]->stream, ready, 0));
+            }
+            auto body = [&](int w) {
+                try {
+                    QIL_CUDA(cudaSetDevice(ctx->device));
+                    SplitCtx<T> s = sc;
+                    s.ctx = sub[w];
+                    for (size_t h = w; h < heavy.size(); h += nworkers) split_node(s, heavy[h]);
+                } catch (const Error& e) {
+                    code[w] = e.code; err[w] = e.msg;
+                } catch (const std::exception& e) {
+                    code[w] = QIL_ERR_RUNTIME; err[w] = e.what();
+                }
+            };
+            std::vector<std::thread> th;
+            for (int w = 1; w < nworkers; ++w) th.emplace_back(body, w);
+            body(0);
+            for (auto& t : th) t.join();
+            for (int w = 0; w < nworkers; ++w) {
+                // the parent stream continues after everything the worker enqueued
+                QIL_CUDA(cudaEventRecord(ready, sub[w]->stream));
+                QIL_CUDA(cudaStreamWaitEvent(ctx->stream, ready, 0));
+                ctx->launches += sub[w]->launches;
+                sub[w]->launches = 0;
+            }
+            cudaEventDestroy(ready);
+            for (size_t h : heavy) { Us[h].ctx = ctx; SVs[h].ctx = ctx; }     // results live on the parent context
+            for (int w = 0; w < nworkers; ++w)
+                if (code[w] != QIL_OK) throw Error(code[w], err[w]);
+        } else {
+            for (size_t h : heavy) split_node(sc, h);
         }
         svd_small_batch<T>(ctx, batch, o.cutoff, o.maxdim, o.mindim);
         for (size_t b = 0; b < batch.size(); ++b) {
@@ -642,6 +694,8 @@ void encode_rsvd_batch(qil_ctx* ctx, const T* d_x, int64_t N, int64_t count, con
         sub[w].sm_count = ctx->sm_count;
         sub[w].smem_optin = ctx->smem_optin;
         sub[w].own_stream = true;
+        sub[w].d_margin = ctx->d_margin;
+        sub[w].is_aux = true;                 // no nested worker threads below a batch worker
         QIL_CUDA(cudaStreamCreateWithFlags(&sub[w].stream, cudaStreamNonBlocking));
         QIL_CUDA(cudaStreamWaitEvent(sub[w].stream, ready, 0));
     }

@@ -16,23 +16,6 @@ constexpr int kJacThreads = 256;        // shared-memory variant
 constexpr int kJacThreadsGlobal = 1024; // single-CTA variant working on an L2-resident scratch copy
 constexpr int kMaxSweeps = 60;
 
-// NDTensors truncate!! on P = sigma^2 (descending): drop while n > maxdim, then while the discarded
-// weight stays <= cutoff * sum(P) and n > mindim.
-__device__ inline int truncate_rank_dev(const double* sig, int n, double cutoff, long long maxdim, long long mindim) {
-    if (n <= 1) return n;
-    int r = n;
-    double err = 0.0;
-    while ((long long)r > maxdim) { err += sig[r - 1] * sig[r - 1]; --r; }
-    double scale = 0.0;
-    for (int i = 0; i < n; ++i) scale += sig[i] * sig[i];
-    if (scale == 0.0) scale = 1.0;
-    while ((long long)r > mindim && err + sig[r - 1] * sig[r - 1] <= cutoff * scale) {
-        err += sig[r - 1] * sig[r - 1];
-        --r;
-    }
-    return r < 1 ? 1 : r;
-}
-
 template <typename T>
 struct JacParams {
     const T* R;      // ns x ns row-major (ld); the kernel works on G = R^H
@@ -43,6 +26,7 @@ struct JacParams {
     T* W;            // out: ns x ns row-major, W = G V (same column order)
     double* S;       // out: ns singular values, descending
     int* rank;       // out: kept rank
+    double* margin;  // closest truncation decision (atomic min), may be null
     double cutoff;
     long long maxdim, mindim;
     int gl;          // lanes per column pair (8, 16 or 32)
@@ -191,7 +175,7 @@ __global__ void __launch_bounds__(GLOBAL ? kJacThreadsGlobal : kJacThreads) jaco
         p.S[j] = mine[cnt++];
     }
     __syncthreads();
-    if (tid == 0) *p.rank = truncate_rank_dev(sig, ns, p.cutoff, p.maxdim, p.mindim);
+    if (tid == 0) *p.rank = truncate_rank_dev(sig, ns, p.cutoff, p.maxdim, p.mindim, p.margin);
     // outputs: row-major with sorted columns
     for (int idx = tid; idx < ns * ns; idx += kJacThreads) {
         const int i = idx / ns, j = idx - i * ns;
@@ -238,6 +222,7 @@ static int jacobi_square(qil_ctx* ctx, int ns, const T* R, int64_t ld, double cu
     JacParams<T> p;
     p.R = R; p.ld = ld; p.ns = ns; p.pad = ns | 1; p.V = V.p; p.W = W.p; p.S = S.p; p.rank = d_rank;
     p.cutoff = cutoff; p.maxdim = maxdim; p.mindim = std::max<int64_t>(mindim, 1);
+    p.margin = ctx->d_margin;
     p.gl = ns <= 32 ? 8 : (ns <= 64 ? 16 : 32);
     p.gscratch = use_global ? gscratch.p : nullptr;
     if (use_global) {

@@ -28,6 +28,7 @@ struct SmallSvdParams {
     T* SVh;          // r x n   or null
     double* S;       // min(m,n) values (first r meaningful) or null
     int* rank;
+    double* margin;  // closest truncation decision (atomic min), may be null
     int mode;        // 0: A is the matrix; 1: A is an MPS core [cl][2][cr] and the matrix is the copy tensor
     int cl, cr;      //    T[(l,s),(s',r)] = delta(s,s') core[l,s,r]  (signal_ztmps, SignalConverters.jl:263)
 };
@@ -57,21 +58,6 @@ template <> __device__ __forceinline__ cplx gsum<cplx>(cplx v, int gl, unsigned 
         v.y += __shfl_xor_sync(mask, v.y, o);
     }
     return v;
-}
-
-__device__ inline int trunc_rank_small(const double* sig, int n, double cutoff, long long maxdim, long long mindim) {
-    if (n <= 1) return n;
-    int r = n;
-    double err = 0.0;
-    while ((long long)r > maxdim) { err += sig[r - 1] * sig[r - 1]; --r; }
-    double scale = 0.0;
-    for (int i = 0; i < n; ++i) scale += sig[i] * sig[i];
-    if (scale == 0.0) scale = 1.0;
-    while ((long long)r > mindim && err + sig[r - 1] * sig[r - 1] <= cutoff * scale) {
-        err += sig[r - 1] * sig[r - 1];
-        --r;
-    }
-    return r < 1 ? 1 : r;
 }
 
 template <typename T>
@@ -214,7 +200,7 @@ __device__ __forceinline__ void svd_small_body(const SmallSvdParams<T>& p, unsig
     if (tid < nt) { order[mypos] = tid; sig[mypos] = mysig; }
     __syncthreads();
     if (tid == 0) {
-        s_rank = trunc_rank_small(sig, nt, p.cutoff, p.maxdim, p.mindim);
+        s_rank = truncate_rank_dev(sig, nt, p.cutoff, p.maxdim, p.mindim, p.margin);
         *p.rank = s_rank;
     }
     __syncthreads();
@@ -301,6 +287,7 @@ int svd_small(qil_ctx* ctx, int64_t m, int64_t n, const T* A, int64_t lda, doubl
     p.mt = (int)std::max(m, n); p.nt = k;
     p.mpad = p.mt | 1; p.npad = p.nt | 1;
     p.cutoff = cutoff; p.maxdim = maxdim < 1 ? 1 : maxdim; p.mindim = std::max<int64_t>(mindim, 1);
+    p.margin = ctx->d_margin;
     Mat<T> bu, bus, bvh, bsvh;
     Mat<double> bs;
     if (U) bu = Mat<T>(ctx, m, k);
@@ -351,6 +338,7 @@ void svd_small_batch(qil_ctx* ctx, std::vector<SmallSvdItem<T>>& items, double c
         p.A = it.A; p.lda = it.lda; p.m = (int)m; p.n = (int)n;
         p.mt = (int)std::max(m, n); p.nt = k; p.mpad = p.mt | 1; p.npad = p.nt | 1;
         p.cutoff = cutoff; p.maxdim = maxdim < 1 ? 1 : maxdim; p.mindim = std::max<int64_t>(mindim, 1);
+        p.margin = ctx->d_margin;
         if (it.want_U) it.U = Mat<T>(ctx, m, k);
         if (it.want_US) it.US = Mat<T>(ctx, m, k);
         if (it.want_Vh) it.Vh = Mat<T>(ctx, k, n);

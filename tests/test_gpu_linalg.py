@@ -100,3 +100,26 @@ def test_svd_small_singular_values_relative_accuracy(q):
     A = (U0 * s) @ np.eye(n)      # columns scaled: Jacobi-friendly grading
     U, S, Vh = q.svd_trunc(A, cutoff=0.0)
     assert np.abs(S / s - 1).max() < 1e-10
+
+
+def test_truncation_margin_reports_the_closest_cutoff_decision(q):
+    """qil_truncation_margin: |w / (cutoff * sum sigma^2) - 1| of the closest decision (rank-parity diagnostic)."""
+    ctx = q.default_context()
+    sig2 = np.array([1.0, 1e-6, 1e-13])
+    rng = np.random.default_rng(3)
+    U, _ = np.linalg.qr(rng.standard_normal((6, 3)))
+    V, _ = np.linalg.qr(rng.standard_normal((5, 3)))
+    A = (U * np.sqrt(sig2)) @ V.T
+    ctx.truncation_margin(reset=True)
+    assert ctx.truncation_margin(reset=False) == float("inf")
+    Uo, S, Vh = q.svd_trunc(A, cutoff=1e-12)
+    assert S.size == 2
+    m = ctx.truncation_margin(reset=True)
+    # dropped weight 1e-13 against the threshold 1e-12 * (1 + 1e-6 + 1e-13): 0.9 away; the kept value is 1e6 away
+    assert abs(m - 0.9) < 1e-3
+    # a knife edge: sigma_3^2 = cutoff * total up to 1e-9 -> the margin says so
+    tot = 1.0 + 1e-6
+    sig2 = np.array([1.0, 1e-6, 1e-12 * tot * (1 + 1e-9)])
+    A = (U * np.sqrt(sig2)) @ V.T
+    q.svd_trunc(A, cutoff=1e-12)
+    assert ctx.truncation_margin(reset=True) < 1e-6
