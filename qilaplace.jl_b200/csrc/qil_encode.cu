@@ -372,7 +372,10 @@ static int rsvd_split(SplitCtx<T>& sc, const T* A, int64_t R, int64_t C, bool to
     }
     Mat<T> Q, Rr;
     qr_thin<T>(ctx, R, l0, Y.p, l0, true, Q, Rr);
-    const int l = shrink_sketch<T>(ctx, o, l0, R, Q, Rr);
+    // only at the top split: the raw signal's rounding floor (~1e-16) is three decades below the threshold, whereas
+    // the factors handed down the tree carry the parent's accuracy floor (eps * sigma_1 / sigma_r ~ 1e-13 .. 1e-12),
+    // i.e. sit right at it, and a rounding-dependent width there was seen to move a bond by one on 4 GPUs
+    const int l = top ? shrink_sketch<T>(ctx, o, l0, R, Q, Rr) : l0;
     for (int it = 0; it < o.q; ++it) {
         Mat<T> Z = mul_AH<T>(sc, A, R, C, l, Q.p, nullptr);
         Mat<T> Qz, Rz;
