@@ -23,7 +23,7 @@ template <typename T>
 __global__ void __launch_bounds__(kCoeffThreads)
 coeff_chain_kernel(const ChainDesc d, const uint8_t* __restrict__ bits, long long B, T* __restrict__ out,
                    double amplitude, int S, int chi_pad) {
-    extern __shared__ __align__(16) unsigned char smem_raw[];
+    extern __shared__ __align__(1024) unsigned char smem_raw[];   // one declaration (and alignment) per translation unit
     T* V0 = reinterpret_cast<T*>(smem_raw);
     T* V1 = V0 + (size_t)S * chi_pad;
     uint8_t* sb = reinterpret_cast<uint8_t*>(V1 + (size_t)S * chi_pad);  // [S][n]

@@ -75,7 +75,7 @@ __global__ void __launch_bounds__(GLOBAL ? kQrThreadsGlobal : kQrThreads) hhqr_k
     const long long r1 = ((long long)(b + 1) * p.m) / p.nblk;
     const int mloc = (int)(r1 - r0);
     const int k = min(mloc, n);
-    const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
+    const int tid = threadIdx.x, lane = tid & 31;
 
     // ---- load (sum of partials), transposing into column-major smem
     for (int idx = tid; idx < mloc * n; idx += kQrThreads) {
