@@ -302,6 +302,7 @@ def run_ours(args):
     x_host = x_pin.numpy()
 
     x_stage = torch.empty(NL, dtype=torch.float64, device=dev) if shard else None
+    cores_pin = torch.empty(256 << 20, dtype=torch.uint8, pin_memory=True)     # host landing zone of the result cores
 
     def step_e2e():
         # the call a user makes: host signal in, host cores out, through the host-buffer C-ABI entry points
@@ -311,7 +312,7 @@ def run_ours(args):
         else:
             z = q.signal_ztmps(x_host, ctx=ctx, method="rsvd", **ALGO)   # H2D of the 2 GiB signal inside
         out = W * z
-        state["host_cores"] = out.cores()                                 # D2H read of the step's result
+        state["host_cores"] = out.cores_into(cores_pin)                   # D2H read of the step's result
 
     def step_coeff_e2e():
         bits_dev.copy_(bits_pin, non_blocking=True)

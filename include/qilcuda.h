@@ -82,6 +82,8 @@ int qil_mps_from_host(qil_ctx* ctx, int n, int is_complex, const int64_t* bond,
 int qil_mps_info(const qil_mps* m, int* n, int* is_complex, double* amplitude);
 int qil_mps_dims(const qil_mps* m, int64_t* bond /* n+1 */);
 int qil_mps_get_core(const qil_mps* m, int site, void* host_buf);
+/* every core, packed back to back in site order, with one synchronisation (pinned host memory makes it one DMA burst) */
+int qil_mps_get_cores(const qil_mps* m, void* host_buf, int64_t host_bytes);
 int qil_mps_set_amplitude(qil_mps* m, double amplitude);
 int qil_mps_clone(const qil_mps* m, qil_mps** out);
 int qil_mps_free(qil_mps* m);

@@ -56,6 +56,7 @@ _SIGS = {
     "qil_mps_info": [c_mps, C.POINTER(C.c_int), C.POINTER(C.c_int), C.POINTER(C.c_double)],
     "qil_mps_dims": [c_mps, i64p],
     "qil_mps_get_core": [c_mps, C.c_int, C.c_void_p],
+    "qil_mps_get_cores": [c_mps, C.c_void_p, C.c_int64],
     "qil_mps_set_amplitude": [c_mps, C.c_double],
     "qil_mps_clone": [c_mps, C.POINTER(c_mps)],
     "qil_mps_free": [c_mps],

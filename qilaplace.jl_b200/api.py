@@ -139,6 +139,27 @@ class _DeviceChain:
             out.append(a)
         return out
 
+    def cores_into(self, host_buffer):
+        """Download every core into one caller-owned host buffer (any object exposing the buffer protocol or a
+        `data_ptr()` / `nbytes`-like pair, e.g. a pinned torch uint8 tensor) with a single synchronisation; returns
+        numpy views into that buffer.  MPS chains only."""
+        b = self._bond_dims()
+        dt = np.dtype(_np_dtype(self.is_complex))
+        if hasattr(host_buffer, "data_ptr"):
+            ptr, nbytes = int(host_buffer.data_ptr()), int(host_buffer.numel() * host_buffer.element_size())
+            raw = (C.c_ubyte * nbytes).from_address(ptr)
+        else:
+            raw = host_buffer
+            ptr, nbytes = C.addressof(C.c_ubyte.from_buffer(raw)), memoryview(raw).nbytes
+        call("qil_mps_get_cores", self.handle, C.c_void_p(ptr), C.c_int64(nbytes))
+        out, off = [], 0
+        for i in range(self.nsites_flat):
+            shape = (b[i], 2, b[i + 1])
+            cnt = b[i] * 2 * b[i + 1]
+            out.append(np.frombuffer(raw, dtype=dt, count=cnt, offset=off).reshape(shape))
+            off += cnt * dt.itemsize
+        return out
+
 
 class SignalMPS(_DeviceChain):
     """SignalMPS (src/mps.jl:70-81): n cores [chi_l, 2, chi_r] on the device + `amplitude`."""

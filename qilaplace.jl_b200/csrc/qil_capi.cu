@@ -264,6 +264,25 @@ int qil_mps_get_core(const qil_mps* m, int site, void* host_buf) {
     QIL_API_END
 }
 
+int qil_mps_get_cores(const qil_mps* m, void* host_buf, int64_t host_bytes) {
+    QIL_API_BEGIN
+    QIL_NONNULL(m); QIL_NONNULL(host_buf);
+    QIL_CUDA(cudaSetDevice(m->ctx->device));
+    const size_t es = elem_size(m->is_complex);
+    size_t need = 0;
+    for (int i = 0; i < m->n; ++i) need += m->core_elems(i) * es;
+    QIL_REQUIRE((size_t)host_bytes >= need, QIL_ERR_ARGUMENT, "get_cores: %lld bytes given, %zu needed",
+                (long long)host_bytes, need);
+    size_t off = 0;
+    for (int i = 0; i < m->n; ++i) {
+        const size_t nb = m->core_elems(i) * es;
+        QIL_CUDA(cudaMemcpyAsync((char*)host_buf + off, m->core[i], nb, cudaMemcpyDeviceToHost, m->ctx->stream));
+        off += nb;
+    }
+    m->ctx->sync();
+    QIL_API_END
+}
+
 int qil_mps_set_amplitude(qil_mps* m, double amplitude) {
     QIL_API_BEGIN
     QIL_NONNULL(m);

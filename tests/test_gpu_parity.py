@@ -190,3 +190,19 @@ def test_zt_tutorial_table_through_apply_and_coefficient(q, goldens):
     ref = np.array([[sum(x[j] * np.exp(-(2 * math.pi * k + 2j * math.pi * l) / N * j) for j in range(N)) / N
                      for l in range(N)] for k in range(N)])
     assert (np.abs(chi - ref) / np.abs(ref)).max() < 1e-13
+
+
+def test_cores_into_one_host_buffer(q):
+    rng = np.random.default_rng(9)
+    for cplx in (False, True):
+        cores = _rand_mps(rng, [1, 2, 4, 3, 2, 1], cplx)
+        psi = q.SignalMPS.from_cores(cores, 2.0)
+        nbytes = sum(c.nbytes for c in cores)
+        buf = bytearray(nbytes + 64)
+        got = psi.cores_into(buf)
+        for a, b in zip(got, psi.cores()):
+            assert a.shape == b.shape and np.array_equal(a, b)
+        for a, b in zip(got, cores):
+            assert np.array_equal(a, b)
+        with pytest.raises(q.ArgumentError):
+            psi.cores_into(bytearray(nbytes - 8))
