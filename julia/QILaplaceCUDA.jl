@@ -157,11 +157,132 @@ mps_to_vector(ψ::ZTMPS; reverse::Bool=false) = mps_to_vector(_as_signal_2n(ψ);
 # and call qil_encode_rsvd_sharded_dev(ctx, Ref(comm), is_complex, d_x_local, N_total, k, p, q, seed, cutoff,
 # maxdim, mindim, C_NULL, 0, out) on every rank; all ranks receive the same MPS handle contents.
 
-# ---- apply (src/linalg/apply.jl:75-122, 201-218) ---------------------------------------------------
-# W is uploaded with qil_mpo_from_host exactly like _upload (cores Array(T, r, s, s', l)), then
-#   qil_apply_mpo_mps(ctx, hW, hψ, out) ; _download_mps(out[], ψ.sites)
-# compress!/canonicalize!/norm: _upload(ψ) ; qil_compress / qil_canonicalize / qil_norm ; download in place.
-# build_qft_mpo / build_dt_mpo / build_zt_mpo: qil_build_*_mpo(ctx, n, [ωr,] cutoff, maxdim, out) ; download cores
-# into ITensors over (bond_l, s', s, bond_r) with the reference's tags ("bond-%d").
+# ---- MPO handles ---------------------------------------------------------------------------------------
+# C-order [l][p][s][r] (p = primed/input leg) is Julia's column-major Array(T, r, s, p, l)
+function _upload(W::SingleSiteMPO)
+    n = length(W.data)
+    T = promote_type(map(eltype, W.data)...)
+    bufs = Vector{Array{T}}(undef, n)
+    bond = ones(Int64, n + 1)
+    for i in 1:n
+        l = i == 1 ? nothing : W.bonds[i-1]
+        r = i == n ? nothing : W.bonds[i]
+        inds = filter(!isnothing, (r, W.sites[i], prime(W.sites[i]), l))
+        bufs[i] = Array{T}(Array(W.data[i], inds...))
+        bond[i+1] = i == n ? 1 : dim(W.bonds[i])
+    end
+    ptrs = [pointer(b) for b in bufs]
+    out = Ref{Ptr{Cvoid}}(C_NULL)
+    GC.@preserve bufs begin
+        _check(ccall((:qil_mpo_from_host, LIB), Cint,
+                     (Ptr{Cvoid}, Cint, Cint, Ptr{Int64}, Ptr{Ptr{Cvoid}}, Ref{Ptr{Cvoid}}),
+                     ctx(), n, _iscomplex(T), bond, ptrs, out))
+    end
+    return out[]
+end
+
+function _download_mpo(h::Ptr{Cvoid}, sites::Vector{<:Index}; bondtag="bond-%d")
+    n = Ref{Cint}(0); ic = Ref{Cint}(0)
+    _check(ccall((:qil_mpo_info, LIB), Cint, (Ptr{Cvoid}, Ref{Cint}, Ref{Cint}), h, n, ic))
+    N = Int(n[]); T = ic[] == 1 ? ComplexF64 : Float64
+    bond = Vector{Int64}(undef, N + 1)
+    _check(ccall((:qil_mpo_dims, LIB), Cint, (Ptr{Cvoid}, Ptr{Int64}), h, bond))
+    bonds = [Index(Int(bond[i+1]); tags=Printf.format(Printf.Format(bondtag), i)) for i in 1:(N-1)]
+    data = Vector{ITensor}(undef, N)
+    for i in 1:N
+        buf = Array{T}(undef, Int(bond[i+1]), 2, 2, Int(bond[i]))       # (r, s, s', l)
+        _check(ccall((:qil_mpo_get_core, LIB), Cint, (Ptr{Cvoid}, Cint, Ptr{Cvoid}), h, i - 1, buf))
+        is = Any[]
+        i < N && push!(is, bonds[i]); push!(is, sites[i]); push!(is, prime(sites[i])); i > 1 && push!(is, bonds[i-1])
+        data[i] = ITensor(reshape(buf, (dim(x) for x in is)...), is...)
+    end
+    ccall((:qil_mpo_free, LIB), Cint, (Ptr{Cvoid},), h)
+    return SingleSiteMPO(data, sites, bonds)
+end
+
+# ---- apply (src/linalg/apply.jl:75-122, 201-218, 233-236): exact, kwargs ignored like the reference -------------
+function apply(W::SingleSiteMPO, ψ::SignalMPS; kwargs...)
+    length(W.data) == length(ψ.data) ||
+        throw(ArgumentError("apply: MPO and MPS must have the same number of sites"))
+    hW = _upload(W); hψ = _upload(ψ)
+    out = Ref{Ptr{Cvoid}}(C_NULL)
+    rc = ccall((:qil_apply_mpo_mps, LIB), Cint, (Ptr{Cvoid}, Ptr{Cvoid}, Ptr{Cvoid}, Ref{Ptr{Cvoid}}), ctx(), hW, hψ, out)
+    ccall((:qil_mpo_free, LIB), Cint, (Ptr{Cvoid},), hW)
+    ccall((:qil_mps_free, LIB), Cint, (Ptr{Cvoid},), hψ)
+    _check(rc)
+    return _download_mps(out[], ψ.sites)
+end
+apply(W::PairedSiteMPO, ψ::ZTMPS; kwargs...) =
+    _writeback_signal_2n(apply(_as_single_site_mpo(W), _as_signal_2n(ψ)), ψ)          # apply.jl:201-218
+Base.:*(W::Union{SingleSiteMPO,PairedSiteMPO}, ψ::Union{SignalMPS,ZTMPS}) = apply(W, ψ)
+
+# ---- signal_ztmps (SignalConverters.jl:247-283): encode, then the copy-tensor split on the device --------------
+function signal_ztmps(x::AbstractVector{<:Number}; cutoff::Real=1e-10, maxdim::Int=typemax(Int), kwargs...)
+    ψ = signal_mps(x; cutoff=cutoff, maxdim=maxdim, kwargs...)
+    h = _upload(ψ)
+    out = Ref{Ptr{Cvoid}}(C_NULL)
+    rc = ccall((:qil_ztmps_split, LIB), Cint, (Ptr{Cvoid}, Ptr{Cvoid}, Cdouble, Int64, Ref{Ptr{Cvoid}}),
+               ctx(), h, cutoff, _maxdim(maxdim), out)
+    ccall((:qil_mps_free, LIB), Cint, (Ptr{Cvoid},), h)
+    _check(rc)
+    n = length(ψ.sites)
+    flat_sites = Index[]
+    for i in 1:n
+        push!(flat_sites, Index(2; tags=@sprintf("site-main-%d", i)))
+        push!(flat_sites, Index(2; tags=@sprintf("site-copy-%d", i)))
+    end
+    return _writeback_signal_2n(_download_mps(out[], flat_sites), nothing)   # 2n-site chain -> ZTMPS (mps.jl:447-472)
+end
+
+# ---- canonicalize! / compress! / norm (src/mps.jl:754-999): in place on the handle, downloaded back ----------
+function _inplace!(f::Function, ψ::SignalMPS)
+    h = _upload(ψ)
+    rc = f(h)
+    rc == 0 || (ccall((:qil_mps_free, LIB), Cint, (Ptr{Cvoid},), h); _check(rc))
+    new = _download_mps(h, ψ.sites)
+    ψ.data .= new.data; ψ.bonds .= new.bonds; ψ.amplitude = new.amplitude
+    return ψ
+end
+function canonicalize!(ψ::SignalMPS, dir::Symbol; center::Int=0, cutoff::Real=1e-12, maxdim::Int=typemax(Int))
+    dir ∈ (:left, :right) || throw(DomainError(dir, "canonicalize!: direction must be :left or :right"))
+    _inplace!(h -> ccall((:qil_canonicalize, LIB), Cint, (Ptr{Cvoid}, Ptr{Cvoid}, Cint, Cint, Cdouble, Int64),
+                         ctx(), h, dir == :right ? 1 : 0, center, cutoff, _maxdim(maxdim)), ψ)
+end
+function compress!(ψ::SignalMPS; maxdim::Int=typemax(Int), tol::Real=1e-12, sweeps::Int=1)
+    sweeps >= 1 || throw(DomainError(sweeps, "compress!: sweeps must be >= 1"))
+    _inplace!(h -> ccall((:qil_compress, LIB), Cint, (Ptr{Cvoid}, Ptr{Cvoid}, Int64, Cdouble, Cint),
+                         ctx(), h, _maxdim(maxdim), tol, sweeps), ψ)
+end
+function LinearAlgebra_norm(ψ::SignalMPS)            # extend LinearAlgebra.norm with this body (mps.jl:754)
+    h = _upload(ψ); v = Ref{Cdouble}(0)
+    rc = ccall((:qil_norm, LIB), Cint, (Ptr{Cvoid}, Ptr{Cvoid}, Ref{Cdouble}), ctx(), h, v)
+    ccall((:qil_mps_free, LIB), Cint, (Ptr{Cvoid},), h)
+    _check(rc)
+    return v[]
+end
+
+# ---- transform MPOs (src/transforms/*.jl): built on the device, downloaded over the caller's site indices ------
+function build_qft_mpo(n::Int, sites::Vector{<:Index}; cutoff::Real=1e-14, maxdim::Int=1000)
+    out = Ref{Ptr{Cvoid}}(C_NULL)
+    _check(ccall((:qil_build_qft_mpo, LIB), Cint, (Ptr{Cvoid}, Cint, Cdouble, Int64, Ref{Ptr{Cvoid}}),
+                 ctx(), n, cutoff, _maxdim(maxdim), out))
+    return _download_mpo(out[], sites)
+end
+function _build_paired(sym::Symbol, n::Int, ωr::Real, sites_main, sites_copy; cutoff::Real=1e-14, maxdim::Int=1000)
+    out = Ref{Ptr{Cvoid}}(C_NULL)
+    rc = sym === :dt ?
+        ccall((:qil_build_dt_mpo, LIB), Cint, (Ptr{Cvoid}, Cint, Cdouble, Cdouble, Int64, Ref{Ptr{Cvoid}}),
+              ctx(), n, ωr, cutoff, _maxdim(maxdim), out) :
+        ccall((:qil_build_zt_mpo, LIB), Cint, (Ptr{Cvoid}, Cint, Cdouble, Cdouble, Int64, Ref{Ptr{Cvoid}}),
+              ctx(), n, ωr, cutoff, _maxdim(maxdim), out)
+    _check(rc)
+    flat = Index[]
+    for i in 1:n
+        push!(flat, sites_main[i]); push!(flat, sites_copy[i])
+    end
+    return _as_paired_site_mpo(_download_mpo(out[], flat))        # 2n-site chain -> PairedSiteMPO (apply.jl:16-33)
+end
+build_dt_mpo(n::Int, ωr::Real, sm, sc; kw...) = _build_paired(:dt, n, ωr, sm, sc; kw...)
+build_zt_mpo(n::Int, ωr::Real, sm, sc; kw...) = _build_paired(:zt, n, ωr, sm, sc; kw...)
 
 end # module
