@@ -52,7 +52,7 @@ __device__ __forceinline__ cplx group_sum<cplx>(cplx v, int gl, unsigned mask) {
 }
 
 template <typename T, bool GLOBAL>
-__global__ void __launch_bounds__(GLOBAL ? kJacThreadsGlobal : kJacThreads) jacobi_kernel(const JacParams<T> p) {
+__global__ void __launch_bounds__(kJacThreadsGlobal) jacobi_kernel(const JacParams<T> p) {
     extern __shared__ __align__(16) unsigned char smem_raw[];
     const int ns = p.ns, pad = p.pad;
     const int kJacThreads = blockDim.x;
@@ -165,7 +165,7 @@ __global__ void __launch_bounds__(GLOBAL ? kJacThreadsGlobal : kJacThreads) jaco
     }
     __syncthreads();
     // sorted sigma (permute through registers), then the sequential truncation rule
-    double mine[8];
+    double mine[8];      // ns <= 8 * blockDim.x is checked by the launcher (blockDim.x >= 256)
     int cnt = 0;
     for (int j = tid; j < ns; j += kJacThreads) mine[cnt++] = sig[order[j]];
     __syncthreads();
@@ -223,8 +223,14 @@ static int jacobi_square(qil_ctx* ctx, int ns, const T* R, int64_t ld, double cu
     p.R = R; p.ld = ld; p.ns = ns; p.pad = ns | 1; p.V = V.p; p.W = W.p; p.S = S.p; p.rank = d_rank;
     p.cutoff = cutoff; p.maxdim = maxdim; p.mindim = std::max<int64_t>(mindim, 1);
     p.margin = ctx->d_margin;
-    p.gl = ns <= 32 ? 8 : (ns <= 64 ? 16 : 32);
+    // lanes per column pair; one round of the round-robin ordering has ceil(ns/2) independent pairs, and every
+    // pass over them costs about the same dependent-latency chain, so the CTA gets enough threads for all pairs of
+    // a round at once whenever 1024 threads allow it
     p.gscratch = use_global ? gscratch.p : nullptr;
+    const int npairs = (ns + 1) / 2;
+    const int threads = use_global ? kJacThreadsGlobal
+                                   : std::max(kJacThreads, std::min(((npairs * 8 + 31) / 32) * 32, kJacThreadsGlobal));
+    p.gl = use_global ? 32 : ((npairs * 32 <= threads) ? 32 : (npairs * 16 <= threads ? 16 : 8));   // L2-resident: keep loads wide
     if (use_global) {
         auto kern = jacobi_kernel<T, true>;
         ensure_dynamic_smem(kern, smem);
@@ -232,7 +238,7 @@ static int jacobi_square(qil_ctx* ctx, int ns, const T* R, int64_t ld, double cu
     } else {
         auto kern = jacobi_kernel<T, false>;
         ensure_dynamic_smem(kern, smem);
-        kern<<<1, kJacThreads, smem, ctx->stream>>>(p);
+        kern<<<1, threads, smem, ctx->stream>>>(p);
     }
     QIL_LAUNCH_CHECK(ctx);
     int rank = 0;

@@ -114,7 +114,9 @@ __device__ __forceinline__ void svd_small_body(const SmallSvdParams<T>& p, unsig
     // ---- one-sided Jacobi on the columns of G (see qil_svd.cu)
     {
         const int ns = nt;
-        const int gl = ns <= 32 ? 8 : (ns <= 64 ? 16 : 32);
+        // widest lane group that still lets every pair of a round run at once (a pass costs one latency chain)
+        const int npr = (ns + 1) / 2;
+        const int gl = (npr * 32 <= kSsThreads) ? 32 : (npr * 16 <= kSsThreads ? 16 : 8);
         const int grp = tid / gl, gln = tid % gl;
         const unsigned gmask = (gl == 32) ? 0xffffffffu : (((1u << gl) - 1u) << ((tid & 31) / gl * gl));
         const int ngr = kSsThreads / gl;
