@@ -10,6 +10,8 @@
 //   A = (Q V) W^H,  sigma_j = |W_j|,  U = Q V,  S*Vh = W^H      -- no division by sigma anywhere.
 #include "qil_dense.cuh"
 
+#include <cstdlib>
+
 namespace qil {
 
 constexpr int kJacThreads = 256;        // shared-memory variant
@@ -185,6 +187,162 @@ __global__ void __launch_bounds__(kJacThreadsGlobal) jacobi_kernel(const JacPara
     }
 }
 
+// ------------------------------------------------------------------------------------------------
+// Multi-CTA variant for bond matrices that do not fit one CTA's shared memory (zT builder, large compress!):
+// G and V live in an L2-resident scratch; the ceil(ns/2) independent pairs of a round are spread over the lane
+// groups of ALL CTAs, rounds are separated by a software grid barrier (the kernel is launched cooperatively, so
+// every CTA is resident).  Data written by other CTAs is read with ld.cg (L2), never through L1.
+// ------------------------------------------------------------------------------------------------
+constexpr int kJacMultiThreads = 256;      // 8 lane groups of 32 per CTA
+
+struct GridSync {
+    unsigned int* counter;   // arrivals of the current barrier
+    unsigned int* gen;       // barrier generation
+    int* rot;                // [3] "some pair was rotated" flags, indexed by sweep % 3
+};
+
+__device__ __forceinline__ void grid_barrier(const GridSync& gs) {
+    __syncthreads();
+    if (threadIdx.x == 0) {
+        __threadfence();
+        const unsigned int g = *((volatile unsigned int*)gs.gen);
+        if (atomicAdd(gs.counter, 1u) == gridDim.x - 1) {
+            *((volatile unsigned int*)gs.counter) = 0u;
+            __threadfence();
+            atomicAdd(gs.gen, 1u);
+        } else {
+            while (*((volatile unsigned int*)gs.gen) == g) { }
+        }
+        __threadfence();
+    }
+    __syncthreads();
+}
+
+template <typename T> __device__ __forceinline__ T ld_l2(const T* p);
+template <> __device__ __forceinline__ double ld_l2<double>(const double* p) { return __ldcg(p); }
+template <> __device__ __forceinline__ cplx ld_l2<cplx>(const cplx* p) { return __ldcg(p); }
+
+template <typename T>
+__global__ void __launch_bounds__(kJacMultiThreads) jacobi_multi_kernel(const JacParams<T> p, const GridSync gs) {
+    extern __shared__ __align__(16) unsigned char smem_raw[];
+    const int ns = p.ns, pad = p.pad;
+    T* G = p.gscratch;                            // [ns][pad] column-major, global
+    T* V = G + (size_t)ns * pad;
+    double* sig = reinterpret_cast<double*>(smem_raw);              // [ns]   (used by CTA 0 at the end)
+    int* order = reinterpret_cast<int*>(sig + ns);                  // [ns]
+
+    const int tid = threadIdx.x;
+    const long long gtid = (long long)blockIdx.x * blockDim.x + tid;
+    const long long gthreads = (long long)gridDim.x * blockDim.x;
+    for (long long idx = gtid; idx < (long long)ns * ns; idx += gthreads) {
+        const int j = (int)(idx / ns), i = (int)(idx - (long long)j * ns);
+        G[(size_t)j * pad + i] = Scalar<T>::conj(p.R[(long long)j * p.ld + i]);
+        V[(size_t)j * pad + i] = (i == j) ? Scalar<T>::one() : Scalar<T>::zero();
+    }
+    if (gtid < 3) gs.rot[gtid] = 0;
+    grid_barrier(gs);
+
+    constexpr int gl = 32;
+    const int grp = (int)(gtid / gl), gln = tid % gl;
+    const int ngroups = (int)(gthreads / gl);
+    const int ne = ns + (ns & 1);
+    const int npairs = ne / 2;
+    const double tol = sqrt((double)ns) * 2.220446049250313e-16;
+
+    for (int sweep = 0; sweep < kMaxSweeps; ++sweep) {
+        int* rot = gs.rot + sweep % 3;
+        if (gtid == 0) gs.rot[(sweep + 1) % 3] = 0;          // the flag of the NEXT sweep (nobody touches it now)
+        for (int r = 0; r < ne - 1; ++r) {
+            for (int pi = grp; pi < npairs; pi += ngroups) {
+                int a, b;
+                if (pi == 0) { a = ne - 1; b = r; }
+                else { a = (r + pi) % (ne - 1); b = (r - pi + (ne - 1)) % (ne - 1); }
+                if (a >= ns || b >= ns) continue;   // warp-uniform (one pair per warp)
+                const int cp = min(a, b), cq = max(a, b);
+                T* gp = G + (size_t)cp * pad;
+                T* gq = G + (size_t)cq * pad;
+                double al = 0.0, be = 0.0;
+                T ga = Scalar<T>::zero();
+                for (int i = gln; i < ns; i += gl) {
+                    const T x = ld_l2<T>(gp + i), y = ld_l2<T>(gq + i);
+                    al += Scalar<T>::abs2(x);
+                    be += Scalar<T>::abs2(y);
+                    ga = Scalar<T>::fma(Scalar<T>::conj(x), y, ga);
+                }
+                al = group_sum<double>(al, gl, 0xffffffffu);
+                be = group_sum<double>(be, gl, 0xffffffffu);
+                ga = group_sum<T>(ga, gl, 0xffffffffu);
+                const double g2 = Scalar<T>::abs2(ga);
+                if (g2 > tol * tol * al * be && g2 > 0.0) {
+                    const double rg = rsqrt(g2);
+                    const double ag = g2 * rg;
+                    const T ph = Scalar<T>::scale(ga, rg);
+                    const double dd = be - al;
+                    const double hh = dd * dd + 4.0 * g2;
+                    const double sq = hh * rsqrt(hh);
+                    const double t = (dd >= 0.0 ? 2.0 : -2.0) * ag / (fabs(dd) + sq);
+                    const double c = rsqrt(1.0 + t * t);
+                    const double sn = c * t;
+                    const T sp = Scalar<T>::scale(ph, sn);
+                    const T spc = Scalar<T>::conj(sp);
+                    for (int i = gln; i < ns; i += gl) {
+                        const T x = ld_l2<T>(gp + i), y = ld_l2<T>(gq + i);
+                        gp[i] = Scalar<T>::sub(Scalar<T>::scale(x, c), Scalar<T>::mul(spc, y));
+                        gq[i] = Scalar<T>::add(Scalar<T>::mul(sp, x), Scalar<T>::scale(y, c));
+                    }
+                    T* vp = V + (size_t)cp * pad;
+                    T* vq = V + (size_t)cq * pad;
+                    for (int i = gln; i < ns; i += gl) {
+                        const T x = ld_l2<T>(vp + i), y = ld_l2<T>(vq + i);
+                        vp[i] = Scalar<T>::sub(Scalar<T>::scale(x, c), Scalar<T>::mul(spc, y));
+                        vq[i] = Scalar<T>::add(Scalar<T>::mul(sp, x), Scalar<T>::scale(y, c));
+                    }
+                    if (gln == 0) *((volatile int*)rot) = 1;
+                }
+            }
+            grid_barrier(gs);
+        }
+        if (*((volatile int*)rot) == 0) break;      // same value in every CTA: written before the last barrier
+    }
+    if (blockIdx.x != 0) return;
+
+    // ---- CTA 0: singular values, order, rank, outputs (all reads through L2)
+    for (int j = tid; j < ns; j += kJacMultiThreads) {
+        double a = 0.0;
+        const T* g = G + (size_t)j * pad;
+        for (int i = 0; i < ns; ++i) a += Scalar<T>::abs2(ld_l2<T>(g + i));
+        sig[j] = sqrt(a);
+    }
+    __syncthreads();
+    for (int j = tid; j < ns; j += kJacMultiThreads) {
+        const double sj = sig[j];
+        int pos = 0;
+        for (int i = 0; i < ns; ++i) {
+            const double si = sig[i];
+            pos += (si > sj || (si == sj && i < j)) ? 1 : 0;
+        }
+        order[pos] = j;
+    }
+    __syncthreads();
+    double mine[8];
+    int cnt = 0;
+    for (int j = tid; j < ns; j += kJacMultiThreads) mine[cnt++] = sig[order[j]];
+    __syncthreads();
+    cnt = 0;
+    for (int j = tid; j < ns; j += kJacMultiThreads) {
+        sig[j] = mine[cnt];
+        p.S[j] = mine[cnt++];
+    }
+    __syncthreads();
+    if (tid == 0) *p.rank = truncate_rank_dev(sig, ns, p.cutoff, p.maxdim, p.mindim, p.margin);
+    for (int idx = tid; idx < ns * ns; idx += kJacMultiThreads) {
+        const int i = idx / ns, j = idx - i * ns;
+        const int src = order[j];
+        p.V[(long long)i * ns + j] = ld_l2<T>(V + (size_t)src * pad + i);
+        p.W[(long long)i * ns + j] = ld_l2<T>(G + (size_t)src * pad + i);
+    }
+}
+
 template <typename T>
 __global__ void sum_partials_kernel(long long count, int nsum, long long stride, const T* __restrict__ in,
                                     T* __restrict__ out) {
@@ -232,6 +390,28 @@ static int jacobi_square(qil_ctx* ctx, int ns, const T* R, int64_t ld, double cu
                                    : std::max(kJacThreads, std::min(((npairs * 8 + 31) / 32) * 32, kJacThreadsGlobal));
     p.gl = use_global ? 32 : ((npairs * 32 <= threads) ? 32 : (npairs * 16 <= threads ? 16 : 8));   // L2-resident: keep loads wide
     if (use_global) {
+        // multi-CTA kernel (cooperative launch: every CTA must be resident for the software grid barrier)
+        const int want = std::min((npairs + 7) / 8, ctx->sm_count);
+        auto mk = jacobi_multi_kernel<T>;
+        ensure_dynamic_smem(mk, smem);
+        int occ = 0;
+        QIL_CUDA(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ, mk, kJacMultiThreads, smem));
+        static const bool single = [] { const char* e = getenv("QIL_JACOBI_SINGLE_CTA"); return e && e[0] == '1'; }();
+        if (occ >= 1 && want >= 2 && !single) {
+            unsigned int* sync_words = (unsigned int*)ctx->alloc(8 * sizeof(unsigned int));
+            QIL_CUDA(cudaMemsetAsync(sync_words, 0, 8 * sizeof(unsigned int), ctx->stream));
+            GridSync gs{sync_words, sync_words + 1, reinterpret_cast<int*>(sync_words + 2)};
+            void* args[] = {(void*)&p, (void*)&gs};
+            QIL_CUDA(cudaLaunchCooperativeKernel((const void*)mk, dim3(want), dim3(kJacMultiThreads), args, smem,
+                                                 ctx->stream));
+            QIL_LAUNCH_CHECK(ctx);
+            int rank = 0;
+            QIL_CUDA(cudaMemcpyAsync(&rank, d_rank, sizeof(int), cudaMemcpyDeviceToHost, ctx->stream));
+            ctx->sync();
+            ctx->free(d_rank);
+            ctx->free(sync_words);
+            return rank;
+        }
         auto kern = jacobi_kernel<T, true>;
         ensure_dynamic_smem(kern, smem);
         kern<<<1, kJacThreadsGlobal, smem, ctx->stream>>>(p);

@@ -46,7 +46,7 @@ def test_qr_rank_deficient_tall(q, cplx):
 
 @pytest.mark.parametrize("cplx", [False, True])
 @pytest.mark.parametrize("shape", [(1, 1), (2, 2), (4, 4), (6, 4), (4, 6), (30, 30), (64, 20), (20, 64), (2, 4096),
-                                   (4096, 6), (60, 16384), (100, 100), (48, 200)])
+                                   (4096, 6), (60, 16384), (100, 100), (48, 200), (300, 260), (130, 500)])
 def test_svd_full(q, shape, cplx):
     m, n = shape
     rng = np.random.default_rng(m * 17 + n * 3 + cplx)
