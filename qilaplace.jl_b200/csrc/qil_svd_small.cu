@@ -73,7 +73,7 @@ __device__ __forceinline__ void svd_small_body(const SmallSvdParams<T>& p, unsig
     int* order = reinterpret_cast<int*>(sig + nt);       // [nt]
     __shared__ int s_rot, s_rank;
 
-    const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
+    const int tid = threadIdx.x, lane = tid & 31;
     const bool tall = p.m >= p.n;
 
     // ---- load M (tall orientation) column-major: M[i][j] = A[i][j] or conj(A[j][i])
