@@ -273,3 +273,34 @@ def test_coefficient_grid_oracle_consistency():
     rng = np.random.default_rng(3)
     cores = [rng.standard_normal(s) for s in [(1, 2, 3), (3, 2, 4), (4, 2, 2), (2, 2, 1)]]
     assert np.allclose(O.coefficient_grid(cores, 2.0, [2] * 4), O.mps_to_vector(cores, 2.0), atol=1e-13)
+
+
+def test_pole_scan_modes_host_logic():
+    """Host-side grid description of a (k, l) pole-scan block (api.pole_scan_modes) against the reference's own loop
+    `coefficient(psi, interleave(lsb(k), lsb(l)))` (docs/src/tutorials/zt.jl:152-157), evaluated by the oracle."""
+    import qilaplace_b200 as q
+    n = 4
+    rng = np.random.default_rng(11)
+    bonds = [1, 2, 3, 4, 3, 4, 3, 2, 1]
+    cores = [rng.standard_normal((bonds[i], 2, bonds[i + 1])) + 1j * rng.standard_normal((bonds[i], 2, bonds[i + 1]))
+             for i in range(2 * n)]
+
+    def direct(ks, ls):
+        return np.array([[O.coefficient(cores, 1.0, O.interleave(O.bits_lsb(k, n), O.bits_lsb(l, n))) for l in ls]
+                         for k in ks])
+
+    # full table
+    mode, ob = q.pole_scan_modes(n, 0, 0, n, n)
+    got = O.coefficient_grid(cores, 1.0, mode, ob).reshape(2**n, 2**n)
+    assert np.allclose(got, direct(range(2**n), range(2**n)), atol=1e-13)
+    # aligned contiguous block k in [8, 12), l in [4, 6)
+    mode, ob = q.pole_scan_modes(n, 8, 4, 2, 1)
+    got = O.coefficient_grid(cores, 1.0, mode, ob).reshape(4, 2)
+    assert np.allclose(got, direct(range(8, 12), range(4, 6)), atol=1e-13)
+    # strided (coarse) scan: k = 1 + 2a (origin bit outside the free range), l = 4b
+    mode, ob = q.pole_scan_modes(n, 1, 0, 3, 2, stride_log2_k=1, stride_log2_l=2)
+    got = O.coefficient_grid(cores, 1.0, mode, ob).reshape(8, 4)
+    assert np.allclose(got, direct(range(1, 16, 2), range(0, 16, 4)), atol=1e-13)
+    # a misaligned origin is rejected
+    with pytest.raises(q.ArgumentError):
+        q.pole_scan_modes(n, 2, 0, 2, 2)
