@@ -86,6 +86,21 @@ __global__ void __launch_bounds__(kJacThreadsGlobal) jacobi_kernel(const JacPara
     const int ne = ns + (ns & 1);
     const int npairs = ne / 2;
     const double tol = sqrt((double)ns) * 2.220446049250313e-16;
+    // ||G||_F^2 in a fixed summation order (column norms, then thread 0), for the skip threshold
+    __shared__ double s_nu;
+    for (int j = tid; j < ns; j += kJacThreads) {
+        double a = 0.0;
+        for (int i = 0; i < ns; ++i) a += Scalar<T>::abs2(G[j * pad + i]);
+        sig[j] = a;
+    }
+    __syncthreads();
+    if (tid == 0) {
+        double tot = 0.0;
+        for (int j = 0; j < ns; ++j) tot += sig[j];
+        s_nu = jacobi_skip_threshold(tot, ns, p.cutoff, p.mindim);
+    }
+    __syncthreads();
+    const double nu = s_nu;
 
     for (int sweep = 0; sweep < kMaxSweeps; ++sweep) {
         if (tid == 0) s_rot = 0;
@@ -111,7 +126,7 @@ __global__ void __launch_bounds__(kJacThreadsGlobal) jacobi_kernel(const JacPara
                 be = group_sum<double>(be, gl, gmask);
                 ga = group_sum<T>(ga, gl, gmask);
                 const double g2 = Scalar<T>::abs2(ga);
-                if (g2 > tol * tol * al * be && g2 > 0.0) {
+                if (g2 > tol * tol * al * be && g2 > 0.0 && !(al < nu && be < nu)) {
                     // t = 2|g| sgn(d) / (|d| + sqrt(d^2 + 4|g|^2)), d = beta - alpha; c = rsqrt(1 + t^2), s = c t.
                     // rsqrt-based: the rotation only has to be orthogonal to rounding (c^2 + s^2 = 1), its angle
                     // may carry a few ulps of error (fixed by the next sweep) -- 3 sqrt + 4 div become 3 rsqrt + 1 div.
@@ -248,6 +263,22 @@ __global__ void __launch_bounds__(kJacMultiThreads) jacobi_multi_kernel(const Ja
     const int ne = ns + (ns & 1);
     const int npairs = ne / 2;
     const double tol = sqrt((double)ns) * 2.220446049250313e-16;
+    // ||G||_F^2, computed redundantly by every CTA in the same fixed order (skip threshold, see qil_common.cuh)
+    __shared__ double s_nu;
+    for (int j = tid; j < ns; j += kJacMultiThreads) {
+        double a = 0.0;
+        const T* g = G + (size_t)j * pad;
+        for (int i = 0; i < ns; ++i) a += Scalar<T>::abs2(ld_l2<T>(g + i));
+        sig[j] = a;
+    }
+    __syncthreads();
+    if (tid == 0) {
+        double tot = 0.0;
+        for (int j = 0; j < ns; ++j) tot += sig[j];
+        s_nu = jacobi_skip_threshold(tot, ns, p.cutoff, p.mindim);
+    }
+    __syncthreads();
+    const double nu = s_nu;
 
     for (int sweep = 0; sweep < kMaxSweeps; ++sweep) {
         int* rot = gs.rot + sweep % 3;
@@ -273,7 +304,7 @@ __global__ void __launch_bounds__(kJacMultiThreads) jacobi_multi_kernel(const Ja
                 be = group_sum<double>(be, gl, 0xffffffffu);
                 ga = group_sum<T>(ga, gl, 0xffffffffu);
                 const double g2 = Scalar<T>::abs2(ga);
-                if (g2 > tol * tol * al * be && g2 > 0.0) {
+                if (g2 > tol * tol * al * be && g2 > 0.0 && !(al < nu && be < nu)) {
                     const double rg = rsqrt(g2);
                     const double ag = g2 * rg;
                     const T ph = Scalar<T>::scale(ga, rg);

@@ -123,6 +123,21 @@ __device__ __forceinline__ void svd_small_body(const SmallSvdParams<T>& p, unsig
         const int ne = ns + (ns & 1);
         const int npairs = ne / 2;
         const double tol = sqrt((double)ns) * 2.220446049250313e-16;
+        // ||G||_F^2 in a fixed order for the skip threshold (qil_common.cuh: jacobi_skip_threshold)
+        __shared__ double s_nu;
+        for (int j = tid; j < ns; j += kSsThreads) {
+            double a = 0.0;
+            for (int i = 0; i < ns; ++i) a += Scalar<T>::abs2(G[j * npad + i]);
+            sig[j] = a;
+        }
+        __syncthreads();
+        if (tid == 0) {
+            double tot = 0.0;
+            for (int j = 0; j < ns; ++j) tot += sig[j];
+            s_nu = jacobi_skip_threshold(tot, ns, p.cutoff, p.mindim);
+        }
+        __syncthreads();
+        const double nu = s_nu;
         for (int sweep = 0; sweep < 60 && ns > 1; ++sweep) {
             if (tid == 0) s_rot = 0;
             __syncthreads();
@@ -147,7 +162,7 @@ __device__ __forceinline__ void svd_small_body(const SmallSvdParams<T>& p, unsig
                     be = gsum<double>(be, gl, gmask);
                     ga = gsum<T>(ga, gl, gmask);
                     const double g2 = Scalar<T>::abs2(ga);
-                    if (g2 > tol * tol * al * be && g2 > 0.0) {
+                    if (g2 > tol * tol * al * be && g2 > 0.0 && !(al < nu && be < nu)) {
                         // rsqrt-based rotation (see qil_svd.cu)
                         const double rg = rsqrt(g2);
                         const double ag = g2 * rg;
