@@ -541,8 +541,10 @@ def run_ours(args):
                       "e2e_ms": ms_scan_e2e, "e2e_coefficients_per_s": world * scan_pts / (ms_scan_e2e / 1e3),
                       "d2h_bytes_per_step": int(16 * scan_pts), "max_rel_dev_vs_chain_kernel": scan_check},
         "pipelined_batch": batch_info,
-        "full_step": {"what": f"encode + split + apply + {B} coefficients", "ms": full_ms,
+        "full_step": {"what": f"encode + split + apply + {B} coefficients of independent random bitstrings", "ms": full_ms,
                       "samples_per_s": units * N / (full_ms / 1e3)},
+        "full_step_pole_scan": {"what": f"encode + split + apply + {scan_pts}-point (k, l) pole scan (BASELINE configs[2] read-out)",
+                                "ms": ms_step + ms_scan, "samples_per_s": units * N / ((ms_step + ms_scan) / 1e3)},
         "stages_ms": stages_ms,
     }
 
