@@ -314,7 +314,9 @@ __global__ void sketch_width_kernel(const T* __restrict__ R, int l, long long ld
 template <typename T>
 static int shrink_sketch(qil_ctx* ctx, const RsvdOpts& o, int l, int64_t rows, Mat<T>& Q, const Mat<T>& Rr) {
     static const bool disabled = [] { const char* e = getenv("QIL_RSVD_ADAPTIVE"); return e && e[0] == '0'; }();
-    if (disabled || !(o.cutoff >= 1e-18) || l <= 1) return l;
+    // q == 0: without a power iteration the basis of the narrowed sketch is visibly noisier than that of the full
+    // one (C2 family at cutoff 1e-14: bonds of 6-7 instead of 4 three levels down the tree), so it keeps all columns
+    if (disabled || o.q < 1 || !(o.cutoff >= 1e-18) || l <= 1) return l;
     int* d_keep = (int*)ctx->alloc(sizeof(int));
     sketch_width_kernel<T><<<1, 32, 0, ctx->stream>>>(Rr.p, l, Rr.cols, kSketchNoise, d_keep);
     QIL_LAUNCH_CHECK(ctx);

@@ -56,3 +56,18 @@ def test_batch_encode_empty_and_errors(q):
     d = torch.zeros(64, dtype=torch.float64, device="cuda")
     with pytest.raises(q.ArgumentError):
         q.signal_mps_batch_dev(ctx, d.data_ptr(), 16, 4, False, k=0)
+
+
+@pytest.mark.parametrize("b", [95, 135])
+def test_c2_family_q0_bonds_follow_the_oracle_deep_in_the_tree(q, b):
+    """Members of the configs[1] family whose bonds three levels down the tree were inflated (6-7 instead of 4) when
+    the sketch was narrowed without a power iteration (q = 0): the narrowing is now limited to q >= 1, and the leading
+    bonds follow the oracle again."""
+    n = 20
+    N = 2**n
+    t = np.arange(N) / (2.5 * N)
+    x = np.sin((1 + 0.01 * b) * t) * np.exp(-0.08 * t) + np.sin((2.5 + 0.01 * b) * t) * np.exp(-0.03 * t)
+    kw = dict(k=20, p=10, q=0, cutoff=1e-14, maxdim=64)
+    psi = q.signal_mps(x, method="rsvd", **kw)
+    co, c = O.tt_rsvd(x, **kw)
+    assert psi.bonds[:6] == O.bonds_of(co)[:6] == [2, 4, 4, 4, 4, 4]
