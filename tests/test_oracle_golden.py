@@ -6,6 +6,8 @@ tests use as their analytic oracle (DFT, analytical_dt, analytical_zt).
 """
 import math
 
+import os
+
 import numpy as np
 import pytest
 
@@ -304,3 +306,64 @@ def test_pole_scan_modes_host_logic():
     # a misaligned origin is rejected
     with pytest.raises(q.ArgumentError):
         q.pole_scan_modes(n, 2, 0, 2, 2)
+
+
+def _c_oracle():
+    import ctypes as C
+    import importlib.util
+    root = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+    spec = importlib.util.spec_from_file_location("qil_build_c", os.path.join(root, "oracle", "build_c.py"))
+    mod = importlib.util.module_from_spec(spec)
+    spec.loader.exec_module(mod)
+    lib = C.CDLL(mod.build())
+    lib.qil_ref_truncate_rank.argtypes = [C.POINTER(C.c_double), C.c_int, C.c_double, C.c_longlong, C.c_longlong]
+    lib.qil_ref_bits_from_integer.argtypes = [C.c_longlong, C.c_int, C.POINTER(C.c_uint8)]
+    lib.qil_ref_coefficient.argtypes = [C.c_int, C.POINTER(C.c_int64), C.POINTER(C.c_double), C.POINTER(C.c_uint8),
+                                        C.c_double, C.POINTER(C.c_double)]
+    return lib, C
+
+
+def test_plain_c_oracle_agrees_with_numpy_oracle_and_kats():
+    """oracle/qil_oracle_c.c (gcc, no numpy) restates the truncation rule, the Integer -> bits convention and the
+    coefficient chain; it must agree with the numpy oracle and with the reference's KATs."""
+    lib, C = _c_oracle()
+    rng = np.random.default_rng(5)
+    # truncation rule (NDTensors truncate!!) on random graded spectra and the edge cases of the rule
+    for trial in range(200):
+        n = int(rng.integers(1, 24))
+        s = np.sort(np.abs(rng.standard_normal(n)) * 10.0 ** (-rng.uniform(0, 14, n)))[::-1].copy()
+        cutoff = float(10.0 ** (-rng.uniform(0, 26))) if trial % 5 else 0.0
+        maxdim = int(rng.integers(1, 30)) if trial % 3 == 0 else O.BIG
+        mindim = int(rng.integers(1, 4))
+        got = lib.qil_ref_truncate_rank(s.ctypes.data_as(C.POINTER(C.c_double)), n, cutoff,
+                                        min(maxdim, 2**62), mindim)
+        assert got == O.truncate_rank(s, cutoff, maxdim, mindim), (s, cutoff, maxdim, mindim)
+    # Integer configurations are big-endian (mps.jl:633-645)
+    bits = (C.c_uint8 * 5)()
+    assert lib.qil_ref_bits_from_integer(5, 3, bits) == 0 and list(bits[:3]) == [1, 0, 1] == O.bits_from_integer(5, 3)
+    assert lib.qil_ref_bits_from_integer(8, 3, bits) == 1 and lib.qil_ref_bits_from_integer(-1, 3, bits) == 1
+    # coefficient chain: x = 1..8 reads back (test/test_signal_converters.jl:146-191) and random complex MPS
+    x = np.arange(1.0, 9.0)
+    cores, c = O.tt_svd(x)
+
+    def c_coeff(cores, amp, b):
+        n = len(cores)
+        bond = np.array([1] + [int(k.shape[2]) for k in cores], dtype=np.int64)
+        flat = np.concatenate([np.ascontiguousarray(k, dtype=np.complex128).ravel() for k in cores]).view(np.float64)
+        bb = np.asarray(b, dtype=np.uint8)
+        out = np.zeros(2)
+        rc = lib.qil_ref_coefficient(n, bond.ctypes.data_as(C.POINTER(C.c_int64)),
+                                     flat.ctypes.data_as(C.POINTER(C.c_double)),
+                                     bb.ctypes.data_as(C.POINTER(C.c_uint8)), float(amp),
+                                     out.ctypes.data_as(C.POINTER(C.c_double)))
+        assert rc == 0
+        return complex(out[0], out[1])
+
+    for i in range(8):
+        assert abs(c_coeff(cores, c, O.bits_msb(i, 3)) - x[i]) < 1e-12
+    bonds = [1, 2, 4, 3, 5, 2, 1]
+    cores = [rng.standard_normal((bonds[i], 2, bonds[i + 1])) + 1j * rng.standard_normal((bonds[i], 2, bonds[i + 1]))
+             for i in range(6)]
+    for _ in range(20):
+        b = rng.integers(0, 2, 6)
+        assert abs(c_coeff(cores, 0.7, b) - O.coefficient(cores, 0.7, b)) < 1e-12
