@@ -135,19 +135,23 @@ int qil_encode_svd_dev(qil_ctx* ctx, int is_complex, const void* d_x, int64_t N,
  * Omega[c][j] = stream[c + C*j] (the column-major `random_itensor` of the reference).  `normal_stream` may
  * be NULL (device generator seeded with `seed`) or point at `stream_len` scalars of the signal's type drawn
  * by the host (`Random.seed!(seed); randn(T, len)` in the Julia shim), len >= max over splits of C*l. */
+/* flags: QIL_RSVD_ADAPTIVE = rank-adaptive sketch width at the top split (after the first QR of Y = A*Omega the
+ * sketch columns whose |R_jj| is at rounding level are dropped for the remaining 2q+1 passes; needs q >= 1 and
+ * cutoff >= 1e-18).  0 = the reference's fixed width k+p everywhere. */
+#define QIL_RSVD_ADAPTIVE 1
 int qil_encode_rsvd(qil_ctx* ctx, int is_complex, const void* x, int64_t N, int k, int p, int q, int64_t seed,
                     double cutoff, int64_t maxdim, int64_t mindim, const void* normal_stream, int64_t stream_len,
-                    int64_t reserved, qil_mps** out);
+                    int64_t flags, qil_mps** out);
 int qil_encode_rsvd_dev(qil_ctx* ctx, int is_complex, const void* d_x, int64_t N, int k, int p, int q, int64_t seed,
                         double cutoff, int64_t maxdim, int64_t mindim, const void* d_normal_stream,
-                        int64_t stream_len, int64_t reserved, qil_mps** out);
+                        int64_t stream_len, int64_t flags, qil_mps** out);
 /* A batch of `count` independent signals of N samples each, stored back to back on the device (BASELINE configs[1]:
  * 256 signals of n = 20).  Same result per signal as qil_encode_rsvd_dev with the device generator; the signals are
  * encoded concurrently by `workers` host threads, each on its own stream (<= 0: default 16).  out[count] receives
  * the handles.  Synchronous. */
 int qil_encode_rsvd_batch_dev(qil_ctx* ctx, int is_complex, const void* d_x, int64_t N, int64_t count, int k, int p,
                               int q, int64_t seed, double cutoff, int64_t maxdim, int64_t mindim, int workers,
-                              qil_mps** out);
+                              int64_t flags, qil_mps** out);
 
 /* ---- one signal row-sharded over several devices (one process per device) ---------------------
  * The length-N signal is split in rank order into world contiguous chunks of N/world samples, i.e. into
@@ -170,7 +174,8 @@ typedef struct qil_comm {
 int qil_get_stream(qil_ctx* ctx, void** cuda_stream);
 int qil_encode_rsvd_sharded_dev(qil_ctx* ctx, const qil_comm* comm, int is_complex, const void* d_x_local,
                                 int64_t N_total, int k, int p, int q, int64_t seed, double cutoff, int64_t maxdim,
-                                int64_t mindim, const void* d_normal_stream, int64_t stream_len, qil_mps** out);
+                                int64_t mindim, const void* d_normal_stream, int64_t stream_len, int64_t flags,
+                                qil_mps** out);
 
 /* Native implementation of the two collectives over NVLink peer memory (qil_peer.cu): every rank allocates a
  * symmetric exchange buffer of `bytes` payload (>= the largest message: 16 * l * 2^ceil(n/2) bytes covers every

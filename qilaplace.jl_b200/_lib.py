@@ -78,10 +78,10 @@ _SIGS = {
     "qil_encode_rsvd_dev": [c_ctx, C.c_int, C.c_void_p, C.c_int64, C.c_int, C.c_int, C.c_int, C.c_int64, C.c_double,
                             C.c_int64, C.c_int64, C.c_void_p, C.c_int64, C.c_int64, C.POINTER(c_mps)],
     "qil_encode_rsvd_batch_dev": [c_ctx, C.c_int, C.c_void_p, C.c_int64, C.c_int64, C.c_int, C.c_int, C.c_int, C.c_int64,
-                                  C.c_double, C.c_int64, C.c_int64, C.c_int, C.POINTER(c_mps)],
+                                  C.c_double, C.c_int64, C.c_int64, C.c_int, C.c_int64, C.POINTER(c_mps)],
     "qil_get_stream": [c_ctx, C.POINTER(C.c_void_p)],
     "qil_encode_rsvd_sharded_dev": [c_ctx, C.c_void_p, C.c_int, C.c_void_p, C.c_int64, C.c_int, C.c_int, C.c_int,
-                                    C.c_int64, C.c_double, C.c_int64, C.c_int64, C.c_void_p, C.c_int64,
+                                    C.c_int64, C.c_double, C.c_int64, C.c_int64, C.c_void_p, C.c_int64, C.c_int64,
                                     C.POINTER(c_mps)],
     "qil_peer_create": [c_ctx, C.c_int, C.c_int, C.c_int64, C.POINTER(C.c_void_p), C.c_void_p],
     "qil_peer_connect": [C.c_void_p, C.c_void_p],

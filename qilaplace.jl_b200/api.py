@@ -16,6 +16,8 @@ import numpy as np
 from . import _lib
 from ._lib import ArgumentError, DomainError, ErrorException, UnsupportedError, CudaError, call
 
+RSVD_ADAPTIVE = 1   # include/qilcuda.h: QIL_RSVD_ADAPTIVE (rank-adaptive sketch width at the top split; opt-in)
+
 BIG = 2**62
 
 
@@ -459,6 +461,7 @@ def signal_mps(x, method="svd", ctx=None, **kwargs):
         seed = int(kwargs.pop("random_seed", 1234)); mindim = int(kwargs.pop("mindim", 1))
         kwargs.pop("verbose", None); kwargs.pop("bondtag", None)
         stream = kwargs.pop("normal_stream", None)
+        flags = RSVD_ADAPTIVE if kwargs.pop("adaptive", False) else 0
         if kwargs:
             raise TypeError(f"signal_mps(method=:rsvd): unexpected keyword(s) {sorted(kwargs)}")
         if stream is not None:
@@ -468,7 +471,7 @@ def signal_mps(x, method="svd", ctx=None, **kwargs):
             sp, slen = None, 0
         call("qil_encode_rsvd", ctx.handle, int(is_complex), C.c_void_p(xa.ctypes.data), C.c_int64(xa.size),
              k, p, q, C.c_int64(seed), cutoff, C.c_int64(maxdim), C.c_int64(mindim), sp, C.c_int64(slen),
-             C.c_int64(0), C.byref(h))
+             C.c_int64(flags), C.byref(h))
     return SignalMPS(ctx, h)
 
 
@@ -690,7 +693,7 @@ def rsvd(A, k=20, p=10, q=0, random_seed=1234, cutoff=1e-15, maxdim=None, mindim
 # device-resident entry points (inputs already in HBM; pointers are raw CUDA device addresses)
 # ------------------------------------------------------------------------------------------
 def signal_mps_dev(ctx, d_x, N, is_complex, method="rsvd", cutoff=1e-15, maxdim=None, k=20, p=10, q=0,
-                   random_seed=1234, mindim=1):
+                   random_seed=1234, mindim=1, adaptive=False):
     """signal_mps on a signal that already lives on the device (stream-ordered, no host copies)."""
     h = _lib.c_mps()
     if method == "svd":
@@ -699,18 +702,18 @@ def signal_mps_dev(ctx, d_x, N, is_complex, method="rsvd", cutoff=1e-15, maxdim=
     else:
         call("qil_encode_rsvd_dev", ctx.handle, int(is_complex), C.c_void_p(int(d_x)), C.c_int64(N), int(k), int(p),
              int(q), C.c_int64(random_seed), float(cutoff), C.c_int64(_maxdim_arg(maxdim)), C.c_int64(mindim), None,
-             C.c_int64(0), C.c_int64(0), C.byref(h))
+             C.c_int64(0), C.c_int64(RSVD_ADAPTIVE if adaptive else 0), C.byref(h))
     return SignalMPS(ctx, h)
 
 
 def signal_mps_batch_dev(ctx, d_x, N, count, is_complex, cutoff=1e-15, maxdim=None, k=20, p=10, q=0, random_seed=1234,
-                         mindim=1, workers=16):
+                         mindim=1, workers=16, adaptive=False):
     """signal_mps(x_b; method=:rsvd) for `count` signals of N samples stored back to back on the device; the
     independent encodes run concurrently on `workers` streams.  Returns a list of SignalMPS."""
     hs = (_lib.c_mps * int(count))()
     call("qil_encode_rsvd_batch_dev", ctx.handle, int(is_complex), C.c_void_p(int(d_x)), C.c_int64(N), C.c_int64(count),
          int(k), int(p), int(q), C.c_int64(random_seed), float(cutoff), C.c_int64(_maxdim_arg(maxdim)),
-         C.c_int64(mindim), int(workers), hs)
+         C.c_int64(mindim), int(workers), C.c_int64(RSVD_ADAPTIVE if adaptive else 0), hs)
     return [SignalMPS(ctx, _lib.c_mps(h)) for h in hs]
 
 

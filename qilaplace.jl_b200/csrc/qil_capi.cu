@@ -484,22 +484,22 @@ int qil_encode_svd(qil_ctx* ctx, int is_complex, const void* x, int64_t N, doubl
 
 int qil_encode_rsvd_dev(qil_ctx* ctx, int is_complex, const void* d_x, int64_t N, int k, int p, int q, int64_t seed,
                         double cutoff, int64_t maxdim, int64_t mindim, const void* d_normal_stream,
-                        int64_t stream_len, int64_t reserved, qil_mps** out) {
+                        int64_t stream_len, int64_t flags, qil_mps** out) {
     QIL_API_BEGIN
-    (void)reserved;
     QIL_NONNULL(ctx); QIL_NONNULL(d_x); QIL_NONNULL(out);
     QIL_CUDA(cudaSetDevice(ctx->device));
     RsvdOpts o;
     o.k = k; o.p = p; o.q = q; o.seed = seed; o.cutoff = cutoff; o.maxdim = fix_maxdim(maxdim);
     o.mindim = mindim < 1 ? 1 : mindim;
     o.omega = d_normal_stream; o.omega_rows = d_normal_stream ? stream_len : 0; o.omega_cols = 1;
+    o.adaptive = (flags & QIL_RSVD_ADAPTIVE) != 0;
     *out = is_complex ? encode_rsvd<cplx>(ctx, (const cplx*)d_x, N, o) : encode_rsvd<double>(ctx, (const double*)d_x, N, o);
     QIL_API_END
 }
 
 int qil_encode_rsvd(qil_ctx* ctx, int is_complex, const void* x, int64_t N, int k, int p, int q, int64_t seed,
                     double cutoff, int64_t maxdim, int64_t mindim, const void* normal_stream, int64_t stream_len,
-                    int64_t reserved, qil_mps** out) {
+                    int64_t flags, qil_mps** out) {
     QIL_API_BEGIN
     QIL_NONNULL(ctx); QIL_NONNULL(x); QIL_NONNULL(out);
     QIL_REQUIRE(N >= 1, QIL_ERR_ARGUMENT, "signal_mps: empty signal");
@@ -513,7 +513,7 @@ int qil_encode_rsvd(qil_ctx* ctx, int is_complex, const void* x, int64_t N, int 
         QIL_CUDA(cudaMemcpyAsync(d_s, normal_stream, (size_t)stream_len * es, cudaMemcpyHostToDevice, ctx->stream));
     }
     int rc = qil_encode_rsvd_dev(ctx, is_complex, d_x, N, k, p, q, seed, cutoff, maxdim, mindim, d_s, stream_len,
-                                 reserved, out);
+                                 flags, out);
     ctx->free(d_x);
     if (d_s) ctx->free(d_s);
     cudaStreamSynchronize(ctx->stream);
@@ -523,7 +523,7 @@ int qil_encode_rsvd(qil_ctx* ctx, int is_complex, const void* x, int64_t N, int 
 
 int qil_encode_rsvd_batch_dev(qil_ctx* ctx, int is_complex, const void* d_x, int64_t N, int64_t count, int k, int p,
                               int q, int64_t seed, double cutoff, int64_t maxdim, int64_t mindim, int workers,
-                              qil_mps** out) {
+                              int64_t flags, qil_mps** out) {
     QIL_API_BEGIN
     QIL_NONNULL(ctx); QIL_NONNULL(out);
     QIL_REQUIRE(count >= 0, QIL_ERR_ARGUMENT, "signal batch: negative count");
@@ -534,6 +534,7 @@ int qil_encode_rsvd_batch_dev(qil_ctx* ctx, int is_complex, const void* d_x, int
     RsvdOpts o;
     o.k = k; o.p = p; o.q = q; o.seed = seed; o.cutoff = cutoff; o.maxdim = fix_maxdim(maxdim);
     o.mindim = mindim < 1 ? 1 : mindim;
+    o.adaptive = (flags & QIL_RSVD_ADAPTIVE) != 0;
     if (is_complex) encode_rsvd_batch<cplx>(ctx, (const cplx*)d_x, N, count, o, workers, out);
     else encode_rsvd_batch<double>(ctx, (const double*)d_x, N, count, o, workers, out);
     QIL_API_END
@@ -548,7 +549,8 @@ int qil_get_stream(qil_ctx* ctx, void** cuda_stream) {
 
 int qil_encode_rsvd_sharded_dev(qil_ctx* ctx, const qil_comm* comm, int is_complex, const void* d_x_local,
                                 int64_t N_total, int k, int p, int q, int64_t seed, double cutoff, int64_t maxdim,
-                                int64_t mindim, const void* d_normal_stream, int64_t stream_len, qil_mps** out) {
+                                int64_t mindim, const void* d_normal_stream, int64_t stream_len, int64_t flags,
+                                qil_mps** out) {
     QIL_API_BEGIN
     QIL_NONNULL(ctx); QIL_NONNULL(comm); QIL_NONNULL(d_x_local); QIL_NONNULL(out);
     QIL_NONNULL(comm->allreduce_sum_f64); QIL_NONNULL(comm->allgather_f64);
@@ -557,6 +559,7 @@ int qil_encode_rsvd_sharded_dev(qil_ctx* ctx, const qil_comm* comm, int is_compl
     o.k = k; o.p = p; o.q = q; o.seed = seed; o.cutoff = cutoff; o.maxdim = fix_maxdim(maxdim);
     o.mindim = mindim < 1 ? 1 : mindim;
     o.omega = d_normal_stream; o.omega_rows = d_normal_stream ? stream_len : 0; o.omega_cols = 1;
+    o.adaptive = (flags & QIL_RSVD_ADAPTIVE) != 0;
     *out = is_complex ? encode_rsvd_sharded<cplx>(ctx, comm, (const cplx*)d_x_local, N_total, o)
                       : encode_rsvd_sharded<double>(ctx, comm, (const double*)d_x_local, N_total, o);
     QIL_API_END

@@ -10,7 +10,7 @@
 // (cR fastest).  We keep exactly that structure -- Omega[c][j] = stream[c + C*j] with one stream per
 // encode -- and let the host pass the stream (the Julia shim passes `randn` after `Random.seed!`), or
 // generate it on the device with a counter-based generator.
-#include "qil_mpsops.cuh"
+#include "qil_fast.cuh"
 
 #include <atomic>
 #include <cstdlib>
@@ -217,7 +217,7 @@ static Mat<T> mul_A(SplitCtx<T>& sc, const T* A, int64_t R, int64_t C, int l, co
     Mat<T> Y(ctx, R, l);
     if (stream_supported(R, C * F, C * F, l * F)) {
         const int nt = stream_nt_for(l * F);
-        const int lpp = nt * 8 + 2;
+        const int lpp = stream_lpp(nt);
         const int64_t rows_pad = (C * F + 31) / 32 * 32;
         Mat<double> X(ctx, rows_pad, lpp);
         prep_x_k1_kernel<T><<<grid_for(ctx, rows_pad * lpp), 256, 0, ctx->stream>>>(
@@ -269,7 +269,7 @@ static Mat<T> mul_AH(SplitCtx<T>& sc, const T* A, int64_t R, int64_t C, int l, c
     Mat<T> Z(ctx, C, l);
     if (stream_supported(R, C * F, C * F, l * F)) {
         const int nt = stream_nt_for(l * F);
-        const int lpp = nt * 8 + 2;
+        const int lpp = stream_lpp(nt);
         const int64_t rows_pad = (R + 31) / 32 * 32;
         Mat<double> X(ctx, rows_pad, lpp);
         prep_x_k2_kernel<T><<<grid_for(ctx, rows_pad * lpp), 256, 0, ctx->stream>>>(Q, R, l, rows_pad, lpp, X.p);
@@ -310,13 +310,13 @@ __global__ void sketch_width_kernel(const T* __restrict__ R, int l, long long ld
         out[0] = keep;
     }
 }
-// l' for the R factor of the first sketch (host read-back); Q (rows x l) is compacted to its first l' columns
+// l' for the R factor of the first sketch (host read-back)
 template <typename T>
-static int shrink_sketch(qil_ctx* ctx, const RsvdOpts& o, int l, int64_t rows, Mat<T>& Q, const Mat<T>& Rr) {
-    static const bool disabled = [] { const char* e = getenv("QIL_RSVD_ADAPTIVE"); return e && e[0] == '0'; }();
+static int shrink_sketch_width(qil_ctx* ctx, const RsvdOpts& o, int l, const Mat<T>& Rr) {
+    // opt-in (RsvdOpts::adaptive, bit 0 of the `flags` argument of qil_encode_rsvd*): the reference keeps all k+p columns
     // q == 0: without a power iteration the basis of the narrowed sketch is visibly noisier than that of the full
     // one (C2 family at cutoff 1e-14: bonds of 6-7 instead of 4 three levels down the tree), so it keeps all columns
-    if (disabled || o.q < 1 || !(o.cutoff >= 1e-18) || l <= 1) return l;
+    if (!o.adaptive || o.q < 1 || !(o.cutoff >= 1e-18) || l <= 1) return l;
     int* d_keep = (int*)ctx->alloc(sizeof(int));
     sketch_width_kernel<T><<<1, 32, 0, ctx->stream>>>(Rr.p, l, Rr.cols, kSketchNoise, d_keep);
     QIL_LAUNCH_CHECK(ctx);
@@ -329,12 +329,136 @@ static int shrink_sketch(qil_ctx* ctx, const RsvdOpts& o, int l, int64_t rows, M
     static const int margin = [] { const char* e = getenv("QIL_RSVD_MARGIN"); return e ? atoi(e) : 3; }();
     keep = std::min(l, keep + margin);
     keep = (int)std::max<int64_t>(keep, std::min<int64_t>(o.mindim, l));
+    return std::min(keep, l);
+}
+// Q (rows x l) is compacted to its first l' columns
+template <typename T>
+static int shrink_sketch(qil_ctx* ctx, const RsvdOpts& o, int l, int64_t rows, Mat<T>& Q, const Mat<T>& Rr) {
+    const int keep = shrink_sketch_width<T>(ctx, o, l, Rr);
     if (keep >= l) return l;
     Mat<T> Qc(ctx, rows, keep);
     QIL_CUDA(cudaMemcpy2DAsync(Qc.p, (size_t)keep * sizeof(T), Q.p, (size_t)l * sizeof(T), (size_t)keep * sizeof(T),
                                (size_t)rows, cudaMemcpyDeviceToDevice, ctx->stream));
     Q = std::move(Qc);
     return keep;
+}
+
+// ---- fast tail of a randomized split (round 2): Bh = A^H Q given (possibly as split-K partials) ------------------
+// Bh = Qb Rb by the warp-synchronous TSQR, Jacobi + truncation on the device (svd_finish), then U = Q Us and
+// S Vh = (Us^H G) Qb^H in one launch.  One host read-back (the rank) instead of ~10 launches and 2 read-backs.
+template <typename T>
+static int rsvd_tail(SplitCtx<T>& sc, int64_t R, int64_t C, int l, const T* Q, int64_t ldq, const T* Bh, int64_t ldbh,
+                     int nsum, int64_t sum_stride, const double* d_scale, Mat<T>& U, Mat<T>* SVh, Mat<T>* Vh,
+                     Mat<double>* S) {
+    qil_ctx* ctx = sc.ctx;
+    const RsvdOpts& o = *sc.o;
+    struct Region {
+        qil_ctx* c;
+        explicit Region(qil_ctx* cc) : c(cc) { c->prof_begin(PROF_SVD); }
+        ~Region() { c->prof_end(); }
+    } region(ctx);
+    Mat<T> Qb(ctx, C, l), Rb(ctx, l, l), Us(ctx, l, l), T2(ctx, l, l);
+    Mat<double> Sv(ctx, l, 1);
+    qr_fast<T>(ctx, C, l, Bh, ldbh, nsum, sum_stride, false, Qb.p, l, l, Rb.p);
+    int* d_rank = (int*)ctx->alloc(sizeof(int));
+    svd_finish<T>(ctx, l, Rb.p, d_scale, o.cutoff, o.maxdim, o.mindim, Us.p, T2.p, Sv.p, d_rank);
+    // worst-case sized outputs, written compactly with leading dimension r
+    Mat<T> Uo(ctx, R, l), SVo, Vo;
+    if (SVh) SVo = Mat<T>(ctx, l, C);
+    if (Vh) Vo = Mat<T>(ctx, l, C);
+    rsvd_outputs<T>(ctx, R, C, l, Q, ldq, Qb.p, l, Us.p, T2.p, Sv.p, d_rank, Uo.p, SVh ? SVo.p : nullptr,
+                    Vh ? Vo.p : nullptr);
+    int r = 0;
+    QIL_CUDA(cudaMemcpyAsync(&r, d_rank, sizeof(int), cudaMemcpyDeviceToHost, ctx->stream));
+    ctx->sync();
+    ctx->free(d_rank);
+    Uo.cols = r;
+    U = std::move(Uo);
+    if (SVh) { SVo.rows = r; *SVh = std::move(SVo); }
+    if (Vh) { Vo.rows = r; *Vh = std::move(Vo); }
+    if (S) { Sv.rows = r; *S = std::move(Sv); }
+    return r;
+}
+
+// ---- fused real split: streaming pass -> TSQR straight from the split-K partials -> Q written in the operand
+// layout of the next pass.  Between two passes over A there are the launches of one QR and nothing else.
+static int rsvd_split_fused(SplitCtx<double>& sc, const double* A, int64_t R, int64_t C, bool top, int l0,
+                            Mat<double>& U, Mat<double>* SVh, Mat<double>* Vh, Mat<double>* S) {
+    qil_ctx* ctx = sc.ctx;
+    const RsvdOpts& o = *sc.o;
+    int nt = stream_nt_for(l0);
+    int lpp = stream_lpp(nt);
+    const int64_t rowsR = (R + 31) / 32 * 32, rowsC = (C + 31) / 32 * 32;
+    Mat<double> XR(ctx, rowsR, lpp), XC(ctx, rowsC, lpp);
+    if (rowsR > R) QIL_CUDA(cudaMemsetAsync(XR.p, 0, XR.elems() * sizeof(double), ctx->stream));
+    if (rowsC > C) QIL_CUDA(cudaMemsetAsync(XC.p, 0, XC.elems() * sizeof(double), ctx->stream));
+    int ks1, ks2; long long kc1, kc2;
+    stream_plan(ctx, R, C, &ks1, &kc1);
+    stream_plan(ctx, C, R, &ks2, &kc2);
+    Mat<double> partR(ctx, (int64_t)ks1 * R, nt * 8), partC(ctx, (int64_t)ks2 * C, nt * 8);
+    // ---- Y = A Omega
+    prep_x_k1_kernel<double><<<grid_for(ctx, rowsC * lpp), 256, 0, ctx->stream>>>(
+        nullptr, sc.stream, (unsigned long long)o.seed, C, l0, rowsC, lpp, XC.p);
+    QIL_LAUNCH_CHECK(ctx);
+    const bool want_sumsq = top && !sc.nrm_ready;
+    Mat<double> ssq;
+    const int grid1 = stream_grid(ctx, R, ks1);
+    if (want_sumsq) ssq = Mat<double>(ctx, grid1, 1);
+    stream_gemm(ctx, false, A, R, C, C, XC.p, lpp, nt, partR.p, ks1, kc1, want_sumsq ? ssq.p : nullptr, l0);
+    if (want_sumsq) {
+        finalize_norm_kernel<<<1, 32, 0, ctx->stream>>>(ssq.p, grid1, sc.d_nrm);
+        QIL_LAUNCH_CHECK(ctx);
+        sc.nrm_ready = true;
+    }
+    int l = l0;
+    {
+        Mat<double> Rtop;
+        const bool adapt = top && o.adaptive;
+        if (adapt) Rtop = Mat<double>(ctx, l0, l0);
+        ctx->prof_begin(PROF_QR);
+        qr_fast<double>(ctx, R, l0, partR.p, nt * 8, ks1, R * (int64_t)nt * 8, true, XR.p, lpp, lpp, adapt ? Rtop.p : nullptr);
+        ctx->prof_end();
+        if (adapt) {
+            l = shrink_sketch_width<double>(ctx, o, l0, Rtop);
+            if (l < l0) {
+                const int nt2 = stream_nt_for(l), lpp2 = stream_lpp(nt2);
+                Mat<double> XR2(ctx, rowsR, lpp2), XC2(ctx, rowsC, lpp2);
+                QIL_CUDA(cudaMemsetAsync(XR2.p, 0, XR2.elems() * sizeof(double), ctx->stream));
+                if (rowsC > C) QIL_CUDA(cudaMemsetAsync(XC2.p, 0, XC2.elems() * sizeof(double), ctx->stream));
+                QIL_CUDA(cudaMemcpy2DAsync(XR2.p, (size_t)lpp2 * sizeof(double), XR.p, (size_t)lpp * sizeof(double),
+                                           (size_t)l * sizeof(double), (size_t)R, cudaMemcpyDeviceToDevice, ctx->stream));
+                XR = std::move(XR2);
+                XC = std::move(XC2);
+                nt = nt2;
+                lpp = lpp2;
+            }
+        }
+    }
+    const int ldo = nt * 8;
+    for (int it = 0; it < o.q; ++it) {
+        stream_gemm(ctx, true, A, R, C, C, XR.p, lpp, nt, partC.p, ks2, kc2, nullptr, l);
+        ctx->prof_begin(PROF_QR);
+        qr_fast<double>(ctx, C, l, partC.p, ldo, ks2, C * (int64_t)ldo, true, XC.p, lpp, lpp, nullptr);
+        ctx->prof_end();
+        stream_gemm(ctx, false, A, R, C, C, XC.p, lpp, nt, partR.p, ks1, kc1, nullptr, l);
+        ctx->prof_begin(PROF_QR);
+        qr_fast<double>(ctx, R, l, partR.p, ldo, ks1, R * (int64_t)ldo, true, XR.p, lpp, lpp, nullptr);
+        ctx->prof_end();
+    }
+    // ---- B^H = A^H Q as partials, then the device-side tail
+    stream_gemm(ctx, true, A, R, C, C, XR.p, lpp, nt, partC.p, ks2, kc2, nullptr, l);
+    return rsvd_tail<double>(sc, R, C, l, XR.p, lpp, partC.p, ldo, ks2, C * (int64_t)ldo, top ? sc.d_nrm + 1 : nullptr, U,
+                             SVh, Vh, S);
+}
+template <typename T>
+static int rsvd_split_fused_dispatch(SplitCtx<T>&, const T*, int64_t, int64_t, bool, int, Mat<T>&, Mat<T>*, Mat<T>*,
+                                     Mat<double>*) {
+    QIL_THROW(QIL_ERR_RUNTIME, "fused split: real signals only");
+}
+template <>
+int rsvd_split_fused_dispatch<double>(SplitCtx<double>& sc, const double* A, int64_t R, int64_t C, bool top, int l0,
+                                      Mat<double>& U, Mat<double>* SVh, Mat<double>* Vh, Mat<double>* S) {
+    return rsvd_split_fused(sc, A, R, C, top, l0, U, SVh, Vh, S);
 }
 
 // rsvd of A (R x C contiguous): U (R x r), SVh (r x C).  `top` => A is the raw signal (scale by 1/||x||,
@@ -364,6 +488,10 @@ static int rsvd_split(SplitCtx<T>& sc, const T* A, int64_t R, int64_t C, bool to
     }
     if (sc.stream) QIL_REQUIRE(C * (int64_t)l0 <= sc.stream_len, QIL_ERR_ARGUMENT,
                                "rsvd: the supplied normal stream is shorter than %lld", (long long)(C * l0));
+    constexpr int F0 = Scalar<T>::is_complex ? 2 : 1;
+    const bool fast_qr = !sc.comm && qr_fast_supported<T>(ctx, R, l0) && qr_fast_supported<T>(ctx, C, l0);
+    if (fast_qr && !Scalar<T>::is_complex && stream_supported(R, C * F0, C * F0, l0 * F0))
+        return rsvd_split_fused_dispatch<T>(sc, A, R, C, top, l0, U, SVh, Vh, S);
     Mat<T> Y = mul_A<T>(sc, A, R, C, l0, nullptr, top && !sc.nrm_ready);
     if (top && !sc.nrm_ready) {
         // generic path: the norm needs its own pass
@@ -386,6 +514,11 @@ static int rsvd_split(SplitCtx<T>& sc, const T* A, int64_t R, int64_t C, bool to
         qr_thin<T>(ctx, R, l, Y2.p, l, true, Q, Rr);
     }
     // B^H = A^H Q (C x l), scaled by 1/||x|| at the top
+    if (fast_qr) {
+        // B^H unscaled; the 1/||x|| of the top split is applied to the l x l triangle inside svd_finish
+        Mat<T> Bh = mul_AH<T>(sc, A, R, C, l, Q.p, nullptr);
+        return rsvd_tail<T>(sc, R, C, l, Q.p, l, Bh.p, l, 1, 0, top ? sc.d_nrm + 1 : nullptr, U, SVh, Vh, S);
+    }
     Mat<T> Bh = mul_AH<T>(sc, A, R, C, l, Q.p, top ? sc.d_nrm + 1 : nullptr);
     Mat<T> Us;
     const int r = svd_trunc_adj<T>(ctx, l, C, Bh.p, l, o.cutoff, o.maxdim, o.mindim, &Us, nullptr, Vh, SVh, S);

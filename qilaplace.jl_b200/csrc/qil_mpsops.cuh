@@ -18,6 +18,7 @@ struct RsvdOpts {
     int64_t mindim = 1;
     const void* omega = nullptr;   // optional host-supplied test matrix (cols x l, row-major), device pointer
     int64_t omega_rows = 0, omega_cols = 0;
+    bool adaptive = false;         // rank-adaptive sketch width at the top split (flags bit 0; off = reference behaviour)
 };
 // signal_mps(x; method=:rsvd, ...)
 template <typename T> qil_mps* encode_rsvd(qil_ctx* ctx, const T* d_x, int64_t N, const RsvdOpts& o);
@@ -48,6 +49,9 @@ qil_mpo* build_zt_mpo(qil_ctx* ctx, int n, double wr, double cutoff, int64_t max
 namespace qil {
 // streaming DMMA/TMA GEMMs (qil_sketch.cu)
 int stream_nt_for(int cols);
+// pitch (doubles) of the X operand: 8*nt + 1 -- odd, so that the B-fragment loads of the DMMA consumers (rows 4t+i,
+// column g) hit 16 distinct bank pairs per half warp (8*nt + 2 gave a 2-way conflict on every load)
+inline int stream_lpp(int nt) { return nt * 8 + 1; }
 bool stream_supported(long long R, long long C, long long ld, int cols);
 void stream_plan(qil_ctx* ctx, long long Mtot, long long Kdim, int* ksplit, long long* kchunk);
 int stream_grid(qil_ctx* ctx, long long Mtot, int ksplit);

@@ -4,7 +4,7 @@
 // QR branch of `factorize` (qft_transformer.jl:52).  Householder reflectors keep Q orthonormal to
 // rounding even when the matrix is numerically rank deficient (the usual case for Y = A*Omega of a
 // structured signal), which Gram/Cholesky shortcuts do not.
-#include "qil_dense.cuh"
+#include "qil_fast.cuh"
 #include "qil_hh.cuh"
 
 namespace qil {
@@ -194,6 +194,14 @@ void qr_thin(qil_ctx* ctx, int64_t m, int64_t n64, const T* A, int64_t lda, bool
     QIL_REQUIRE(m >= 1 && n64 >= 1, QIL_ERR_ARGUMENT, "qr: empty matrix");
     QIL_REQUIRE(n64 < (1 << 20), QIL_ERR_UNSUPPORTED, "qr: too many columns");
     const int n = (int)n64;
+    if (qr_fast_supported<T>(ctx, m, n)) {
+        // skinny panels (n <= 32): warp-synchronous TSQR (qil_tsqr.cu), one launch (or three for tall ones)
+        Mat<T> Qf(ctx, m, n);
+        R = Mat<T>(ctx, n, n);
+        qr_fast<T>(ctx, m, n, A, lda, nsum, sum_stride, positive, Qf.p, n, n, R.p);
+        if (want_q) Q = std::move(Qf);
+        return;
+    }
     const int cap = qr_capacity<T>(ctx, n);
     const int64_t k = std::min<int64_t>(m, n);
     if (m <= cap) {

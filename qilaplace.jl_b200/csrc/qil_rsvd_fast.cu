@@ -1,0 +1,178 @@
+// qil_rsvd_fast.cu -- the small-matrix end of a randomized split without host round trips (rsvd.jl:98-121):
+//   B = Q^H A is l x C; its adjoint Bh = A^H Q comes out of the streaming kernel, Bh = Qb Rb by the fast TSQR, then
+//   svd_finish   : one warp runs the one-sided Jacobi on G = Rb^H (l <= 32), sorts, applies the NDTensors
+//                  truncation rule on the device and writes the two small factors,
+//   rsvd_outputs : U = Q Us (rows x r) and S*Vh = (Us^H G) Qb^H (r x C), rank read from device memory.
+#include "qil_fast.cuh"
+#include "qil_wqr.cuh"
+
+namespace qil {
+
+template <typename T>
+struct FinishParams {
+    const T* Rb;        // l x l, ld l (upper triangular)
+    int l;
+    const double* scale;
+    double cutoff;
+    long long maxdim, mindim;
+    T* Us;              // l x r, ld r
+    T* T2;              // r x l, ld l
+    double* S;          // l
+    int* rank;
+    double* margin;
+};
+
+// shared-memory image of one finish: G (column-major, pitch pg), G0 copy, sig, order.  Called by all threads of a
+// CTA; `G0` must already hold the (scaled) matrix whose columns are to be orthogonalised, column-major with pitch pg.
+// On return (after a barrier): Gw = W, sig sorted descending, order, *s_rank.
+template <typename T>
+__device__ __forceinline__ void cta_jacobi_rank(T* Gw, const T* G0, int pg, int ns, double cutoff, long long maxdim,
+                                                long long mindim, double* sig, int* order, int* s_rank, double* margin,
+                                                double* s_nu) {
+    const int tid = threadIdx.x;
+    for (int idx = tid; idx < ns * pg; idx += blockDim.x) Gw[idx] = G0[idx];
+    // ||G||_F^2 in a fixed order (skip threshold, qil_common.cuh)
+    for (int j = tid; j < ns; j += blockDim.x) {
+        double a = 0.0;
+        for (int i = 0; i < ns; ++i) a += Scalar<T>::abs2(G0[j * pg + i]);
+        sig[j] = a;
+    }
+    __syncthreads();
+    if (tid == 0) {
+        double tot = 0.0;
+        for (int j = 0; j < ns; ++j) tot += sig[j];
+        *s_nu = jacobi_skip_threshold(tot, ns, cutoff, mindim);
+    }
+    __syncthreads();
+    if (tid < 32) {
+        wjacobi<T>(Gw, pg, ns, *s_nu, sig, order);
+        if (tid == 0) *s_rank = truncate_rank_dev(sig, ns, cutoff, maxdim < 1 ? 1 : maxdim, mindim < 1 ? 1 : mindim, margin);
+    }
+    __syncthreads();
+}
+
+template <typename T>
+__global__ void __launch_bounds__(128) svd_finish_kernel(const FinishParams<T> p) {
+    extern __shared__ __align__(16) unsigned char smem_raw[];
+    const int l = p.l, pg = l | 1;
+    T* G0 = reinterpret_cast<T*>(smem_raw);            // [l][pg] column-major
+    T* Gw = G0 + l * pg;
+    T* Us = Gw + l * pg;                               // [l][pg] row-major (i, j)
+    double* sig = reinterpret_cast<double*>(Us + l * pg);
+    int* order = reinterpret_cast<int*>(sig + l);
+    __shared__ int s_rank;
+    __shared__ double s_nu;
+    const int tid = threadIdx.x;
+    const double sc = p.scale ? p.scale[0] : 1.0;
+    // G = scale * Rb^H: column j of G is the conjugated row j of Rb
+    for (int idx = tid; idx < l * l; idx += blockDim.x) {
+        const int j = idx / l, i = idx - j * l;
+        G0[j * pg + i] = Scalar<T>::scale(Scalar<T>::conj(p.Rb[(size_t)j * l + i]), sc);
+    }
+    __syncthreads();
+    cta_jacobi_rank<T>(Gw, G0, pg, l, p.cutoff, p.maxdim, p.mindim, sig, order, &s_rank, p.margin, &s_nu);
+    const int r = s_rank;
+    if (tid == 0) *p.rank = r;
+    for (int j = tid; j < l; j += blockDim.x) p.S[j] = sig[j];
+    // Us = W Sigma^-1 (sorted columns)
+    for (int idx = tid; idx < l * r; idx += blockDim.x) {
+        const int i = idx / r, j = idx - i * r;
+        const double sj = sig[j];
+        const T v = Scalar<T>::scale(Gw[order[j] * pg + i], sj > 0.0 ? 1.0 / sj : 0.0);
+        Us[i * pg + j] = v;
+        p.Us[(size_t)i * r + j] = v;
+    }
+    __syncthreads();
+    // T2 = Us^H G  (r x l)
+    for (int idx = tid; idx < r * l; idx += blockDim.x) {
+        const int j = idx / l, c = idx - j * l;
+        T acc = Scalar<T>::zero();
+        for (int k = 0; k < l; ++k) acc = Scalar<T>::fma(Scalar<T>::conj(Us[k * pg + j]), G0[c * pg + k], acc);
+        p.T2[(size_t)j * l + c] = acc;
+    }
+}
+
+template <typename T>
+void svd_finish(qil_ctx* ctx, int l, const T* Rb, const double* d_scale, double cutoff, int64_t maxdim, int64_t mindim,
+                T* Us, T* T2, double* S, int* d_rank) {
+    QIL_REQUIRE(l >= 1 && l <= kWqrMaxN, QIL_ERR_UNSUPPORTED, "svd_finish: l = %d", l);
+    FinishParams<T> p;
+    p.Rb = Rb; p.l = l; p.scale = d_scale; p.cutoff = cutoff; p.maxdim = maxdim; p.mindim = mindim;
+    p.Us = Us; p.T2 = T2; p.S = S; p.rank = d_rank; p.margin = ctx->d_margin;
+    const int pg = l | 1;
+    const size_t smem = (size_t)3 * l * pg * sizeof(T) + (size_t)l * (sizeof(double) + sizeof(int)) + 64;
+    svd_finish_kernel<T><<<1, 128, smem, ctx->stream>>>(p);
+    QIL_LAUNCH_CHECK(ctx);
+}
+template void svd_finish<double>(qil_ctx*, int, const double*, const double*, double, int64_t, int64_t, double*, double*,
+                                 double*, int*);
+template void svd_finish<cplx>(qil_ctx*, int, const cplx*, const double*, double, int64_t, int64_t, cplx*, cplx*, double*,
+                               int*);
+
+// one thread per output element; Us / T2 staged in shared memory
+template <typename T>
+__global__ void __launch_bounds__(256) rsvd_outputs_kernel(long long R, long long C, int l, const T* __restrict__ Q,
+                                                           long long ldq, const T* __restrict__ Qb, long long ldqb,
+                                                           const T* __restrict__ Us, const T* __restrict__ T2,
+                                                           const double* __restrict__ S, const int* __restrict__ d_rank,
+                                                           T* __restrict__ U, T* __restrict__ SVh, T* __restrict__ Vh) {
+    extern __shared__ __align__(16) unsigned char smem_raw[];
+    const int r = *d_rank;
+    T* sU = reinterpret_cast<T*>(smem_raw);     // [l][r]
+    T* sT = sU + l * r;                         // [r][l]
+    double* sS = reinterpret_cast<double*>(sT + r * l);
+    for (int idx = threadIdx.x; idx < l * r; idx += blockDim.x) { sU[idx] = Us[idx]; sT[idx] = T2[idx]; }
+    for (int j = threadIdx.x; j < r; j += blockDim.x) sS[j] = S[j];
+    __syncthreads();
+    const long long gstride = (long long)gridDim.x * blockDim.x;
+    if (U) {
+        for (long long row = (long long)blockIdx.x * blockDim.x + threadIdx.x; row < R; row += gstride) {
+            const T* qr = Q + row * ldq;
+            T q[kWqrMaxN];
+#pragma unroll
+            for (int i = 0; i < kWqrMaxN; ++i) q[i] = (i < l) ? qr[i] : Scalar<T>::zero();
+            for (int j = 0; j < r; ++j) {
+                T acc = Scalar<T>::zero();
+#pragma unroll
+                for (int i = 0; i < kWqrMaxN; ++i)
+                    if (i < l) acc = Scalar<T>::fma(q[i], sU[i * r + j], acc);
+                U[row * r + j] = acc;
+            }
+        }
+    }
+    if (SVh || Vh) {
+        for (long long c = (long long)blockIdx.x * blockDim.x + threadIdx.x; c < C; c += gstride) {
+            const T* qr = Qb + c * ldqb;
+            T q[kWqrMaxN];
+#pragma unroll
+            for (int i = 0; i < kWqrMaxN; ++i) q[i] = (i < l) ? Scalar<T>::conj(qr[i]) : Scalar<T>::zero();
+            for (int j = 0; j < r; ++j) {
+                T acc = Scalar<T>::zero();
+#pragma unroll
+                for (int i = 0; i < kWqrMaxN; ++i)
+                    if (i < l) acc = Scalar<T>::fma(sT[j * l + i], q[i], acc);
+                if (SVh) SVh[(long long)j * C + c] = acc;
+                if (Vh) {
+                    const double sj = sS[j];
+                    Vh[(long long)j * C + c] = Scalar<T>::scale(acc, sj > 0.0 ? 1.0 / sj : 0.0);
+                }
+            }
+        }
+    }
+}
+
+template <typename T>
+void rsvd_outputs(qil_ctx* ctx, int64_t R, int64_t C, int l, const T* Q, int64_t ldq, const T* Qb, int64_t ldqb,
+                  const T* Us, const T* T2, const double* S, const int* d_rank, T* U, T* SVh, T* Vh) {
+    const size_t smem = (size_t)2 * l * l * sizeof(T) + (size_t)l * sizeof(double) + 32;
+    const int64_t work = std::max(R, C);
+    const int grid = (int)std::max<int64_t>(1, std::min<int64_t>((work + 255) / 256, (int64_t)ctx->sm_count * 4));
+    rsvd_outputs_kernel<T><<<grid, 256, smem, ctx->stream>>>(R, C, l, Q, ldq, Qb, ldqb, Us, T2, S, d_rank, U, SVh, Vh);
+    QIL_LAUNCH_CHECK(ctx);
+}
+template void rsvd_outputs<double>(qil_ctx*, int64_t, int64_t, int, const double*, int64_t, const double*, int64_t,
+                                   const double*, const double*, const double*, const int*, double*, double*, double*);
+template void rsvd_outputs<cplx>(qil_ctx*, int64_t, int64_t, int, const cplx*, int64_t, const cplx*, int64_t, const cplx*,
+                                 const cplx*, const double*, const int*, cplx*, cplx*, cplx*);
+
+}  // namespace qil

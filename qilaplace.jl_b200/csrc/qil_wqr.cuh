@@ -1,0 +1,543 @@
+// qil_wqr.cuh -- warp-synchronous building blocks for the latency path of the encoder (round 2).
+//
+// The divide-and-conquer encoder (SignalConverters.jl:107-196 + rsvd.jl:38-121) is, apart from the
+// 2+2q streaming passes of the top split, a chain of ~n small dependent factorizations: Householder QRs
+// of l-column panels (rsvd.jl:83,90,94), SVDs of l x l triangles (rsvd.jl:103).  What bounds them is
+// the number of dependent reductions, not flops, so the blocks below avoid CTA barriers altogether:
+//
+//   * wqr_factor      one WARP factors a block of <= 256 rows x <= 32 columns held in shared memory
+//                     (row-major, odd pitch: lane <-> row is conflict free); ONE shuffle all-reduce per
+//                     column step yields the column norm and all reflector dot products at once
+//                     (x^H a_c for c >= j; u^H a_c = x^H a_c - conj(beta) a_jc follows algebraically),
+//   * wqr_apply_chunk one warp applies the reflectors of a block to an 8-column (complex: 4) chunk
+//                     held in REGISTERS (explicit Q / apply-down of a TSQR tree); the chunks of one
+//                     block are independent, so ceil(n/8) warps work on a block at once,
+//   * cta_qr          multi-level TSQR of an m x n panel inside one CTA from these two,
+//   * wjacobi         one warp runs the one-sided Jacobi SVD of an ns x ns (ns <= 32) triangle; pairs of
+//                     a round-robin round are spread over sub-warp lane groups, no block barrier,
+//   * cta_gemm        panel GEMMs on DMMA m16n8k16 with fragments read straight from global / shared.
+//
+// Same reflector convention as qil_hh.cuh: H_j = I - tau_j u_j u_j^H, H_j x = beta_j e_1, u_j stored in
+// column j rows j.. (head u_j[j] = x_j - beta_j), R strictly above the diagonal, diag(R) in beta.
+#pragma once
+#include "qil_common.cuh"
+
+namespace qil {
+
+constexpr int kWqrMaxN = 32;   // columns of a fast-path panel
+constexpr int kWqrRpl = 8;     // rows per lane  => a warp block has at most 256 rows
+constexpr int kWqrMaxRows = 32 * kWqrRpl;
+
+template <typename T> struct WqrChunk { static constexpr int CH = 4; };      // register chunk of the apply-down (cta_qr)
+template <> struct WqrChunk<cplx> { static constexpr int CH = 2; };
+
+template <typename T> __device__ __forceinline__ T wq_sum(T v);
+template <> __device__ __forceinline__ double wq_sum<double>(double v) {
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) v += __shfl_xor_sync(0xffffffffu, v, o);
+    return v;
+}
+template <> __device__ __forceinline__ cplx wq_sum<cplx>(cplx v) {
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) {
+        v.x += __shfl_xor_sync(0xffffffffu, v.x, o);
+        v.y += __shfl_xor_sync(0xffffffffu, v.y, o);
+    }
+    return v;
+}
+
+template <typename T> __device__ __forceinline__ T wq_shfl_xor(T v, int o);
+template <> __device__ __forceinline__ double wq_shfl_xor<double>(double v, int o) { return __shfl_xor_sync(0xffffffffu, v, o); }
+template <> __device__ __forceinline__ cplx wq_shfl_xor<cplx>(cplx v, int o) {
+    return make_double2(__shfl_xor_sync(0xffffffffu, v.x, o), __shfl_xor_sync(0xffffffffu, v.y, o));
+}
+
+// ---- Householder factorisation of one block by one warp -----------------------------------------------
+// blk: m x n, row-major, pitch (elements, odd) in shared memory; m <= 256, n <= 32.  k = min(m, n) reflectors.
+template <typename T> struct WqrWidth { static constexpr int CW = 32; };     // trailing columns reduced at once
+template <> struct WqrWidth<cplx> { static constexpr int CW = 16; };
+
+template <typename T, int RPL = kWqrRpl>
+__device__ __forceinline__ void wqr_factor(T* blk, int pitch, int m, int n, T* beta, double* tau) {
+    constexpr int CW = WqrWidth<T>::CW;
+    const int lane = threadIdx.x & 31;
+    const int k = min(m, n);
+    for (int j = 0; j < k; ++j) {
+        T u[RPL];
+#pragma unroll
+        for (int t = 0; t < RPL; ++t) {
+            const int i = lane + 32 * t;
+            u[t] = (i >= j && i < m) ? blk[i * pitch + j] : Scalar<T>::zero();
+        }
+        const T x0 = blk[j * pitch + j];
+        T bj = Scalar<T>::zero();
+        T head = x0;
+        double tj = 0.0;
+        for (int c0 = 0; j + c0 < n; c0 += CW) {
+            // s[cc] = sum_{i >= j} conj(x_i) a_{i, j+c0+cc}: column j itself gives |x|^2, the rest the reflector dots
+            T s[CW];
+#pragma unroll
+            for (int cc = 0; cc < CW; ++cc) s[cc] = Scalar<T>::zero();
+#pragma unroll
+            for (int t = 0; t < RPL; ++t) {
+                const int i = lane + 32 * t;
+                if (i >= j && i < m) {
+                    const T uc = Scalar<T>::conj(u[t]);
+                    const T* row = blk + i * pitch + j + c0;
+#pragma unroll
+                    for (int cc = 0; cc < CW; ++cc)
+                        if (j + c0 + cc < n) s[cc] = Scalar<T>::fma(uc, row[cc], s[cc]);
+                }
+            }
+#pragma unroll
+            for (int cc = 0; cc < CW; ++cc)
+                if (j + c0 + cc < n) s[cc] = wq_sum<T>(s[cc]);
+            if (c0 == 0) {
+                const double nx2 = Scalar<T>::real(s[0]);
+                if (nx2 > 0.0) {
+                    const double a02 = Scalar<T>::abs2(x0);
+                    const double a0 = sqrt(a02);
+                    const double nx = sqrt(nx2);
+                    const T ph = (a02 > 0.0) ? Scalar<T>::scale(x0, 1.0 / a0) : Scalar<T>::one();
+                    bj = Scalar<T>::scale(ph, -nx);
+                    tj = 1.0 / (nx * (nx + a0));
+                }
+                head = Scalar<T>::sub(x0, bj);       // u_j[j]
+            }
+            if (tj == 0.0) break;
+            // f[cc] = -tau * (s[cc] - conj(beta) a_{j, c}),  u^H a_c = x^H a_c - conj(beta) a_{jc}
+            const T cb = Scalar<T>::conj(bj);
+            const T* rowj = blk + j * pitch + j + c0;
+#pragma unroll
+            for (int cc = 0; cc < CW; ++cc)
+                if (j + c0 + cc < n && (c0 + cc) > 0)
+                    s[cc] = Scalar<T>::scale(Scalar<T>::sub(s[cc], Scalar<T>::mul(cb, rowj[cc])), -tj);
+            __syncwarp();   // every lane has read row j before its owner updates it
+#pragma unroll
+            for (int t = 0; t < RPL; ++t) {
+                const int i = lane + 32 * t;
+                if (i >= j && i < m) {
+                    const T uu = (i == j) ? head : u[t];
+                    T* row = blk + i * pitch + j + c0;
+#pragma unroll
+                    for (int cc = 0; cc < CW; ++cc)
+                        if (j + c0 + cc < n && (c0 + cc) > 0) row[cc] = Scalar<T>::fma(s[cc], uu, row[cc]);
+                }
+            }
+            __syncwarp();
+        }
+        if (lane == 0) {
+            blk[j * pitch + j] = head;
+            beta[j] = bj;
+            tau[j] = tj;
+        }
+        __syncwarp();
+    }
+}
+
+// ---- reflectors of one block applied to a register chunk -----------------------------------------------
+// b[t][q] holds element (row lane + 32 t, chunk column q).  b <- H_0 H_1 ... H_{k-1} b.
+template <typename T, int RPL, int CH>
+__device__ __forceinline__ void wqr_apply_chunk(const T* V, int pitch, int m, int k, const double* tau,
+                                                T (&b)[RPL][CH]) {
+    const int lane = threadIdx.x & 31;
+    for (int j = k - 1; j >= 0; --j) {
+        const double tj = tau[j];
+        if (tj == 0.0) continue;
+        T u[RPL];
+#pragma unroll
+        for (int t = 0; t < RPL; ++t) {
+            const int i = lane + 32 * t;
+            u[t] = (i >= j && i < m) ? V[i * pitch + j] : Scalar<T>::zero();
+        }
+        T w[CH];
+#pragma unroll
+        for (int q = 0; q < CH; ++q) w[q] = Scalar<T>::zero();
+#pragma unroll
+        for (int t = 0; t < RPL; ++t) {
+            const T uc = Scalar<T>::conj(u[t]);
+#pragma unroll
+            for (int q = 0; q < CH; ++q) w[q] = Scalar<T>::fma(uc, b[t][q], w[q]);
+        }
+#pragma unroll
+        for (int q = 0; q < CH; ++q) w[q] = Scalar<T>::scale(wq_sum<T>(w[q]), -tj);
+#pragma unroll
+        for (int t = 0; t < RPL; ++t) {
+#pragma unroll
+            for (int q = 0; q < CH; ++q) b[t][q] = Scalar<T>::fma(w[q], u[t], b[t][q]);
+        }
+    }
+}
+
+// unit phase of a diagonal entry of R (ITensors qr(...; positive=true): Q <- Q diag(ph), R <- diag(conj ph) R)
+template <typename T>
+__device__ __forceinline__ T wqr_phase(T b) {
+    const double a2 = Scalar<T>::abs2(b);
+    return a2 > 0.0 ? Scalar<T>::scale(b, rsqrt(a2)) : Scalar<T>::one();
+}
+
+// ---- multi-level TSQR of an m x n panel inside one CTA ---------------------------------------------------
+// Level 0 is the caller's panel (row-major, `pitch`), split into nb[0] balanced blocks of <= 256 rows, one warp
+// each; the n x n triangles are stacked into the level-1 panel, and so on until one block remains.
+struct CtaQrPlan {
+    int nlev;
+    int rows[4];
+    int nb[4];
+    int stack_rows;      // rows of all panels above level 0
+    int blocks;          // blocks over all levels (beta / tau slots)
+};
+
+__host__ __device__ inline int cta_qr_blocks_for(int rows) { return (rows + kWqrMaxRows - 1) / kWqrMaxRows; }
+
+__host__ __device__ inline CtaQrPlan cta_qr_plan(int m, int n) {
+    CtaQrPlan p;
+    p.nlev = 0;
+    p.stack_rows = 0;
+    p.blocks = 0;
+    int rows = m;
+    for (;;) {
+        const int nb = cta_qr_blocks_for(rows);
+        p.rows[p.nlev] = rows;
+        p.nb[p.nlev] = nb;
+        p.blocks += nb;
+        ++p.nlev;
+        if (nb == 1 || p.nlev == 4) break;
+        rows = nb * n;          // every block of a multi-block level has >= n rows (rows / nb >= 128 >= n)
+        p.stack_rows += rows;
+    }
+    return p;
+}
+
+// shared memory (in elements of T) a cta_qr call needs beyond the level-0 panel
+template <typename T>
+__host__ __device__ inline size_t cta_qr_extra_elems(int m, int n) {
+    const CtaQrPlan p = cta_qr_plan(m, n);
+    const int pitch = n | 1;
+    // stack panels + beta[blocks][n] + tau[blocks][n] (tau as doubles: at most one T each)
+    return (size_t)p.stack_rows * pitch + 2 * (size_t)p.blocks * n + 8;
+}
+
+__device__ __forceinline__ void blk_range(int rows, int nb, int b, int& r0, int& r1) {
+    r0 = (int)(((long long)b * rows) / nb);
+    r1 = (int)(((long long)(b + 1) * rows) / nb);
+}
+
+// Factor + explicit Q.  All threads of the CTA call it (blockDim.x a multiple of 32, >= 32 * ceil(n / CH)).
+//   panel : m x n row-major (pitch), m >= n; overwritten by Q (m x n) when `Qout` == nullptr, else left holding the
+//           reflectors and Q is written to Qout (row-major, ldq; GLOBAL or shared), columns n..qcols-1 zero filled
+//   Rout  : n x n row-major (ldr) upper triangular, or nullptr
+//   work  : cta_qr_extra_elems<T>(m, n) elements of shared memory
+template <typename T>
+__device__ __forceinline__ void cta_qr(T* panel, int pitch, int m, int n, bool positive, T* Rout, int ldr, T* Qout,
+                                       long long ldq, int qcols, T* work) {
+    constexpr int CH = WqrChunk<T>::CH;
+    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+    const int nwarps = blockDim.x >> 5;
+    const CtaQrPlan pl = cta_qr_plan(m, n);
+    const int spitch = n | 1;
+    T* lev_panel[4];
+    int lev_pitch[4];
+    lev_panel[0] = panel;
+    lev_pitch[0] = pitch;
+    {
+        T* w = work;
+        for (int L = 1; L < pl.nlev; ++L) {
+            lev_panel[L] = w;
+            lev_pitch[L] = spitch;
+            w += (size_t)pl.rows[L] * spitch;
+        }
+    }
+    T* beta = work + (size_t)pl.stack_rows * spitch;                 // [blocks][n]
+    double* tau = reinterpret_cast<double*>(beta + (size_t)pl.blocks * n);   // [blocks][n]
+    int lev_slot[4];
+    {
+        int s = 0;
+        for (int L = 0; L < pl.nlev; ++L) { lev_slot[L] = s; s += pl.nb[L]; }
+    }
+
+    // ---- factor, level by level; each block's triangle goes to the next level's panel
+    for (int L = 0; L < pl.nlev; ++L) {
+        T* P = lev_panel[L];
+        const int pp = lev_pitch[L];
+        for (int b = warp; b < pl.nb[L]; b += nwarps) {
+            int r0, r1;
+            blk_range(pl.rows[L], pl.nb[L], b, r0, r1);
+            T* bb = beta + (size_t)(lev_slot[L] + b) * n;
+            double* tt = tau + (size_t)(lev_slot[L] + b) * n;
+            wqr_factor<T>(P + (size_t)r0 * pp, pp, r1 - r0, n, bb, tt);
+            if (L + 1 < pl.nlev) {
+                T* S = lev_panel[L + 1] + (size_t)b * n * spitch;
+                for (int idx = lane; idx < n * n; idx += 32) {
+                    const int j = idx / n, c = idx - j * n;
+                    T v = Scalar<T>::zero();
+                    if (c == j) v = bb[j];
+                    else if (c > j) v = P[(size_t)(r0 + j) * pp + c];
+                    S[j * spitch + c] = v;
+                }
+            }
+        }
+        __syncthreads();
+    }
+    // ---- R of the top level (k = min(rows_top, n) rows; rows_top >= n whenever m >= n)
+    const int Lt = pl.nlev - 1;
+    const T* btop = beta + (size_t)lev_slot[Lt] * n;
+    if (Rout) {
+        const T* P = lev_panel[Lt];
+        const int pp = lev_pitch[Lt];
+        const int kk = min(pl.rows[Lt], n);
+        for (int idx = threadIdx.x; idx < n * n; idx += blockDim.x) {
+            const int j = idx / n, c = idx - j * n;
+            T v = Scalar<T>::zero();
+            if (j < kk) {
+                if (c == j) v = btop[j];
+                else if (c > j) v = P[(size_t)j * pp + c];
+                if (positive) v = Scalar<T>::mul(Scalar<T>::conj(wqr_phase<T>(btop[j])), v);
+            }
+            Rout[(size_t)j * ldr + c] = v;
+        }
+    }
+    __syncthreads();
+    // ---- apply down: level L's explicit Q rows are the n x n seeds of level L-1's blocks
+    const int nch = (n + CH - 1) / CH;
+    for (int L = Lt; L >= 0; --L) {
+        T* P = lev_panel[L];
+        const int pp = lev_pitch[L];
+        const int items = pl.nb[L] * nch;
+        // rounds of whole blocks: all chunks of a block run in the same round, results are stored after the barrier
+        const int blocks_per_round = max(1, nwarps / nch);
+        for (int b0 = 0; b0 < pl.nb[L]; b0 += blocks_per_round) {
+            const int b = b0 + warp / nch;
+            const int ch = warp % nch;
+            const bool active = (warp < blocks_per_round * nch) && (b < pl.nb[L]);
+            T reg[kWqrRpl][CH];
+            int r0 = 0, r1 = 0;
+            if (active) {
+                blk_range(pl.rows[L], pl.nb[L], b, r0, r1);
+                const int mloc = r1 - r0;
+                const int c0 = ch * CH;
+#pragma unroll
+                for (int t = 0; t < kWqrRpl; ++t) {
+                    const int i = lane + 32 * t;
+#pragma unroll
+                    for (int q = 0; q < CH; ++q) {
+                        const int c = c0 + q;
+                        T v = Scalar<T>::zero();
+                        if (i < n && i < mloc && c < n) {
+                            if (L == Lt) {
+                                if (i == c) v = positive ? wqr_phase<T>(btop[c]) : Scalar<T>::one();
+                            } else {
+                                v = lev_panel[L + 1][(size_t)(b * n + i) * spitch + c];
+                            }
+                        }
+                        reg[t][q] = v;
+                    }
+                }
+                const double* tt = tau + (size_t)(lev_slot[L] + b) * n;
+                wqr_apply_chunk<T, kWqrRpl, CH>(P + (size_t)r0 * pp, pp, mloc, min(mloc, n), tt, reg);
+            }
+            __syncthreads();
+            if (active) {
+                const int mloc = r1 - r0;
+                const int c0 = ch * CH;
+#pragma unroll
+                for (int t = 0; t < kWqrRpl; ++t) {
+                    const int i = lane + 32 * t;
+                    if (i < mloc) {
+#pragma unroll
+                        for (int q = 0; q < CH; ++q) {
+                            const int c = c0 + q;
+                            if (L == 0 && Qout) {
+                                if (c < n) Qout[(long long)(r0 + i) * ldq + c] = reg[t][q];
+                                else if (c < qcols) Qout[(long long)(r0 + i) * ldq + c] = Scalar<T>::zero();
+                            } else if (c < n) {
+                                P[(size_t)(r0 + i) * pp + c] = reg[t][q];
+                            }
+                        }
+                    }
+                }
+            }
+            __syncthreads();
+        }
+        (void)items;
+    }
+    // zero fill of the padding columns beyond the last chunk (Qout only)
+    if (Qout && qcols > nch * CH) {
+        const int c0 = nch * CH;
+        const int wdt = qcols - c0;
+        for (int idx = threadIdx.x; idx < m * wdt; idx += blockDim.x) {
+            const int i = idx / wdt, c = c0 + idx % wdt;
+            Qout[(long long)i * ldq + c] = Scalar<T>::zero();
+        }
+    }
+    __syncthreads();
+}
+
+// ---- one-sided Jacobi by one warp -------------------------------------------------------------------------
+// G: ns x ns, COLUMN-major (column j at G + j * pg, pg odd), ns <= 32.  Rotates the columns of G until they are
+// mutually orthogonal: G V = W.  Returns with W in G, sig[pos] = descending column norms, order[pos] = column index.
+// Pairs whose columns are both below `nu` are not rotated against each other (qil_common.cuh).
+template <typename T>
+__device__ __forceinline__ void wjacobi(T* G, int pg, int ns, double nu, double* sig, int* order) {
+    const int lane = threadIdx.x & 31;
+    const int ne = ns + (ns & 1);
+    const int npairs = ne / 2;
+    int gl = 32;
+    while (gl > 2 && (32 / gl) < npairs) gl >>= 1;       // lanes per pair: 32 / gl >= npairs (gl >= 2 since ns <= 32)
+    const int grp = lane / gl, gln = lane % gl;
+    const double tol = sqrt((double)ns) * 2.220446049250313e-16;
+    for (int sweep = 0; sweep < 60 && ns > 1; ++sweep) {
+        int rotated = 0;
+        for (int r = 0; r < ne - 1; ++r) {
+            int a, b;
+            if (grp == 0) { a = ne - 1; b = r; }
+            else { a = (r + grp) % (ne - 1); b = (r - grp + (ne - 1)) % (ne - 1); }
+            const bool act = (grp < npairs) && a < ns && b < ns;
+            const int cp = min(a, b), cq = max(a, b);
+            T* gp = G + cp * pg;
+            T* gq = G + cq * pg;
+            double al = 0.0, be = 0.0;
+            T ga = Scalar<T>::zero();
+            if (act) {
+                for (int i = gln; i < ns; i += gl) {
+                    const T x = gp[i], y = gq[i];
+                    al += Scalar<T>::abs2(x);
+                    be += Scalar<T>::abs2(y);
+                    ga = Scalar<T>::fma(Scalar<T>::conj(x), y, ga);
+                }
+            }
+            for (int o = gl >> 1; o > 0; o >>= 1) {
+                al += __shfl_xor_sync(0xffffffffu, al, o);
+                be += __shfl_xor_sync(0xffffffffu, be, o);
+                ga = Scalar<T>::add(ga, wq_shfl_xor<T>(ga, o));
+            }
+            const double g2 = Scalar<T>::abs2(ga);
+            if (act && g2 > tol * tol * al * be && g2 > 0.0 && !(al < nu && be < nu)) {
+                const double rg = rsqrt(g2);
+                const double ag = g2 * rg;
+                const T ph = Scalar<T>::scale(ga, rg);
+                const double dd = be - al;
+                const double hh = dd * dd + 4.0 * g2;
+                const double sq = hh * rsqrt(hh);
+                const double t = (dd >= 0.0 ? 2.0 : -2.0) * ag / (fabs(dd) + sq);
+                const double c = rsqrt(1.0 + t * t);
+                const double s = c * t;
+                const T sp = Scalar<T>::scale(ph, s);
+                const T spc = Scalar<T>::conj(sp);
+                for (int i = gln; i < ns; i += gl) {
+                    const T x = gp[i], y = gq[i];
+                    gp[i] = Scalar<T>::sub(Scalar<T>::scale(x, c), Scalar<T>::mul(spc, y));
+                    gq[i] = Scalar<T>::add(Scalar<T>::mul(sp, x), Scalar<T>::scale(y, c));
+                }
+                rotated = 1;
+            }
+            __syncwarp();
+        }
+        if (!__any_sync(0xffffffffu, rotated)) break;
+    }
+    // column norms, rank sort (descending, ties by index)
+    double mysig = 0.0;
+    if (lane < ns) {
+        const T* g = G + lane * pg;
+        double a = 0.0;
+        for (int i = 0; i < ns; ++i) a += Scalar<T>::abs2(g[i]);
+        mysig = sqrt(a);
+        sig[lane] = mysig;          // unsorted, for the ranking below
+    }
+    __syncwarp();
+    int pos = 0;
+    if (lane < ns) {
+        for (int i = 0; i < ns; ++i) {
+            const double si = sig[i];
+            pos += (si > mysig || (si == mysig && i < lane)) ? 1 : 0;
+        }
+    }
+    __syncwarp();
+    if (lane < ns) { sig[pos] = mysig; order[pos] = lane; }
+    __syncwarp();
+}
+
+// ---- panel GEMM on the FP64 tensor pipe, fragments straight from memory -----------------------------------
+// Cs[M x ncol] (shared, row-major, pc)  = scale * op(A)[M x K] * B[K x ncol] (shared, row-major, pb; rows >= K need
+// not exist: the k range is guarded, columns >= ncol are never read).  A is GLOBAL (or shared) row-major with lda:
+//   TRANS = false: op(A)[m][k] = A[m * lda + k]          TRANS = true: op(A)[m][k] = A[k * lda + m]   (real: A^T)
+// Warps take 16-row tiles round robin; at most 4 column tiles of 8 (ncol <= 32).
+__device__ __forceinline__ void wq_dmma(double* c, const double* a, const double* b) {
+    asm volatile(
+        "mma.sync.aligned.m16n8k16.row.col.f64.f64.f64.f64 {%0,%1,%2,%3}, {%4,%5,%6,%7,%8,%9,%10,%11}, "
+        "{%12,%13,%14,%15}, {%0,%1,%2,%3};"
+        : "+d"(c[0]), "+d"(c[1]), "+d"(c[2]), "+d"(c[3])
+        : "d"(a[0]), "d"(a[1]), "d"(a[2]), "d"(a[3]), "d"(a[4]), "d"(a[5]), "d"(a[6]), "d"(a[7]), "d"(b[0]), "d"(b[1]),
+          "d"(b[2]), "d"(b[3]));
+}
+
+template <bool TRANS>
+__device__ __forceinline__ void cta_gemm(const double* __restrict__ A, long long lda, int M, int K, const double* B,
+                                         int pb, int ncol, double* Cs, int pc, double scale) {
+    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+    const int nwarps = blockDim.x >> 5;
+    const int g = lane >> 2, t = lane & 3;
+    const int ntl = (ncol + 7) >> 3;
+    const int mtiles = (M + 15) >> 4;
+    for (int mt = warp; mt < mtiles; mt += nwarps) {
+        double acc[4][4];
+#pragma unroll
+        for (int i = 0; i < 4; ++i) { acc[i][0] = acc[i][1] = acc[i][2] = acc[i][3] = 0.0; }
+        const int r0 = mt * 16 + g, r1 = r0 + 8;
+        auto load_a = [&](int k0, double (&af)[8]) {
+            // A fragment: rows r0 / r1, k = k0 + 4t + {0..3}  (same k permutation for the B fragment below)
+#pragma unroll
+            for (int i = 0; i < 4; ++i) {
+                const int k = k0 + 4 * t + i;
+                double v0 = 0.0, v1 = 0.0;
+                if (k < K) {
+                    if (!TRANS) {
+                        if (r0 < M) v0 = A[(long long)r0 * lda + k];
+                        if (r1 < M) v1 = A[(long long)r1 * lda + k];
+                    } else {
+                        if (r0 < M) v0 = A[(long long)k * lda + r0];
+                        if (r1 < M) v1 = A[(long long)k * lda + r1];
+                    }
+                }
+                af[2 * i] = v0;
+                af[2 * i + 1] = v1;
+            }
+        };
+        double anext[8];
+        load_a(0, anext);
+        for (int k0 = 0; k0 < K; k0 += 16) {
+            double af[8];
+#pragma unroll
+            for (int i = 0; i < 8; ++i) af[i] = anext[i];
+            if (k0 + 16 < K) load_a(k0 + 16, anext);     // in flight while the tensor pipe works on this step
+#pragma unroll
+            for (int nt = 0; nt < 4; ++nt) {
+                if (nt < ntl) {
+                    double bf[4];
+                    const int col = nt * 8 + g;
+#pragma unroll
+                    for (int i = 0; i < 4; ++i) {
+                        const int k = k0 + 4 * t + i;
+                        bf[i] = (k < K && col < ncol) ? B[(size_t)k * pb + col] : 0.0;
+                    }
+                    wq_dmma(acc[nt], af, bf);
+                }
+            }
+        }
+#pragma unroll
+        for (int nt = 0; nt < 4; ++nt) {
+            if (nt < ntl) {
+                const int c0 = nt * 8 + 2 * t;
+                if (r0 < M) {
+                    if (c0 < ncol) Cs[(size_t)r0 * pc + c0] = scale * acc[nt][0];
+                    if (c0 + 1 < ncol) Cs[(size_t)r0 * pc + c0 + 1] = scale * acc[nt][1];
+                }
+                if (r1 < M) {
+                    if (c0 < ncol) Cs[(size_t)r1 * pc + c0] = scale * acc[nt][2];
+                    if (c0 + 1 < ncol) Cs[(size_t)r1 * pc + c0 + 1] = scale * acc[nt][3];
+                }
+            }
+        }
+    }
+}
+
+}  // namespace qil

@@ -192,7 +192,7 @@ def encode_exchange_bytes(N_total, k, p, is_complex):
 
 
 def signal_mps_sharded_dev(comm, d_x_local, N_total, is_complex, cutoff=1e-15, maxdim=None, k=20, p=10, q=0,
-                           random_seed=1234, mindim=1):
+                           random_seed=1234, mindim=1, adaptive=False):
     """signal_mps(x; method=:rsvd) for ONE signal whose rank-th contiguous chunk of N_total / world samples lives at
     device pointer d_x_local on this rank.  Every rank makes the call and receives the same SignalMPS."""
     import ctypes as C
@@ -201,7 +201,8 @@ def signal_mps_sharded_dev(comm, d_x_local, N_total, is_complex, cutoff=1e-15, m
     try:
         _lib.call("qil_encode_rsvd_sharded_dev", comm.ctx.handle, C.byref(comm.struct), int(is_complex),
                   C.c_void_p(int(d_x_local)), C.c_int64(N_total), int(k), int(p), int(q), C.c_int64(random_seed),
-                  float(cutoff), C.c_int64(api._maxdim_arg(maxdim)), C.c_int64(mindim), None, C.c_int64(0), C.byref(h))
+                  float(cutoff), C.c_int64(api._maxdim_arg(maxdim)), C.c_int64(mindim), None, C.c_int64(0),
+                  C.c_int64(api.RSVD_ADAPTIVE if adaptive else 0), C.byref(h))
     except Exception:
         if comm.error is not None:
             raise comm.error
