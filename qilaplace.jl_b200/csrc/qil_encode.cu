@@ -11,37 +11,13 @@
 // encode -- and let the host pass the stream (the Julia shim passes `randn` after `Random.seed!`), or
 // generate it on the device with a counter-based generator.
 #include "qil_fast.cuh"
+#include "qil_rng.cuh"
 
 #include <atomic>
 #include <cstdlib>
 #include <thread>
 
 namespace qil {
-
-// ---- counter-based N(0,1) stream -------------------------------------------------------------------
-__device__ __forceinline__ unsigned long long splitmix64(unsigned long long z) {
-    z += 0x9E3779B97F4A7C15ull;
-    z = (z ^ (z >> 30)) * 0xBF58476D1CE4E5B9ull;
-    z = (z ^ (z >> 27)) * 0x94D049BB133111EBull;
-    return z ^ (z >> 31);
-}
-__device__ __forceinline__ double gauss_at(unsigned long long seed, unsigned long long idx) {
-    // Box-Muller on two 53-bit uniforms derived from (seed, idx)
-    const unsigned long long h1 = splitmix64(seed * 0xD1342543DE82EF95ull + 2 * idx);
-    const unsigned long long h2 = splitmix64(seed * 0xD1342543DE82EF95ull + 2 * idx + 1);
-    const double u1 = ((double)(h1 >> 11) + 1.0) * (1.0 / 9007199254740992.0);  // (0,1]
-    const double u2 = (double)(h2 >> 11) * (1.0 / 9007199254740992.0);          // [0,1)
-    return sqrt(-2.0 * log(u1)) * cospi(2.0 * u2);
-}
-template <typename T> __device__ __forceinline__ T stream_at(const T* host_stream, unsigned long long seed, long long i);
-template <> __device__ __forceinline__ double stream_at<double>(const double* s, unsigned long long seed, long long i) {
-    return s ? s[i] : gauss_at(seed, (unsigned long long)i);
-}
-template <> __device__ __forceinline__ cplx stream_at<cplx>(const cplx* s, unsigned long long seed, long long i) {
-    if (s) return s[i];
-    const double f = 0.70710678118654752440;
-    return make_double2(f * gauss_at(seed, 2ull * i), f * gauss_at(seed, 2ull * i + 1));
-}
 
 // dense Omega (C x l, row-major) for the generic (small) path
 template <typename T>
@@ -346,10 +322,17 @@ static int shrink_sketch(qil_ctx* ctx, const RsvdOpts& o, int l, int64_t rows, M
 // ---- fast tail of a randomized split (round 2): Bh = A^H Q given (possibly as split-K partials) ------------------
 // Bh = Qb Rb by the warp-synchronous TSQR, Jacobi + truncation on the device (svd_finish), then U = Q Us and
 // S Vh = (Us^H G) Qb^H in one launch.  One host read-back (the rank) instead of ~10 launches and 2 read-backs.
+// preallocated worst-case outputs of a split whose rank stays on the device (no host read-back)
+template <typename T>
+struct DevOut {
+    T* U;          // R x r, ld r
+    T* SVh;        // r x C, ld C
+    int* rank;     // device
+};
 template <typename T>
 static int rsvd_tail(SplitCtx<T>& sc, int64_t R, int64_t C, int l, const T* Q, int64_t ldq, const T* Bh, int64_t ldbh,
                      int nsum, int64_t sum_stride, const double* d_scale, Mat<T>& U, Mat<T>* SVh, Mat<T>* Vh,
-                     Mat<double>* S) {
+                     Mat<double>* S, const DevOut<T>* dev = nullptr) {
     qil_ctx* ctx = sc.ctx;
     const RsvdOpts& o = *sc.o;
     struct Region {
@@ -360,6 +343,11 @@ static int rsvd_tail(SplitCtx<T>& sc, int64_t R, int64_t C, int l, const T* Q, i
     Mat<T> Qb(ctx, C, l), Rb(ctx, l, l), Us(ctx, l, l), T2(ctx, l, l);
     Mat<double> Sv(ctx, l, 1);
     qr_fast<T>(ctx, C, l, Bh, ldbh, nsum, sum_stride, false, Qb.p, l, l, Rb.p);
+    if (dev) {
+        svd_finish<T>(ctx, l, Rb.p, d_scale, o.cutoff, o.maxdim, o.mindim, Us.p, T2.p, Sv.p, dev->rank);
+        rsvd_outputs<T>(ctx, R, C, l, Q, ldq, Qb.p, l, Us.p, T2.p, Sv.p, dev->rank, dev->U, dev->SVh, nullptr);
+        return -1;
+    }
     int* d_rank = (int*)ctx->alloc(sizeof(int));
     svd_finish<T>(ctx, l, Rb.p, d_scale, o.cutoff, o.maxdim, o.mindim, Us.p, T2.p, Sv.p, d_rank);
     // worst-case sized outputs, written compactly with leading dimension r
@@ -383,7 +371,8 @@ static int rsvd_tail(SplitCtx<T>& sc, int64_t R, int64_t C, int l, const T* Q, i
 // ---- fused real split: streaming pass -> TSQR straight from the split-K partials -> Q written in the operand
 // layout of the next pass.  Between two passes over A there are the launches of one QR and nothing else.
 static int rsvd_split_fused(SplitCtx<double>& sc, const double* A, int64_t R, int64_t C, bool top, int l0,
-                            Mat<double>& U, Mat<double>* SVh, Mat<double>* Vh, Mat<double>* S) {
+                            Mat<double>& U, Mat<double>* SVh, Mat<double>* Vh, Mat<double>* S,
+                            const DevOut<double>* dev = nullptr) {
     qil_ctx* ctx = sc.ctx;
     const RsvdOpts& o = *sc.o;
     int nt = stream_nt_for(l0);
@@ -410,13 +399,25 @@ static int rsvd_split_fused(SplitCtx<double>& sc, const double* A, int64_t R, in
         QIL_LAUNCH_CHECK(ctx);
         sc.nrm_ready = true;
     }
+    // split-K partials -> dense panel (one full-grid launch: 22 MB read by 148 SMs; a leaf CTA of the TSQR summing
+    // its own 7 partials needs ~10 dependent L2 round trips instead), then the TSQR writes Q in operand layout
+    Mat<double> YR(ctx, R, l0), ZC(ctx, C, l0);
+    auto sum_R = [&](int l_) {
+        reduce_k1_kernel<double><<<grid_for(ctx, R * l_), 256, 0, ctx->stream>>>(partR.p, ks1, R, nt * 8, l_, YR.p);
+        QIL_LAUNCH_CHECK(ctx);
+    };
+    auto sum_C = [&](int l_) {
+        reduce_k2_kernel<double><<<grid_for(ctx, C * l_), 256, 0, ctx->stream>>>(partC.p, ks2, C, nt * 8, l_, nullptr, ZC.p);
+        QIL_LAUNCH_CHECK(ctx);
+    };
     int l = l0;
     {
         Mat<double> Rtop;
         const bool adapt = top && o.adaptive;
         if (adapt) Rtop = Mat<double>(ctx, l0, l0);
         ctx->prof_begin(PROF_QR);
-        qr_fast<double>(ctx, R, l0, partR.p, nt * 8, ks1, R * (int64_t)nt * 8, true, XR.p, lpp, lpp, adapt ? Rtop.p : nullptr);
+        sum_R(l0);
+        qr_fast<double>(ctx, R, l0, YR.p, l0, 1, 0, true, XR.p, lpp, lpp, adapt ? Rtop.p : nullptr);
         ctx->prof_end();
         if (adapt) {
             l = shrink_sketch_width<double>(ctx, o, l0, Rtop);
@@ -434,21 +435,22 @@ static int rsvd_split_fused(SplitCtx<double>& sc, const double* A, int64_t R, in
             }
         }
     }
-    const int ldo = nt * 8;
     for (int it = 0; it < o.q; ++it) {
         stream_gemm(ctx, true, A, R, C, C, XR.p, lpp, nt, partC.p, ks2, kc2, nullptr, l);
         ctx->prof_begin(PROF_QR);
-        qr_fast<double>(ctx, C, l, partC.p, ldo, ks2, C * (int64_t)ldo, true, XC.p, lpp, lpp, nullptr);
+        sum_C(l);
+        qr_fast<double>(ctx, C, l, ZC.p, l, 1, 0, true, XC.p, lpp, lpp, nullptr);
         ctx->prof_end();
         stream_gemm(ctx, false, A, R, C, C, XC.p, lpp, nt, partR.p, ks1, kc1, nullptr, l);
         ctx->prof_begin(PROF_QR);
-        qr_fast<double>(ctx, R, l, partR.p, ldo, ks1, R * (int64_t)ldo, true, XR.p, lpp, lpp, nullptr);
+        sum_R(l);
+        qr_fast<double>(ctx, R, l, YR.p, l, 1, 0, true, XR.p, lpp, lpp, nullptr);
         ctx->prof_end();
     }
-    // ---- B^H = A^H Q as partials, then the device-side tail
+    // ---- B^H = A^H Q, then the device-side tail
     stream_gemm(ctx, true, A, R, C, C, XR.p, lpp, nt, partC.p, ks2, kc2, nullptr, l);
-    return rsvd_tail<double>(sc, R, C, l, XR.p, lpp, partC.p, ldo, ks2, C * (int64_t)ldo, top ? sc.d_nrm + 1 : nullptr, U,
-                             SVh, Vh, S);
+    sum_C(l);
+    return rsvd_tail<double>(sc, R, C, l, XR.p, lpp, ZC.p, l, 1, 0, top ? sc.d_nrm + 1 : nullptr, U, SVh, Vh, S, dev);
 }
 template <typename T>
 static int rsvd_split_fused_dispatch(SplitCtx<T>&, const T*, int64_t, int64_t, bool, int, Mat<T>&, Mat<T>*, Mat<T>*,
@@ -721,6 +723,119 @@ static void dc_encode(SplitCtx<T>& sc, std::vector<DcNode<T>> level, std::vector
     }
 }
 
+// ---- sync-free encoder (round 2): streaming top split with its rank left on the device, then ONE launch per tree
+// level (qil_node.cu: one CTA per node, bond dimensions read from the device-side bond array).  The launch sequence
+// depends on (n, k, p, q) only; the single host synchronisation is the final read-back of the bonds.  Real signals
+// with k + p <= 32; everything else (and any node that overflows a CTA's shared memory) takes the general path.
+__global__ void init_tree_state_kernel(int* state, int nbonds) {      // bonds = 1, overflow flag = 0
+    for (int i = threadIdx.x; i <= nbonds; i += blockDim.x) state[i] = (i < nbonds) ? 1 : 0;
+}
+static int64_t bond_cap(int n, int pos, int kp) {
+    const int a = std::min(pos, n - pos);
+    return a >= 30 ? kp : std::min<int64_t>(kp, (int64_t)1 << a);
+}
+static qil_mps* encode_rsvd_tree(SplitCtx<double>& sc, const double* x, int n) {
+    qil_ctx* ctx = sc.ctx;
+    const RsvdOpts& o = *sc.o;
+    const int kp = o.k + o.p;
+    static const bool disabled = [] { const char* e = getenv("QIL_ENCODE_TREE"); return e && e[0] == '0'; }();
+    if (disabled || kp > 32 || n < 4 || sc.comm) return nullptr;
+    const int mid = n / 2 - 1;                                  // 0-based (first+last-1)/2 of the root
+    const int64_t R = (int64_t)1 << (mid + 1), C = (int64_t)1 << (n - 1 - mid);
+    const int l0 = (int)std::min<int64_t>(kp, std::min(R, C));
+    if (std::min(R, C) <= kp || !stream_supported(R, C, C, l0) || !qr_fast_supported<double>(ctx, R, l0) ||
+        !qr_fast_supported<double>(ctx, C, l0))
+        return nullptr;
+    if (sc.stream && C * (int64_t)l0 > sc.stream_len) return nullptr;   // the general path reports the short stream
+
+    std::vector<int> h_bonds(n + 1, 1);
+    int* d_state = (int*)ctx->alloc(sizeof(int) * (n + 2));     // bonds[0..n], overflow flag
+    int* d_bonds = d_state;
+    int* d_over = d_state + n + 1;
+    init_tree_state_kernel<<<1, 128, 0, ctx->stream>>>(d_state, n + 1);
+    QIL_LAUNCH_CHECK(ctx);
+    struct Pending { int first, last; double* A; };
+    std::vector<void*> cores(n, nullptr);
+    std::vector<double*> temps;                                  // buffers that are not cores
+    std::vector<std::vector<NodeDesc>> levels;
+    auto fail_cleanup = [&]() {
+        for (double* t : temps) ctx->free(t);
+        for (void* c : cores) if (c) ctx->free(c);
+        ctx->free(d_state);
+    };
+    try {
+        // top split -> device buffers
+        double* Utop = (double*)ctx->alloc((size_t)R * l0 * sizeof(double));
+        double* SVtop = (double*)ctx->alloc((size_t)l0 * C * sizeof(double));
+        std::vector<Pending> cur{{0, mid, Utop}, {mid + 1, n - 1, SVtop}}, next;
+        while (!cur.empty()) {
+            std::vector<NodeDesc> lvl;
+            next.clear();
+            for (const Pending& pd : cur) {
+                if (pd.first == pd.last) { cores[pd.first] = pd.A; continue; }
+                temps.push_back(pd.A);
+                const int m2 = (pd.first + pd.last + 1) / 2 - 1;
+                NodeDesc d;
+                d.A = pd.A; d.bonds_off = 0;
+                d.lb_pos = pd.first; d.rb_pos = pd.last + 1; d.out_pos = m2 + 1;
+                d.nl = m2 - pd.first + 1; d.nr = pd.last - m2;
+                const int64_t Rmax = bond_cap(n, pd.first, kp) << d.nl, Cmax = bond_cap(n, pd.last + 1, kp) << d.nr;
+                const int64_t rmax = std::min<int64_t>(bond_cap(n, m2 + 1, kp), std::min(Rmax, Cmax));
+                d.U = (double*)ctx->alloc((size_t)(Rmax * rmax) * sizeof(double));
+                d.SVh = (double*)ctx->alloc((size_t)(rmax * Cmax) * sizeof(double));
+                lvl.push_back(d);
+                next.push_back({pd.first, m2, d.U});
+                next.push_back({m2 + 1, pd.last, d.SVh});
+            }
+            if (!lvl.empty()) levels.push_back(std::move(lvl));
+            cur = next;
+        }
+        size_t total = 0;
+        for (auto& lv : levels) total += lv.size();
+        std::vector<NodeDesc> flat;
+        flat.reserve(total);
+        for (auto& lv : levels) flat.insert(flat.end(), lv.begin(), lv.end());
+        NodeDesc* d_nodes = nullptr;
+        if (total) {
+            d_nodes = (NodeDesc*)ctx->alloc(sizeof(NodeDesc) * total);
+            temps.push_back(reinterpret_cast<double*>(d_nodes));
+            QIL_CUDA(cudaMemcpyAsync(d_nodes, flat.data(), sizeof(NodeDesc) * total, cudaMemcpyHostToDevice, ctx->stream));
+        }
+        Mat<double> Udummy;
+        DevOut<double> dev{Utop, SVtop, d_bonds + mid + 1};
+        rsvd_split_fused(sc, x, R, C, true, l0, Udummy, nullptr, nullptr, nullptr, &dev);
+        size_t off = 0;
+        for (auto& lv : levels) {
+            node_level_launch(ctx, d_nodes + off, (int)lv.size(), d_bonds, d_over, o, sc.stream, sc.stream_len);
+            off += lv.size();
+        }
+        std::vector<int> h_state(n + 2);
+        double h_nrm[2];
+        QIL_CUDA(cudaMemcpyAsync(h_state.data(), d_state, sizeof(int) * (n + 2), cudaMemcpyDeviceToHost, ctx->stream));
+        QIL_CUDA(cudaMemcpyAsync(h_nrm, sc.d_nrm, 2 * sizeof(double), cudaMemcpyDeviceToHost, ctx->stream));
+        ctx->sync();                                             // flat / h_state stay alive until here
+        if (h_state[n + 1] != 0) {                               // a node overflowed: general path
+            fail_cleanup();
+            return nullptr;
+        }
+        for (double* t : temps) ctx->free(t);
+        ctx->free(d_state);
+        std::vector<int64_t> bond(n + 1);
+        for (int i = 0; i <= n; ++i) bond[i] = h_state[i];
+        qil_mps* m = new_mps(ctx, n, 0, bond.data(), false);
+        m->core = cores;
+        m->amplitude = h_nrm[0];
+        return m;
+    } catch (...) {
+        fail_cleanup();
+        throw;
+    }
+}
+template <typename T> static qil_mps* encode_rsvd_tree_dispatch(SplitCtx<T>&, const T*, int) { return nullptr; }
+template <> qil_mps* encode_rsvd_tree_dispatch<double>(SplitCtx<double>& sc, const double* x, int n) {
+    return encode_rsvd_tree(sc, x, n);
+}
+
 template <typename T>
 qil_mps* encode_rsvd(qil_ctx* ctx, const T* d_x, int64_t N, const RsvdOpts& o) {
     QIL_REQUIRE(N >= 1, QIL_ERR_ARGUMENT, "signal_mps: empty signal");
@@ -752,6 +867,8 @@ qil_mps* encode_rsvd(qil_ctx* ctx, const T* d_x, int64_t N, const RsvdOpts& o) {
         m->amplitude = c;
         return m;
     }
+    if (qil_mps* fastm = encode_rsvd_tree_dispatch<T>(sc, x, n)) return fastm;
+    sc.nrm_ready = false;                                    // (a tree attempt that overflowed is repeated from scratch)
     {
         std::vector<DcNode<T>> level(1);
         DcNode<T>& root = level[0];

@@ -25,4 +25,18 @@ template <typename T>
 void rsvd_outputs(qil_ctx* ctx, int64_t R, int64_t C, int l, const T* Q, int64_t ldq, const T* Qb, int64_t ldqb,
                   const T* Us, const T* T2, const double* S, const int* d_rank, T* U, T* SVh, T* Vh);
 
+// ---- one CTA per tree node (qil_node.cu) -------------------------------------------------------------------
+// Node matrix A = T[lb * 2^nl, 2^nr * rb] (compact, row-major) with lb = bonds[bonds_off + lb_pos], rb likewise;
+// outputs U (R x r, ld r) and SVh (r x C, ld C) and the new bond bonds[bonds_off + out_pos] = r.
+struct NodeDesc {
+    const double* A;
+    double* U;
+    double* SVh;
+    int bonds_off;
+    int lb_pos, rb_pos, out_pos;
+    int nl, nr;
+};
+void node_level_launch(qil_ctx* ctx, const NodeDesc* d_nodes, int count, int* d_bonds, int* d_overflow, const RsvdOpts& o,
+                       const double* d_stream, int64_t stream_len);
+
 }  // namespace qil

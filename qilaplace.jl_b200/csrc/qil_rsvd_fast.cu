@@ -22,35 +22,6 @@ struct FinishParams {
     double* margin;
 };
 
-// shared-memory image of one finish: G (column-major, pitch pg), G0 copy, sig, order.  Called by all threads of a
-// CTA; `G0` must already hold the (scaled) matrix whose columns are to be orthogonalised, column-major with pitch pg.
-// On return (after a barrier): Gw = W, sig sorted descending, order, *s_rank.
-template <typename T>
-__device__ __forceinline__ void cta_jacobi_rank(T* Gw, const T* G0, int pg, int ns, double cutoff, long long maxdim,
-                                                long long mindim, double* sig, int* order, int* s_rank, double* margin,
-                                                double* s_nu) {
-    const int tid = threadIdx.x;
-    for (int idx = tid; idx < ns * pg; idx += blockDim.x) Gw[idx] = G0[idx];
-    // ||G||_F^2 in a fixed order (skip threshold, qil_common.cuh)
-    for (int j = tid; j < ns; j += blockDim.x) {
-        double a = 0.0;
-        for (int i = 0; i < ns; ++i) a += Scalar<T>::abs2(G0[j * pg + i]);
-        sig[j] = a;
-    }
-    __syncthreads();
-    if (tid == 0) {
-        double tot = 0.0;
-        for (int j = 0; j < ns; ++j) tot += sig[j];
-        *s_nu = jacobi_skip_threshold(tot, ns, cutoff, mindim);
-    }
-    __syncthreads();
-    if (tid < 32) {
-        wjacobi<T>(Gw, pg, ns, *s_nu, sig, order);
-        if (tid == 0) *s_rank = truncate_rank_dev(sig, ns, cutoff, maxdim < 1 ? 1 : maxdim, mindim < 1 ? 1 : mindim, margin);
-    }
-    __syncthreads();
-}
-
 template <typename T>
 __global__ void __launch_bounds__(128) svd_finish_kernel(const FinishParams<T> p) {
     extern __shared__ __align__(16) unsigned char smem_raw[];

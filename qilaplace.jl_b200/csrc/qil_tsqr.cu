@@ -17,8 +17,9 @@
 
 namespace qil {
 
-constexpr int kLeafRpl = 16;                 // leaf blocks: up to 512 rows per warp
-constexpr int kLeafRows = 32 * kLeafRpl;
+// leaf blocks: up to 512 rows (complex: 256) per CTA, 16 (8) row slots per lane
+template <typename T> struct Leaf { static constexpr int RPL = 16; static constexpr int ROWS = 512; };
+template <> struct Leaf<cplx> { static constexpr int RPL = 8; static constexpr int ROWS = 256; };
 constexpr int kLeafThreads = 256;             // <= 256 threads: the Householder warp may use up to 255 registers
 constexpr int kTreeThreads = 512;
 template <typename T> struct LeafChunk { static constexpr int CH = 4; };
@@ -55,39 +56,41 @@ __global__ void __launch_bounds__(kLeafThreads) tsqr_leaf_factor_kernel(const Ts
     const long long bat = blockIdx.y;
     const long long r0 = ((long long)b * p.m) / p.nblk, r1 = ((long long)(b + 1) * p.m) / p.nblk;
     const int mloc = (int)(r1 - r0), n = p.n, pitch = p.pitch;
-    T* beta = blk + (size_t)kLeafRows * pitch;
+    T* beta = blk + (size_t)Leaf<T>::ROWS * pitch;
     double* tau = reinterpret_cast<double*>(beta + n);
     const T* A = p.A + bat * p.a_bs;
     {
-        // 4 elements x nsum partials in flight per thread: the load phase is one L2 round trip per ~28 loads
-        const int total = mloc * n;
-        for (int base = threadIdx.x; base < total; base += 4 * blockDim.x) {
-            T v[4];
+        // one row per warp and iteration, lanes = columns (no index division); 8 rows in flight per warp
+        const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31, nwarps = blockDim.x >> 5;
+        for (int i0 = warp; i0 < mloc; i0 += 8 * nwarps) {
+            T v[8];
 #pragma unroll
-            for (int e = 0; e < 4; ++e) {
-                const int idx = base + e * blockDim.x;
-                if (idx < total) {
-                    const int i = idx / n, c = idx - i * n;
-                    v[e] = load_sum<T>(A + (r0 + i) * p.lda + c, p.nsum, p.sum_stride);
-                }
+            for (int e = 0; e < 8; ++e) {
+                const int i = i0 + e * nwarps;
+                v[e] = Scalar<T>::zero();
+                if (i < mloc && lane < n) v[e] = load_sum<T>(A + (r0 + i) * p.lda + lane, p.nsum, p.sum_stride);
             }
 #pragma unroll
-            for (int e = 0; e < 4; ++e) {
-                const int idx = base + e * blockDim.x;
-                if (idx < total) {
-                    const int i = idx / n, c = idx - i * n;
-                    blk[i * pitch + c] = v[e];
-                }
+            for (int e = 0; e < 8; ++e) {
+                const int i = i0 + e * nwarps;
+                if (i < mloc && lane < pitch) blk[i * pitch + lane] = v[e];     // padding columns (n .. pitch-1) zeroed
+            }
+        }
+        if (pitch > 32) {
+            for (int idx = threadIdx.x; idx < mloc * (pitch - 32); idx += blockDim.x) {
+                const int i = idx / (pitch - 32), c = 32 + idx % (pitch - 32);
+                blk[i * pitch + c] = Scalar<T>::zero();
             }
         }
     }
     __syncthreads();
-    if (threadIdx.x < 32) wqr_factor<T, kLeafRpl>(blk, pitch, mloc, n, beta, tau);
+    wqr_factor<T, Leaf<T>::RPL, 64>(blk, pitch, mloc, n, beta, tau, threadIdx.x >> 5, blockDim.x >> 5, 1);
     __syncthreads();
     T* V = p.V + bat * p.v_bs;
-    for (int idx = threadIdx.x; idx < mloc * n; idx += blockDim.x) {
-        const int i = idx / n, c = idx - i * n;
-        V[(r0 + i) * n + c] = blk[i * pitch + c];
+    {
+        const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31, nwarps = blockDim.x >> 5;
+        if (lane < n)
+            for (int i = warp; i < mloc; i += nwarps) V[(r0 + i) * n + lane] = blk[i * pitch + lane];
     }
     T* Rst = p.Rst + bat * p.rst_bs + (size_t)b * n * n;
     for (int idx = threadIdx.x; idx < n * n; idx += blockDim.x) {
@@ -112,12 +115,24 @@ __global__ void __launch_bounds__(kLeafThreads) tsqr_leaf_apply_kernel(const Tsq
     const long long bat = blockIdx.y;
     const long long r0 = ((long long)b * p.m) / p.nblk, r1 = ((long long)(b + 1) * p.m) / p.nblk;
     const int mloc = (int)(r1 - r0), n = p.n, pitch = p.pitch;
-    T* seed = blk + (size_t)kLeafRows * pitch;          // n x n, pitch n
+    T* seed = blk + (size_t)Leaf<T>::ROWS * pitch;          // n x n, pitch n
     double* tau = reinterpret_cast<double*>(seed + n * n);
     const T* V = p.V + bat * p.v_bs;
-    for (int idx = threadIdx.x; idx < mloc * n; idx += blockDim.x) {
-        const int i = idx / n, c = idx - i * n;
-        blk[i * pitch + c] = V[(r0 + i) * n + c];
+    {
+        const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31, nwarps = blockDim.x >> 5;
+        for (int i0 = warp; i0 < mloc; i0 += 8 * nwarps) {
+            T v[8];
+#pragma unroll
+            for (int e = 0; e < 8; ++e) {
+                const int i = i0 + e * nwarps;
+                v[e] = (i < mloc && lane < n) ? V[(r0 + i) * n + lane] : Scalar<T>::zero();
+            }
+#pragma unroll
+            for (int e = 0; e < 8; ++e) {
+                const int i = i0 + e * nwarps;
+                if (i < mloc && lane < n) blk[i * pitch + lane] = v[e];
+            }
+        }
     }
     const T* M = p.M + bat * p.m_bs + (size_t)b * n * n;
     for (int idx = threadIdx.x; idx < n * n; idx += blockDim.x) seed[idx] = M[idx];
@@ -129,17 +144,17 @@ __global__ void __launch_bounds__(kLeafThreads) tsqr_leaf_apply_kernel(const Tsq
     T* Q = p.Q + bat * p.q_bs;
     for (int ch = warp; ch < nch; ch += nwarps) {
         const int c0 = ch * CH;
-        T reg[kLeafRpl][CH];
+        T reg[Leaf<T>::RPL][CH];
 #pragma unroll
-        for (int t = 0; t < kLeafRpl; ++t) {
+        for (int t = 0; t < Leaf<T>::RPL; ++t) {
             const int i = lane + 32 * t;
 #pragma unroll
             for (int q = 0; q < CH; ++q)
                 reg[t][q] = (i < n && i < mloc && c0 + q < n) ? seed[i * n + c0 + q] : Scalar<T>::zero();
         }
-        wqr_apply_chunk<T, kLeafRpl, CH>(blk, pitch, mloc, min(mloc, n), tau, reg);
+        wqr_apply_chunk<T, Leaf<T>::RPL, CH>(blk, pitch, mloc, min(mloc, n), tau, reg);
 #pragma unroll
-        for (int t = 0; t < kLeafRpl; ++t) {
+        for (int t = 0; t < Leaf<T>::RPL; ++t) {
             const int i = lane + 32 * t;
             if (i < mloc) {
 #pragma unroll
@@ -171,9 +186,9 @@ __global__ void __launch_bounds__(kTreeThreads) tsqr_cta_kernel(const TsqrParams
     const int m = (int)p.m, n = p.n, pitch = p.pitch;
     T* work = panel + (size_t)m * pitch;
     const T* A = p.A + bat * p.a_bs;
-    for (int idx = threadIdx.x; idx < m * n; idx += blockDim.x) {
-        const int i = idx / n, c = idx - i * n;
-        panel[i * pitch + c] = load_sum<T>(A + (long long)i * p.lda + c, p.nsum, p.sum_stride);
+    for (int idx = threadIdx.x; idx < m * pitch; idx += blockDim.x) {
+        const int i = idx / pitch, c = idx - i * pitch;
+        panel[idx] = (c < n) ? load_sum<T>(A + (long long)i * p.lda + c, p.nsum, p.sum_stride) : Scalar<T>::zero();
     }
     __syncthreads();
     cta_qr<T>(panel, pitch, m, n, p.positive != 0, p.R ? p.R + bat * p.r_bs : nullptr, n,
@@ -182,13 +197,13 @@ __global__ void __launch_bounds__(kTreeThreads) tsqr_cta_kernel(const TsqrParams
 
 template <typename T>
 static size_t tsqr_cta_smem(int64_t m, int n) {
-    const int pitch = n | 1;
+    const int pitch = wqr_pitch(n);
     return ((size_t)m * pitch + cta_qr_extra_elems<T>((int)m, n)) * sizeof(T) + 64;
 }
 template <typename T>
 static size_t tsqr_leaf_smem(int n) {
-    const int pitch = n | 1;
-    return ((size_t)kLeafRows * pitch + (size_t)n * n + 2 * n + 8) * sizeof(T) + 64;
+    const int pitch = wqr_pitch(n);
+    return ((size_t)Leaf<T>::ROWS * pitch + (size_t)n * n + 2 * n + 8) * sizeof(T) + 64;
 }
 
 template <typename T>
@@ -208,10 +223,12 @@ void qr_fast(qil_ctx* ctx, int64_t m, int n, const T* A, int64_t lda, int nsum, 
     const size_t budget = std::min<size_t>(ctx->smem_optin, 225 * 1024);
     TsqrParams<T> p{};
     p.A = A; p.lda = lda; p.nsum = nsum; p.sum_stride = sum_stride; p.a_bs = a_bs;
-    p.m = m; p.n = n; p.positive = positive ? 1 : 0; p.pitch = n | 1;
+    p.m = m; p.n = n; p.positive = positive ? 1 : 0; p.pitch = wqr_pitch(n);
     p.Q = Q; p.ldq = ldq; p.qcols = std::max(qcols, n); p.q_bs = q_bs;
     p.R = R; p.r_bs = r_bs;
-    if (tsqr_cta_smem<T>(m, n) <= budget) {
+    // one CTA only for a single block (<= 256 rows): the leaf kernels (256 threads, 255 registers, 8 warps per block,
+    // trailing values kept in registers) are ~2x faster per column step than the multi-block levels of cta_qr
+    if (m <= kWqrMaxRows && tsqr_cta_smem<T>(m, n) <= budget) {
         auto kern = tsqr_cta_kernel<T>;
         const size_t smem = tsqr_cta_smem<T>(m, n);
         ensure_dynamic_smem(kern, smem);
@@ -219,7 +236,7 @@ void qr_fast(qil_ctx* ctx, int64_t m, int n, const T* A, int64_t lda, int nsum, 
         QIL_LAUNCH_CHECK(ctx);
         return;
     }
-    const int nblk = (int)((m + kLeafRows - 1) / kLeafRows);
+    const int nblk = (int)((m + Leaf<T>::ROWS - 1) / Leaf<T>::ROWS);
     const int64_t m2 = (int64_t)nblk * n;
     Mat<T> V(ctx, (int64_t)batch * m, n), Rst(ctx, (int64_t)batch * m2, n), Mq(ctx, (int64_t)batch * m2, n);
     Mat<double> tau(ctx, (int64_t)batch * nblk, n);

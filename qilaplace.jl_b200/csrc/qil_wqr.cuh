@@ -25,8 +25,9 @@
 namespace qil {
 
 constexpr int kWqrMaxN = 32;   // columns of a fast-path panel
-constexpr int kWqrRpl = 8;     // rows per lane  => a warp block has at most 256 rows
-constexpr int kWqrMaxRows = 32 * kWqrRpl;
+constexpr int kWqrRpl = 8;     // default row slots per lane
+constexpr int kWqrMaxRpl = 8;  // a block inside a CTA has at most 256 rows: its trailing values and its apply-down chunk
+constexpr int kWqrMaxRows = 32 * kWqrMaxRpl;   // stay in registers under the 128-register cap of a 512-thread CTA
 
 template <typename T> struct WqrChunk { static constexpr int CH = 4; };      // register chunk of the apply-down (cta_qr)
 template <> struct WqrChunk<cplx> { static constexpr int CH = 2; };
@@ -54,102 +55,218 @@ template <> __device__ __forceinline__ cplx wq_shfl_xor<cplx>(cplx v, int o) {
 
 // ---- Householder factorisation of one block by one warp -----------------------------------------------
 // blk: m x n, row-major, pitch (elements, odd) in shared memory; m <= 256, n <= 32.  k = min(m, n) reflectors.
-template <typename T> struct WqrWidth { static constexpr int CW = 32; };     // trailing columns reduced at once
-template <> struct WqrWidth<cplx> { static constexpr int CW = 16; };
+// Pitch of a panel of n columns: odd (lane <-> row is conflict free) and >= n + 3: column n is a ZERO padding column
+// that the factorisation uses as the target of "no column" slots (read as zero, never written).
+__host__ __device__ inline int wqr_pitch(int n) { return (n + 3) | 1; }
 
-template <typename T, int RPL = kWqrRpl>
-__device__ __forceinline__ void wqr_factor(T* blk, int pitch, int m, int n, T* beta, double* tau) {
-    constexpr int CW = WqrWidth<T>::CW;
-    const int lane = threadIdx.x & 31;
-    const int k = min(m, n);
-    for (int j = 0; j < k; ++j) {
-        T u[RPL];
+__device__ __forceinline__ void wq_bar(int id, int nthreads) {
+    asm volatile("bar.sync %0, %1;" ::"r"(id), "r"(nthreads) : "memory");
+}
+
+// W warps factor one block together, column parallel: at step j warp wi owns the trailing columns
+// j+1+wi, j+1+wi+W, ... (at most NI per pass), computes x^H a_c for them (and |x|^2 redundantly), one shuffle
+// all-reduce, the reflector scalars (identical in every warp), updates its columns; one named barrier per step.
+// Per warp and step that is ~RPL*(1+NI) loads/FMAs and NI+1 reduced values instead of the whole trailing matrix:
+// the step is a short latency chain (~600 cycles) rather than ~1000 instructions issued by one warp.
+//   blk: m x n row-major, pitch = wqr_pitch(n), padding columns zero; m <= 32*RPL rows; all W*32 threads call with
+//   the same arguments except wi; `bar` is a named-barrier id (1..15) private to this group of warps (W == 1: unused).
+template <typename T> struct WqrNI { static constexpr int NI = 4; };      // trailing columns per warp and pass
+template <> struct WqrNI<cplx> { static constexpr int NI = 2; };
+
+// reflector scalars from |x|^2 (rows >= j) and the diagonal element: beta = -ph |x|, tau = 1 / (|x| (|x| + |x0|)).
+// rsqrt-based (one MUFU + Newton each) -- this sits on the critical path of every column step.
+template <typename T>
+__device__ __forceinline__ void wqr_reflector(double s0, T x0, T& bj, double& tj, T& head) {
+    bj = Scalar<T>::zero();
+    tj = 0.0;
+    if (s0 > 0.0) {
+        const double a02 = Scalar<T>::abs2(x0);
+        const double ra = (a02 > 0.0) ? rsqrt(a02) : 0.0;
+        const double a0 = a02 * ra;
+        const double nx = s0 * rsqrt(s0);
+        const T ph = (a02 > 0.0) ? Scalar<T>::scale(x0, ra) : Scalar<T>::one();
+        bj = Scalar<T>::scale(ph, -nx);
+        // tau = 1 / (|x| (|x| + |x0|)): hardware reciprocal seed (2^-23) + three Newton steps instead of the IEEE
+        // division sequence (this scalar chain is executed once per column step, on the critical path)
+        const double d = s0 + nx * a0;
+        double r;
+        asm("rcp.approx.ftz.f64 %0, %1;" : "=d"(r) : "d"(d));
+        r = fma(r, fma(-d, r, 1.0), r);
+        r = fma(r, fma(-d, r, 1.0), r);
+        r = fma(r, fma(-d, r, 1.0), r);
+        tj = (d > 1e-290 && d < 1e290) ? r : 1.0 / d;
+    }
+    head = Scalar<T>::sub(x0, bj);       // u_j[j]
+}
+
+#ifdef QIL_WQR_PROFILE
+#define WQR_CLK(slot) do { if (j == 0 && threadIdx.x == 0) { const long long c_ = clock64(); g_clk[slot] = c_ - clk_; clk_ = c_; } } while (0)
+#else
+#define WQR_CLK(slot) do { } while (0)
+#endif
+
+// One pass of a column step for NV (compile-time) columns c0, c0 + W, ... of this warp: everything inside is
+// unconditional straight-line code (rows clamped, no per-slot branches), so the loads of the pass are all in flight
+// together; the trailing values stay in registers between the dot products and the update.
+template <typename T, int RPL, int NV, bool FIRST, int KEEPMAX>
+__device__ __forceinline__ void wqr_pass(T* blk, int pitch, const int (&roff)[RPL], const T (&u)[RPL], int j, int m,
+                                         int lane, int c0, int W, T x0, T& bj, double& tj, T& head, long long& clk_) {
+    constexpr int NVV = NV > 0 ? NV : 1;
+    constexpr bool KEEP = RPL * NV <= KEEPMAX;      // trailing values stay in registers between dots and update
+    T ajc[NVV], s[NVV], a[KEEP ? RPL : 1][NVV];
+    double s0 = 0.0;
+#pragma unroll
+    for (int q = 0; q < NV; ++q) {
+        ajc[q] = blk[j * pitch + c0 + W * q];
+        s[q] = Scalar<T>::zero();
+    }
+    if (KEEP) {
 #pragma unroll
         for (int t = 0; t < RPL; ++t) {
-            const int i = lane + 32 * t;
-            u[t] = (i >= j && i < m) ? blk[i * pitch + j] : Scalar<T>::zero();
+#pragma unroll
+            for (int q = 0; q < NV; ++q) a[KEEP ? t : 0][q] = blk[roff[t] + c0 + W * q];
         }
-        const T x0 = blk[j * pitch + j];
+    }
+#pragma unroll
+    for (int t = 0; t < RPL; ++t) {
+        const T uc = Scalar<T>::conj(u[t]);
+        if (FIRST) s0 += Scalar<T>::abs2(u[t]);
+#pragma unroll
+        for (int q = 0; q < NV; ++q) s[q] = Scalar<T>::fma(uc, KEEP ? a[KEEP ? t : 0][q] : blk[roff[t] + c0 + W * q], s[q]);
+    }
+    WQR_CLK(101);
+    if (FIRST) s0 = wq_sum<double>(s0);
+#pragma unroll
+    for (int q = 0; q < NV; ++q) s[q] = wq_sum<T>(s[q]);
+    WQR_CLK(102);
+    if (FIRST) wqr_reflector<T>(s0, x0, bj, tj, head);
+    WQR_CLK(103);
+    if (tj == 0.0 || NV == 0) return;
+    // f = -tau * (x^H a_c - conj(beta) a_{jc})  (= -tau u^H a_c)
+    const T cb = Scalar<T>::conj(bj);
+#pragma unroll
+    for (int q = 0; q < NV; ++q) s[q] = Scalar<T>::scale(Scalar<T>::sub(s[q], Scalar<T>::mul(cb, ajc[q])), -tj);
+    WQR_CLK(104);
+#pragma unroll
+    for (int t = 0; t < RPL; ++t) {
+        const int i = lane + 32 * t;
+        const T uu = (i == j) ? head : u[t];
+        T v[NVV];
+#pragma unroll
+        for (int q = 0; q < NV; ++q) v[q] = KEEP ? a[KEEP ? t : 0][q] : blk[roff[t] + c0 + W * q];
+        if (i >= j && i < m) {
+#pragma unroll
+            for (int q = 0; q < NV; ++q) blk[roff[t] + c0 + W * q] = Scalar<T>::fma(s[q], uu, v[q]);
+        }
+    }
+    __syncwarp();
+    WQR_CLK(105);
+}
+
+template <typename T, int RPL = kWqrRpl, int KEEPMAX = 16>
+__device__ __forceinline__ void wqr_factor(T* blk, int pitch, int m, int n, T* beta, double* tau, int wi = 0, int W = 1,
+                                           int bar = 0) {
+    constexpr int NI = WqrNI<T>::NI;
+    const int lane = threadIdx.x & 31;
+    const int k = min(m, n);
+    const int lgW = 31 - __clz(W);
+    int roff[RPL];
+#pragma unroll
+    for (int t = 0; t < RPL; ++t) roff[t] = min(lane + 32 * t, m - 1) * pitch;
+    long long clk_ = 0;
+#ifdef QIL_WQR_PROFILE
+    clk_ = clock64();
+    long long clk_step_ = clk_;
+#endif
+    for (int j = 0; j < k; ++j) {
+        // columns of this warp at this step: j+1+wi, j+1+wi+W, ...  (round robin from the pivot: balanced as j grows)
+        const int ncols_w = max(0, (n - (j + 1) - wi + W - 1) >> lgW);     // W is a power of two
         T bj = Scalar<T>::zero();
-        T head = x0;
+        T head = Scalar<T>::zero();
         double tj = 0.0;
-        for (int c0 = 0; j + c0 < n; c0 += CW) {
-            // s[cc] = sum_{i >= j} conj(x_i) a_{i, j+c0+cc}: column j itself gives |x|^2, the rest the reflector dots
-            T s[CW];
-#pragma unroll
-            for (int cc = 0; cc < CW; ++cc) s[cc] = Scalar<T>::zero();
+        if (wi == 0 || ncols_w > 0) {
+            T u[RPL];
 #pragma unroll
             for (int t = 0; t < RPL; ++t) {
                 const int i = lane + 32 * t;
-                if (i >= j && i < m) {
-                    const T uc = Scalar<T>::conj(u[t]);
-                    const T* row = blk + i * pitch + j + c0;
-#pragma unroll
-                    for (int cc = 0; cc < CW; ++cc)
-                        if (j + c0 + cc < n) s[cc] = Scalar<T>::fma(uc, row[cc], s[cc]);
-                }
+                const T v = blk[roff[t] + j];
+                u[t] = (i >= j && i < m) ? v : Scalar<T>::zero();
             }
-#pragma unroll
-            for (int cc = 0; cc < CW; ++cc)
-                if (j + c0 + cc < n) s[cc] = wq_sum<T>(s[cc]);
-            if (c0 == 0) {
-                const double nx2 = Scalar<T>::real(s[0]);
-                if (nx2 > 0.0) {
-                    const double a02 = Scalar<T>::abs2(x0);
-                    const double a0 = sqrt(a02);
-                    const double nx = sqrt(nx2);
-                    const T ph = (a02 > 0.0) ? Scalar<T>::scale(x0, 1.0 / a0) : Scalar<T>::one();
-                    bj = Scalar<T>::scale(ph, -nx);
-                    tj = 1.0 / (nx * (nx + a0));
+            const T x0 = blk[j * pitch + j];
+            WQR_CLK(100);
+            bool first = true;
+            for (int base = 0; first || base < ncols_w; base += NI) {
+                const int nv = min(NI, ncols_w - base);
+                const int c0 = j + 1 + wi + W * base;
+#define WQR_PASS(NVC, FST) wqr_pass<T, RPL, (NVC <= NI ? NVC : NI), FST, KEEPMAX>(blk, pitch, roff, u, j, m, lane, c0, W, x0, bj, tj, head, clk_)
+                if (first) {
+                    if (nv <= 0) WQR_PASS(0, true);
+                    else if (nv == 1) WQR_PASS(1, true);
+                    else if (nv == 2) WQR_PASS(2, true);
+                    else if (nv == 3) WQR_PASS(3, true);
+                    else WQR_PASS(4, true);
+                    first = false;
+                } else {
+                    if (nv == 1) WQR_PASS(1, false);
+                    else if (nv == 2) WQR_PASS(2, false);
+                    else if (nv == 3) WQR_PASS(3, false);
+                    else WQR_PASS(4, false);
                 }
-                head = Scalar<T>::sub(x0, bj);       // u_j[j]
+#undef WQR_PASS
+                if (tj == 0.0) break;
             }
-            if (tj == 0.0) break;
-            // f[cc] = -tau * (s[cc] - conj(beta) a_{j, c}),  u^H a_c = x^H a_c - conj(beta) a_{jc}
-            const T cb = Scalar<T>::conj(bj);
-            const T* rowj = blk + j * pitch + j + c0;
-#pragma unroll
-            for (int cc = 0; cc < CW; ++cc)
-                if (j + c0 + cc < n && (c0 + cc) > 0)
-                    s[cc] = Scalar<T>::scale(Scalar<T>::sub(s[cc], Scalar<T>::mul(cb, rowj[cc])), -tj);
-            __syncwarp();   // every lane has read row j before its owner updates it
-#pragma unroll
-            for (int t = 0; t < RPL; ++t) {
-                const int i = lane + 32 * t;
-                if (i >= j && i < m) {
-                    const T uu = (i == j) ? head : u[t];
-                    T* row = blk + i * pitch + j + c0;
-#pragma unroll
-                    for (int cc = 0; cc < CW; ++cc)
-                        if (j + c0 + cc < n && (c0 + cc) > 0) row[cc] = Scalar<T>::fma(s[cc], uu, row[cc]);
-                }
-            }
-            __syncwarp();
         }
-        if (lane == 0) {
-            blk[j * pitch + j] = head;
+        if (W > 1) wq_bar(bar, W * 32);      // column j+1 is final before anybody reads it as the next x
+        if (wi == 0 && lane == 0) {
+            blk[j * pitch + j] = head;       // after the barrier: nobody reads the diagonal of column j any more
             beta[j] = bj;
             tau[j] = tj;
         }
         __syncwarp();
+        WQR_CLK(106);
+#ifdef QIL_WQR_PROFILE
+        if (threadIdx.x == 0) { const long long c_ = clock64(); g_clk[j] = c_ - clk_step_; clk_step_ = c_; clk_ = c_; }
+#endif
     }
+    if (W > 1) wq_bar(bar, W * 32);
+}
+
+// run-time row-slot count -> compile-time RPL (1, 2, 4, 8): a block of m rows costs ceil(m/32) slots, not 8
+template <typename T>
+__device__ __forceinline__ void wqr_factor_any(T* blk, int pitch, int m, int n, T* beta, double* tau, int wi, int W,
+                                               int bar) {
+    const int rpl = (m + 31) >> 5;
+    if (rpl <= 1) wqr_factor<T, 1>(blk, pitch, m, n, beta, tau, wi, W, bar);
+    else if (rpl <= 2) wqr_factor<T, 2>(blk, pitch, m, n, beta, tau, wi, W, bar);
+    else if (rpl <= 4) wqr_factor<T, 4>(blk, pitch, m, n, beta, tau, wi, W, bar);
+    else wqr_factor<T, 8>(blk, pitch, m, n, beta, tau, wi, W, bar);
 }
 
 // ---- reflectors of one block applied to a register chunk -----------------------------------------------
-// b[t][q] holds element (row lane + 32 t, chunk column q).  b <- H_0 H_1 ... H_{k-1} b.
+// b[t][q] holds element (row lane + 32 t, chunk column q).  b <- H_0 H_1 ... H_{k-1} b.  The next reflector column is
+// loaded while the current reduction is in flight.
 template <typename T, int RPL, int CH>
 __device__ __forceinline__ void wqr_apply_chunk(const T* V, int pitch, int m, int k, const double* tau,
                                                 T (&b)[RPL][CH]) {
     const int lane = threadIdx.x & 31;
+    int roff[RPL];
+#pragma unroll
+    for (int t = 0; t < RPL; ++t) roff[t] = min(lane + 32 * t, m - 1) * pitch;
+    T un[RPL];
+#pragma unroll
+    for (int t = 0; t < RPL; ++t) un[t] = (k > 0) ? V[roff[t] + k - 1] : Scalar<T>::zero();
     for (int j = k - 1; j >= 0; --j) {
         const double tj = tau[j];
-        if (tj == 0.0) continue;
         T u[RPL];
 #pragma unroll
         for (int t = 0; t < RPL; ++t) {
             const int i = lane + 32 * t;
-            u[t] = (i >= j && i < m) ? V[i * pitch + j] : Scalar<T>::zero();
+            u[t] = (i >= j && i < m) ? un[t] : Scalar<T>::zero();
         }
+        const int jn = max(j - 1, 0);
+#pragma unroll
+        for (int t = 0; t < RPL; ++t) un[t] = V[roff[t] + jn];       // next reflector, in flight during the reduction
+        if (tj == 0.0) continue;
         T w[CH];
 #pragma unroll
         for (int q = 0; q < CH; ++q) w[q] = Scalar<T>::zero();
@@ -212,7 +329,7 @@ __host__ __device__ inline CtaQrPlan cta_qr_plan(int m, int n) {
 template <typename T>
 __host__ __device__ inline size_t cta_qr_extra_elems(int m, int n) {
     const CtaQrPlan p = cta_qr_plan(m, n);
-    const int pitch = n | 1;
+    const int pitch = wqr_pitch(n);
     // stack panels + beta[blocks][n] + tau[blocks][n] (tau as doubles: at most one T each)
     return (size_t)p.stack_rows * pitch + 2 * (size_t)p.blocks * n + 8;
 }
@@ -220,6 +337,80 @@ __host__ __device__ inline size_t cta_qr_extra_elems(int m, int n) {
 __device__ __forceinline__ void blk_range(int rows, int nb, int b, int& r0, int& r1) {
     r0 = (int)(((long long)b * rows) / nb);
     r1 = (int)(((long long)(b + 1) * rows) / nb);
+}
+
+// one level of the apply-down: every block's seed (n x n, rows of the level above; identity * phases at the top)
+// is extended by zero rows and multiplied by the block's reflectors, CH columns per warp in registers.
+template <typename T>
+struct CtaQrLevel {
+    T* P; int pp; int rows; int nb; int n;
+    const T* seed; int spitch;
+    const T* btop; bool positive;
+    const double* tau;
+    T* Qout; long long ldq; int qcols;
+};
+template <typename T, int RPL, int CH>
+__device__ __forceinline__ void cta_qr_apply_level(const CtaQrLevel<T>& lv) {
+    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+    const int nwarps = blockDim.x >> 5;
+    const int n = lv.n;
+    const int nch = (n + CH - 1) / CH;
+    // rounds of whole blocks: all chunks of a block run in the same round, results are stored after the barrier.
+    // More chunks than warps (nch > nwarps): the chunks of a block take several rounds and go through Qout or, for an
+    // in-place level, are not supported (callers keep n / CH <= nwarps).
+    const int blocks_per_round = max(1, nwarps / nch);
+    for (int b0 = 0; b0 < lv.nb; b0 += blocks_per_round) {
+        const int b = b0 + warp / nch;
+        const int ch = warp % nch;
+        const bool active = (warp < blocks_per_round * nch) && (b < lv.nb);
+        T reg[RPL][CH];
+        int r0 = 0, r1 = 0;
+        if (active) {
+            blk_range(lv.rows, lv.nb, b, r0, r1);
+            const int mloc = r1 - r0;
+            const int c0 = ch * CH;
+#pragma unroll
+            for (int t = 0; t < RPL; ++t) {
+                const int i = lane + 32 * t;
+#pragma unroll
+                for (int q = 0; q < CH; ++q) {
+                    const int c = c0 + q;
+                    T v = Scalar<T>::zero();
+                    if (i < n && i < mloc && c < n) {
+                        if (lv.seed == nullptr) {
+                            if (i == c) v = lv.positive ? wqr_phase<T>(lv.btop[c]) : Scalar<T>::one();
+                        } else {
+                            v = lv.seed[(size_t)(b * n + i) * lv.spitch + c];
+                        }
+                    }
+                    reg[t][q] = v;
+                }
+            }
+            wqr_apply_chunk<T, RPL, CH>(lv.P + (size_t)r0 * lv.pp, lv.pp, mloc, min(mloc, n), lv.tau + (size_t)b * n, reg);
+        }
+        __syncthreads();
+        if (active) {
+            const int mloc = r1 - r0;
+            const int c0 = ch * CH;
+#pragma unroll
+            for (int t = 0; t < RPL; ++t) {
+                const int i = lane + 32 * t;
+                if (i < mloc) {
+#pragma unroll
+                    for (int q = 0; q < CH; ++q) {
+                        const int c = c0 + q;
+                        if (lv.Qout) {
+                            if (c < n) lv.Qout[(long long)(r0 + i) * lv.ldq + c] = reg[t][q];
+                            else if (c < lv.qcols) lv.Qout[(long long)(r0 + i) * lv.ldq + c] = Scalar<T>::zero();
+                        } else if (c < n) {
+                            lv.P[(size_t)(r0 + i) * lv.pp + c] = reg[t][q];
+                        }
+                    }
+                }
+            }
+        }
+        __syncthreads();
+    }
 }
 
 // Factor + explicit Q.  All threads of the CTA call it (blockDim.x a multiple of 32, >= 32 * ceil(n / CH)).
@@ -230,11 +421,10 @@ __device__ __forceinline__ void blk_range(int rows, int nb, int b, int& r0, int&
 template <typename T>
 __device__ __forceinline__ void cta_qr(T* panel, int pitch, int m, int n, bool positive, T* Rout, int ldr, T* Qout,
                                        long long ldq, int qcols, T* work) {
-    constexpr int CH = WqrChunk<T>::CH;
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
     const int nwarps = blockDim.x >> 5;
     const CtaQrPlan pl = cta_qr_plan(m, n);
-    const int spitch = n | 1;
+    const int spitch = wqr_pitch(n);
     T* lev_panel[4];
     int lev_pitch[4];
     lev_panel[0] = panel;
@@ -255,24 +445,32 @@ __device__ __forceinline__ void cta_qr(T* panel, int pitch, int m, int n, bool p
         for (int L = 0; L < pl.nlev; ++L) { lev_slot[L] = s; s += pl.nb[L]; }
     }
 
-    // ---- factor, level by level; each block's triangle goes to the next level's panel
+    // ---- factor, level by level; each block's triangle goes to the next level's panel.  The warps of the CTA are
+    // split into groups of W, one group per block (column-parallel wqr_factor, named barrier = group + 1).
     for (int L = 0; L < pl.nlev; ++L) {
         T* P = lev_panel[L];
         const int pp = lev_pitch[L];
-        for (int b = warp; b < pl.nb[L]; b += nwarps) {
-            int r0, r1;
-            blk_range(pl.rows[L], pl.nb[L], b, r0, r1);
-            T* bb = beta + (size_t)(lev_slot[L] + b) * n;
-            double* tt = tau + (size_t)(lev_slot[L] + b) * n;
-            wqr_factor<T>(P + (size_t)r0 * pp, pp, r1 - r0, n, bb, tt);
-            if (L + 1 < pl.nlev) {
-                T* S = lev_panel[L + 1] + (size_t)b * n * spitch;
-                for (int idx = lane; idx < n * n; idx += 32) {
-                    const int j = idx / n, c = idx - j * n;
-                    T v = Scalar<T>::zero();
-                    if (c == j) v = bb[j];
-                    else if (c > j) v = P[(size_t)(r0 + j) * pp + c];
-                    S[j * spitch + c] = v;
+        int W = max(1, min(nwarps / pl.nb[L], 8));
+        W = 1 << (31 - __clz(W));                         // power of two (wqr_factor shifts by log2 W)
+        const int bpr = max(1, min(nwarps / W, W > 1 ? 15 : nwarps));   // blocks per round
+        const int group = warp / W, wi = warp % W;
+        for (int b0 = 0; b0 < pl.nb[L]; b0 += bpr) {
+            const int b = b0 + group;
+            if (group < bpr && b < pl.nb[L]) {
+                int r0, r1;
+                blk_range(pl.rows[L], pl.nb[L], b, r0, r1);
+                T* bb = beta + (size_t)(lev_slot[L] + b) * n;
+                double* tt = tau + (size_t)(lev_slot[L] + b) * n;
+                wqr_factor_any<T>(P + (size_t)r0 * pp, pp, r1 - r0, n, bb, tt, wi, W, group + 1);
+                if (L + 1 < pl.nlev) {
+                    T* S = lev_panel[L + 1] + (size_t)b * n * spitch;
+                    for (int idx = wi * 32 + lane; idx < n * spitch; idx += W * 32) {   // padding columns zeroed too
+                        const int j = idx / spitch, c = idx - j * spitch;
+                        T v = Scalar<T>::zero();
+                        if (c == j) v = bb[j];
+                        else if (c > j && c < n) v = P[(size_t)(r0 + j) * pp + c];
+                        S[j * spitch + c] = v;
+                    }
                 }
             }
         }
@@ -298,71 +496,25 @@ __device__ __forceinline__ void cta_qr(T* panel, int pitch, int m, int n, bool p
     }
     __syncthreads();
     // ---- apply down: level L's explicit Q rows are the n x n seeds of level L-1's blocks
-    const int nch = (n + CH - 1) / CH;
+    int nch_last = 1, ch_last = 1;
     for (int L = Lt; L >= 0; --L) {
-        T* P = lev_panel[L];
-        const int pp = lev_pitch[L];
-        const int items = pl.nb[L] * nch;
-        // rounds of whole blocks: all chunks of a block run in the same round, results are stored after the barrier
-        const int blocks_per_round = max(1, nwarps / nch);
-        for (int b0 = 0; b0 < pl.nb[L]; b0 += blocks_per_round) {
-            const int b = b0 + warp / nch;
-            const int ch = warp % nch;
-            const bool active = (warp < blocks_per_round * nch) && (b < pl.nb[L]);
-            T reg[kWqrRpl][CH];
-            int r0 = 0, r1 = 0;
-            if (active) {
-                blk_range(pl.rows[L], pl.nb[L], b, r0, r1);
-                const int mloc = r1 - r0;
-                const int c0 = ch * CH;
-#pragma unroll
-                for (int t = 0; t < kWqrRpl; ++t) {
-                    const int i = lane + 32 * t;
-#pragma unroll
-                    for (int q = 0; q < CH; ++q) {
-                        const int c = c0 + q;
-                        T v = Scalar<T>::zero();
-                        if (i < n && i < mloc && c < n) {
-                            if (L == Lt) {
-                                if (i == c) v = positive ? wqr_phase<T>(btop[c]) : Scalar<T>::one();
-                            } else {
-                                v = lev_panel[L + 1][(size_t)(b * n + i) * spitch + c];
-                            }
-                        }
-                        reg[t][q] = v;
-                    }
-                }
-                const double* tt = tau + (size_t)(lev_slot[L] + b) * n;
-                wqr_apply_chunk<T, kWqrRpl, CH>(P + (size_t)r0 * pp, pp, mloc, min(mloc, n), tt, reg);
-            }
-            __syncthreads();
-            if (active) {
-                const int mloc = r1 - r0;
-                const int c0 = ch * CH;
-#pragma unroll
-                for (int t = 0; t < kWqrRpl; ++t) {
-                    const int i = lane + 32 * t;
-                    if (i < mloc) {
-#pragma unroll
-                        for (int q = 0; q < CH; ++q) {
-                            const int c = c0 + q;
-                            if (L == 0 && Qout) {
-                                if (c < n) Qout[(long long)(r0 + i) * ldq + c] = reg[t][q];
-                                else if (c < qcols) Qout[(long long)(r0 + i) * ldq + c] = Scalar<T>::zero();
-                            } else if (c < n) {
-                                P[(size_t)(r0 + i) * pp + c] = reg[t][q];
-                            }
-                        }
-                    }
-                }
-            }
-            __syncthreads();
-        }
-        (void)items;
+        CtaQrLevel<T> lv;
+        lv.P = lev_panel[L]; lv.pp = lev_pitch[L]; lv.rows = pl.rows[L]; lv.nb = pl.nb[L]; lv.n = n;
+        lv.seed = (L == Lt) ? nullptr : lev_panel[L + 1]; lv.spitch = spitch;
+        lv.btop = btop; lv.positive = positive;
+        lv.tau = tau + (size_t)lev_slot[L] * n;
+        lv.Qout = (L == 0) ? Qout : nullptr; lv.ldq = ldq; lv.qcols = qcols;
+        const int rpl = ((pl.rows[L] + pl.nb[L] - 1) / pl.nb[L] + 31) >> 5;
+        constexpr int C8 = Scalar<T>::is_complex ? 2 : 4;
+        if (rpl <= 2) cta_qr_apply_level<T, 2, C8>(lv);
+        else if (rpl <= 4) cta_qr_apply_level<T, 4, C8>(lv);
+        else cta_qr_apply_level<T, 8, C8>(lv);
+        ch_last = C8;
+        nch_last = (n + ch_last - 1) / ch_last;
     }
     // zero fill of the padding columns beyond the last chunk (Qout only)
-    if (Qout && qcols > nch * CH) {
-        const int c0 = nch * CH;
+    if (Qout && qcols > nch_last * ch_last) {
+        const int c0 = nch_last * ch_last;
         const int wdt = qcols - c0;
         for (int idx = threadIdx.x; idx < m * wdt; idx += blockDim.x) {
             const int i = idx / wdt, c = c0 + idx % wdt;
@@ -456,10 +608,40 @@ __device__ __forceinline__ void wjacobi(T* G, int pg, int ns, double nu, double*
     __syncwarp();
 }
 
+// shared-memory image of one finish: G (column-major, pitch pg), G0 copy, sig, order.  Called by all threads of a
+// CTA; `G0` must already hold the (scaled) matrix whose columns are to be orthogonalised, column-major with pitch pg.
+// On return (after a barrier): Gw = W, sig sorted descending, order, *s_rank.
+template <typename T>
+__device__ __forceinline__ void cta_jacobi_rank(T* Gw, const T* G0, int pg, int ns, double cutoff, long long maxdim,
+                                                long long mindim, double* sig, int* order, int* s_rank, double* margin,
+                                                double* s_nu) {
+    const int tid = threadIdx.x;
+    for (int idx = tid; idx < ns * pg; idx += blockDim.x) Gw[idx] = G0[idx];
+    // ||G||_F^2 in a fixed order (skip threshold, qil_common.cuh)
+    for (int j = tid; j < ns; j += blockDim.x) {
+        double a = 0.0;
+        for (int i = 0; i < ns; ++i) a += Scalar<T>::abs2(G0[j * pg + i]);
+        sig[j] = a;
+    }
+    __syncthreads();
+    if (tid == 0) {
+        double tot = 0.0;
+        for (int j = 0; j < ns; ++j) tot += sig[j];
+        *s_nu = jacobi_skip_threshold(tot, ns, cutoff, mindim);
+    }
+    __syncthreads();
+    if (tid < 32) {
+        wjacobi<T>(Gw, pg, ns, *s_nu, sig, order);
+        if (tid == 0) *s_rank = truncate_rank_dev(sig, ns, cutoff, maxdim < 1 ? 1 : maxdim, mindim < 1 ? 1 : mindim, margin);
+    }
+    __syncthreads();
+}
+
 // ---- panel GEMM on the FP64 tensor pipe, fragments straight from memory -----------------------------------
 // Cs[M x ncol] (shared, row-major, pc)  = scale * op(A)[M x K] * B[K x ncol] (shared, row-major, pb; rows >= K need
 // not exist: the k range is guarded, columns >= ncol are never read).  A is GLOBAL (or shared) row-major with lda:
 //   TRANS = false: op(A)[m][k] = A[m * lda + k]          TRANS = true: op(A)[m][k] = A[k * lda + m]   (real: A^T)
+// (TRANS is a run-time flag: one instance of the code per kernel)
 // Warps take 16-row tiles round robin; at most 4 column tiles of 8 (ncol <= 32).
 __device__ __forceinline__ void wq_dmma(double* c, const double* a, const double* b) {
     asm volatile(
@@ -470,9 +652,8 @@ __device__ __forceinline__ void wq_dmma(double* c, const double* a, const double
           "d"(b[2]), "d"(b[3]));
 }
 
-template <bool TRANS>
-__device__ __forceinline__ void cta_gemm(const double* __restrict__ A, long long lda, int M, int K, const double* B,
-                                         int pb, int ncol, double* Cs, int pc, double scale) {
+__device__ __forceinline__ void cta_gemm(const bool TRANS, const double* __restrict__ A, long long lda, int M, int K,
+                                         const double* B, int pb, int ncol, double* Cs, int pc, double scale) {
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
     const int nwarps = blockDim.x >> 5;
     const int g = lane >> 2, t = lane & 3;
