@@ -26,8 +26,9 @@ namespace qil {
 
 constexpr int kWqrMaxN = 32;   // columns of a fast-path panel
 constexpr int kWqrRpl = 8;     // default row slots per lane
-constexpr int kWqrMaxRpl = 8;  // a block inside a CTA has at most 256 rows: its trailing values and its apply-down chunk
-constexpr int kWqrMaxRows = 32 * kWqrMaxRpl;   // stay in registers under the 128-register cap of a 512-thread CTA
+constexpr int kWqrMaxRpl = 8;  // a block inside a CTA has at most 256 rows (measured: 16 warps on one 512-row block are
+constexpr int kWqrMaxRows = 32 * kWqrMaxRpl;   // slower per column step than 8 warps on 256 rows -- the redundant scalar work and the
+                                               // shuffles of all warps share the SM's FP64 / shuffle pipes)
 
 template <typename T> struct WqrChunk { static constexpr int CH = 4; };      // register chunk of the apply-down (cta_qr)
 template <> struct WqrChunk<cplx> { static constexpr int CH = 2; };

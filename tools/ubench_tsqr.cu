@@ -8,8 +8,8 @@ __device__ long long g_clk[256];
 #include "../qilaplace.jl_b200/csrc/qil_wqr.cuh"
 using namespace qil;
 
-template <int RPL>
-__global__ void __launch_bounds__(256) k_factor(double* out, int m, int n, int pitch) {
+template <int RPL, int THREADS>
+__global__ void __launch_bounds__(THREADS) k_factor(double* out, int m, int n, int pitch) {
     extern __shared__ __align__(16) unsigned char smem_raw[];
     double* blk = reinterpret_cast<double*>(smem_raw);
     double* beta = blk + (size_t)(32 * RPL) * pitch;
@@ -20,11 +20,11 @@ __global__ void __launch_bounds__(256) k_factor(double* out, int m, int n, int p
     }
     __syncthreads();
     const long long t0 = clock64();
-    wqr_factor<double, RPL, (RPL >= 16 ? 64 : 16)>(blk, pitch, m, n, beta, tau, threadIdx.x >> 5, blockDim.x >> 5, 1);
+    wqr_factor<double, RPL, (THREADS > 256 ? 32 : (RPL >= 16 ? 64 : 16))>(blk, pitch, m, n, beta, tau, threadIdx.x >> 5, blockDim.x >> 5, 1);
     const long long t1 = clock64();
     if (threadIdx.x == 0) { g_clk[200] = t1 - t0; }
     __syncthreads();
-    constexpr int CH = 4;
+    constexpr int CH = (THREADS > 256 && RPL >= 16) ? 2 : 4;
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
     double reg[RPL][CH];
     for (int t = 0; t < RPL; ++t)
@@ -39,18 +39,18 @@ __global__ void __launch_bounds__(256) k_factor(double* out, int m, int n, int p
     out[blockIdx.x * blockDim.x + threadIdx.x] = acc + beta[0];
 }
 
-template <int RPL>
+template <int RPL, int THREADS = 256>
 void run(int m, int n, int threads) {
     const int pitch = wqr_pitch(n);
     double* out;
     cudaMalloc(&out, 1 << 20);
     size_t smem = ((size_t)32 * RPL * pitch + 4 * n + 16) * 8;
-    cudaFuncSetAttribute(k_factor<RPL>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+    cudaFuncSetAttribute(k_factor<RPL, THREADS>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
     cudaEvent_t e0, e1;
     cudaEventCreate(&e0); cudaEventCreate(&e1);
     for (int rep = 0; rep < 3; ++rep) {
         cudaEventRecord(e0);
-        k_factor<RPL><<<1, threads, smem>>>(out, m, n, pitch);
+        k_factor<RPL, THREADS><<<1, threads, smem>>>(out, m, n, pitch);
         cudaEventRecord(e1);
         cudaDeviceSynchronize();
     }
@@ -68,6 +68,9 @@ void run(int m, int n, int threads) {
 
 int main() {
     run<16>(512, 20, 256);
+    run<16, 512>(512, 20, 512);
+    run<8, 512>(256, 20, 512);
+    run<4, 512>(128, 20, 512);
     run<16>(512, 20, 32);
     run<8>(256, 20, 256);
     run<8>(213, 20, 160);
