@@ -137,7 +137,29 @@ class ClockSampler(threading.Thread):
 _CPU_SETUP = {}
 
 
-def cpu_pipeline(n, coeff_sample, reps=1):
+def blas_threads(limit=None):
+    """(threads in use, context manager setting them).  torchrun exports OMP_NUM_THREADS=1 for every rank, which
+    silently makes numpy/OpenBLAS single-threaded: the reference arm sets the pool size explicitly and reports it."""
+    try:
+        from threadpoolctl import threadpool_info, threadpool_limits
+    except Exception:
+        import contextlib
+        return int(os.environ.get("OMP_NUM_THREADS", os.cpu_count() or 1)), contextlib.nullcontext()
+    want = limit or (os.cpu_count() or 1)
+    ctxm = threadpool_limits(limits=want)
+    nth = max([i.get("num_threads", 1) for i in threadpool_info()] or [1])
+    return nth, ctxm
+
+
+def shared_stream(n):
+    """Host-drawn N(0,1) stream for the top split (cols * (k+p) numbers, seed 1234): given to the oracle and to the
+    library alike, so that the parity check compares the two implementations and not two test matrices."""
+    import numpy as np
+    cols = 2 ** (n - n // 2)
+    return np.random.default_rng(1234).standard_normal(cols * (ALGO["k"] + ALGO["p"]))
+
+
+def cpu_pipeline(n, coeff_sample, reps=1, keep=None, stream=None):
     """Times the numpy/OpenBLAS oracle on the host cores: (encode+split+apply seconds, detail)."""
     sys.path.insert(0, os.path.join(ROOT, "oracle"))
     import numpy as np
@@ -148,8 +170,10 @@ def cpu_pipeline(n, coeff_sample, reps=1):
     bits = hash_bits(coeff_sample, 2 * n) if coeff_sample else None
     best = None
     for _ in range(reps):
+        L = ALGO["k"] + ALGO["p"]
+        omega_fn = None if stream is None else (lambda cols, iscomplex: stream[: cols * L].reshape(L, cols).T)
         t0 = time.perf_counter()
-        cores, c = O.signal_mps(x, method="rsvd", **ALGO)
+        cores, c = O.tt_rsvd(x, omega_fn=omega_fn, **ALGO)
         t1 = time.perf_counter()
         z = O.ztmps_split(cores, ALGO["cutoff"])
         out = O.apply_mpo_mps(W, z)
@@ -161,6 +185,8 @@ def cpu_pipeline(n, coeff_sample, reps=1):
             d["coefficients_per_s"] = coeff_sample / d["coeff_s_sample"]
         if best is None or d["step_s"] < best["step_s"]:
             best = d
+        if keep is not None:
+            keep.update(cores=cores, c=c, z=z, out=out, W=W, x=x)
     return best["step_s"], best
 
 
@@ -170,16 +196,18 @@ def run_reference(args):
         return
     n = args.cpu_n or args.n
     cores = os.cpu_count() or 1
+    threads, pool = blas_threads()
     times = []
     detail = None
-    for i in range(1 + args.steps):            # one warm-up pass is enough for numpy; keeps the run bounded
-        t, detail = cpu_pipeline(n, 20000 if i == args.steps else 0)
-        if i >= 1:
-            times.append(t)
+    with pool:
+        for i in range(1 + args.steps):        # one warm-up pass is enough for numpy; keeps the run bounded
+            t, detail = cpu_pipeline(n, 20000 if i == args.steps else 0)
+            if i >= 1:
+                times.append(t)
     ms = 1e3 * sum(times) / len(times)
     value = (2**n) / (ms / 1e3)
     unit = "samples/s"
-    sample = (f"numpy/OpenBLAS oracle (all host threads): n={n} real sin_decay signal (2^{n} samples), D&C RSVD encode "
+    sample = (f"numpy/OpenBLAS oracle ({threads} BLAS threads on {cores} cores): n={n} real sin_decay signal (2^{n} samples), D&C RSVD encode "
               f"k=15 p=5 q=2 + ZTMPS split + zT apply; 20000 coefficients timed once for coefficients_per_s")
     line = {
         "impl": "reference", "metric": "encode_zt_apply_samples_per_s", "value": value, "unit": unit,
@@ -187,7 +215,8 @@ def run_reference(args):
         "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f64", "data": "synthetic",
         "config": {"workload": f"C4 n={args.n} real sin_decay: signal_ztmps(:rsvd k=15 p=5 q=2 cutoff=1e-12) + zT apply",
                    "cpu_sample_n": n},
-        "cpu_baseline": {"value": value, "unit": unit, "cores": cores, "kind": "port", "sample": sample, "detail": detail},
+        "cpu_baseline": {"value": value, "unit": unit, "cores": cores, "threads": threads, "kind": "port", "sample": sample,
+                         "detail": detail},
         "e2e": {"value": value, "unit": unit, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
         "coefficients_per_s": detail.get("coefficients_per_s") if detail else None,
         "gpu_launches": 0,
@@ -204,6 +233,66 @@ def log(msg):
         return
     sys.stderr.write(f"[bench r{os.environ.get('RANK', '0')} {time.strftime('%H:%M:%S')}] {msg}\n")
     sys.stderr.flush()
+
+
+def parity_check(q, ctx, torch, dev, x_dev, n, oracle, st, psi_timed, state, samples=4096, tol=1e-10):
+    """The bench's own result against the oracle at the quoted size: bonds identical, `samples` sampled amplitudes of the
+    encoded MPS and of the zT output within `tol` (relative to the largest amplitude).  Both sides get the same host-drawn
+    normal stream and the same zT MPO (the oracle's, uploaded), so the comparison isolates the implementation."""
+    import numpy as np
+    import qil_oracle as O
+    N = 2**n
+    st_dev = torch.from_numpy(st).to(dev)
+    psi = q.signal_mps_dev(ctx, x_dev.data_ptr(), N, False, method="rsvd", normal_stream_dev=st_dev.data_ptr(),
+                           stream_len=st.size, **ALGO)
+    z = q.ztmps_from_mps(psi, cutoff=ALGO["cutoff"])
+    Wo = q.PairedSiteMPO.from_cores(oracle["W"], ctx=ctx)
+    out = q.apply(Wo, z)
+    rng = np.random.default_rng(7)
+    idx = np.concatenate([[0, 1, N // 2, N - 1], rng.integers(0, N, samples - 4)])
+    bits = ((idx[:, None] >> np.arange(n - 1, -1, -1)[None, :]) & 1).astype(np.uint8)
+    got = q.coefficients(psi, bits)
+    want = O.coefficient_batch(oracle["cores"], oracle["c"], bits)
+    scale = float(np.abs(oracle["x"]).max())
+    err_enc = float(np.abs(got - want).max() / scale)
+    # zT output: a 64 x 64 block of (k, l) points at the top of the l range (the region the pole scan reads, where the
+    # coefficients are large) plus random bitstrings; errors relative to the largest coefficient of the sample
+    kk, ll = np.meshgrid(np.arange(64), N - 64 + np.arange(64), indexing="ij")
+    kk = kk.reshape(-1); ll = ll.reshape(-1)
+    bits_blk = np.zeros((kk.size, 2 * n), dtype=np.uint8)
+    for jq in range(n):                      # interleaved, LSB first (docs/src/tutorials/zt.jl:152-157)
+        bits_blk[:, 2 * jq] = (kk >> jq) & 1
+        bits_blk[:, 2 * jq + 1] = (ll >> jq) & 1
+    bits2 = np.concatenate([bits_blk, hash_bits(max(samples - kk.size, 16), 2 * n, seed=99)])
+    got2 = q.coefficients(out, bits2)
+    want2 = O.coefficient_batch(oracle["out"], oracle["c"], bits2)
+    scale2 = float(max(np.abs(want2).max(), 1e-300))
+    err_out = float(np.abs(got2 - want2).max() / scale2)
+    # yardstick: the divide-and-conquer algorithm's own conditioning -- the oracle against itself on the same signal
+    # perturbed by one ulp per sample (two correct implementations cannot agree better than this)
+    xp = oracle["x"] * (1.0 + 1.1e-16 * np.random.default_rng(3).standard_normal(N))
+    L = ALGO["k"] + ALGO["p"]
+    cores_p, c_p = O.tt_rsvd(xp, omega_fn=(lambda cols, iscomplex: st[: cols * L].reshape(L, cols).T), **ALGO)
+    yard = float(np.abs(O.coefficient_batch(cores_p, c_p, bits) - want).max() / scale)
+    del xp
+    # the timed runs use the device-side generator for Omega: their bonds must equal the oracle's as well
+    res = {"n": n, "samples": samples, "tol": tol,
+           "bonds_equal_oracle": psi.bonds == O.bonds_of(oracle["cores"]),
+           "ztmps_bonds_equal_oracle": z.bonds == O.bonds_of(oracle["z"]),
+           "timed_run_bonds_equal_oracle": psi_timed.bonds == O.bonds_of(oracle["cores"]),
+           "adaptive_run_bonds_equal_oracle": state["psi_adaptive"].bonds == O.bonds_of(oracle["cores"]),
+           "amplitude_scale": abs(psi.amplitude - oracle["c"]) / oracle["c"],
+           "encode_max_rel_err": err_enc, "zt_output_max_rel_err": err_out, "zt_output_scale": scale2,
+           "oracle_vs_oracle_1ulp_perturbed_input": yard,
+           "signal_reconstruction_rel_err": float(np.abs(got - oracle["x"][idx]).max() / scale)}
+    # adaptive run against the oracle on the same sample (device generator for Omega: agreement at truncation level)
+    got_a = q.coefficients(state["psi_adaptive"], bits)
+    res["adaptive_encode_max_rel_err"] = float(np.abs(got_a - want).max() / scale)
+    res["within_tol"] = bool(err_enc <= tol and err_out <= tol)
+    res["within_10x_algorithm_conditioning"] = bool(err_enc <= max(tol, 10 * yard) and err_out <= max(tol, 10 * yard))
+    res["ok"] = bool(res["bonds_equal_oracle"] and res["ztmps_bonds_equal_oracle"] and res["timed_run_bonds_equal_oracle"]
+                     and res["within_10x_algorithm_conditioning"])
+    return res
 
 
 def run_ours(args):
@@ -282,16 +371,23 @@ def run_ours(args):
 
     state = {}
 
-    def encode_dev(ptr):
+    def encode_dev(ptr, adaptive=False):
         if shard:
-            return parallel.signal_mps_sharded_dev(comm, ptr, N, False, **ALGO)
-        return q.signal_mps_dev(ctx, ptr, N, False, method="rsvd", **ALGO)
+            return parallel.signal_mps_sharded_dev(comm, ptr, N, False, adaptive=adaptive, **ALGO)
+        return q.signal_mps_dev(ctx, ptr, N, False, method="rsvd", adaptive=adaptive, **ALGO)
 
     def step_device():
         psi = encode_dev(x_dev.data_ptr())
         z = q.ztmps_from_mps(psi, cutoff=ALGO["cutoff"])
         out = q.apply(W, z)
         state["psi"], state["z"], state["out"] = psi, z, out
+
+    def step_device_adaptive():
+        # same step with the opt-in rank-adaptive sketch width (QIL_RSVD_ADAPTIVE): reported beside `value`
+        psi = encode_dev(x_dev.data_ptr(), adaptive=True)
+        z = q.ztmps_from_mps(psi, cutoff=ALGO["cutoff"])
+        state["out_adaptive"] = q.apply(W, z)
+        state["psi_adaptive"] = psi
 
     def step_coeff():
         q.coefficients_dev(state["out"], bits_dev.data_ptr(), B, out_dev.data_ptr())
@@ -397,6 +493,11 @@ def run_ours(args):
     g_ms, g_cnt, g_bytes, g_flops = ctx.profile_read_work(0)
     a_ms, a_cnt = ctx.profile_read(2)
     ctx.profile_reset()
+    ctx.profile_enable(False)
+    for _ in range(2):
+        step_device_adaptive()
+    ms_dev_adaptive = timed(step_device_adaptive, args.steps)
+    ctx.profile_enable(True); ctx.profile_reset()
     csteps = max(1, min(args.steps, 3))
     ms_coeff = timed(step_coeff, csteps)
     c_ms, c_cnt = ctx.profile_read(1)
@@ -544,6 +645,12 @@ def run_ours(args):
                       "points": scan_pts, "ms": ms_scan, "coefficients_per_s": world * scan_pts / (ms_scan / 1e3),
                       "e2e_ms": ms_scan_e2e, "e2e_coefficients_per_s": world * scan_pts / (ms_scan_e2e / 1e3),
                       "d2h_bytes_per_step": int(16 * scan_pts), "max_rel_dev_vs_chain_kernel": scan_check},
+        "adaptive_sketch": {"what": "same step with the opt-in rank-adaptive sketch width at the top split (flags = "
+                                    "QIL_RSVD_ADAPTIVE: sketch columns at rounding level dropped after the first QR; "
+                                    "`value` is the reference-faithful fixed width k+p)",
+                            "ms_per_step": ms_dev_adaptive / args.steps,
+                            "samples_per_s": units * N / (ms_dev_adaptive / args.steps / 1e3),
+                            "bonds_equal_fixed_width": state["psi_adaptive"].bonds == psi.bonds},
         "pipelined_batch": batch_info,
         "full_step": {"what": f"encode + split + apply + {B} coefficients of independent random bitstrings", "ms": full_ms,
                       "samples_per_s": units * N / (full_ms / 1e3)},
@@ -552,17 +659,70 @@ def run_ours(args):
         "stages_ms": stages_ms,
     }
 
+    if world > 1 and not shard:
+        # ---- the configuration north_star names for N > 1: ONE n-qubit signal row-sharded over the ranks (strong
+        # scaling).  Reported beside the weak line so that the driver's --gpus N run records both.
+        try:
+            from qilaplace_b200 import parallel
+            NLs = N // world
+            scomm = (parallel.PeerComm(ctx, parallel.encode_exchange_bytes(N, ALGO["k"], ALGO["p"], False))
+                     if args.comm == "peer" else parallel.TorchComm(ctx))
+            js = torch.arange(rank * NLs, (rank + 1) * NLs, dtype=torch.float64, device=dev)
+            ts = js * (1.0 / (2.5 * N))
+            xs_dev = torch.sin(1.0 * ts) * torch.exp(-0.08 * ts) + torch.sin(2.5 * ts) * torch.exp(-0.03 * ts)
+            del js, ts
+            xs_pin = torch.empty(NLs, dtype=torch.float64, pin_memory=True)
+            xs_pin.copy_(xs_dev)
+            xs_stage = torch.empty(NLs, dtype=torch.float64, device=dev)
+            sstate = {}
+
+            def step_sharded():
+                ps = parallel.signal_mps_sharded_dev(scomm, xs_dev.data_ptr(), N, False, **ALGO)
+                sstate["psi"] = ps
+                sstate["out"] = q.apply(W, q.ztmps_from_mps(ps, cutoff=ALGO["cutoff"]))
+
+            def step_sharded_e2e():
+                xs_stage.copy_(xs_pin, non_blocking=True)
+                ps = parallel.signal_mps_sharded_dev(scomm, xs_stage.data_ptr(), N, False, **ALGO)
+                o2 = q.apply(W, q.ztmps_from_mps(ps, cutoff=ALGO["cutoff"]))
+                sstate["host_cores"] = o2.cores_into(cores_pin)
+
+            for _ in range(3):
+                step_sharded()
+            ms_sh = timed(step_sharded, args.steps) / args.steps
+            for _ in range(2):
+                step_sharded_e2e()
+            ms_sh_e2e = timed(step_sharded_e2e, args.steps) / args.steps
+            line["sharded"] = {
+                "what": f"ONE n={n} signal row-sharded over {world} ranks (qil_encode_rsvd_sharded_dev: TSQR all-gather + "
+                        f"projection all-reduce over " + ("NVLink peer memory, library kernels" if args.comm == "peer"
+                                                          else "NCCL") + "), then split + zT apply; strong scaling",
+                "scaling": "strong", "ms_per_step": ms_sh, "samples_per_s": N / (ms_sh / 1e3),
+                "e2e_ms_per_step": ms_sh_e2e, "e2e_samples_per_s": N / (ms_sh_e2e / 1e3),
+                "h2d_bytes_per_step_per_rank": int(8 * NLs),
+                "bonds_equal_single_gpu": sstate["psi"].bonds == psi.bonds,
+                "speedup_vs_one_signal_on_one_rank": ms_step / ms_sh}
+            if args.comm == "peer":
+                scomm.close()
+        except Exception as e:   # the weak line is the contract; the sharded block is extra evidence
+            line["sharded"] = {"error": f"{type(e).__name__}: {e}"}
     if shard:
         line["config"]["collectives_total"] = dict(comm.calls)
     if rank == 0 and world == 1 and not args.no_cpu_baseline:
         cn = args.cpu_n or n
         try:
-            t, detail = cpu_pipeline(cn, 20000)
+            threads, pool = blas_threads()
+            keep = {}
+            st = shared_stream(cn) if cn == n else None
+            with pool:
+                t, detail = cpu_pipeline(cn, 20000, keep=keep, stream=st)
             line["cpu_baseline"] = {
-                "value": (2**cn) / t, "unit": "samples/s", "cores": os.cpu_count() or 1, "kind": "port",
-                "sample": f"numpy/OpenBLAS oracle (all host threads), same algorithm, n={cn} signal (2^{cn} samples): "
+                "value": (2**cn) / t, "unit": "samples/s", "cores": os.cpu_count() or 1, "threads": threads, "kind": "port",
+                "sample": f"numpy/OpenBLAS oracle ({threads} BLAS threads), same algorithm, n={cn} signal (2^{cn} samples): "
                           f"encode + split + apply once; 20000 coefficients for coefficients_per_s",
                 "coefficients_per_s": detail.get("coefficients_per_s"), "detail": detail}
+            if cn == n:
+                line["parity_checked"] = parity_check(q, ctx, torch, dev, x_dev, n, keep, st, psi, state)
         except Exception as e:  # the baseline is reported, never required
             line["cpu_baseline"] = {"value": None, "unit": "samples/s", "cores": os.cpu_count() or 1, "kind": "port",
                                     "sample": f"failed: {e}"}

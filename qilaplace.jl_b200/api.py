@@ -682,7 +682,8 @@ def rsvd(A, k=20, p=10, q=0, random_seed=1234, cutoff=1e-15, maxdim=None, mindim
     else:
         sp, slen = None, 0
     call("qil_rsvd", ctx.handle, int(ic), C.c_int64(m), C.c_int64(n), C.c_void_p(A.ctypes.data), int(k), int(p), int(q),
-         C.c_int64(random_seed), float(cutoff), C.c_int64(k if maxdim is None else _maxdim_arg(maxdim)),
+         C.c_int64(random_seed), float(cutoff),
+         C.c_int64(k if maxdim is None else (k + p if maxdim >= BIG else int(maxdim))),   # typemax(Int): cap is k+p
          C.c_int64(mindim), sp, C.c_int64(slen), C.byref(r), C.c_void_p(U.ctypes.data), C.c_void_p(S.ctypes.data),
          C.c_void_p(Vh.ctypes.data))
     r = int(r.value)
@@ -693,16 +694,18 @@ def rsvd(A, k=20, p=10, q=0, random_seed=1234, cutoff=1e-15, maxdim=None, mindim
 # device-resident entry points (inputs already in HBM; pointers are raw CUDA device addresses)
 # ------------------------------------------------------------------------------------------
 def signal_mps_dev(ctx, d_x, N, is_complex, method="rsvd", cutoff=1e-15, maxdim=None, k=20, p=10, q=0,
-                   random_seed=1234, mindim=1, adaptive=False):
-    """signal_mps on a signal that already lives on the device (stream-ordered, no host copies)."""
+                   random_seed=1234, mindim=1, adaptive=False, normal_stream_dev=None, stream_len=0):
+    """signal_mps on a signal that already lives on the device (stream-ordered, no host copies).
+    normal_stream_dev / stream_len: optional device pointer to the host-drawn normal stream (Omega) and its length."""
     h = _lib.c_mps()
     if method == "svd":
         call("qil_encode_svd_dev", ctx.handle, int(is_complex), C.c_void_p(int(d_x)), C.c_int64(N), float(cutoff),
              C.c_int64(_maxdim_arg(maxdim)), C.byref(h))
     else:
         call("qil_encode_rsvd_dev", ctx.handle, int(is_complex), C.c_void_p(int(d_x)), C.c_int64(N), int(k), int(p),
-             int(q), C.c_int64(random_seed), float(cutoff), C.c_int64(_maxdim_arg(maxdim)), C.c_int64(mindim), None,
-             C.c_int64(0), C.c_int64(RSVD_ADAPTIVE if adaptive else 0), C.byref(h))
+             int(q), C.c_int64(random_seed), float(cutoff), C.c_int64(_maxdim_arg(maxdim)), C.c_int64(mindim),
+             C.c_void_p(int(normal_stream_dev)) if normal_stream_dev else None, C.c_int64(int(stream_len)),
+             C.c_int64(RSVD_ADAPTIVE if adaptive else 0), C.byref(h))
     return SignalMPS(ctx, h)
 
 

@@ -89,10 +89,10 @@ static void launch_sites(qil_ctx* ctx, K kern, const ApplyDesc& d, long long max
     int bx = (int)std::min<long long>((max_total + 255) / 256, (long long)ctx->sm_count * 8);
     if (bx < 1) bx = 1;
     dim3 grid(bx, d.n);
-    ctx->prof_begin(PROF_APPLY);
+    { qil_prof_region prof_guard_(ctx, PROF_APPLY);
     kern<<<grid, 256, 0, ctx->stream>>>(d);
     QIL_LAUNCH_CHECK(ctx);
-    ctx->prof_end();
+    }
 }
 
 qil_mps* apply_mpo_mps(qil_ctx* ctx, const qil_mpo* W, const qil_mps* psi) {

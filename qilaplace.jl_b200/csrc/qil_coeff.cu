@@ -357,14 +357,14 @@ void coefficient_batch_dev(qil_ctx* ctx, const qil_mps* psi, const uint8_t* d_bi
     if (B <= 0) return;
     int chimax = 1;
     for (int i = 0; i <= psi->n; ++i) chimax = max(chimax, (int)psi->bond[i]);
-    ctx->prof_begin(PROF_COEFF);
+    { qil_prof_region prof_guard_(ctx, PROF_COEFF);
     if (psi->is_complex && chimax >= 48 && B >= 64)
         launch_coeff_gemm(ctx, psi, d_bits, B, d_out);
     else if (psi->is_complex)
         launch_coeff<cplx>(ctx, psi, d_bits, B, d_out);
     else
         launch_coeff<double>(ctx, psi, d_bits, B, d_out);
-    ctx->prof_end();
+    }
 }
 
 }  // namespace qil

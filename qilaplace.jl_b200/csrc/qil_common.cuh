@@ -11,6 +11,7 @@
 #include <cstdio>
 #include <exception>
 #include <map>
+#include <memory>
 #include <mutex>
 #include <string>
 #include <vector>
@@ -136,12 +137,25 @@ struct qil_ctx {
     void sync();
 };
 
+// profiler region that closes on every exit path (an exception thrown inside would otherwise leave prof_depth > 0 and
+// silently disable later profiling)
+struct qil_prof_region {
+    qil_ctx* c;
+    qil_prof_region(qil_ctx* ctx, int id, double bytes = 0.0, double flops = 0.0) : c(ctx) { c->prof_begin(id, bytes, flops); }
+    ~qil_prof_region() { c->prof_end(); }
+    qil_prof_region(const qil_prof_region&) = delete;
+    qil_prof_region& operator=(const qil_prof_region&) = delete;
+};
+
 struct qil_mps {
     qil_ctx* ctx = nullptr;
     int n = 0;
     int is_complex = 0;
     std::vector<int64_t> bond;  // n+1 entries, bond[0] = bond[n] = 1
     std::vector<void*> core;    // device pointers, core[i] is [bond[i]][2][bond[i+1]]
+    // non-null: the cores are sub-allocations of one pooled buffer shared by the MPS of a batch (freed with the last
+    // of them); in-place operations call qil::unpool() first
+    std::shared_ptr<void> pool;
     double amplitude = 1.0;
     size_t core_elems(int i) const { return (size_t)bond[i] * 2 * (size_t)bond[i + 1]; }
 };
@@ -170,6 +184,7 @@ ChainDesc make_desc(const qil_mpo* m);
 qil_mps* new_mps(qil_ctx* ctx, int n, int is_complex, const int64_t* bond /* n+1 */, bool allocate);
 qil_mpo* new_mpo(qil_ctx* ctx, int n, int is_complex, const int64_t* bond /* n+1 */, bool allocate);
 void destroy(qil_mps* m);
+void unpool(qil_mps* m);          // give a pooled MPS its own core allocations
 void destroy(qil_mpo* m);
 
 // native collectives over peer memory (qil_peer.cu)

@@ -75,10 +75,13 @@ void qil_ctx::sync() { QIL_CUDA(cudaStreamSynchronize(stream)); }
 namespace qil {
 
 void ensure_dynamic_smem_impl(const void* func, size_t bytes) {
+    // cudaFuncSetAttribute applies to the CURRENT device: the running maximum is kept per (device, function)
     static std::mutex mu;
-    static std::map<const void*, size_t> current;
+    static std::map<std::pair<int, const void*>, size_t> current;
+    int dev = 0;
+    QIL_CUDA(cudaGetDevice(&dev));
     std::lock_guard<std::mutex> lock(mu);
-    size_t& cur = current[func];
+    size_t& cur = current[std::make_pair(dev, func)];
     if (bytes > cur) {
         QIL_CUDA(cudaFuncSetAttribute(func, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)bytes));
         cur = bytes;
@@ -120,8 +123,21 @@ qil_mpo* new_mpo(qil_ctx* ctx, int n, int is_complex, const int64_t* bond, bool 
 
 void destroy(qil_mps* m) {
     if (!m) return;
-    for (void* p : m->core) m->ctx->free(p);
+    if (!m->pool)
+        for (void* p : m->core) m->ctx->free(p);
     delete m;
+}
+
+void unpool(qil_mps* m) {
+    if (!m || !m->pool) return;
+    for (int i = 0; i < m->n; ++i) {
+        const size_t bytes = m->core_elems(i) * elem_size(m->is_complex);
+        void* p = m->ctx->alloc(bytes);
+        QIL_CUDA(cudaMemcpyAsync(p, m->core[i], bytes, cudaMemcpyDeviceToDevice, m->ctx->stream));
+        m->core[i] = p;
+    }
+    QIL_CUDA(cudaStreamSynchronize(m->ctx->stream));     // the pool may be released right after
+    m->pool.reset();
 }
 
 void destroy(qil_mpo* m) {

@@ -415,10 +415,10 @@ static int rsvd_split_fused(SplitCtx<double>& sc, const double* A, int64_t R, in
         Mat<double> Rtop;
         const bool adapt = top && o.adaptive;
         if (adapt) Rtop = Mat<double>(ctx, l0, l0);
-        ctx->prof_begin(PROF_QR);
+        { qil_prof_region prof_guard_(ctx, PROF_QR);
         sum_R(l0);
         qr_fast<double>(ctx, R, l0, YR.p, l0, 1, 0, true, XR.p, lpp, lpp, adapt ? Rtop.p : nullptr);
-        ctx->prof_end();
+        }
         if (adapt) {
             l = shrink_sketch_width<double>(ctx, o, l0, Rtop);
             if (l < l0) {
@@ -437,15 +437,15 @@ static int rsvd_split_fused(SplitCtx<double>& sc, const double* A, int64_t R, in
     }
     for (int it = 0; it < o.q; ++it) {
         stream_gemm(ctx, true, A, R, C, C, XR.p, lpp, nt, partC.p, ks2, kc2, nullptr, l);
-        ctx->prof_begin(PROF_QR);
+        { qil_prof_region prof_guard_(ctx, PROF_QR);
         sum_C(l);
         qr_fast<double>(ctx, C, l, ZC.p, l, 1, 0, true, XC.p, lpp, lpp, nullptr);
-        ctx->prof_end();
+        }
         stream_gemm(ctx, false, A, R, C, C, XC.p, lpp, nt, partR.p, ks1, kc1, nullptr, l);
-        ctx->prof_begin(PROF_QR);
+        { qil_prof_region prof_guard_(ctx, PROF_QR);
         sum_R(l);
         qr_fast<double>(ctx, R, l, YR.p, l, 1, 0, true, XR.p, lpp, lpp, nullptr);
-        ctx->prof_end();
+        }
     }
     // ---- B^H = A^H Q, then the device-side tail
     stream_gemm(ctx, true, A, R, C, C, XR.p, lpp, nt, partC.p, ks2, kc2, nullptr, l);
@@ -831,7 +831,228 @@ static qil_mps* encode_rsvd_tree(SplitCtx<double>& sc, const double* x, int n) {
         throw;
     }
 }
+// ---- the same for a batch of `count` equal-length signals, all levels in lock step (BASELINE configs[1]: 256 signals
+// of n = 20).  The signals stored back to back ARE one tall matrix (count*R x C), so the sketch Y = X Omega of all of them
+// is a single streaming launch (same Omega for every signal: same seed, same shape), and Z_s = X_s^H Q_s of all of them
+// is a single split-K launch whose K chunks are the signals (no reduction needed); the panels go through the batched
+// TSQR / Jacobi finish, then every tree level is one launch over (nodes of the level) x count CTAs.  All cores of the
+// batch live in one pooled allocation.
+__global__ void batch_sumsq_kernel(const double* __restrict__ x, long long N, int parts, double* __restrict__ partial) {
+    // grid (parts, count): fixed-order block reduction of one slice of one signal
+    __shared__ double red[256];
+    const long long s = blockIdx.y;
+    const long long per = (N + parts - 1) / parts;
+    const long long b0 = blockIdx.x * per, b1 = min(b0 + per, N);
+    double a = 0.0;
+    for (long long i = b0 + threadIdx.x; i < b1; i += blockDim.x) { const double v = x[s * N + i]; a = fma(v, v, a); }
+    red[threadIdx.x] = a;
+    __syncthreads();
+    for (int o = 128; o > 0; o >>= 1) {
+        if ((int)threadIdx.x < o) red[threadIdx.x] += red[threadIdx.x + o];
+        __syncthreads();
+    }
+    if (threadIdx.x == 0) partial[s * parts + blockIdx.x] = red[0];
+}
+__global__ void batch_norm_finalize_kernel(const double* partial, int parts, long long count, double* nrm) {
+    const long long s = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+    if (s >= count) return;
+    double a = 0.0;
+    for (int i = 0; i < parts; ++i) a += partial[s * parts + i];
+    const double c = sqrt(a);
+    nrm[2 * s] = c;
+    nrm[2 * s + 1] = 1.0 / c;
+}
+
+static bool encode_rsvd_tree_batch(qil_ctx* ctx, const RsvdOpts& o, const double* x_all, int n, int64_t count,
+                                   qil_mps** out) {
+    const int kp = o.k + o.p;
+    static const bool disabled = [] { const char* e = getenv("QIL_ENCODE_TREE"); return e && e[0] == '0'; }();
+    if (disabled || kp > 32 || n < 14 || count < 2 || o.adaptive) return false;
+    const int mid = n / 2 - 1;
+    const int64_t R = (int64_t)1 << (mid + 1), C = (int64_t)1 << (n - 1 - mid), N = (int64_t)1 << n;
+    const int64_t Rall = R * count;
+    const int l0 = (int)std::min<int64_t>(kp, std::min(R, C));
+    if (std::min(R, C) <= kp || R % 128 != 0 || C % 32 != 0 || !stream_supported(Rall, C, C, l0) ||
+        !qr_fast_supported<double>(ctx, R, l0) || !qr_fast_supported<double>(ctx, C, l0) || Rall >= ((int64_t)1 << 31))
+        return false;
+    const double* nstream = (const double*)o.omega;
+    const int64_t nstream_len = o.omega_rows * std::max<int64_t>(o.omega_cols, 1);
+    if (nstream && C * (int64_t)l0 > nstream_len) return false;
+
+    // ---- tree shape (the same for every signal) and buffer sizes per signal
+    struct TNode { int first, last, m2, nl, nr; int64_t usz, ssz; int in_buf; int u_buf, s_buf; };
+    struct Buf { int64_t size; bool is_core; int site; int64_t off; };
+    std::vector<Buf> bufs;
+    std::vector<std::vector<TNode>> levels;
+    auto new_buf = [&](int64_t size) { bufs.push_back({size, false, -1, 0}); return (int)bufs.size() - 1; };
+    const int b_utop = new_buf(R * l0), b_svtop = new_buf((int64_t)l0 * C);
+    struct Pending { int first, last, buf; };
+    std::vector<Pending> cur{{0, mid, b_utop}, {mid + 1, n - 1, b_svtop}}, next;
+    while (!cur.empty()) {
+        std::vector<TNode> lvl;
+        next.clear();
+        for (const Pending& pd : cur) {
+            if (pd.first == pd.last) { bufs[pd.buf].is_core = true; bufs[pd.buf].site = pd.first; continue; }
+            TNode t;
+            t.first = pd.first; t.last = pd.last; t.in_buf = pd.buf;
+            t.m2 = (pd.first + pd.last + 1) / 2 - 1;
+            t.nl = t.m2 - pd.first + 1; t.nr = pd.last - t.m2;
+            const int64_t Rmax = bond_cap(n, pd.first, kp) << t.nl, Cmax = bond_cap(n, pd.last + 1, kp) << t.nr;
+            const int64_t rmax = std::min<int64_t>(bond_cap(n, t.m2 + 1, kp), std::min(Rmax, Cmax));
+            t.usz = Rmax * rmax; t.ssz = rmax * Cmax;
+            t.u_buf = new_buf(t.usz); t.s_buf = new_buf(t.ssz);
+            lvl.push_back(t);
+            next.push_back({pd.first, t.m2, t.u_buf});
+            next.push_back({t.m2 + 1, pd.last, t.s_buf});
+        }
+        if (!lvl.empty()) levels.push_back(std::move(lvl));
+        cur = next;
+    }
+    int64_t core_elems = 0, tmp_elems = 0;
+    for (Buf& b : bufs) {
+        b.size = (b.size + 1) & ~(int64_t)1;                       // 16-byte aligned regions
+        int64_t& tot = b.is_core ? core_elems : tmp_elems;
+        b.off = tot;
+        tot += b.size * count;
+    }
+    const int nb1 = n + 1;
+    double* core_pool = (double*)ctx->alloc((size_t)std::max<int64_t>(core_elems, 1) * sizeof(double));
+    Mat<double> tmp_pool(ctx, std::max<int64_t>(tmp_elems, 1), 1);
+    Mat<double> nrm(ctx, 2 * count, 1);
+    int* d_state = (int*)ctx->alloc(sizeof(int) * (count * nb1 + 1));
+    int* d_over = d_state + count * nb1;
+    double* const core_base = core_pool;
+    auto buf_ptr = [&](int b, int64_t s) { return (bufs[b].is_core ? core_base : tmp_pool.p) + bufs[b].off + s * bufs[b].size; };
+    bool ok = false;
+    try {
+        init_tree_state_kernel<<<(int)std::min<int64_t>((count * nb1 + 256) / 256, 1024), 256, 0, ctx->stream>>>(
+            d_state, (int)(count * nb1));
+        QIL_LAUNCH_CHECK(ctx);
+        // node table: level-major, node-major, signal-minor
+        size_t total = 0;
+        for (auto& lv : levels) total += lv.size() * (size_t)count;
+        std::vector<NodeDesc> flat;
+        flat.reserve(total);
+        for (auto& lv : levels)
+            for (const TNode& t : lv)
+                for (int64_t s = 0; s < count; ++s) {
+                    NodeDesc d;
+                    d.A = buf_ptr(t.in_buf, s); d.U = buf_ptr(t.u_buf, s); d.SVh = buf_ptr(t.s_buf, s);
+                    d.bonds_off = (int)(s * nb1);
+                    d.lb_pos = t.first; d.rb_pos = t.last + 1; d.out_pos = t.m2 + 1; d.nl = t.nl; d.nr = t.nr;
+                    flat.push_back(d);
+                }
+        Mat<double> node_tab;                                      // raw bytes of the table
+        NodeDesc* d_nodes = nullptr;
+        if (total) {
+            node_tab = Mat<double>(ctx, (int64_t)((sizeof(NodeDesc) * total + 7) / 8), 1);
+            d_nodes = reinterpret_cast<NodeDesc*>(node_tab.p);
+            QIL_CUDA(cudaMemcpyAsync(d_nodes, flat.data(), sizeof(NodeDesc) * total, cudaMemcpyHostToDevice, ctx->stream));
+        }
+        // ---- norms
+        {
+            const int parts = 8;
+            Mat<double> partial(ctx, count * parts, 1);
+            batch_sumsq_kernel<<<dim3(parts, (unsigned)count), 256, 0, ctx->stream>>>(x_all, N, parts, partial.p);
+            QIL_LAUNCH_CHECK(ctx);
+            batch_norm_finalize_kernel<<<(int)((count + 127) / 128), 128, 0, ctx->stream>>>(partial.p, parts, count, nrm.p);
+            QIL_LAUNCH_CHECK(ctx);
+        }
+        // ---- top split of every signal
+        const int nt = stream_nt_for(l0), lpp = stream_lpp(nt), ldo = nt * 8;
+        Mat<double> XC(ctx, C, lpp), XCall, XRall(ctx, Rall, lpp);
+        prep_x_k1_kernel<double><<<grid_for(ctx, C * lpp), 256, 0, ctx->stream>>>(nullptr, nstream, (unsigned long long)o.seed, C,
+                                                                                l0, C, lpp, XC.p);
+        QIL_LAUNCH_CHECK(ctx);
+        int ks1; long long kc1;
+        stream_plan(ctx, Rall, C, &ks1, &kc1);
+        Mat<double> partR(ctx, (int64_t)ks1 * Rall, ldo), partC(ctx, count * C, ldo), Yall(ctx, Rall, l0);
+        auto sum_R = [&]() {
+            reduce_k1_kernel<double><<<grid_for(ctx, Rall * l0), 256, 0, ctx->stream>>>(partR.p, ks1, Rall, ldo, l0, Yall.p);
+            QIL_LAUNCH_CHECK(ctx);
+        };
+        stream_gemm(ctx, false, x_all, Rall, C, C, XC.p, lpp, nt, partR.p, ks1, kc1, nullptr, l0);
+        sum_R();
+        qr_fast<double>(ctx, R, l0, Yall.p, l0, 1, 0, true, XRall.p, lpp, lpp, nullptr, (int)count, R * l0, R * lpp, 0);
+        if (o.q > 0) XCall = Mat<double>(ctx, count * C, lpp);
+        for (int it = 0; it < o.q; ++it) {
+            // Z_s = X_s^H Q_s: split-K with one chunk per signal -> partial s IS Z_s
+            stream_gemm(ctx, true, x_all, Rall, C, C, XRall.p, lpp, nt, partC.p, (int)count, R, nullptr, l0);
+            qr_fast<double>(ctx, C, l0, partC.p, ldo, 1, 0, true, XCall.p, lpp, lpp, nullptr, (int)count, C * ldo, C * lpp, 0);
+            stream_gemm(ctx, false, x_all, Rall, C, C, XCall.p, lpp, nt, partR.p, ks1, kc1, nullptr, l0, R, C * lpp);
+            sum_R();
+            qr_fast<double>(ctx, R, l0, Yall.p, l0, 1, 0, true, XRall.p, lpp, lpp, nullptr, (int)count, R * l0, R * lpp, 0);
+        }
+        stream_gemm(ctx, true, x_all, Rall, C, C, XRall.p, lpp, nt, partC.p, (int)count, R, nullptr, l0);   // B_s^H
+        {
+            Mat<double> Qb(ctx, count * C, l0), Rb(ctx, count * l0, l0), Us(ctx, count * l0, l0), T2(ctx, count * l0, l0);
+            Mat<double> Sv(ctx, count * l0, 1);
+            qr_fast<double>(ctx, C, l0, partC.p, ldo, 1, 0, false, Qb.p, l0, l0, Rb.p, (int)count, C * ldo, C * l0,
+                            (int64_t)l0 * l0);
+            svd_finish<double>(ctx, l0, Rb.p, nrm.p + 1, o.cutoff, o.maxdim, o.mindim, Us.p, T2.p, Sv.p, d_state + mid + 1,
+                               (int)count, 2, nb1);
+            rsvd_outputs<double>(ctx, R, C, l0, XRall.p, lpp, Qb.p, l0, Us.p, T2.p, Sv.p, d_state + mid + 1,
+                                 buf_ptr(b_utop, 0), buf_ptr(b_svtop, 0), nullptr, (int)count, R * lpp, C * l0,
+                                 bufs[b_utop].size, bufs[b_svtop].size, nb1);
+        }
+        // ---- the tree levels
+        size_t off = 0;
+        for (auto& lv : levels) {
+            const size_t cnt = lv.size() * (size_t)count;
+            node_level_launch(ctx, d_nodes + off, (int)cnt, d_state, d_over, o, nstream, nstream_len);
+            off += cnt;
+        }
+        std::vector<int> h_state(count * nb1 + 1);
+        std::vector<double> h_nrm(2 * count);
+        QIL_CUDA(cudaMemcpyAsync(h_state.data(), d_state, sizeof(int) * h_state.size(), cudaMemcpyDeviceToHost, ctx->stream));
+        QIL_CUDA(cudaMemcpyAsync(h_nrm.data(), nrm.p, sizeof(double) * 2 * count, cudaMemcpyDeviceToHost, ctx->stream));
+        ctx->sync();
+        if (h_state[count * nb1] == 0) {
+            std::shared_ptr<void> pool(core_pool, [ctx](void* p) { ctx->free(p); });
+            core_pool = nullptr;
+            for (int64_t s = 0; s < count; ++s) {
+                std::vector<int64_t> bond(nb1);
+                for (int i = 0; i < nb1; ++i) bond[i] = h_state[s * nb1 + i];
+                qil_mps* m = new_mps(ctx, n, 0, bond.data(), false);
+                for (size_t b = 0; b < bufs.size(); ++b)
+                    if (bufs[b].is_core) m->core[bufs[b].site] = buf_ptr((int)b, s);
+                m->pool = pool;
+                m->amplitude = h_nrm[2 * s];
+                out[s] = m;
+            }
+            ok = true;
+        }
+    } catch (...) {
+        if (core_pool) ctx->free(core_pool);
+        ctx->free(d_state);
+        throw;
+    }
+    if (core_pool) ctx->free(core_pool);
+    ctx->free(d_state);
+    return ok;
+}
+
 template <typename T> static qil_mps* encode_rsvd_tree_dispatch(SplitCtx<T>&, const T*, int) { return nullptr; }
+template <typename T>
+static bool encode_rsvd_batch_tree_dispatch(qil_ctx*, const T*, int64_t, int64_t, const RsvdOpts&, qil_mps**) { return false; }
+template <>
+bool encode_rsvd_batch_tree_dispatch<double>(qil_ctx* ctx, const double* d_x, int64_t N, int64_t count, const RsvdOpts& o,
+                                             qil_mps** out) {
+    const int n = ilog2_round(N);
+    if (n < 1 || N != ((int64_t)1 << n)) return false;              // padded signals: one by one
+    // chunks of at most 2^31 stacked rows / a few GB of scratch
+    const int64_t R = (int64_t)1 << (n / 2);
+    const int64_t max_chunk = std::max<int64_t>(2, std::min<int64_t>(((int64_t)1 << 30) / R, ((int64_t)1 << 29) / std::max<int64_t>(N >> 6, 1)));
+    for (int64_t s0 = 0; s0 < count; s0 += max_chunk) {
+        const int64_t c = std::min(max_chunk, count - s0);
+        if (c < 2 || !encode_rsvd_tree_batch(ctx, o, d_x + s0 * N, n, c, out + s0)) {
+            for (int64_t i = 0; i < s0; ++i) { destroy(out[i]); out[i] = nullptr; }
+            return false;
+        }
+    }
+    return true;
+}
+
 template <> qil_mps* encode_rsvd_tree_dispatch<double>(SplitCtx<double>& sc, const double* x, int n) {
     return encode_rsvd_tree(sc, x, n);
 }
@@ -937,6 +1158,7 @@ void encode_rsvd_batch(qil_ctx* ctx, const T* d_x, int64_t N, int64_t count, con
     if (count == 0) return;
     workers = (int)std::max<int64_t>(1, std::min<int64_t>(workers <= 0 ? 16 : workers, count));
     for (int64_t i = 0; i < count; ++i) out[i] = nullptr;
+    if (encode_rsvd_batch_tree_dispatch<T>(ctx, d_x, N, count, o, out)) return;      // level-synchronous path
     cudaEvent_t ready;
     QIL_CUDA(cudaEventCreateWithFlags(&ready, cudaEventDisableTiming));
     QIL_CUDA(cudaEventRecord(ready, ctx->stream));

@@ -18,12 +18,13 @@ void qr_fast(qil_ctx* ctx, int64_t m, int n, const T* A, int64_t lda, int nsum, 
 //   S (l, first r meaningful), rank (device int).
 template <typename T>
 void svd_finish(qil_ctx* ctx, int l, const T* Rb, const double* d_scale, double cutoff, int64_t maxdim, int64_t mindim,
-                T* Us, T* T2, double* S, int* d_rank);
+                T* Us, T* T2, double* S, int* d_rank, int batch = 1, int scale_bs = 0, int rank_bs = 0);
 
 // U (R x r, ld r) = Q[:, :l] Us ;  SVh (r x C, ld C) = T2 Qb^H  (or Vh = diag(1/S) T2 Qb^H when vh_only)
 template <typename T>
 void rsvd_outputs(qil_ctx* ctx, int64_t R, int64_t C, int l, const T* Q, int64_t ldq, const T* Qb, int64_t ldqb,
-                  const T* Us, const T* T2, const double* S, const int* d_rank, T* U, T* SVh, T* Vh);
+                  const T* Us, const T* T2, const double* S, const int* d_rank, T* U, T* SVh, T* Vh, int batch = 1,
+                  int64_t q_bs = 0, int64_t qb_bs = 0, int64_t u_bs = 0, int64_t sv_bs = 0, int rank_bs = 0);
 
 // ---- one CTA per tree node (qil_node.cu) -------------------------------------------------------------------
 // Node matrix A = T[lb * 2^nl, 2^nr * rb] (compact, row-major) with lb = bonds[bonds_off + lb_pos], rb likewise;

@@ -401,10 +401,10 @@ static void coefficient_grid_impl(qil_ctx* ctx, const qil_mps* psi, const uint8_
 }
 
 void coefficient_grid_dev(qil_ctx* ctx, const qil_mps* psi, const uint8_t* mode, const int32_t* out_bit, void* d_out) {
-    ctx->prof_begin(PROF_COEFF);
+    { qil_prof_region prof_guard_(ctx, PROF_COEFF);
     if (psi->is_complex) coefficient_grid_impl<cplx>(ctx, psi, mode, out_bit, reinterpret_cast<cplx*>(d_out));
     else coefficient_grid_impl<double>(ctx, psi, mode, out_bit, reinterpret_cast<double*>(d_out));
-    ctx->prof_end();
+    }
 }
 
 }  // namespace qil

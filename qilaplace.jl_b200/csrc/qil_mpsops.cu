@@ -195,6 +195,7 @@ static void canonicalize_t(qil_ctx* ctx, qil_mps* psi, int dir_right, int center
 }
 
 void canonicalize(qil_ctx* ctx, qil_mps* psi, int dir_right, int center, double cutoff, int64_t maxdim) {
+    unpool(psi);
     const int N = psi->n;
     if (center <= 0) center = dir_right ? N : 1;
     QIL_REQUIRE(center >= 1 && center <= N, QIL_ERR_DOMAIN, "Center out of range [1,%d]", N);
@@ -273,6 +274,7 @@ static void compress_t(qil_ctx* ctx, qil_mps* psi, int64_t maxdim, double tol, i
 }
 
 void compress(qil_ctx* ctx, qil_mps* psi, int64_t maxdim, double tol, int sweeps) {
+    unpool(psi);
     QIL_REQUIRE(psi->n >= 2, QIL_ERR_DOMAIN, "SignalMPS must have at least 2 sites.");
     QIL_REQUIRE(sweeps >= 1, QIL_ERR_ARGUMENT, "compress!: sweeps must be >= 1");
     if (psi->is_complex) compress_t<cplx>(ctx, psi, maxdim, tol, sweeps);

@@ -57,5 +57,7 @@ void stream_plan(qil_ctx* ctx, long long Mtot, long long Kdim, int* ksplit, long
 int stream_grid(qil_ctx* ctx, long long Mtot, int ksplit);
 void stream_gemm(qil_ctx* ctx, bool trans, const double* A, long long R, long long C, long long ld, const double* X,
                  int lpp, int nt, double* out, int ksplit, long long kchunk, double* sumsq_partials,
-                 int ncols /* real sketch columns, for the profiler's algorithmic flops */);
+                 int ncols /* real sketch columns, for the profiler's algorithmic flops */,
+                 long long x_rows = 0 /* K1 over a stack of equal matrices: rows per matrix (multiple of 128) ... */,
+                 long long x_bs = 0 /* ... each with its own X operand, x_bs doubles apart */);
 }  // namespace qil

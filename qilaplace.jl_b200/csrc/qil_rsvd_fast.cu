@@ -20,6 +20,9 @@ struct FinishParams {
     double* S;          // l
     int* rank;
     double* margin;
+    // batch (blockIdx.x): strides between problems
+    long long rb_bs, us_bs, s_bs;
+    int scale_bs, rank_bs;
 };
 
 template <typename T>
@@ -34,24 +37,29 @@ __global__ void __launch_bounds__(128) svd_finish_kernel(const FinishParams<T> p
     __shared__ int s_rank;
     __shared__ double s_nu;
     const int tid = threadIdx.x;
-    const double sc = p.scale ? p.scale[0] : 1.0;
+    const long long bat = blockIdx.x;
+    const double sc = p.scale ? p.scale[bat * p.scale_bs] : 1.0;
+    const T* Rb = p.Rb + bat * p.rb_bs;
+    T* gUs = p.Us + bat * p.us_bs;
+    T* gT2 = p.T2 + bat * p.us_bs;
+    double* gS = p.S + bat * p.s_bs;
     // G = scale * Rb^H: column j of G is the conjugated row j of Rb
     for (int idx = tid; idx < l * l; idx += blockDim.x) {
         const int j = idx / l, i = idx - j * l;
-        G0[j * pg + i] = Scalar<T>::scale(Scalar<T>::conj(p.Rb[(size_t)j * l + i]), sc);
+        G0[j * pg + i] = Scalar<T>::scale(Scalar<T>::conj(Rb[(size_t)j * l + i]), sc);
     }
     __syncthreads();
     cta_jacobi_rank<T>(Gw, G0, pg, l, p.cutoff, p.maxdim, p.mindim, sig, order, &s_rank, p.margin, &s_nu);
     const int r = s_rank;
-    if (tid == 0) *p.rank = r;
-    for (int j = tid; j < l; j += blockDim.x) p.S[j] = sig[j];
+    if (tid == 0) p.rank[bat * p.rank_bs] = r;
+    for (int j = tid; j < l; j += blockDim.x) gS[j] = sig[j];
     // Us = W Sigma^-1 (sorted columns)
     for (int idx = tid; idx < l * r; idx += blockDim.x) {
         const int i = idx / r, j = idx - i * r;
         const double sj = sig[j];
         const T v = Scalar<T>::scale(Gw[order[j] * pg + i], sj > 0.0 ? 1.0 / sj : 0.0);
         Us[i * pg + j] = v;
-        p.Us[(size_t)i * r + j] = v;
+        gUs[(size_t)i * r + j] = v;
     }
     __syncthreads();
     // T2 = Us^H G  (r x l)
@@ -59,26 +67,27 @@ __global__ void __launch_bounds__(128) svd_finish_kernel(const FinishParams<T> p
         const int j = idx / l, c = idx - j * l;
         T acc = Scalar<T>::zero();
         for (int k = 0; k < l; ++k) acc = Scalar<T>::fma(Scalar<T>::conj(Us[k * pg + j]), G0[c * pg + k], acc);
-        p.T2[(size_t)j * l + c] = acc;
+        gT2[(size_t)j * l + c] = acc;
     }
 }
 
 template <typename T>
 void svd_finish(qil_ctx* ctx, int l, const T* Rb, const double* d_scale, double cutoff, int64_t maxdim, int64_t mindim,
-                T* Us, T* T2, double* S, int* d_rank) {
+                T* Us, T* T2, double* S, int* d_rank, int batch, int scale_bs, int rank_bs) {
     QIL_REQUIRE(l >= 1 && l <= kWqrMaxN, QIL_ERR_UNSUPPORTED, "svd_finish: l = %d", l);
     FinishParams<T> p;
     p.Rb = Rb; p.l = l; p.scale = d_scale; p.cutoff = cutoff; p.maxdim = maxdim; p.mindim = mindim;
     p.Us = Us; p.T2 = T2; p.S = S; p.rank = d_rank; p.margin = ctx->d_margin;
+    p.rb_bs = (long long)l * l; p.us_bs = (long long)l * l; p.s_bs = l; p.scale_bs = scale_bs; p.rank_bs = rank_bs;
     const int pg = l | 1;
     const size_t smem = (size_t)3 * l * pg * sizeof(T) + (size_t)l * (sizeof(double) + sizeof(int)) + 64;
-    svd_finish_kernel<T><<<1, 128, smem, ctx->stream>>>(p);
+    svd_finish_kernel<T><<<batch, 128, smem, ctx->stream>>>(p);
     QIL_LAUNCH_CHECK(ctx);
 }
 template void svd_finish<double>(qil_ctx*, int, const double*, const double*, double, int64_t, int64_t, double*, double*,
-                                 double*, int*);
+                                 double*, int*, int, int, int);
 template void svd_finish<cplx>(qil_ctx*, int, const cplx*, const double*, double, int64_t, int64_t, cplx*, cplx*, double*,
-                               int*);
+                               int*, int, int, int);
 
 // one thread per output element; Us / T2 staged in shared memory
 template <typename T>
@@ -86,8 +95,18 @@ __global__ void __launch_bounds__(256) rsvd_outputs_kernel(long long R, long lon
                                                            long long ldq, const T* __restrict__ Qb, long long ldqb,
                                                            const T* __restrict__ Us, const T* __restrict__ T2,
                                                            const double* __restrict__ S, const int* __restrict__ d_rank,
-                                                           T* __restrict__ U, T* __restrict__ SVh, T* __restrict__ Vh) {
+                                                           T* __restrict__ U, T* __restrict__ SVh, T* __restrict__ Vh,
+                                                           long long q_bs, long long qb_bs, long long u_bs,
+                                                           long long sv_bs, int rank_bs) {
     extern __shared__ __align__(16) unsigned char smem_raw[];
+    {   // batch member blockIdx.y
+        const long long bat = blockIdx.y;
+        Q += bat * q_bs; Qb += bat * qb_bs; Us += bat * (long long)l * l; T2 += bat * (long long)l * l; S += bat * l;
+        d_rank += bat * rank_bs;
+        if (U) U += bat * u_bs;
+        if (SVh) SVh += bat * sv_bs;
+        if (Vh) Vh += bat * sv_bs;
+    }
     const int r = *d_rank;
     T* sU = reinterpret_cast<T*>(smem_raw);     // [l][r]
     T* sT = sU + l * r;                         // [r][l]
@@ -134,16 +153,20 @@ __global__ void __launch_bounds__(256) rsvd_outputs_kernel(long long R, long lon
 
 template <typename T>
 void rsvd_outputs(qil_ctx* ctx, int64_t R, int64_t C, int l, const T* Q, int64_t ldq, const T* Qb, int64_t ldqb,
-                  const T* Us, const T* T2, const double* S, const int* d_rank, T* U, T* SVh, T* Vh) {
+                  const T* Us, const T* T2, const double* S, const int* d_rank, T* U, T* SVh, T* Vh, int batch,
+                  int64_t q_bs, int64_t qb_bs, int64_t u_bs, int64_t sv_bs, int rank_bs) {
     const size_t smem = (size_t)2 * l * l * sizeof(T) + (size_t)l * sizeof(double) + 32;
     const int64_t work = std::max(R, C);
     const int grid = (int)std::max<int64_t>(1, std::min<int64_t>((work + 255) / 256, (int64_t)ctx->sm_count * 4));
-    rsvd_outputs_kernel<T><<<grid, 256, smem, ctx->stream>>>(R, C, l, Q, ldq, Qb, ldqb, Us, T2, S, d_rank, U, SVh, Vh);
+    rsvd_outputs_kernel<T><<<dim3(grid, batch), 256, smem, ctx->stream>>>(R, C, l, Q, ldq, Qb, ldqb, Us, T2, S, d_rank, U,
+                                                                       SVh, Vh, q_bs, qb_bs, u_bs, sv_bs, rank_bs);
     QIL_LAUNCH_CHECK(ctx);
 }
 template void rsvd_outputs<double>(qil_ctx*, int64_t, int64_t, int, const double*, int64_t, const double*, int64_t,
-                                   const double*, const double*, const double*, const int*, double*, double*, double*);
+                                   const double*, const double*, const double*, const int*, double*, double*, double*, int,
+                                   int64_t, int64_t, int64_t, int64_t, int);
 template void rsvd_outputs<cplx>(qil_ctx*, int64_t, int64_t, int, const cplx*, int64_t, const cplx*, int64_t, const cplx*,
-                                 const cplx*, const double*, const int*, cplx*, cplx*, cplx*);
+                                 const cplx*, const double*, const int*, cplx*, cplx*, cplx*, int, int64_t, int64_t, int64_t,
+                                 int64_t, int);
 
 }  // namespace qil

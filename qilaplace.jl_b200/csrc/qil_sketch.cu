@@ -85,6 +85,8 @@ struct StreamParams {
     double* out;         // [ksplit][Mtot][ldo]
     const double* X;     // [ceil32(Kdim)][lpp]
     double* sumsq;       // optional [gridDim.x] partial sums of A^2 (K1 only)
+    long long x_rows;    // K1 on a stack of equal matrices (batch of signals): output rows per matrix, 0 = one shared X
+    long long x_bs;      // ... and the distance (doubles) between their X operands
 };
 
 template <int NT, bool TRANS, int STAGES>
@@ -136,7 +138,9 @@ stream_gemm_kernel(const __grid_constant__ CUtensorMap tmA, const StreamParams p
                         for (int w = 0; w < 8; ++w)
                             tma_load_2d(a + w * 4096, &tmA, &full[stage], tm * kBM + w * 16, (int)k);
                     }
-                    bulk_load(sX + (size_t)stage * xstride, p.X + k * p.lpp, (uint32_t)xbytes, &full[stage]);
+                    const double* xsrc = p.X + k * p.lpp;
+                    if (!TRANS && p.x_rows) xsrc += ((long long)tm * kBM / p.x_rows) * p.x_bs;
+                    bulk_load(sX + (size_t)stage * xstride, xsrc, (uint32_t)xbytes, &full[stage]);
                     if (++stage == STAGES) { stage = 0; phase ^= 1; }
                 }
             }
@@ -297,8 +301,11 @@ bool stream_supported(long long R, long long C, long long ld, int cols) {
 
 // out[ksplit][Mtot][8*nt] partials of A*X (trans=false) or A^T*X (trans=true); A is a REAL R x C view.
 void stream_gemm(qil_ctx* ctx, bool trans, const double* A, long long R, long long C, long long ld, const double* X,
-                 int lpp, int nt, double* out, int ksplit, long long kchunk, double* sumsq_partials, int ncols) {
+                 int lpp, int nt, double* out, int ksplit, long long kchunk, double* sumsq_partials, int ncols,
+                 long long x_rows, long long x_bs) {
     StreamParams p;
+    p.x_rows = x_rows;
+    p.x_bs = x_bs;
     p.Mtot = trans ? C : R;
     p.Kdim = trans ? R : C;
     p.tilesM = (int)((p.Mtot + kBM - 1) / kBM);
@@ -311,10 +318,10 @@ void stream_gemm(qil_ctx* ctx, bool trans, const double* A, long long R, long lo
     p.sumsq = sumsq_partials;
     const CUtensorMap tm = trans ? make_tmap(A, R, C, ld, 16, kBK) : make_tmap(A, R, C, ld, 16, kBM);
     // algorithmic work: one read of the R x C view, 2 flops per element and sketch column
-    ctx->prof_begin(PROF_STREAM_GEMM, 8.0 * (double)R * (double)C, 2.0 * (double)R * (double)C * (double)ncols);
+    { qil_prof_region prof_guard_(ctx, PROF_STREAM_GEMM, 8.0 * (double)R * (double)C, 2.0 * (double)R * (double)C * (double)ncols);
     if (!trans) dispatch_stream<false>(ctx, nt, tm, p);
     else dispatch_stream<true>(ctx, nt, tm, p);
-    ctx->prof_end();
+    }
 }
 
 void stream_plan(qil_ctx* ctx, long long Mtot, long long Kdim, int* ksplit, long long* kchunk) {

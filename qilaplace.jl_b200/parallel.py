@@ -178,7 +178,8 @@ class PeerComm:
     def close(self):
         from . import _lib
         if self.handle:
-            _dist().barrier(group=self.group)   # nobody unmaps while a peer may still read
+            self.ctx.sync()                     # this rank's exchange kernels are done before it reports in ...
+            _dist().barrier(group=self.group)   # ... so after the barrier nobody can still be reading a peer's buffer
             _lib.load().qil_peer_destroy(self.handle)
             self.handle = None
 

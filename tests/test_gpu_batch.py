@@ -16,15 +16,15 @@ def _family(n, count):
                      for b in range(count)])
 
 
-@pytest.mark.parametrize("n,count,workers", [(14, 9, 4), (20, 6, 16)])
-def test_batch_encode_matches_single_and_oracle(q, n, count, workers):
+@pytest.mark.parametrize("n,count,workers,qit", [(14, 9, 4, 0), (20, 6, 16, 0), (16, 5, 4, 2), (20, 3, 4, 1)])
+def test_batch_encode_matches_single_and_oracle(q, n, count, workers, qit):
     import torch
     N = 2**n
     xs = _family(n, count)
     ctx = q.default_context()
     d = torch.from_numpy(xs).cuda()
     torch.cuda.synchronize()
-    kw = dict(k=20, p=10, q=0, cutoff=1e-14, maxdim=64)
+    kw = dict(k=20, p=10, q=qit, cutoff=1e-14, maxdim=64)
     batch = q.signal_mps_batch_dev(ctx, d.data_ptr(), N, count, False, workers=workers, **kw)
     assert len(batch) == count
     W = q.build_qft_mpo(n, cutoff=1e-14, maxdim=128, ctx=ctx)
@@ -41,7 +41,8 @@ def test_batch_encode_matches_single_and_oracle(q, n, count, workers):
         if b in (0, count - 1):
             co, c = O.tt_rsvd(xs[b], **kw)
             assert batch[b].bonds == O.bonds_of(co)
-            assert np.abs(got - O.coefficient_batch(co, c, bits)).max() <= 1e-10 * np.abs(xs[b]).max()
+            # (the oracle draws its own Omega: with power iterations the two sketches agree to the truncation level only)
+            assert np.abs(got - O.coefficient_batch(co, c, bits)).max() <= (1e-10 if qit == 0 else 5e-8) * np.abs(xs[b]).max()
             # QFT apply on the batched result == FFT with bit-reversed output (test_qft_transformer.jl:427-463)
             out = W * batch[b]
             f = np.fft.fft(xs[b]) / np.sqrt(N)
