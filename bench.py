@@ -295,6 +295,92 @@ def parity_check(q, ctx, torch, dev, x_dev, n, oracle, st, psi_timed, state, sam
     return res
 
 
+C2 = dict(n=20, count=256, kw=dict(k=20, p=10, q=0, cutoff=1e-14, maxdim=64), qft=dict(cutoff=1e-14, maxdim=128))
+
+
+def c2_leg(q, ctx, torch, dev, timed, steps, hbm_peak, with_oracle):
+    """BASELINE configs[1] / SURVEY 8d C2: 256 sin_decay signals of n = 20 (freq = [1 + 0.01 b, 2.5 + 0.01 b]),
+    signal_mps(:rsvd, maxdim=64; k=20 p=10 q=0 defaults) + QFT MPO (maxdim 128, cutoff 1e-14) apply -- the level-synchronous
+    batched encoder (one launch per stage for all signals) and the one-launch batched apply."""
+    import numpy as np
+    n, count, kw = C2["n"], C2["count"], C2["kw"]
+    N = 2**n
+    t = torch.arange(N, dtype=torch.float64, device=dev) / (2.5 * N)
+    b = torch.arange(count, dtype=torch.float64, device=dev)[:, None]
+    x = (torch.sin((1 + 0.01 * b) * t) * torch.exp(-0.08 * t) + torch.sin((2.5 + 0.01 * b) * t) * torch.exp(-0.03 * t)).contiguous()
+    del t, b
+    Wq = q.build_qft_mpo(n, ctx=ctx, **C2["qft"])
+    st = {}
+
+    def step():
+        ms = q.signal_mps_batch_dev(ctx, x.data_ptr(), N, count, False, **kw)
+        st["mps"] = ms
+        st["out"] = q.apply_batch(Wq, ms)
+
+    x_pin = torch.empty((count, N), dtype=torch.float64, pin_memory=True)
+    x_pin.copy_(x)
+    x_stage = torch.empty_like(x)
+    host = torch.empty(64 << 20, dtype=torch.uint8, pin_memory=True)
+
+    def step_e2e():
+        x_stage.copy_(x_pin, non_blocking=True)
+        ms = q.signal_mps_batch_dev(ctx, x_stage.data_ptr(), N, count, False, **kw)
+        outs = q.apply_batch(Wq, ms)
+        off = 0
+        for o in outs:                      # device -> host read of every result (packed cores, one copy per signal)
+            cs = o.cores_into(host[off:])
+            off += int(sum(c.nbytes for c in cs))
+        st["d2h"] = off
+
+    for _ in range(3):
+        step()
+    ms_step = timed(step, steps) / steps
+    for _ in range(2):
+        step_e2e()
+    ms_e2e = timed(step_e2e, steps) / steps
+    bytes_alg = 2.0 * count * N * 8          # (2 + 2q) passes over every signal, q = 0
+    res = {"what": f"{count} sin_decay signals of n={n}: signal_mps(:rsvd k=20 p=10 q=0 cutoff=1e-14 maxdim=64) in lock step "
+                   f"(qil_encode_rsvd_batch_dev) + QFT MPO apply (qil_apply_mpo_mps_batch)",
+           "signals": count, "n": n, "ms_per_step": ms_step, "samples_per_s": count * N / (ms_step / 1e3),
+           "roofline": {"bound": "hbm", "algorithmic_bytes": bytes_alg, "achieved": bytes_alg / (ms_step / 1e3) / 1e9,
+                        "peak": hbm_peak, "unit": "GB/s", "frac": bytes_alg / (ms_step / 1e3) / 1e9 / hbm_peak,
+                        "note": "whole step (encode + apply) against two passes over the batch"},
+           "e2e": {"ms_per_step": ms_e2e, "samples_per_s": count * N / (ms_e2e / 1e3), "h2d_bytes_per_step": int(8 * count * N),
+                   "d2h_bytes_per_step": int(st.get("d2h", 0))},
+           "max_bond": max(max(m.bonds) for m in st["mps"]), "out_max_bond": max(max(o.bonds) for o in st["out"])}
+    if with_oracle:
+        sys.path.insert(0, os.path.join(ROOT, "oracle"))
+        import qil_oracle as O
+        xs = x.cpu().numpy()
+        t0 = time.perf_counter()
+        same = 0
+        worst = 0.0
+        rng = np.random.default_rng(5)
+        idx = rng.integers(0, N, 256)
+        bits = ((idx[:, None] >> np.arange(n - 1, -1, -1)[None, :]) & 1).astype(np.uint8)
+        # same host-drawn normal stream for both sides (every signal and every split reuse it: the reference reseeds at
+        # every rsvd call, rsvd.jl:74)
+        L = kw["k"] + kw["p"]
+        cols = 2 ** (n - n // 2)
+        stream = np.random.default_rng(1234).standard_normal(cols * L)
+        st_dev = torch.from_numpy(stream).to(dev)
+        par = q.signal_mps_batch_dev(ctx, x.data_ptr(), N, count, False, normal_stream_dev=st_dev.data_ptr(),
+                                     stream_len=stream.size, **kw)
+        omega_fn = lambda c_, iscomplex: stream[: c_ * L].reshape(L, c_).T
+        for bb in range(count):
+            co, c = O.tt_rsvd(xs[bb], omega_fn=omega_fn, **kw)
+            same += int(par[bb].bonds == O.bonds_of(co))
+            if bb % 32 == 0:
+                got = q.coefficients(par[bb], bits)
+                worst = max(worst, float(np.abs(got - O.coefficient_batch(co, c, bits)).max() / np.abs(xs[bb]).max()))
+        t_cpu = time.perf_counter() - t0
+        res["parity"] = {"signals_with_bonds_equal_oracle": same, "of": count, "encode_max_rel_err_sampled": worst,
+                         "note": "both sides use the same host-drawn normal stream"}
+        res["cpu_baseline"] = {"value": count * N / t_cpu, "unit": "samples/s", "kind": "port",
+                               "sample": f"numpy oracle, encode only, all {count} signals, {t_cpu:.1f} s"}
+    return res
+
+
 def run_ours(args):
     import numpy as np
     import torch
@@ -659,6 +745,12 @@ def run_ours(args):
         "stages_ms": stages_ms,
     }
 
+    if not shard and n >= 20:
+        try:
+            line["c2_batch256"] = c2_leg(q, ctx, torch, dev, timed, max(args.steps, 3), hbm_peak,
+                                         rank == 0 and world == 1 and not args.no_cpu_baseline)
+        except Exception as e:
+            line["c2_batch256"] = {"error": f"{type(e).__name__}: {e}"}
     if world > 1 and not shard:
         # ---- the configuration north_star names for N > 1: ONE n-qubit signal row-sharded over the ranks (strong
         # scaling).  Reported beside the weak line so that the driver's --gpus N run records both.

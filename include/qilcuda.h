@@ -119,6 +119,9 @@ int qil_coefficient_grid_dev(qil_ctx* ctx, const qil_mps* psi, const uint8_t* si
  * Exact MPO x MPS: out core = [D_l*chi_l][2][D_r*chi_r] with the MPO bond fastest; never truncates;
  * amplitude is copied.  Paired operands are passed as 2n-site chains. */
 int qil_apply_mpo_mps(qil_ctx* ctx, const qil_mpo* W, const qil_mps* psi, qil_mps** out);
+/* `[W * psi for psi in psis]` (BASELINE configs[1]: one QFT MPO applied to a batch of encoded signals) in one launch;
+ * the `count` results share one pooled device allocation. */
+int qil_apply_mpo_mps_batch(qil_ctx* ctx, const qil_mpo* W, const qil_mps* const* psis, int64_t count, qil_mps** outs);
 /* MPO o MPO over the matching window; W1 acts first; start1/start2 = first matching site (0-based). */
 int qil_apply_mpo_mpo(qil_ctx* ctx, const qil_mpo* W1, const qil_mpo* W2, int start1, int start2,
                       qil_mpo** out);
@@ -146,12 +149,15 @@ int qil_encode_rsvd_dev(qil_ctx* ctx, int is_complex, const void* d_x, int64_t N
                         double cutoff, int64_t maxdim, int64_t mindim, const void* d_normal_stream,
                         int64_t stream_len, int64_t flags, qil_mps** out);
 /* A batch of `count` independent signals of N samples each, stored back to back on the device (BASELINE configs[1]:
- * 256 signals of n = 20).  Same result per signal as qil_encode_rsvd_dev with the device generator; the signals are
- * encoded concurrently by `workers` host threads, each on its own stream (<= 0: default 16).  out[count] receives
- * the handles.  Synchronous. */
+ * 256 signals of n = 20).  Same result per signal as qil_encode_rsvd_dev (every signal uses the same normal stream, like
+ * the reference, which reseeds at every rsvd call).  Real power-of-two signals with k + p <= 32 are encoded in lock
+ * step: the stacked signals are sketched by one streaming launch, projected by one split-K launch (one chunk per
+ * signal), factored by batched TSQR / Jacobi kernels, and every tree level is one launch for all signals; the cores of
+ * the batch share one pooled allocation.  Anything else falls back to `workers` host threads, each encoding whole
+ * signals on its own stream (<= 0: default 16).  out[count] receives the handles.  Synchronous. */
 int qil_encode_rsvd_batch_dev(qil_ctx* ctx, int is_complex, const void* d_x, int64_t N, int64_t count, int k, int p,
                               int q, int64_t seed, double cutoff, int64_t maxdim, int64_t mindim, int workers,
-                              int64_t flags, qil_mps** out);
+                              const void* d_normal_stream, int64_t stream_len, int64_t flags, qil_mps** out);
 
 /* ---- one signal row-sharded over several devices (one process per device) ---------------------
  * The length-N signal is split in rank order into world contiguous chunks of N/world samples, i.e. into

@@ -70,6 +70,7 @@ _SIGS = {
     "qil_coefficient_grid": [c_ctx, c_mps, C.c_void_p, C.c_void_p, C.c_void_p],
     "qil_coefficient_grid_dev": [c_ctx, c_mps, C.c_void_p, C.c_void_p, C.c_void_p],
     "qil_apply_mpo_mps": [c_ctx, c_mpo, c_mps, C.POINTER(c_mps)],
+    "qil_apply_mpo_mps_batch": [c_ctx, c_mpo, C.c_void_p, C.c_int64, C.c_void_p],
     "qil_apply_mpo_mpo": [c_ctx, c_mpo, c_mpo, C.c_int, C.c_int, C.POINTER(c_mpo)],
     "qil_encode_svd": [c_ctx, C.c_int, C.c_void_p, C.c_int64, C.c_double, C.c_int64, C.POINTER(c_mps)],
     "qil_encode_svd_dev": [c_ctx, C.c_int, C.c_void_p, C.c_int64, C.c_double, C.c_int64, C.POINTER(c_mps)],
@@ -78,7 +79,8 @@ _SIGS = {
     "qil_encode_rsvd_dev": [c_ctx, C.c_int, C.c_void_p, C.c_int64, C.c_int, C.c_int, C.c_int, C.c_int64, C.c_double,
                             C.c_int64, C.c_int64, C.c_void_p, C.c_int64, C.c_int64, C.POINTER(c_mps)],
     "qil_encode_rsvd_batch_dev": [c_ctx, C.c_int, C.c_void_p, C.c_int64, C.c_int64, C.c_int, C.c_int, C.c_int, C.c_int64,
-                                  C.c_double, C.c_int64, C.c_int64, C.c_int, C.c_int64, C.POINTER(c_mps)],
+                                  C.c_double, C.c_int64, C.c_int64, C.c_int, C.c_void_p, C.c_int64, C.c_int64,
+                                  C.POINTER(c_mps)],
     "qil_get_stream": [c_ctx, C.POINTER(C.c_void_p)],
     "qil_encode_rsvd_sharded_dev": [c_ctx, C.c_void_p, C.c_int, C.c_void_p, C.c_int64, C.c_int, C.c_int, C.c_int,
                                     C.c_int64, C.c_double, C.c_int64, C.c_int64, C.c_void_p, C.c_int64, C.c_int64,

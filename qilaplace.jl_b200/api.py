@@ -378,6 +378,19 @@ def apply(W, other, **kwargs):
 # ------------------------------------------------------------------------------------------
 # signals (src/signals/Signals.jl:188-235) -- trivial elementwise host code, out of kernel scope
 # ------------------------------------------------------------------------------------------
+def apply_batch(W, psis):
+    """[W * psi for psi in psis] in one launch (qil_apply_mpo_mps_batch); psis: SignalMPS / ZTMPS of one context."""
+    psis = list(psis)
+    if not psis:
+        return []
+    count = len(psis)
+    hin = (_lib.c_mps * count)(*[p.handle for p in psis])
+    hout = (_lib.c_mps * count)()
+    call("qil_apply_mpo_mps_batch", W.ctx.handle, W.handle, hin, C.c_int64(count), hout)
+    cls = ZTMPS if isinstance(psis[0], ZTMPS) else SignalMPS
+    return [cls(W.ctx, _lib.c_mps(h)) for h in hout]
+
+
 def generate_signal(n, kind="sin", dt=None, freq=None, **kw):
     """generate_signal(n; kind, dt, freq, kwargs...) for the deterministic kinds of the reference
     (:sin, :sin_decay, :abs_cos_power_p8) plus :random via numpy's generator (the reference's
@@ -710,13 +723,14 @@ def signal_mps_dev(ctx, d_x, N, is_complex, method="rsvd", cutoff=1e-15, maxdim=
 
 
 def signal_mps_batch_dev(ctx, d_x, N, count, is_complex, cutoff=1e-15, maxdim=None, k=20, p=10, q=0, random_seed=1234,
-                         mindim=1, workers=16, adaptive=False):
+                         mindim=1, workers=16, adaptive=False, normal_stream_dev=None, stream_len=0):
     """signal_mps(x_b; method=:rsvd) for `count` signals of N samples stored back to back on the device; the
     independent encodes run concurrently on `workers` streams.  Returns a list of SignalMPS."""
     hs = (_lib.c_mps * int(count))()
     call("qil_encode_rsvd_batch_dev", ctx.handle, int(is_complex), C.c_void_p(int(d_x)), C.c_int64(N), C.c_int64(count),
          int(k), int(p), int(q), C.c_int64(random_seed), float(cutoff), C.c_int64(_maxdim_arg(maxdim)),
-         C.c_int64(mindim), int(workers), C.c_int64(RSVD_ADAPTIVE if adaptive else 0), hs)
+         C.c_int64(mindim), int(workers), C.c_void_p(int(normal_stream_dev)) if normal_stream_dev else None,
+         C.c_int64(int(stream_len)), C.c_int64(RSVD_ADAPTIVE if adaptive else 0), hs)
     return [SignalMPS(ctx, _lib.c_mps(h)) for h in hs]
 
 

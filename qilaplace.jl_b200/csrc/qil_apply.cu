@@ -95,37 +95,126 @@ static void launch_sites(qil_ctx* ctx, K kern, const ApplyDesc& d, long long max
     }
 }
 
+// ---- MPO x MPS for one or many MPS in ONE launch -------------------------------------------------------------
+// A job is a block of fused-left-bond rows of one site of one MPS.  2-D indexing: the (l, a) split is done once per row,
+// the (r, b) split with 32-bit arithmetic per element; consecutive threads write consecutive elements of a row
+// (16-byte stores for complex).  All output cores of the call live in one pooled allocation (one cudaMallocAsync
+// instead of one per site), shared by the returned handles.
+struct ApplyJob {
+    const void* w;
+    const void* p;
+    void* o;
+    int Da, Db, cl, cr;
+    int row0, rows;
+};
+
+template <typename TW, typename TP, typename TO>
+__global__ void __launch_bounds__(256) apply_jobs_kernel(const ApplyJob* __restrict__ jobs) {
+    const ApplyJob j = jobs[blockIdx.x];
+    const TW* __restrict__ W = reinterpret_cast<const TW*>(j.w);
+    const TP* __restrict__ P = reinterpret_cast<const TP*>(j.p);
+    TO* __restrict__ O = reinterpret_cast<TO*>(j.o);
+    const unsigned Da = j.Da, Db = j.Db, cr = j.cr;
+    const unsigned R = cr * Db;
+    // 32 x 8 threads: x along the fused right bond (coalesced stores), y over the rows of the job
+    const unsigned tx = threadIdx.x & 31, ty = threadIdx.x >> 5;
+    for (unsigned row = ty; row < (unsigned)j.rows; row += 8) {
+        const unsigned LA = j.row0 + row;
+        const unsigned l = LA / Da, a = LA - l * Da;
+        const TW* __restrict__ wa = W + (size_t)a * 4 * Db;
+        const TP* __restrict__ p0r = P + (size_t)l * 2 * cr;
+        TO* __restrict__ o0 = O + (size_t)LA * 2 * R;
+        for (unsigned RB = tx; RB < R; RB += 32) {
+            const unsigned r = RB / Db, b = RB - r * Db;
+            const TO p0 = promote<TO, TP>(p0r[r]);
+            const TO p1 = promote<TO, TP>(p0r[cr + r]);
+            const TO w00 = promote<TO, TW>(wa[b]);            // p=0,s=0
+            const TO w01 = promote<TO, TW>(wa[Db + b]);       // p=0,s=1
+            const TO w10 = promote<TO, TW>(wa[2 * Db + b]);   // p=1,s=0
+            const TO w11 = promote<TO, TW>(wa[3 * Db + b]);   // p=1,s=1
+            TO v0 = Scalar<TO>::mul(w00, p0);
+            v0 = Scalar<TO>::fma(w10, p1, v0);
+            TO v1 = Scalar<TO>::mul(w01, p0);
+            v1 = Scalar<TO>::fma(w11, p1, v1);
+            o0[RB] = v0;
+            o0[R + RB] = v1;
+        }
+    }
+}
+
+void apply_mpo_mps_many(qil_ctx* ctx, const qil_mpo* W, const qil_mps* const* psis, int64_t count, qil_mps** outs) {
+    if (count <= 0) return;
+    const int n = W->n;
+    const int pc = psis[0]->is_complex;
+    for (int64_t s = 0; s < count; ++s) {
+        QIL_REQUIRE(psis[s] != nullptr, QIL_ERR_ARGUMENT, "apply: null MPS handle in the batch");
+        QIL_REQUIRE(W->n == psis[s]->n, QIL_ERR_ARGUMENT,
+                    "apply: MPO and MPS must have the same number of sites. Found length(W)=%d, length(psi)=%d", W->n,
+                    psis[s]->n);
+        QIL_REQUIRE(psis[s]->is_complex == pc, QIL_ERR_ARGUMENT, "apply: the MPS of a batch must share their element type");
+    }
+    const int oc = (W->is_complex || pc) ? 1 : 0;
+    const size_t es = elem_size(oc);
+    // output layout
+    std::vector<std::vector<int64_t>> ob(count, std::vector<int64_t>(n + 1));
+    size_t total = 0;
+    std::vector<size_t> core_off((size_t)count * n);
+    for (int64_t s = 0; s < count; ++s) {
+        for (int i = 0; i <= n; ++i) {
+            ob[s][i] = W->bond[i] * psis[s]->bond[i];
+            QIL_REQUIRE(ob[s][i] < ((int64_t)1 << 28), QIL_ERR_UNSUPPORTED, "apply: fused bond too large");
+        }
+        for (int i = 0; i < n; ++i) {
+            core_off[s * n + i] = total;
+            total += ((size_t)ob[s][i] * 2 * ob[s][i + 1] + 1) & ~(size_t)1;
+        }
+    }
+    void* pool_raw = ctx->alloc(std::max<size_t>(total, 1) * es);
+    std::shared_ptr<void> pool(pool_raw, [ctx](void* p) { ctx->free(p); });
+    // jobs: ~256 KB of output each (at least 8 rows: one per thread row)
+    std::vector<ApplyJob> jobs;
+    for (int64_t s = 0; s < count; ++s)
+        for (int i = 0; i < n; ++i) {
+            const int64_t L = ob[s][i], R = ob[s][i + 1];
+            int64_t rows_per = std::max<int64_t>(8, (int64_t)(262144 / es) / std::max<int64_t>(2 * R, 1));
+            rows_per = std::min(rows_per, L);
+            for (int64_t r0 = 0; r0 < L; r0 += rows_per) {
+                ApplyJob j;
+                j.w = W->core[i]; j.p = psis[s]->core[i];
+                j.o = (char*)pool_raw + core_off[s * n + i] * es;
+                j.Da = (int)W->bond[i]; j.Db = (int)W->bond[i + 1];
+                j.cl = (int)psis[s]->bond[i]; j.cr = (int)psis[s]->bond[i + 1];
+                j.row0 = (int)r0; j.rows = (int)std::min(rows_per, L - r0);
+                jobs.push_back(j);
+            }
+        }
+    ApplyJob* d_jobs = (ApplyJob*)ctx->alloc(sizeof(ApplyJob) * jobs.size());
+    QIL_CUDA(cudaMemcpyAsync(d_jobs, jobs.data(), sizeof(ApplyJob) * jobs.size(), cudaMemcpyHostToDevice, ctx->stream));
+    {
+        qil_prof_region prof_guard_(ctx, PROF_APPLY);
+        const unsigned grid = (unsigned)jobs.size();
+        if (W->is_complex && pc) apply_jobs_kernel<cplx, cplx, cplx><<<grid, 256, 0, ctx->stream>>>(d_jobs);
+        else if (W->is_complex) apply_jobs_kernel<cplx, double, cplx><<<grid, 256, 0, ctx->stream>>>(d_jobs);
+        else if (pc) apply_jobs_kernel<double, cplx, cplx><<<grid, 256, 0, ctx->stream>>>(d_jobs);
+        else apply_jobs_kernel<double, double, double><<<grid, 256, 0, ctx->stream>>>(d_jobs);
+        QIL_LAUNCH_CHECK(ctx);
+    }
+    ctx->free(d_jobs);
+    for (int64_t s = 0; s < count; ++s) {
+        qil_mps* out = new_mps(ctx, n, oc, ob[s].data(), false);
+        for (int i = 0; i < n; ++i) out->core[i] = (char*)pool_raw + core_off[s * n + i] * es;
+        out->pool = pool;
+        out->amplitude = psis[s]->amplitude;
+        outs[s] = out;
+    }
+}
+
 qil_mps* apply_mpo_mps(qil_ctx* ctx, const qil_mpo* W, const qil_mps* psi) {
     QIL_REQUIRE(W->n == psi->n, QIL_ERR_ARGUMENT,
                 "apply: MPO and MPS must have the same number of sites. Found length(W)=%d, length(psi)=%d",
                 W->n, psi->n);
-    const int n = psi->n;
-    std::vector<int64_t> ob(n + 1);
-    for (int i = 0; i <= n; ++i) ob[i] = W->bond[i] * psi->bond[i];
-    const int oc = (W->is_complex || psi->is_complex) ? 1 : 0;
-    qil_mps* out = new_mps(ctx, n, oc, ob.data(), true);
-    out->amplitude = psi->amplitude;
-    ApplyDesc d;
-    d.n = n;
-    long long mx = 1;
-    for (int i = 0; i <= n; ++i) {
-        d.wb[i] = (int)W->bond[i];
-        d.pb[i] = (int)psi->bond[i];
-    }
-    for (int i = 0; i < n; ++i) {
-        d.w[i] = W->core[i];
-        d.p[i] = psi->core[i];
-        d.o[i] = out->core[i];
-        mx = std::max<long long>(mx, ob[i] * ob[i + 1]);
-    }
-    if (W->is_complex && psi->is_complex)
-        launch_sites(ctx, apply_mpo_mps_kernel<cplx, cplx, cplx>, d, mx);
-    else if (W->is_complex)
-        launch_sites(ctx, apply_mpo_mps_kernel<cplx, double, cplx>, d, mx);
-    else if (psi->is_complex)
-        launch_sites(ctx, apply_mpo_mps_kernel<double, cplx, cplx>, d, mx);
-    else
-        launch_sites(ctx, apply_mpo_mps_kernel<double, double, double>, d, mx);
+    qil_mps* out = nullptr;
+    apply_mpo_mps_many(ctx, W, &psi, 1, &out);
     return out;
 }
 

@@ -438,6 +438,18 @@ int qil_apply_mpo_mps(qil_ctx* ctx, const qil_mpo* W, const qil_mps* psi, qil_mp
     QIL_API_END
 }
 
+int qil_apply_mpo_mps_batch(qil_ctx* ctx, const qil_mpo* W, const qil_mps* const* psis, int64_t count, qil_mps** outs) {
+    QIL_API_BEGIN
+    QIL_NONNULL(ctx); QIL_NONNULL(W);
+    QIL_REQUIRE(count >= 0, QIL_ERR_ARGUMENT, "apply: negative batch size");
+    if (count == 0) return QIL_OK;
+    QIL_NONNULL(psis); QIL_NONNULL(outs);
+    QIL_CUDA(cudaSetDevice(ctx->device));
+    for (int64_t i = 0; i < count; ++i) outs[i] = nullptr;
+    apply_mpo_mps_many(ctx, W, psis, count, outs);
+    QIL_API_END
+}
+
 int qil_apply_mpo_mpo(qil_ctx* ctx, const qil_mpo* W1, const qil_mpo* W2, int start1, int start2,
                       qil_mpo** out) {
     QIL_API_BEGIN
@@ -523,7 +535,7 @@ int qil_encode_rsvd(qil_ctx* ctx, int is_complex, const void* x, int64_t N, int 
 
 int qil_encode_rsvd_batch_dev(qil_ctx* ctx, int is_complex, const void* d_x, int64_t N, int64_t count, int k, int p,
                               int q, int64_t seed, double cutoff, int64_t maxdim, int64_t mindim, int workers,
-                              int64_t flags, qil_mps** out) {
+                              const void* d_normal_stream, int64_t stream_len, int64_t flags, qil_mps** out) {
     QIL_API_BEGIN
     QIL_NONNULL(ctx); QIL_NONNULL(out);
     QIL_REQUIRE(count >= 0, QIL_ERR_ARGUMENT, "signal batch: negative count");
@@ -535,6 +547,7 @@ int qil_encode_rsvd_batch_dev(qil_ctx* ctx, int is_complex, const void* d_x, int
     o.k = k; o.p = p; o.q = q; o.seed = seed; o.cutoff = cutoff; o.maxdim = fix_maxdim(maxdim);
     o.mindim = mindim < 1 ? 1 : mindim;
     o.adaptive = (flags & QIL_RSVD_ADAPTIVE) != 0;
+    o.omega = d_normal_stream; o.omega_rows = d_normal_stream ? stream_len : 0; o.omega_cols = 1;
     if (is_complex) encode_rsvd_batch<cplx>(ctx, (const cplx*)d_x, N, count, o, workers, out);
     else encode_rsvd_batch<double>(ctx, (const double*)d_x, N, count, o, workers, out);
     QIL_API_END

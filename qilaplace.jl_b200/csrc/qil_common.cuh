@@ -259,6 +259,8 @@ void coefficient_batch_dev(qil_ctx* ctx, const qil_mps* psi, const uint8_t* d_bi
 void coefficient_grid_dev(qil_ctx* ctx, const qil_mps* psi, const uint8_t* mode, const int32_t* out_bit, void* d_out);
 // K6: exact MPO x MPS (apply.jl:75-122)
 qil_mps* apply_mpo_mps(qil_ctx* ctx, const qil_mpo* W, const qil_mps* psi);
+// the same MPO applied to `count` MPS in one launch; outputs share one pooled allocation
+void apply_mpo_mps_many(qil_ctx* ctx, const qil_mpo* W, const qil_mps* const* psis, int64_t count, qil_mps** outs);
 // K7: MPO o MPO (apply.jl:124-199), W1 acts first, equal lengths or windowed
 qil_mpo* apply_mpo_mpo(qil_ctx* ctx, const qil_mpo* W1, const qil_mpo* W2, int start1, int start2);
 

@@ -24,7 +24,7 @@ for workers in (16,):
         ms = q.signal_mps_batch_dev(ctx, x.data_ptr(), N, count, False, workers=workers, **kw)
         torch.cuda.synchronize()
         t1 = time.perf_counter()
-        outs = [W * m for m in ms]
+        outs = q.apply_batch(W, ms)
         torch.cuda.synchronize()
         t2 = time.perf_counter()
     print(f"workers {workers:3d}: encode {1e3 * (t1 - t0):8.2f} ms ({count * N / (t1 - t0) / 1e9:7.2f} G samples/s), "
