@@ -115,7 +115,14 @@ class TorchComm:
                 with torch.cuda.stream(self.stream):
                     t = wrap(d_buf, count)
                     if self.nccl:
-                        dist.all_reduce(t, group=group)
+                        # all-gather + summation in RANK ORDER on every rank: the same bits everywhere and the same
+                        # bits as the library's peer-memory exchange (qil_peer.cu) -- ncclAllReduce sums in an order
+                        # that depends on the ring/tree it picks, which moved a knife-edge bond at 4 ranks in round 1
+                        parts = torch.empty((self.world, int(count)), dtype=torch.float64, device=self.device)
+                        dist.all_gather_into_tensor(parts.view(-1), t, group=group)
+                        t.copy_(parts[0])
+                        for r in range(1, self.world):
+                            t.add_(parts[r])
                     else:
                         h = t.cpu()
                         dist.all_reduce(h, group=group)

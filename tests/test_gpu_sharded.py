@@ -75,11 +75,67 @@ def _worker(rank, world, port, ret, default_stream=False, peer=False):
 
 
 @pytest.mark.parametrize("world,default_stream,peer", [(1, False, False), (2, False, False), (2, True, False),
-                                                       (1, False, True), (2, False, True), (2, True, True)])
+                                                       (1, False, True), (2, False, True), (2, True, True),
+                                                       (4, False, False), (4, False, True)])
 def test_row_sharded_encode_matches_single_device_and_oracle(world, default_stream, peer):
     import torch.multiprocessing as mp
     port = 33500 + (os.getpid() % 2000) + 4 * world + 2 * int(default_stream) + int(peer)
     mgr = mp.Manager()
     ret = mgr.dict()
     mp.spawn(_worker, args=(world, port, ret, default_stream, peer), nprocs=world, join=True)
+    assert dict(ret) == {r: "ok" for r in range(world)}
+
+
+def _worker_big(rank, world, port, ret, peer):
+    """n = 26 bench-family signal over `world` real devices (NCCL / NVLink): bonds identical to the one-GPU encode."""
+    sys.path.insert(0, ROOT)
+    os.environ["MASTER_ADDR"] = "127.0.0.1"
+    os.environ["MASTER_PORT"] = str(port)
+    import torch
+    import torch.distributed as dist
+    import qilaplace_b200 as q
+    from qilaplace_b200 import parallel
+    torch.cuda.set_device(rank)
+    dist.init_process_group("nccl", rank=rank, world_size=world, device_id=torch.device("cuda", rank))
+    try:
+        ctx = q.Context(rank)
+        n = 26
+        N = 2**n
+        kw = dict(k=15, p=5, q=2, cutoff=1e-12)
+        comm = (parallel.PeerComm(ctx, parallel.encode_exchange_bytes(N, 15, 5, False)) if peer else parallel.TorchComm(ctx))
+        j = torch.arange(N, dtype=torch.float64, device=f"cuda:{rank}")
+        t = j / (2.5 * N)
+        x = torch.sin(1.0 * t) * torch.exp(-0.08 * t) + torch.sin(2.5 * t) * torch.exp(-0.03 * t)
+        del j, t
+        lo, hi = rank * N // world, (rank + 1) * N // world
+        xl = x[lo:hi].contiguous()
+        torch.cuda.synchronize()
+        one = q.signal_mps_dev(ctx, x.data_ptr(), N, False, method="rsvd", **kw)
+        for rep in range(3):
+            psi = parallel.signal_mps_sharded_dev(comm, xl.data_ptr(), N, False, **kw)
+            assert psi.bonds == one.bonds, (rep, psi.bonds, one.bonds)
+            assert abs(psi.amplitude - one.amplitude) < 1e-12 * one.amplitude
+        rng = np.random.default_rng(0)
+        idx = rng.integers(0, N, 2048)
+        bits = ((idx[:, None] >> np.arange(n - 1, -1, -1)[None, :]) & 1).astype(np.uint8)
+        a, b = q.coefficients(psi, bits), q.coefficients(one, bits)
+        assert np.abs(a - b).max() < 1e-8 * np.abs(b).max()
+        if peer:
+            comm.close()
+        ret[rank] = "ok"
+    finally:
+        dist.destroy_process_group()
+
+
+@pytest.mark.parametrize("world", [4, 8])
+@pytest.mark.parametrize("peer", [False, True])
+def test_row_sharded_encode_many_gpus_bonds_identical(world, peer):
+    import torch
+    import torch.multiprocessing as mp
+    if torch.cuda.device_count() < world:
+        pytest.skip(f"needs {world} GPUs")
+    port = 35500 + (os.getpid() % 2000) + 8 * world + int(peer)
+    mgr = mp.Manager()
+    ret = mgr.dict()
+    mp.spawn(_worker_big, args=(world, port, ret, peer), nprocs=world, join=True)
     assert dict(ret) == {r: "ok" for r in range(world)}
