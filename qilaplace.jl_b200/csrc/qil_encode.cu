@@ -576,12 +576,21 @@ static int rsvd_split_sharded(SplitCtx<T>& sc, const T* A, int64_t Rg, int64_t C
         Mat<T> Y2 = mul_A<T>(sc, A, Rg, C, l, Qz.p, false);
         tsqr_sharded<T>(sc, Y2, Rg, l, Q);
     }
-    Mat<T> Bh = mul_AH<T>(sc, A, Rg, C, l, Q.p, sc.d_nrm + 1);
-    comm_allreduce(sc.comm, Bh.p, C * l * F);
-    Mat<T> Us;
-    const int r = svd_trunc_adj<T>(ctx, l, C, Bh.p, l, o.cutoff, o.maxdim, o.mindim, &Us, nullptr, nullptr, &SVh, nullptr);
-    Mat<T> Ug(ctx, Rg, r);
-    gemm<T>(ctx, OP_N, OP_N, Rg, r, l, 1.0, Q.p, l, Us.p, r, 0.0, Ug.p, r);
+    int r;
+    Mat<T> Ug;
+    if (qr_fast_supported<T>(ctx, C, l)) {
+        // device-side tail (TSQR of B^H, one-warp Jacobi, both products in one launch); replicated on every rank
+        Mat<T> Bh = mul_AH<T>(sc, A, Rg, C, l, Q.p, nullptr);
+        comm_allreduce(sc.comm, Bh.p, C * l * F);
+        r = rsvd_tail<T>(sc, Rg, C, l, Q.p, l, Bh.p, l, 1, 0, sc.d_nrm + 1, Ug, &SVh, nullptr, nullptr);
+    } else {
+        Mat<T> Bh = mul_AH<T>(sc, A, Rg, C, l, Q.p, sc.d_nrm + 1);
+        comm_allreduce(sc.comm, Bh.p, C * l * F);
+        Mat<T> Us;
+        r = svd_trunc_adj<T>(ctx, l, C, Bh.p, l, o.cutoff, o.maxdim, o.mindim, &Us, nullptr, nullptr, &SVh, nullptr);
+        Ug = Mat<T>(ctx, Rg, r);
+        gemm<T>(ctx, OP_N, OP_N, Rg, r, l, 1.0, Q.p, l, Us.p, r, 0.0, Ug.p, r);
+    }
     U = Mat<T>(ctx, R, r);
     comm_allgather(sc.comm, Ug.p, U.p, Rg * r * F);
     return r;
@@ -734,19 +743,27 @@ static int64_t bond_cap(int n, int pos, int kp) {
     const int a = std::min(pos, n - pos);
     return a >= 30 ? kp : std::min<int64_t>(kp, (int64_t)1 << a);
 }
-static qil_mps* encode_rsvd_tree(SplitCtx<double>& sc, const double* x, int n) {
+__global__ void set_int_kernel(int* p, int v) { if (threadIdx.x == 0 && blockIdx.x == 0) *p = v; }
+
+// Ugiven / SVgiven / rgiven: the top split was already done by the caller (row-sharded encode): U (R x r) and S Vh
+// (r x C), compact, stay owned by the caller; only the levels below run here.
+static qil_mps* encode_rsvd_tree(SplitCtx<double>& sc, const double* x, int n, double* Ugiven = nullptr,
+                                 double* SVgiven = nullptr, int rgiven = 0) {
     qil_ctx* ctx = sc.ctx;
     const RsvdOpts& o = *sc.o;
     const int kp = o.k + o.p;
+    const bool given = Ugiven != nullptr;
     static const bool disabled = [] { const char* e = getenv("QIL_ENCODE_TREE"); return e && e[0] == '0'; }();
-    if (disabled || kp > 32 || n < 4 || sc.comm) return nullptr;
+    if (disabled || kp > 32 || n < 4 || (sc.comm && !given)) return nullptr;
     const int mid = n / 2 - 1;                                  // 0-based (first+last-1)/2 of the root
     const int64_t R = (int64_t)1 << (mid + 1), C = (int64_t)1 << (n - 1 - mid);
     const int l0 = (int)std::min<int64_t>(kp, std::min(R, C));
-    if (std::min(R, C) <= kp || !stream_supported(R, C, C, l0) || !qr_fast_supported<double>(ctx, R, l0) ||
-        !qr_fast_supported<double>(ctx, C, l0))
-        return nullptr;
-    if (sc.stream && C * (int64_t)l0 > sc.stream_len) return nullptr;   // the general path reports the short stream
+    if (!given) {
+        if (std::min(R, C) <= kp || !stream_supported(R, C, C, l0) || !qr_fast_supported<double>(ctx, R, l0) ||
+            !qr_fast_supported<double>(ctx, C, l0))
+            return nullptr;
+        if (sc.stream && C * (int64_t)l0 > sc.stream_len) return nullptr;   // the general path reports the short stream
+    }
 
     std::vector<int> h_bonds(n + 1, 1);
     int* d_state = (int*)ctx->alloc(sizeof(int) * (n + 2));     // bonds[0..n], overflow flag
@@ -765,15 +782,15 @@ static qil_mps* encode_rsvd_tree(SplitCtx<double>& sc, const double* x, int n) {
     };
     try {
         // top split -> device buffers
-        double* Utop = (double*)ctx->alloc((size_t)R * l0 * sizeof(double));
-        double* SVtop = (double*)ctx->alloc((size_t)l0 * C * sizeof(double));
+        double* Utop = given ? Ugiven : (double*)ctx->alloc((size_t)R * l0 * sizeof(double));
+        double* SVtop = given ? SVgiven : (double*)ctx->alloc((size_t)l0 * C * sizeof(double));
         std::vector<Pending> cur{{0, mid, Utop}, {mid + 1, n - 1, SVtop}}, next;
         while (!cur.empty()) {
             std::vector<NodeDesc> lvl;
             next.clear();
             for (const Pending& pd : cur) {
                 if (pd.first == pd.last) { cores[pd.first] = pd.A; continue; }
-                temps.push_back(pd.A);
+                if (!(given && (pd.A == Ugiven || pd.A == SVgiven))) temps.push_back(pd.A);
                 const int m2 = (pd.first + pd.last + 1) / 2 - 1;
                 NodeDesc d;
                 d.A = pd.A; d.bonds_off = 0;
@@ -801,9 +818,14 @@ static qil_mps* encode_rsvd_tree(SplitCtx<double>& sc, const double* x, int n) {
             temps.push_back(reinterpret_cast<double*>(d_nodes));
             QIL_CUDA(cudaMemcpyAsync(d_nodes, flat.data(), sizeof(NodeDesc) * total, cudaMemcpyHostToDevice, ctx->stream));
         }
-        Mat<double> Udummy;
-        DevOut<double> dev{Utop, SVtop, d_bonds + mid + 1};
-        rsvd_split_fused(sc, x, R, C, true, l0, Udummy, nullptr, nullptr, nullptr, &dev);
+        if (given) {
+            set_int_kernel<<<1, 32, 0, ctx->stream>>>(d_bonds + mid + 1, rgiven);
+            QIL_LAUNCH_CHECK(ctx);
+        } else {
+            Mat<double> Udummy;
+            DevOut<double> dev{Utop, SVtop, d_bonds + mid + 1};
+            rsvd_split_fused(sc, x, R, C, true, l0, Udummy, nullptr, nullptr, nullptr, &dev);
+        }
         size_t off = 0;
         for (auto& lv : levels) {
             node_level_launch(ctx, d_nodes + off, (int)lv.size(), d_bonds, d_over, o, sc.stream, sc.stream_len);
@@ -1056,6 +1078,10 @@ bool encode_rsvd_batch_tree_dispatch<double>(qil_ctx* ctx, const double* d_x, in
 template <> qil_mps* encode_rsvd_tree_dispatch<double>(SplitCtx<double>& sc, const double* x, int n) {
     return encode_rsvd_tree(sc, x, n);
 }
+template <typename T> static qil_mps* encode_tree_lower_dispatch(SplitCtx<T>&, int, T*, T*, int) { return nullptr; }
+template <> qil_mps* encode_tree_lower_dispatch<double>(SplitCtx<double>& sc, int n, double* U, double* SVh, int r) {
+    return encode_rsvd_tree(sc, nullptr, n, U, SVh, r);
+}
 
 template <typename T>
 qil_mps* encode_rsvd(qil_ctx* ctx, const T* d_x, int64_t N, const RsvdOpts& o) {
@@ -1128,6 +1154,7 @@ qil_mps* encode_rsvd_sharded(qil_ctx* ctx, const qil_comm* comm, const T* d_x_lo
     const int r = rsvd_split_sharded<T>(sc, d_x_local, R / G, C, U, SVh);
     bond[mid + 1] = r;
     sc.comm = nullptr;                                       // the lower levels are replicated, no collectives
+    if (qil_mps* fastm = encode_tree_lower_dispatch<T>(sc, n, U.p, SVh.p, r)) return fastm;   // one launch per level
     {
         std::vector<DcNode<T>> level(2);
         DcNode<T>& a = level[0];
