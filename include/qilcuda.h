@@ -115,6 +115,27 @@ int qil_coefficient_grid(qil_ctx* ctx, const qil_mps* psi, const uint8_t* site_m
 int qil_coefficient_grid_dev(qil_ctx* ctx, const qil_mps* psi, const uint8_t* site_mode, const int32_t* out_bit,
                              void* d_out);
 
+/* ---- read-out reductions on the device ---------------------------------------------------------------------
+ * arg-max of |chi| (first maximum on ties) -- the `argmax(abs.(chi))` that ends every stage of the coarse / fine /
+ * superfine pole scan (docs/src/tutorials/zt.jl:324-326, 372-375, 412-415); only the index, |value| and value (one
+ * scalar of the element type, may be NULL) come back to the host. */
+int qil_argmax_abs_dev(qil_ctx* ctx, int is_complex, const void* d_values, int64_t count, int64_t* index, double* absval,
+                       void* value);
+/* qil_coefficient_grid / qil_coefficient_batch followed by the arg-max, without the D2H copy of the grid */
+int qil_coefficient_grid_argmax(qil_ctx* ctx, const qil_mps* psi, const uint8_t* site_mode, const int32_t* out_bit,
+                                int64_t* index, double* absval, void* value);
+int qil_coefficient_batch_argmax(qil_ctx* ctx, const qil_mps* psi, const uint8_t* bits, int64_t B, int64_t* index,
+                                 double* absval, void* value);
+/* Sum over every configuration of the sites with sum_mask[i] != 0 (HOST array, n entries): they are contracted with
+ * the all-ones vector and absorbed into a neighbouring kept site; the result is an MPS over the kept sites.  With the
+ * copy register of a ZTMPS masked this is the inner sum of `laplace_coefficient` (docs/src/tutorials/dt.jl:187-197)
+ * for every k at once: read it out with qil_coefficient_grid (all sites free). */
+int qil_mps_sum_sites(qil_ctx* ctx, const qil_mps* psi, const uint8_t* sum_mask, qil_mps** out);
+/* An MPS with uninitialised cores of the given bonds and the device address of a core: lets a multi-process host move
+ * cores between devices with its own transport (e.g. an NCCL broadcast before a sharded pole scan). */
+int qil_mps_alloc(qil_ctx* ctx, int n, int is_complex, const int64_t* bond, double amplitude, qil_mps** out);
+int qil_mps_core_ptr(const qil_mps* m, int site, void** d_ptr, int64_t* elems);
+
 /* ---- apply (src/linalg/apply.jl:75-122, 124-199, 201-236) ----------------------------------
  * Exact MPO x MPS: out core = [D_l*chi_l][2][D_r*chi_r] with the MPO bond fastest; never truncates;
  * amplitude is copied.  Paired operands are passed as 2n-site chains. */

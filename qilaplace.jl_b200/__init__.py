@@ -11,4 +11,6 @@ from .api import (Context, default_context, SignalMPS, ZTMPS, SingleSiteMPO, Pai
                   canonicalize, canonicalize_, compress, compress_, norm, mps_to_vector,
                   build_qft_mpo, build_dt_mpo, build_zt_mpo, qr, svd_trunc, rsvd,
                   signal_mps_dev, signal_mps_batch_dev, ztmps_from_mps, coefficients_dev,
-                  coefficient_grid, coefficient_grid_dev, pole_scan, pole_scan_modes)
+                  coefficient_grid, coefficient_grid_dev, pole_scan, pole_scan_modes, apply_batch,
+                  coefficient_grid_argmax, coefficients_argmax, sum_sites, laplace_coefficients, z_from_kl, kl_bits,
+                  pole_scan_argmax, pole_scan_list_argmax, pole_scan_driver)

@@ -431,6 +431,19 @@ def generate_signal(n, kind="sin", dt=None, freq=None, **kw):
         return np.sin(f * dt * j + kw.get("phase", 0.0)) * np.exp(-dr * dt * j)
     if kind == "abs_cos_power_p8":
         return np.abs(np.cos(2 * math.pi * dt * j)) ** kw.get("power", 0.8)
+    if kind in ("multi_sin", "multi_sin_exp"):
+        # Signals.jl:23-85: n_terms (10) random tones.  The reference draws amplitudes / frequencies / decays from
+        # Xoshiro(seed_amp / seed_freq / seed_decay), a Julia-specific stream; this is the same construction on numpy's
+        # generator with the same seeds (a deterministic SURROGATE of the same family, not the same numbers).
+        nt = int(kw.get("n_terms", 10))
+        ak = np.random.default_rng(kw.get("seed_amp", 1001)).random(nt)
+        ak = ak / np.linalg.norm(ak)
+        wk = (kw.get("ω_scale", kw.get("omega_scale", 40.0)) * dt) * (np.random.default_rng(kw.get("seed_freq", 2002)).random(nt) - 0.5)
+        if kind == "multi_sin":
+            ph = 2 * math.pi * np.random.default_rng(kw.get("seed_phase", 3003)).random(nt)
+            return sum(a * np.sin(w * j + p) for a, w, p in zip(ak, wk, ph))
+        lk = -(kw.get("λ_scale", kw.get("lambda_scale", 2.0)) * dt) * np.random.default_rng(kw.get("seed_decay", 4004)).random(nt)
+        return sum(a * np.sin(w * j) * np.exp(l * j) for a, w, l in zip(ak, wk, lk))
     raise ArgumentError(
         f"Unsupported signal kind: {kind}. Supported kinds are :sin, :multi_sin, :sin_decay, "
         ":multi_sin_exp, :abs_cos_power_p8, :random.")
@@ -603,6 +616,123 @@ def pole_scan(psi, k0=0, l0=0, log2_k=None, log2_l=None, stride_log2_k=0, stride
     log2_l = n - stride_log2_l if log2_l is None else log2_l
     mode, ob = pole_scan_modes(n, k0, l0, log2_k, log2_l, stride_log2_k, stride_log2_l)
     return coefficient_grid(psi, mode, ob).reshape(2**log2_k, 2**log2_l)
+
+
+def _argmax_result(psi, idx, av, val):
+    v = complex(val[0], val[1]) if psi.is_complex else float(val[0])
+    return int(idx.value), float(av.value), v
+
+
+def coefficient_grid_argmax(psi, site_mode, out_bit=None):
+    """(flat index, |value|, value) of the largest coefficient of a dense grid, reduced on the device."""
+    mode8, F, ob = _grid_args(psi, site_mode, out_bit)
+    idx, av, val = C.c_int64(), C.c_double(), (C.c_double * 2)()
+    call("qil_coefficient_grid_argmax", psi.ctx.handle, psi.handle, C.c_void_p(mode8.ctypes.data),
+         C.c_void_p(ob.ctypes.data) if ob is not None else None, C.byref(idx), C.byref(av), val)
+    return _argmax_result(psi, idx, av, val)
+
+
+def coefficients_argmax(psi, bits):
+    """(row index, |value|, value) of the largest coefficient of a batch of bitstrings, reduced on the device."""
+    b = np.ascontiguousarray(bits, dtype=np.uint8)
+    if b.ndim != 2 or b.shape[1] != psi.nsites_flat:
+        raise ArgumentError(f"coefficient: expected B x {psi.nsites_flat} bits, got {b.shape}")
+    idx, av, val = C.c_int64(), C.c_double(), (C.c_double * 2)()
+    call("qil_coefficient_batch_argmax", psi.ctx.handle, psi.handle, C.c_void_p(b.ctypes.data), C.c_int64(b.shape[0]),
+         C.byref(idx), C.byref(av), val)
+    return _argmax_result(psi, idx, av, val)
+
+
+def sum_sites(psi, mask):
+    """Sum over every configuration of the masked sites (contract them with the all-ones vector); returns an MPS over
+    the remaining sites."""
+    m = np.ascontiguousarray(mask, dtype=np.uint8)
+    if m.shape != (psi.nsites_flat,):
+        raise ArgumentError(f"sum_sites: expected {psi.nsites_flat} mask entries")
+    h = _lib.c_mps()
+    call("qil_mps_sum_sites", psi.ctx.handle, psi.handle, C.c_void_p(m.ctypes.data), C.byref(h))
+    return SignalMPS(psi.ctx, h)
+
+
+def laplace_coefficients(psi_out, dt):
+    """L(s_k) ~ dt * sqrt(N) * sum_j <k_LSB, j | psi_out> for EVERY k (docs/src/tutorials/dt.jl:187-197 calls
+    `coefficient` N times per value): the copy register is summed once on the device and the main register read out as
+    a dense vector (main sites are LSB first, dt.jl:176-178)."""
+    n = psi_out.nsites_flat // 2
+    mask = np.zeros(2 * n, dtype=np.uint8)
+    mask[1::2] = 1
+    red = sum_sites(psi_out, mask)
+    return dt * math.sqrt(2.0**n) * mps_to_vector(red, reverse=True)
+
+
+def z_from_kl(k, l, n, omega_r, omega_i=2 * math.pi):
+    """z = exp(-(omega_r k + i omega_i l) / N) (docs/src/tutorials/zt.jl:140-150)."""
+    N = 2.0**n
+    return np.exp(-(omega_r * np.asarray(k, dtype=np.float64) + 1j * omega_i * np.asarray(l, dtype=np.float64)) / N)
+
+
+def kl_bits(ks, ls, n):
+    """Interleaved LSB-first bitstrings of (k, l) pairs (zt.jl:152-157): uint8 [len, 2n]."""
+    ks = np.asarray(ks, dtype=np.int64).reshape(-1)
+    ls = np.asarray(ls, dtype=np.int64).reshape(-1)
+    bits = np.zeros((ks.size, 2 * n), dtype=np.uint8)
+    for j in range(n):
+        bits[:, 2 * j] = (ks >> j) & 1
+        bits[:, 2 * j + 1] = (ls >> j) & 1
+    return bits
+
+
+def pole_scan_argmax(psi, k0=0, l0=0, log2_k=None, log2_l=None, stride_log2_k=0, stride_log2_l=0):
+    """(k, l, |chi|, chi) of the peak of an aligned strided (k, l) block, grid and arg-max both on the device."""
+    n = psi.nsites_flat // 2
+    log2_k = n - stride_log2_k if log2_k is None else log2_k
+    log2_l = n - stride_log2_l if log2_l is None else log2_l
+    mode, ob = pole_scan_modes(n, k0, l0, log2_k, log2_l, stride_log2_k, stride_log2_l)
+    idx, av, v = coefficient_grid_argmax(psi, mode, ob)
+    a, b = divmod(idx, 2**log2_l)
+    return k0 + (a << stride_log2_k), l0 + (b << stride_log2_l), av, v
+
+
+def pole_scan_list_argmax(psi, ks, ls):
+    """(k, l, |chi|, chi) of the peak over the Cartesian product ks x ls (arbitrary index lists: the fine and superfine
+    stages of the tutorial, zt.jl:345-415); first maximum in Julia's column-major order (k fastest)."""
+    n = psi.nsites_flat // 2
+    ks = np.asarray(ks, dtype=np.int64)
+    ls = np.asarray(ls, dtype=np.int64)
+    K, L = np.meshgrid(ks, ls, indexing="ij")
+    order_k = K.T.reshape(-1)           # column-major: k varies fastest
+    order_l = L.T.reshape(-1)
+    idx, av, v = coefficients_argmax(psi, kl_bits(order_k, order_l, n))
+    return int(order_k[idx]), int(order_l[idx]), av, v
+
+
+def pole_scan_driver(psi_coarse, psi_fine, omega_r_coarse, omega_r_fine, omega_i=2 * math.pi, step_coarse_log2=12,
+                     r_window=(1 - 1.6e-4, 1.0), theta_window=(-5e-3, 9e-3), n_fine=128, z_target=None, half=24):
+    """The three-stage pole search of docs/src/tutorials/zt.jl:296-415 on two transformed ZTMPS (coarse omega_r and fine
+    omega_r): strided coarse grid -> polar window near the unit circle -> full-resolution block around `z_target`
+    (default: the fine-stage peak).  Every stage evaluates its grid and reduces |chi| on the device."""
+    n = psi_coarse.nsites_flat // 2
+    N = 2**n
+    out = {}
+    k, l, av, v = pole_scan_argmax(psi_coarse, 0, 0, n - step_coarse_log2, n - step_coarse_log2, step_coarse_log2,
+                                   step_coarse_log2)
+    out["coarse"] = dict(k=k, l=l, abs=av, z=complex(z_from_kl(k, l, n, omega_r_coarse, omega_i)))
+    r_t = np.linspace(r_window[0], r_window[1], n_fine)
+    ks = np.clip(np.round((-N / omega_r_fine) * np.log(r_t)).astype(np.int64), 0, N - 1)
+    th = np.mod(np.linspace(theta_window[0], theta_window[1], n_fine), 2 * math.pi)
+    ls = np.mod(np.round((N / omega_i) * th).astype(np.int64), N)
+    k, l, av, v = pole_scan_list_argmax(psi_fine, ks, ls)
+    out["fine"] = dict(k=k, l=l, abs=av, z=complex(z_from_kl(k, l, n, omega_r_fine, omega_i)))
+    zt = out["fine"]["z"] if z_target is None else complex(z_target)
+    th_t = (-np.angle(zt)) % (2 * math.pi)
+    kc = int(np.clip(round((-N / omega_r_fine) * math.log(abs(zt))), 0, N - 1))
+    lc = int(round((N / omega_i) * th_t)) % N
+    ks2 = np.arange(kc - half, kc + half + 1)
+    ks2 = ks2[(ks2 >= 0) & (ks2 < N)]
+    ls2 = np.mod(np.arange(lc - half, lc + half + 1), N)
+    k, l, av, v = pole_scan_list_argmax(psi_fine, ks2, ls2)
+    out["superfine"] = dict(k=k, l=l, abs=av, z=complex(z_from_kl(k, l, n, omega_r_fine, omega_i)))
+    return out
 
 
 # ------------------------------------------------------------------------------------------

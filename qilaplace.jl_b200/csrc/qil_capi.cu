@@ -429,6 +429,89 @@ int qil_coefficient_grid(qil_ctx* ctx, const qil_mps* psi, const uint8_t* site_m
     QIL_API_END
 }
 
+int qil_argmax_abs_dev(qil_ctx* ctx, int is_complex, const void* d_values, int64_t count, int64_t* index, double* absval,
+                       void* value) {
+    QIL_API_BEGIN
+    QIL_NONNULL(ctx); QIL_NONNULL(d_values); QIL_NONNULL(index); QIL_NONNULL(absval);
+    QIL_CUDA(cudaSetDevice(ctx->device));
+    if (is_complex) argmax_abs<cplx>(ctx, (const cplx*)d_values, count, index, absval, (cplx*)value);
+    else argmax_abs<double>(ctx, (const double*)d_values, count, index, absval, (double*)value);
+    QIL_API_END
+}
+
+int qil_coefficient_grid_argmax(qil_ctx* ctx, const qil_mps* psi, const uint8_t* site_mode, const int32_t* out_bit,
+                                int64_t* index, double* absval, void* value) {
+    QIL_API_BEGIN
+    QIL_NONNULL(ctx); QIL_NONNULL(psi); QIL_NONNULL(site_mode); QIL_NONNULL(index); QIL_NONNULL(absval);
+    QIL_CUDA(cudaSetDevice(ctx->device));
+    const int F = grid_free_sites(psi, site_mode);
+    QIL_REQUIRE(F <= 34, QIL_ERR_UNSUPPORTED, "coefficient grid: 2^%d results do not fit device scratch here", F);
+    const int64_t count = (int64_t)1 << F;
+    void* d_out = ctx->alloc((size_t)count * elem_size(psi->is_complex));
+    try {
+        coefficient_grid_dev(ctx, psi, site_mode, out_bit, d_out);
+        if (psi->is_complex) argmax_abs<cplx>(ctx, (const cplx*)d_out, count, index, absval, (cplx*)value);
+        else argmax_abs<double>(ctx, (const double*)d_out, count, index, absval, (double*)value);
+    } catch (...) {
+        ctx->free(d_out);
+        throw;
+    }
+    ctx->free(d_out);
+    QIL_API_END
+}
+
+int qil_coefficient_batch_argmax(qil_ctx* ctx, const qil_mps* psi, const uint8_t* bits, int64_t B, int64_t* index,
+                                 double* absval, void* value) {
+    QIL_API_BEGIN
+    QIL_NONNULL(ctx); QIL_NONNULL(psi); QIL_NONNULL(bits); QIL_NONNULL(index); QIL_NONNULL(absval);
+    QIL_REQUIRE(B >= 1, QIL_ERR_ARGUMENT, "coefficient: empty batch");
+    QIL_CUDA(cudaSetDevice(ctx->device));
+    const size_t nb = (size_t)B * psi->n;
+    for (size_t i = 0; i < nb; ++i)
+        QIL_REQUIRE(bits[i] <= 1, QIL_ERR_ARGUMENT, "coefficient: bit value %d outside [0,1]", (int)bits[i]);
+    uint8_t* d_bits = (uint8_t*)ctx->alloc(nb);
+    void* d_out = ctx->alloc((size_t)B * elem_size(psi->is_complex));
+    try {
+        QIL_CUDA(cudaMemcpyAsync(d_bits, bits, nb, cudaMemcpyHostToDevice, ctx->stream));
+        coefficient_batch_dev(ctx, psi, d_bits, B, d_out);
+        if (psi->is_complex) argmax_abs<cplx>(ctx, (const cplx*)d_out, B, index, absval, (cplx*)value);
+        else argmax_abs<double>(ctx, (const double*)d_out, B, index, absval, (double*)value);
+    } catch (...) {
+        ctx->free(d_bits); ctx->free(d_out);
+        throw;
+    }
+    ctx->free(d_bits);
+    ctx->free(d_out);
+    QIL_API_END
+}
+
+int qil_mps_sum_sites(qil_ctx* ctx, const qil_mps* psi, const uint8_t* sum_mask, qil_mps** out) {
+    QIL_API_BEGIN
+    QIL_NONNULL(ctx); QIL_NONNULL(psi); QIL_NONNULL(sum_mask); QIL_NONNULL(out);
+    QIL_CUDA(cudaSetDevice(ctx->device));
+    *out = mps_sum_sites(ctx, psi, sum_mask);
+    QIL_API_END
+}
+
+int qil_mps_alloc(qil_ctx* ctx, int n, int is_complex, const int64_t* bond, double amplitude, qil_mps** out) {
+    QIL_API_BEGIN
+    QIL_NONNULL(ctx); QIL_NONNULL(bond); QIL_NONNULL(out);
+    QIL_CUDA(cudaSetDevice(ctx->device));
+    qil_mps* m = new_mps(ctx, n, is_complex, bond, true);
+    m->amplitude = amplitude;
+    *out = m;
+    QIL_API_END
+}
+
+int qil_mps_core_ptr(const qil_mps* m, int site, void** d_ptr, int64_t* elems) {
+    QIL_API_BEGIN
+    QIL_NONNULL(m); QIL_NONNULL(d_ptr);
+    QIL_REQUIRE(site >= 0 && site < m->n, QIL_ERR_ARGUMENT, "site %d outside [0,%d)", site, m->n);
+    *d_ptr = m->core[site];
+    if (elems) *elems = (int64_t)m->core_elems(site);
+    QIL_API_END
+}
+
 // ---- apply ---------------------------------------------------------------------------------
 int qil_apply_mpo_mps(qil_ctx* ctx, const qil_mpo* W, const qil_mps* psi, qil_mps** out) {
     QIL_API_BEGIN

@@ -39,6 +39,9 @@ qil_mps* ztmps_split(qil_ctx* ctx, const qil_mps* psi, double cutoff, int64_t ma
 void canonicalize(qil_ctx* ctx, qil_mps* psi, int dir_right, int center, double cutoff, int64_t maxdim);
 void compress(qil_ctx* ctx, qil_mps* psi, int64_t maxdim, double tol, int sweeps);
 double mps_norm(qil_ctx* ctx, const qil_mps* psi);
+// read-out reductions (qil_scan.cu)
+template <typename T> void argmax_abs(qil_ctx* ctx, const T* d_v, int64_t count, int64_t* index, double* absval, T* value);
+qil_mps* mps_sum_sites(qil_ctx* ctx, const qil_mps* psi, const uint8_t* mask);
 
 qil_mpo* build_qft_mpo(qil_ctx* ctx, int n, double cutoff, int64_t maxdim);
 qil_mpo* build_dt_mpo(qil_ctx* ctx, int n, double wr, double cutoff, int64_t maxdim);

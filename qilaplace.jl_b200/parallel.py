@@ -29,6 +29,73 @@ def broadcast_cores(cores, amplitude, src=0, group=None):
     return payload[0], payload[1]
 
 
+def broadcast_mps(psi, ctx, src=0, group=None):
+    """Device-to-device broadcast of an MPS over the process group (NCCL over NVLink on the GPU box): bonds and amplitude
+    travel as a small object, every core goes straight from the source rank's HBM into a freshly allocated core on each
+    receiver (qil_mps_alloc / qil_mps_core_ptr) -- no host staging of the tensor data.  `psi` is ignored off `src`."""
+    import ctypes as C
+    import torch
+    from . import _lib, api
+    dist = _dist()
+    rank = dist.get_rank(group)
+    meta = [None]
+    if rank == src:
+        meta = [(psi.nsites_flat, bool(psi.is_complex), [1] + list(psi.bonds) + [1], float(psi.amplitude),
+                 isinstance(psi, api.ZTMPS))]
+    dist.broadcast_object_list(meta, src=src, group=group)
+    nsites, is_c, bond, amp, is_zt = meta[0]
+    if rank == src:
+        out = psi
+    else:
+        b = np.asarray(bond, dtype=np.int64)
+        h = _lib.c_mps()
+        _lib.call("qil_mps_alloc", ctx.handle, int(nsites), int(is_c), C.c_void_p(b.ctypes.data), float(amp), C.byref(h))
+        out = (api.ZTMPS if is_zt else api.SignalMPS)(ctx, h)
+    dev = torch.device("cuda", ctx.device)
+    nccl = dist.get_backend(group) == "nccl"
+    ctx.sync()
+    for i in range(nsites):
+        ptr, cnt = C.c_void_p(), C.c_int64()
+        _lib.call("qil_mps_core_ptr", out.handle, i, C.byref(ptr), C.byref(cnt))
+        t = torch.as_tensor(_DevBuf(ptr.value, cnt.value * (2 if is_c else 1)), device=dev)
+        if nccl:
+            dist.broadcast(t, src=src, group=group)
+        else:                       # functional fallback (gloo): through the host
+            hbuf = t.cpu()
+            dist.broadcast(hbuf, src=src, group=group)
+            if rank != src:
+                t.copy_(hbuf)
+    torch.cuda.synchronize(dev)
+    return out
+
+
+def pole_scan_argmax_sharded(psi, k0=0, l0=0, log2_k=None, log2_l=None, stride_log2_k=0, stride_log2_l=0, group=None):
+    """Aligned (k, l) block split by k-rows over the ranks: rank g evaluates the 2^(log2_k - log2 G) rows
+    whose top free k-bits equal g (grid + arg-max on its own device), then a 3-number all-gather picks the global peak
+    (largest |chi|, lowest flat index on ties).  Every rank must hold the same MPS (see broadcast_mps)."""
+    import torch
+    from . import api
+    dist = _dist()
+    world, rank = dist.get_world_size(group), dist.get_rank(group)
+    n = psi.nsites_flat // 2
+    log2_k = n - stride_log2_k if log2_k is None else log2_k
+    log2_l = n - stride_log2_l if log2_l is None else log2_l
+    lg = int(np.log2(world))
+    if (1 << lg) != world or lg > log2_k:
+        raise api.ArgumentError("pole_scan_argmax_sharded: world size must be a power of two <= the number of k rows")
+    sub = log2_k - lg
+    k0_loc = k0 + (rank << (stride_log2_k + sub))
+    k, l, av, v = api.pole_scan_argmax(psi, k0_loc, l0, sub, log2_l, stride_log2_k, stride_log2_l)
+    flat = ((k - k0) >> stride_log2_k) * (1 << log2_l) + ((l - l0) >> stride_log2_l)
+    mine = torch.tensor([av, float(flat), float(k), float(l)], dtype=torch.float64)
+    if dist.get_backend(group) == "nccl":
+        mine = mine.cuda(psi.ctx.device)
+    allv = [torch.zeros_like(mine) for _ in range(world)]
+    dist.all_gather(allv, mine, group=group)
+    best = max((t.cpu().tolist() for t in allv), key=lambda t: (t[0], -t[1]))
+    return int(best[2]), int(best[3]), float(best[0])
+
+
 def coefficients_sharded(cores, amplitude, bits, compute=None, group=None):
     """Every rank evaluates its contiguous slice of `bits` (B x n) and all ranks receive all B results."""
     import torch

@@ -204,3 +204,58 @@ def test_c3_pole_scan_n20_tutorial_peaks(q, goldens):
     # (no closed-form check here: at omega_r = 0.5 the exact chi near k ~ 320 is ~1e-54 of the state's largest
     #  entries, so what the reference's tutorial -- and this test -- read off the MPS at these points is the
     #  deterministic truncation-error field of the cutoff-1e-12 MPO; reproducing its golden peak is the parity check)
+
+
+def test_scan_driver_device_argmax_reproduces_tutorial_peaks(q, goldens):
+    """The three-stage pole search of docs/src/tutorials/zt.jl:296-415 through pole_scan_driver: grids and arg-max on
+    the device.  Golden peaks of the executed tutorial (zt.md:473-475, 521-523, 562-564): coarse (0, 0), fine
+    (0, 1047889), superfine (320, 1047872)."""
+    g = goldens["zt_tutorial_n20"]
+    n = g["n"]
+    N = 2**n
+    a = g["a_abs"] * np.exp(1j * g["a_arg"])
+    w0 = g["omega0"]
+    j = np.arange(N)
+    x = a**j * np.cos(w0 * j)
+    z = q.signal_ztmps(x, method="rsvd", k=g["k"], p=g["p"], q=g["q"], cutoff=g["cutoff"], maxdim=g["maxdim"])
+    out_c = q.build_zt_mpo(z, 2 * math.pi, cutoff=1e-12, maxdim=128) * z
+    out_f = q.build_zt_mpo(z, 0.5, cutoff=1e-12, maxdim=128) * z
+    z_pole = (1 / a) * np.exp(1j * w0)
+    res = q.pole_scan_driver(out_c, out_f, 2 * math.pi, 0.5, z_target=z_pole)
+    assert (res["coarse"]["k"], res["coarse"]["l"]) == (0, 0)
+    assert (res["fine"]["k"], res["fine"]["l"]) == (0, 1047889)
+    assert (res["superfine"]["k"], res["superfine"]["l"]) == (320, 1047872)
+    # device arg-max == host arg-max of the same grid
+    chi = q.pole_scan(out_c, log2_k=8, log2_l=8, stride_log2_k=12, stride_log2_l=12)
+    k, l, av, v = q.pole_scan_argmax(out_c, 0, 0, 8, 8, 12, 12)
+    i = np.unravel_index(np.abs(chi).argmax(), chi.shape)
+    assert (k, l) == (i[0] * 4096, i[1] * 4096) and abs(av - np.abs(chi).max()) <= 1e-14 * av and v == chi[i]
+
+
+@pytest.mark.parametrize("n,cplx", [(3, False), (5, True), (8, False)])
+def test_laplace_coefficients_and_sum_sites_match_oracle(q, n, cplx):
+    """laplace_coefficient for every k at once (docs/src/tutorials/dt.jl:187-197): the copy register summed on the
+    device, against the explicit double loop over `coefficient` in the oracle."""
+    N = 2**n
+    rng = np.random.default_rng(n)
+    x = rng.standard_normal(N) + (1j * rng.standard_normal(N) if cplx else 0)
+    z = q.signal_ztmps(x, cutoff=1e-14)
+    W = q.build_dt_mpo(z, 1.3, cutoff=1e-14)
+    out = W * z
+    dt = 0.01
+    got = q.laplace_coefficients(out, dt)
+    cores, amp = out.cores(), out.amplitude
+    want = np.zeros(N, dtype=complex)
+    for k in range(N):
+        kb = O.bits_lsb(k, n)
+        s = 0
+        for jj in range(N):
+            s += O.coefficient(cores, amp, O.interleave(kb, O.bits_msb(jj, n)))
+        want[k] = dt * math.sqrt(N) * s
+    assert np.abs(got - want).max() <= 1e-11 * max(np.abs(want).max(), 1e-300)
+    # generic site sums: trace out an arbitrary subset
+    mask = np.zeros(2 * n, dtype=np.uint8)
+    mask[[0, 2 * n - 1]] = 1
+    red = q.sum_sites(out, mask)
+    dense = q.mps_to_vector(out).reshape((2,) * (2 * n))
+    assert np.abs(q.mps_to_vector(red) - dense.sum(axis=(0, 2 * n - 1)).reshape(-1)).max() <= 1e-11 * np.abs(dense).max()

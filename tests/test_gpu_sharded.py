@@ -139,3 +139,52 @@ def test_row_sharded_encode_many_gpus_bonds_identical(world, peer):
     ret = mgr.dict()
     mp.spawn(_worker_big, args=(world, port, ret, peer), nprocs=world, join=True)
     assert dict(ret) == {r: "ok" for r in range(world)}
+
+
+def _worker_scan(rank, world, port, ret):
+    """MPS broadcast (device to device over the group) + k-row-sharded pole scan with the 3-number arg-max exchange
+    (docs/src/tutorials/zt.jl:296-326) against the one-device scan."""
+    sys.path.insert(0, ROOT)
+    os.environ["MASTER_ADDR"] = "127.0.0.1"
+    os.environ["MASTER_PORT"] = str(port)
+    import math
+    import torch
+    import torch.distributed as dist
+    import qilaplace_b200 as q
+    from qilaplace_b200 import parallel
+    ngpu = torch.cuda.device_count()
+    nccl = ngpu >= world
+    dev = rank if nccl else 0
+    torch.cuda.set_device(dev)
+    dist.init_process_group("nccl" if nccl else "gloo", rank=rank, world_size=world)
+    try:
+        ctx = q.Context(dev)
+        n = 12
+        N = 2**n
+        psi = None
+        if rank == 0:
+            j = np.arange(N)
+            x = (1.0002 * np.exp(0.002j)) ** j * np.cos(0.11 * j)
+            z = q.signal_ztmps(x, ctx=ctx, cutoff=1e-12)
+            W = q.build_zt_mpo(z, 2 * math.pi, cutoff=1e-12, maxdim=128, ctx=ctx)
+            psi = W * z
+        out = parallel.broadcast_mps(psi, ctx, src=0)
+        k, l, av = parallel.pole_scan_argmax_sharded(out, 0, 0, 6, 6, n - 6, n - 6)
+        k1, l1, av1, _ = q.pole_scan_argmax(out, 0, 0, 6, 6, n - 6, n - 6)
+        assert (k, l) == (k1, l1) and abs(av - av1) <= 1e-14 * av1
+        gathered = [None] * world
+        dist.all_gather_object(gathered, (k, l, av, out.bonds))
+        assert all(g == gathered[0] for g in gathered)          # every rank holds the same MPS and the same peak
+        ret[rank] = "ok"
+    finally:
+        dist.destroy_process_group()
+
+
+@pytest.mark.parametrize("world", [2, 4])
+def test_broadcast_mps_and_sharded_pole_scan(world):
+    import torch.multiprocessing as mp
+    port = 36500 + (os.getpid() % 2000) + world
+    mgr = mp.Manager()
+    ret = mgr.dict()
+    mp.spawn(_worker_scan, args=(world, port, ret), nprocs=world, join=True)
+    assert dict(ret) == {r: "ok" for r in range(world)}
