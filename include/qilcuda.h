@@ -115,6 +115,15 @@ int qil_coefficient_grid(qil_ctx* ctx, const qil_mps* psi, const uint8_t* site_m
 int qil_coefficient_grid_dev(qil_ctx* ctx, const qil_mps* psi, const uint8_t* site_mode, const int32_t* out_bit,
                              void* d_out);
 
+/* ---- on-disk container (dims + raw cores; the reference itself persists only JLD2 benchmark dicts,
+ * scripts/benchmark/common.jl:193-203).  Layout, little endian: "QILTN001" | u32 kind (0 MPS, 1 MPO) | u32 is_complex |
+ * u32 n | u32 0 | f64 amplitude | i64 bond[n+1] | cores back to back in C order ([l][s][r] / [l][p][s][r]).  Written and
+ * read by this library, by oracle/qil_container.py and by the Julia reader in julia/QILContainer.jl. */
+int qil_mps_save(const qil_mps* m, const char* path);
+int qil_mps_load(qil_ctx* ctx, const char* path, qil_mps** out);
+int qil_mpo_save(const qil_mpo* m, const char* path);
+int qil_mpo_load(qil_ctx* ctx, const char* path, qil_mpo** out);
+
 /* ---- read-out reductions on the device ---------------------------------------------------------------------
  * arg-max of |chi| (first maximum on ties) -- the `argmax(abs.(chi))` that ends every stage of the coarse / fine /
  * superfine pole scan (docs/src/tutorials/zt.jl:324-326, 372-375, 412-415); only the index, |value| and value (one
@@ -140,6 +149,11 @@ int qil_mps_core_ptr(const qil_mps* m, int site, void** d_ptr, int64_t* elems);
  * Exact MPO x MPS: out core = [D_l*chi_l][2][D_r*chi_r] with the MPO bond fastest; never truncates;
  * amplitude is copied.  Paired operands are passed as 2n-site chains. */
 int qil_apply_mpo_mps(qil_ctx* ctx, const qil_mpo* W, const qil_mps* psi, qil_mps** out);
+/* Truncating MPO x MPS (zip-up): psi is brought to right-canonical form, then one sweep contracts carry x psi_i x W_i and
+ * splits it with the truncated SVD of the path (cutoff relative and cumulative on sigma^2, maxdim <= 0 = no limit).  The
+ * result has single (unfused) bonds.  Not a reference function: the remedy SURVEY.md 8f-3 names for the D*chi bonds of
+ * the exact apply on high-rank inputs (docs/src/benchmarking.md:309). */
+int qil_apply_mpo_mps_zipup(qil_ctx* ctx, const qil_mpo* W, const qil_mps* psi, double cutoff, int64_t maxdim, qil_mps** out);
 /* `[W * psi for psi in psis]` (BASELINE configs[1]: one QFT MPO applied to a batch of encoded signals) in one launch;
  * the `count` results share one pooled device allocation. */
 int qil_apply_mpo_mps_batch(qil_ctx* ctx, const qil_mpo* W, const qil_mps* const* psis, int64_t count, qil_mps** outs);

@@ -444,6 +444,43 @@ def apply_mpo_mps(W, psi):
     return out
 
 
+def right_canonical(cores):
+    """Orthogonality centre to site 1 by untruncated SVDs from the right (each site i > 1 becomes Vh)."""
+    cores = [c.copy() for c in cores]
+    for i in range(len(cores) - 1, 0, -1):
+        l, _, r = cores[i].shape
+        U, S, Vh = svd_trunc(cores[i].reshape(l, 2 * r), 0.0, BIG, 1)
+        k = S.size
+        cores[i] = Vh.reshape(k, 2, r)
+        prv = cores[i - 1]
+        cores[i - 1] = (prv.reshape(-1, l) @ (U * S)).reshape(prv.shape[0], 2, k)
+    return cores
+
+
+def apply_zipup(W, psi, cutoff=1e-12, maxdim=BIG):
+    """Truncating MPO x MPS (zip-up; NOT a reference function -- SURVEY.md 8f-3): right-canonical psi, then a
+    left-to-right sweep T[b,s,d,c] = sum C[b,a,l] psi_i[l,p,c] W_i[a,p,s,d], (b s) x (d c) = U S Vh with the path's
+    truncation rule, core_i = U, carry = S Vh.  Restated here so that the CUDA sweep has a checker."""
+    if len(W) != len(psi):
+        raise ValueError("apply: MPO and MPS must have the same number of sites.")
+    psi = right_canonical(psi)
+    n = len(psi)
+    C = np.ones((1, 1, 1))
+    out = []
+    for i in range(n):
+        X = np.einsum("bal,lpc->bapc", C, psi[i])
+        T = np.einsum("bapc,apsd->bsdc", X, W[i])
+        b, _, d, c = T.shape
+        if i == n - 1:
+            out.append(T.reshape(b, 2, 1))
+        else:
+            U, S, Vh = svd_trunc(T.reshape(b * 2, d * c), cutoff, maxdim, 1)
+            r = S.size
+            out.append(U.reshape(b, 2, r))
+            C = (S[:, None] * Vh).reshape(r, d, c)
+    return out
+
+
 def apply_mpo_mpo(W1, W2, start1=0, start2=0):
     """apply(W1, W2) (apply.jl:124-199): W1 acts first; fused bond has the W1 bond fastest.
 

@@ -69,6 +69,10 @@ _SIGS = {
     "qil_coefficient_batch_dev": [c_ctx, c_mps, C.c_void_p, C.c_int64, C.c_void_p],
     "qil_coefficient_grid": [c_ctx, c_mps, C.c_void_p, C.c_void_p, C.c_void_p],
     "qil_coefficient_grid_dev": [c_ctx, c_mps, C.c_void_p, C.c_void_p, C.c_void_p],
+    "qil_mps_save": [c_mps, C.c_char_p],
+    "qil_mps_load": [c_ctx, C.c_char_p, C.POINTER(c_mps)],
+    "qil_mpo_save": [c_mpo, C.c_char_p],
+    "qil_mpo_load": [c_ctx, C.c_char_p, C.POINTER(c_mpo)],
     "qil_argmax_abs_dev": [c_ctx, C.c_int, C.c_void_p, C.c_int64, C.POINTER(C.c_int64), C.POINTER(C.c_double), C.c_void_p],
     "qil_coefficient_grid_argmax": [c_ctx, c_mps, C.c_void_p, C.c_void_p, C.POINTER(C.c_int64), C.POINTER(C.c_double),
                                     C.c_void_p],
@@ -78,6 +82,7 @@ _SIGS = {
     "qil_mps_alloc": [c_ctx, C.c_int, C.c_int, C.c_void_p, C.c_double, C.POINTER(c_mps)],
     "qil_mps_core_ptr": [c_mps, C.c_int, C.POINTER(C.c_void_p), C.POINTER(C.c_int64)],
     "qil_apply_mpo_mps": [c_ctx, c_mpo, c_mps, C.POINTER(c_mps)],
+    "qil_apply_mpo_mps_zipup": [c_ctx, c_mpo, c_mps, C.c_double, C.c_int64, C.POINTER(c_mps)],
     "qil_apply_mpo_mps_batch": [c_ctx, c_mpo, C.c_void_p, C.c_int64, C.c_void_p],
     "qil_apply_mpo_mpo": [c_ctx, c_mpo, c_mpo, C.c_int, C.c_int, C.POINTER(c_mpo)],
     "qil_encode_svd": [c_ctx, C.c_int, C.c_void_p, C.c_int64, C.c_double, C.c_int64, C.POINTER(c_mps)],

@@ -378,6 +378,14 @@ def apply(W, other, **kwargs):
 # ------------------------------------------------------------------------------------------
 # signals (src/signals/Signals.jl:188-235) -- trivial elementwise host code, out of kernel scope
 # ------------------------------------------------------------------------------------------
+def apply_zipup(W, psi, cutoff=1e-12, maxdim=None):
+    """Truncating W * psi (zip-up sweep with the path's truncated SVD); see qil_apply_mpo_mps_zipup."""
+    h = _lib.c_mps()
+    call("qil_apply_mpo_mps_zipup", W.ctx.handle, W.handle, psi.handle, float(cutoff), C.c_int64(_maxdim_arg(maxdim)),
+         C.byref(h))
+    return (ZTMPS if isinstance(psi, ZTMPS) else SignalMPS)(W.ctx, h)
+
+
 def apply_batch(W, psis):
     """[W * psi for psi in psis] in one launch (qil_apply_mpo_mps_batch); psis: SignalMPS / ZTMPS of one context."""
     psis = list(psis)
@@ -616,6 +624,26 @@ def pole_scan(psi, k0=0, l0=0, log2_k=None, log2_l=None, stride_log2_k=0, stride
     log2_l = n - stride_log2_l if log2_l is None else log2_l
     mode, ob = pole_scan_modes(n, k0, l0, log2_k, log2_l, stride_log2_k, stride_log2_l)
     return coefficient_grid(psi, mode, ob).reshape(2**log2_k, 2**log2_l)
+
+
+def save(obj, path):
+    """Write an MPS / ZTMPS / MPO to the QILTN001 container (include/qilcuda.h)."""
+    fn = "qil_mpo_save" if isinstance(obj, SingleSiteMPO) else "qil_mps_save"
+    call(fn, obj.handle, str(path).encode())
+
+
+def load_mps(path, ctx=None, paired=False):
+    ctx = ctx or default_context()
+    h = _lib.c_mps()
+    call("qil_mps_load", ctx.handle, str(path).encode(), C.byref(h))
+    return (ZTMPS if paired else SignalMPS)(ctx, h)
+
+
+def load_mpo(path, ctx=None, paired=False):
+    ctx = ctx or default_context()
+    h = _lib.c_mpo()
+    call("qil_mpo_load", ctx.handle, str(path).encode(), C.byref(h))
+    return (PairedSiteMPO if paired else SingleSiteMPO)(ctx, h)
 
 
 def _argmax_result(psi, idx, av, val):

@@ -512,12 +512,123 @@ int qil_mps_core_ptr(const qil_mps* m, int site, void** d_ptr, int64_t* elems) {
     QIL_API_END
 }
 
+
+// ---- on-disk container: dims + raw cores, shared by the library, the numpy oracle and a Julia reader
+//   bytes 0..7   "QILTN001"
+//   uint32 kind (0 = MPS, 1 = MPO), uint32 is_complex, uint32 n, uint32 0
+//   float64 amplitude (MPO: 1.0)
+//   int64 bond[n+1]
+//   cores back to back, C order ([l][s][r] / [l][p][s][r]), float64 or interleaved complex128, little endian
+namespace {
+struct FileCloser { FILE* f; ~FileCloser() { if (f) fclose(f); } };
+
+void container_save(const char* path, int kind, int is_complex, int n, double amplitude, const std::vector<int64_t>& bond,
+                    const std::vector<void*>& core, qil_ctx* ctx) {
+    FileCloser fc{fopen(path, "wb")};
+    QIL_REQUIRE(fc.f != nullptr, QIL_ERR_RUNTIME, "cannot open %s for writing", path);
+    const char magic[8] = {'Q', 'I', 'L', 'T', 'N', '0', '0', '1'};
+    const uint32_t hdr[4] = {(uint32_t)kind, (uint32_t)is_complex, (uint32_t)n, 0u};
+    bool ok = fwrite(magic, 1, 8, fc.f) == 8 && fwrite(hdr, 4, 4, fc.f) == 4 && fwrite(&amplitude, 8, 1, fc.f) == 1 &&
+              fwrite(bond.data(), 8, (size_t)n + 1, fc.f) == (size_t)n + 1;
+    const size_t es = elem_size(is_complex), legs = kind == 0 ? 2 : 4;
+    std::vector<char> buf;
+    for (int i = 0; i < n && ok; ++i) {
+        const size_t bytes = (size_t)bond[i] * legs * (size_t)bond[i + 1] * es;
+        buf.resize(bytes);
+        QIL_CUDA(cudaMemcpyAsync(buf.data(), core[i], bytes, cudaMemcpyDeviceToHost, ctx->stream));
+        ctx->sync();
+        ok = fwrite(buf.data(), 1, bytes, fc.f) == bytes;
+    }
+    QIL_REQUIRE(ok, QIL_ERR_RUNTIME, "short write to %s", path);
+}
+
+struct ContainerData {
+    int kind, is_complex, n;
+    double amplitude;
+    std::vector<int64_t> bond;
+    std::vector<std::vector<char>> cores;
+};
+ContainerData container_load(const char* path) {
+    FileCloser fc{fopen(path, "rb")};
+    QIL_REQUIRE(fc.f != nullptr, QIL_ERR_RUNTIME, "cannot open %s", path);
+    char magic[8];
+    uint32_t hdr[4];
+    ContainerData d;
+    QIL_REQUIRE(fread(magic, 1, 8, fc.f) == 8 && memcmp(magic, "QILTN001", 8) == 0, QIL_ERR_ARGUMENT,
+                "%s is not a QILTN001 container", path);
+    QIL_REQUIRE(fread(hdr, 4, 4, fc.f) == 4 && fread(&d.amplitude, 8, 1, fc.f) == 1, QIL_ERR_ARGUMENT, "%s: truncated header", path);
+    d.kind = (int)hdr[0]; d.is_complex = (int)hdr[1]; d.n = (int)hdr[2];
+    QIL_REQUIRE(d.kind <= 1 && d.is_complex <= 1 && d.n >= 1 && d.n <= kMaxSites, QIL_ERR_ARGUMENT, "%s: bad header", path);
+    d.bond.resize(d.n + 1);
+    QIL_REQUIRE(fread(d.bond.data(), 8, (size_t)d.n + 1, fc.f) == (size_t)d.n + 1, QIL_ERR_ARGUMENT, "%s: truncated bonds", path);
+    const size_t es = elem_size(d.is_complex), legs = d.kind == 0 ? 2 : 4;
+    d.cores.resize(d.n);
+    for (int i = 0; i < d.n; ++i) {
+        QIL_REQUIRE(d.bond[i] >= 1 && d.bond[i + 1] >= 1 && d.bond[i] < (1ll << 30), QIL_ERR_ARGUMENT, "%s: bad bond", path);
+        const size_t bytes = (size_t)d.bond[i] * legs * (size_t)d.bond[i + 1] * es;
+        d.cores[i].resize(bytes);
+        QIL_REQUIRE(fread(d.cores[i].data(), 1, bytes, fc.f) == bytes, QIL_ERR_ARGUMENT, "%s: truncated core %d", path, i);
+    }
+    return d;
+}
+}  // namespace
+
+int qil_mps_save(const qil_mps* m, const char* path) {
+    QIL_API_BEGIN
+    QIL_NONNULL(m); QIL_NONNULL(path);
+    QIL_CUDA(cudaSetDevice(m->ctx->device));
+    container_save(path, 0, m->is_complex, m->n, m->amplitude, m->bond, m->core, m->ctx);
+    QIL_API_END
+}
+int qil_mpo_save(const qil_mpo* m, const char* path) {
+    QIL_API_BEGIN
+    QIL_NONNULL(m); QIL_NONNULL(path);
+    QIL_CUDA(cudaSetDevice(m->ctx->device));
+    container_save(path, 1, m->is_complex, m->n, 1.0, m->bond, m->core, m->ctx);
+    QIL_API_END
+}
+int qil_mps_load(qil_ctx* ctx, const char* path, qil_mps** out) {
+    QIL_API_BEGIN
+    QIL_NONNULL(ctx); QIL_NONNULL(path); QIL_NONNULL(out);
+    QIL_CUDA(cudaSetDevice(ctx->device));
+    ContainerData d = container_load(path);
+    QIL_REQUIRE(d.kind == 0, QIL_ERR_ARGUMENT, "%s holds an MPO, not an MPS", path);
+    qil_mps* m = new_mps(ctx, d.n, d.is_complex, d.bond.data(), true);
+    m->amplitude = d.amplitude;
+    for (int i = 0; i < d.n; ++i)
+        QIL_CUDA(cudaMemcpyAsync(m->core[i], d.cores[i].data(), d.cores[i].size(), cudaMemcpyHostToDevice, ctx->stream));
+    ctx->sync();
+    *out = m;
+    QIL_API_END
+}
+int qil_mpo_load(qil_ctx* ctx, const char* path, qil_mpo** out) {
+    QIL_API_BEGIN
+    QIL_NONNULL(ctx); QIL_NONNULL(path); QIL_NONNULL(out);
+    QIL_CUDA(cudaSetDevice(ctx->device));
+    ContainerData d = container_load(path);
+    QIL_REQUIRE(d.kind == 1, QIL_ERR_ARGUMENT, "%s holds an MPS, not an MPO", path);
+    qil_mpo* m = new_mpo(ctx, d.n, d.is_complex, d.bond.data(), true);
+    for (int i = 0; i < d.n; ++i)
+        QIL_CUDA(cudaMemcpyAsync(m->core[i], d.cores[i].data(), d.cores[i].size(), cudaMemcpyHostToDevice, ctx->stream));
+    ctx->sync();
+    *out = m;
+    QIL_API_END
+}
+
 // ---- apply ---------------------------------------------------------------------------------
 int qil_apply_mpo_mps(qil_ctx* ctx, const qil_mpo* W, const qil_mps* psi, qil_mps** out) {
     QIL_API_BEGIN
     QIL_NONNULL(ctx); QIL_NONNULL(W); QIL_NONNULL(psi); QIL_NONNULL(out);
     QIL_CUDA(cudaSetDevice(ctx->device));
     *out = apply_mpo_mps(ctx, W, psi);
+    QIL_API_END
+}
+
+int qil_apply_mpo_mps_zipup(qil_ctx* ctx, const qil_mpo* W, const qil_mps* psi, double cutoff, int64_t maxdim, qil_mps** out) {
+    QIL_API_BEGIN
+    QIL_NONNULL(ctx); QIL_NONNULL(W); QIL_NONNULL(psi); QIL_NONNULL(out);
+    QIL_CUDA(cudaSetDevice(ctx->device));
+    *out = apply_mpo_mps_zipup(ctx, W, psi, cutoff, fix_maxdim(maxdim));
     QIL_API_END
 }
 

@@ -281,4 +281,95 @@ void compress(qil_ctx* ctx, qil_mps* psi, int64_t maxdim, double tol, int sweeps
     else compress_t<double>(ctx, psi, maxdim, tol, sweeps);
 }
 
+
+// ------------------------------------------------------------------------------------------------
+// Truncating MPO x MPS ("zip-up").  Not in the reference, whose exact apply (apply.jl:75-122) fuses the
+// bonds to D*chi -- 200 s / 35 GB on a :random n=16 input (docs/src/benchmarking.md:309).  Here the MPS is brought to
+// right-canonical form, then one left-to-right sweep contracts carry x psi_i x W_i and splits it by the same truncated
+// SVD (NDTensors rule: relative cumulative cutoff on sigma^2, maxdim) the rest of the path uses:
+//   T[b,s,d,c] = sum_{a,p,l} C[b,a,l] psi_i[l,p,c] W_i[a,p,s,d];  T as (b s) x (d c) = U S Vh;  core_i = U,  C <- S Vh.
+// ------------------------------------------------------------------------------------------------
+template <typename TO, typename TP, typename TW>
+static qil_mps* apply_zipup_t(qil_ctx* ctx, const qil_mpo* W, const qil_mps* psi_in, double cutoff, int64_t maxdim) {
+    const int n = psi_in->n;
+    // right-canonical copy of psi (orthogonality centre on site 1), untruncated (cutoff 0 drops exact zeros only)
+    qil_mps* psi = new_mps(ctx, n, psi_in->is_complex, psi_in->bond.data(), true);
+    for (int i = 0; i < n; ++i)
+        QIL_CUDA(cudaMemcpyAsync(psi->core[i], psi_in->core[i], psi_in->core_elems(i) * elem_size(psi_in->is_complex),
+                                 cudaMemcpyDeviceToDevice, ctx->stream));
+    psi->amplitude = psi_in->amplitude;
+    std::vector<int64_t> ob(n + 1, 1);
+    std::vector<void*> cores(n, nullptr);
+    try {
+        canonicalize(ctx, psi, 0, 1, 0.0, (int64_t)1 << 62);
+        Mat<TO> carry(ctx, 1, 1);
+        {
+            const TO one = Scalar<TO>::one();
+            QIL_CUDA(cudaMemcpyAsync(carry.p, &one, sizeof(TO), cudaMemcpyHostToDevice, ctx->stream));
+            ctx->sync();
+        }
+        int64_t b = 1;
+        for (int i = 0; i < n; ++i) {
+            const int64_t Da = W->bond[i], Dd = W->bond[i + 1], cl = psi->bond[i], cr = psi->bond[i + 1];
+            // X[b,a,p,c] = sum_l C[(b,a), l] psi[l, (p,c)]
+            Mat<TO> X(ctx, b * Da, 2 * cr);
+            {
+                ContractDesc d{};
+                d.nout = 2; d.ncon = 1;
+                d.od[0] = b * Da; d.od[1] = 2 * cr; d.cd[0] = cl;
+                d.sa_o[0] = cl; d.sa_o[1] = 0; d.sb_o[0] = 0; d.sb_o[1] = 1; d.sc_o[0] = 2 * cr; d.sc_o[1] = 1;
+                d.sa_c[0] = 1; d.sb_c[0] = 2 * cr; d.conj_a = 0;
+                contract<TO, TP, TO>(ctx, d, carry.p, (const TP*)psi->core[i], X.p);
+            }
+            // T[b,s,d,c] = sum_{a,p} X[b,a,p,c] W[a,p,s,d]
+            Mat<TO> T(ctx, b * 2, Dd * cr);
+            {
+                ContractDesc d{};
+                d.nout = 4; d.ncon = 2;
+                d.od[0] = b; d.od[1] = 2; d.od[2] = Dd; d.od[3] = cr;
+                d.cd[0] = Da; d.cd[1] = 2;
+                d.sa_o[0] = Da * 2 * cr; d.sa_o[1] = 0; d.sa_o[2] = 0; d.sa_o[3] = 1;
+                d.sb_o[0] = 0; d.sb_o[1] = Dd; d.sb_o[2] = 1; d.sb_o[3] = 0;
+                d.sc_o[0] = 2 * Dd * cr; d.sc_o[1] = Dd * cr; d.sc_o[2] = cr; d.sc_o[3] = 1;
+                d.sa_c[0] = 2 * cr; d.sa_c[1] = cr;
+                d.sb_c[0] = 4 * Dd; d.sb_c[1] = 2 * Dd;
+                d.conj_a = 0;
+                contract<TO, TW, TO>(ctx, d, X.p, (const TW*)W->core[i], T.p);
+            }
+            if (i == n - 1) {
+                QIL_REQUIRE(Dd == 1 && cr == 1, QIL_ERR_ARGUMENT, "apply: boundary bonds must have dimension 1");
+                cores[i] = T.take();
+                ob[i + 1] = 1;
+            } else {
+                Mat<TO> U, SVh;
+                const int r = svd_trunc<TO>(ctx, b * 2, Dd * cr, T.p, Dd * cr, cutoff, maxdim, 1, &U, nullptr, nullptr, &SVh, nullptr);
+                cores[i] = U.take();
+                carry = std::move(SVh);
+                ob[i + 1] = r;
+                b = r;
+            }
+        }
+    } catch (...) {
+        for (void* c : cores) ctx->free(c);
+        destroy(psi);
+        throw;
+    }
+    qil_mps* out = new_mps(ctx, n, Scalar<TO>::is_complex ? 1 : 0, ob.data(), false);
+    out->core = cores;
+    out->amplitude = psi_in->amplitude;
+    destroy(psi);
+    ctx->sync();
+    return out;
+}
+
+qil_mps* apply_mpo_mps_zipup(qil_ctx* ctx, const qil_mpo* W, const qil_mps* psi, double cutoff, int64_t maxdim) {
+    QIL_REQUIRE(W->n == psi->n, QIL_ERR_ARGUMENT,
+                "apply: MPO and MPS must have the same number of sites. Found length(W)=%d, length(psi)=%d", W->n, psi->n);
+    if (maxdim < 1) maxdim = (int64_t)1 << 62;
+    if (W->is_complex && psi->is_complex) return apply_zipup_t<cplx, cplx, cplx>(ctx, W, psi, cutoff, maxdim);
+    if (W->is_complex) return apply_zipup_t<cplx, double, cplx>(ctx, W, psi, cutoff, maxdim);
+    if (psi->is_complex) return apply_zipup_t<cplx, cplx, double>(ctx, W, psi, cutoff, maxdim);
+    return apply_zipup_t<double, double, double>(ctx, W, psi, cutoff, maxdim);
+}
+
 }  // namespace qil

@@ -39,6 +39,7 @@ qil_mps* ztmps_split(qil_ctx* ctx, const qil_mps* psi, double cutoff, int64_t ma
 void canonicalize(qil_ctx* ctx, qil_mps* psi, int dir_right, int center, double cutoff, int64_t maxdim);
 void compress(qil_ctx* ctx, qil_mps* psi, int64_t maxdim, double tol, int sweeps);
 double mps_norm(qil_ctx* ctx, const qil_mps* psi);
+qil_mps* apply_mpo_mps_zipup(qil_ctx* ctx, const qil_mpo* W, const qil_mps* psi, double cutoff, int64_t maxdim);
 // read-out reductions (qil_scan.cu)
 template <typename T> void argmax_abs(qil_ctx* ctx, const T* d_v, int64_t count, int64_t* index, double* absval, T* value);
 qil_mps* mps_sum_sites(qil_ctx* ctx, const qil_mps* psi, const uint8_t* mask);
