@@ -56,6 +56,7 @@ def parse():
                     help="N > 1: ONE signal row-sharded over the ranks (strong scaling, SURVEY.md 8e) instead of one "
                          "signal per rank (weak scaling, the default)")
     ap.add_argument("--cpu-n", type=int, default=0, help="n of the bounded CPU sample (default: n)")
+    ap.add_argument("--no-c5", action="store_true", help="skip the n=30 leg (BASELINE configs[4])")
     return ap.parse_args()
 
 
@@ -379,6 +380,66 @@ def c2_leg(q, ctx, torch, dev, timed, steps, hbm_peak, with_oracle):
         res["cpu_baseline"] = {"value": count * N / t_cpu, "unit": "samples/s", "kind": "port",
                                "sample": f"numpy oracle, encode only, all {count} signals, {t_cpu:.1f} s"}
     return res
+
+
+def c5_leg(q, ctx, torch, dev, timed, steps):
+    """BASELINE configs[4] / SURVEY 8d C5: n = 30 multi-tone decaying signal (multi_sin_exp surrogate with the parameters
+    of scripts/benchmark/common.jl:72), the reference's own headline zT benchmark (scripts/benchmark/zt_full_runtime.jl:
+    signal_ztmps(:rsvd k=15 p=5 q=2 cutoff=1e-15 maxdim=15) + zT apply, docs/src/benchmarking.md:307: 19.7 s on an M2 Max),
+    then the coarse -> fine -> superfine pole scan of docs/src/tutorials/zt.jl:296-415 with device arg-max."""
+    import numpy as np
+    n = 30
+    N = 2**n
+    free, _total = torch.cuda.mem_get_info(dev)
+    if free < 40 * 2**30:
+        return {"skipped": f"needs ~40 GiB of free HBM, {free / 2**30:.0f} GiB available"}
+    dt = 5.0 / N
+    nt = 10
+    ak = np.random.default_rng(1001).random(nt); ak /= np.linalg.norm(ak)
+    wk = (150.0 * dt) * (np.random.default_rng(2002).random(nt) - 0.5)
+    lk = -(2.0 * dt) * np.random.default_rng(4004).random(nt)
+    x = torch.zeros(N, dtype=torch.float64, device=dev)
+    chunk = 1 << 26
+    for s0 in range(0, N, chunk):                     # generated on the device in chunks (temporaries stay small)
+        j = torch.arange(s0, s0 + chunk, dtype=torch.float64, device=dev)
+        acc = torch.zeros(chunk, dtype=torch.float64, device=dev)
+        for a, w, l in zip(ak, wk, lk):
+            acc += float(a) * torch.sin(float(w) * j) * torch.exp(float(l) * j)
+        x[s0:s0 + chunk] = acc
+    del j, acc
+    kw = dict(k=15, p=5, q=2, cutoff=1e-15, maxdim=15)
+    t0 = time.perf_counter()
+    Wc = q.build_zt_mpo(n, 2 * math.pi, cutoff=1e-15, maxdim=512, ctx=ctx)
+    Wf = q.build_zt_mpo(n, 0.5, cutoff=1e-15, maxdim=512, ctx=ctx)
+    ctx.sync()
+    build_s = time.perf_counter() - t0
+    st = {}
+
+    def step():
+        psi = q.signal_mps_dev(ctx, x.data_ptr(), N, False, method="rsvd", **kw)
+        z = q.ztmps_from_mps(psi, cutoff=kw["cutoff"], maxdim=kw["maxdim"])
+        st["psi"], st["z"] = psi, z
+        st["out"] = q.apply(Wc, z)
+
+    for _ in range(2):
+        step()
+    ms = timed(step, steps) / steps
+    out_f = q.apply(Wf, st["z"])
+    torch.cuda.synchronize()
+    t0 = time.perf_counter()
+    peaks = q.pole_scan_driver(st["out"], out_f, 2 * math.pi, 0.5, step_coarse_log2=n - 8, r_window=(1 - 1e-6, 1.0),
+                               theta_window=(-2e-7, 2e-7), n_fine=128, half=24)
+    torch.cuda.synchronize()
+    scan_s = time.perf_counter() - t0
+    for v in peaks.values():
+        v["z"] = [v["z"].real, v["z"].imag]
+    return {"what": "n=30 multi_sin_exp surrogate (10 tones, dt=5/N, omega_scale=150): signal_ztmps(:rsvd k=15 p=5 q=2 "
+                    "cutoff=1e-15 maxdim=15) + zT apply (omega_r=2pi MPO cutoff 1e-15 maxdim 512, built in setup), then "
+                    "coarse(256x256, stride 2^22) -> fine(128x128 polar window) -> superfine(49x49) scan, arg-max on device",
+            "n": n, "ms_per_step": ms, "samples_per_s": N / (ms / 1e3), "mps_bonds": st["psi"].bonds,
+            "ztmps_max_bond": max(st["z"].bonds), "out_max_bond": max(st["out"].bonds), "zt_mpo_max_bond": max(Wc.bonds),
+            "zt_mpo_build_s_two_mpos": build_s, "scan_s": scan_s, "peaks": peaks,
+            "reference_published": "19.745 s (encode 19.6 + apply 0.147) on an Apple M2 Max, docs/src/benchmarking.md:307"}
 
 
 def run_ours(args):
@@ -818,6 +879,12 @@ def run_ours(args):
         except Exception as e:  # the baseline is reported, never required
             line["cpu_baseline"] = {"value": None, "unit": "samples/s", "cores": os.cpu_count() or 1, "kind": "port",
                                     "sample": f"failed: {e}"}
+    if not shard and world == 1 and n >= 28 and not args.no_c5:
+        try:
+            torch.cuda.empty_cache()
+            line["c5_n30"] = c5_leg(q, ctx, torch, dev, timed, max(3, min(args.steps, 5)))
+        except Exception as e:
+            line["c5_n30"] = {"error": f"{type(e).__name__}: {e}"}
     if rank == 0:
         print(json.dumps(line))
     if shard and args.comm == "peer":
