@@ -1,5 +1,7 @@
-# QILaplaceCUDA.jl -- the reference-side binding of libqilcuda.so (UNTESTED in this environment: Julia is not
-# installed in the build container; the identical C ABI is exercised by the Python ctypes harness).
+# QILaplaceCUDA.jl -- the reference-side binding of libqilcuda.so.  NON-FUNCTIONAL UNTIL RUN UNDER JULIA: Julia is not
+# installed in the build container, so this file has never been executed (round-1 review found four symbol / arity
+# mistakes in it, fixed in round 2 by reading the reference; there may be more).  The identical C ABI is exercised by the
+# Python ctypes harness.
 #
 # Drop this file into QILaplace.jl's `src/` and `include` it after `mps.jl`/`mpo.jl`.  It overrides the BODIES of
 # the hot-path functions; signatures, return types and exception types stay those of the reference.  ITensor
@@ -7,8 +9,10 @@
 module QILaplaceCUDA
 
 using ITensors, Random, Printf
+import LinearAlgebra
 using ..Mps: SignalMPS, ZTMPS, PairCore, _as_signal_2n, _writeback_signal_2n
 using ..Mpo: SingleSiteMPO, PairedSiteMPO
+using ..ApplyMPO: _as_single_site_mpo, _paired_from_single      # src/linalg/apply.jl:16-58
 
 const LIB = get(ENV, "QILCUDA_LIB", "libqilcuda.so")
 const CTX = Ref{Ptr{Cvoid}}(C_NULL)
@@ -108,7 +112,7 @@ function signal_mps(x::AbstractVector{<:Number}; method::Symbol=:svd, cutoff::Re
                      (Ptr{Cvoid}, Cint, Ptr{Cvoid}, Int64, Cint, Cint, Cint, Int64, Cdouble, Int64, Int64,
                       Ptr{Cvoid}, Int64, Int64, Ref{Ptr{Cvoid}}),
                      ctx(), _iscomplex(T), xv, length(xv), k, p, q, random_seed, cutoff, _maxdim(maxdim), mindim,
-                     stream, length(stream), 0, out))
+                     stream, length(stream), 0 #= flags: 1 = QIL_RSVD_ADAPTIVE (opt-in) =#, out))
     end
     return _download_mps(out[], sites)
 end
@@ -155,7 +159,7 @@ mps_to_vector(ψ::ZTMPS; reverse::Bool=false) = mps_to_vector(_as_signal_2n(ψ);
 # struct qil_comm { Cint rank; Cint world; Ptr{Cvoid} user; allreduce_sum_f64; allgather_f64 }: build it with
 #   @cfunction((user, buf, n) -> (NCCL.Allreduce!(unsafe_wrap(CuArray, Ptr{Float64}(buf), n), +, comm); Cint(0)), ...)
 # and call qil_encode_rsvd_sharded_dev(ctx, Ref(comm), is_complex, d_x_local, N_total, k, p, q, seed, cutoff,
-# maxdim, mindim, C_NULL, 0, out) on every rank; all ranks receive the same MPS handle contents.
+# maxdim, mindim, C_NULL, 0, flags, out) on every rank; all ranks receive the same MPS handle contents.
 
 # ---- MPO handles ---------------------------------------------------------------------------------------
 # C-order [l][p][s][r] (p = primed/input leg) is Julia's column-major Array(T, r, s, p, l)
@@ -212,8 +216,11 @@ function apply(W::SingleSiteMPO, ψ::SignalMPS; kwargs...)
     _check(rc)
     return _download_mps(out[], ψ.sites)
 end
-apply(W::PairedSiteMPO, ψ::ZTMPS; kwargs...) =
-    _writeback_signal_2n(apply(_as_single_site_mpo(W), _as_signal_2n(ψ)), ψ)          # apply.jl:201-218
+function apply(W::PairedSiteMPO, ψ::ZTMPS; kwargs...)                                 # apply.jl:201-218
+    result = _writeback_signal_2n(apply(_as_single_site_mpo(W), _as_signal_2n(ψ)))   # 1-argument method, mps.jl:447
+    result.amplitude = ψ.amplitude                                                   # apply.jl:214-217
+    return result
+end
 Base.:*(W::Union{SingleSiteMPO,PairedSiteMPO}, ψ::Union{SignalMPS,ZTMPS}) = apply(W, ψ)
 
 # ---- signal_ztmps (SignalConverters.jl:247-283): encode, then the copy-tensor split on the device --------------
@@ -231,7 +238,9 @@ function signal_ztmps(x::AbstractVector{<:Number}; cutoff::Real=1e-10, maxdim::I
         push!(flat_sites, Index(2; tags=@sprintf("site-main-%d", i)))
         push!(flat_sites, Index(2; tags=@sprintf("site-copy-%d", i)))
     end
-    return _writeback_signal_2n(_download_mps(out[], flat_sites), nothing)   # 2n-site chain -> ZTMPS (mps.jl:447-472)
+    result = _writeback_signal_2n(_download_mps(out[], flat_sites))          # 2n-site chain -> ZTMPS (mps.jl:447-472)
+    result.amplitude = ψ.amplitude
+    return result
 end
 
 # ---- canonicalize! / compress! / norm (src/mps.jl:754-999): in place on the handle, downloaded back ----------
@@ -244,7 +253,7 @@ function _inplace!(f::Function, ψ::SignalMPS)
     return ψ
 end
 function canonicalize!(ψ::SignalMPS, dir::Symbol; center::Int=0, cutoff::Real=1e-12, maxdim::Int=typemax(Int))
-    dir ∈ (:left, :right) || throw(DomainError(dir, "canonicalize!: direction must be :left or :right"))
+    dir ∈ (:left, :right) || throw(ArgumentError("Direction must be :right or :left"))      # mps.jl:794
     _inplace!(h -> ccall((:qil_canonicalize, LIB), Cint, (Ptr{Cvoid}, Ptr{Cvoid}, Cint, Cint, Cdouble, Int64),
                          ctx(), h, dir == :right ? 1 : 0, center, cutoff, _maxdim(maxdim)), ψ)
 end
@@ -253,7 +262,7 @@ function compress!(ψ::SignalMPS; maxdim::Int=typemax(Int), tol::Real=1e-12, swe
     _inplace!(h -> ccall((:qil_compress, LIB), Cint, (Ptr{Cvoid}, Ptr{Cvoid}, Int64, Cdouble, Cint),
                          ctx(), h, _maxdim(maxdim), tol, sweeps), ψ)
 end
-function LinearAlgebra_norm(ψ::SignalMPS)            # extend LinearAlgebra.norm with this body (mps.jl:754)
+function LinearAlgebra.norm(ψ::SignalMPS)            # mps.jl:754-771 (ignores `amplitude`)
     h = _upload(ψ); v = Ref{Cdouble}(0)
     rc = ccall((:qil_norm, LIB), Cint, (Ptr{Cvoid}, Ptr{Cvoid}, Ref{Cdouble}), ctx(), h, v)
     ccall((:qil_mps_free, LIB), Cint, (Ptr{Cvoid},), h)
@@ -280,7 +289,7 @@ function _build_paired(sym::Symbol, n::Int, ωr::Real, sites_main, sites_copy; c
     for i in 1:n
         push!(flat, sites_main[i]); push!(flat, sites_copy[i])
     end
-    return _as_paired_site_mpo(_download_mpo(out[], flat))        # 2n-site chain -> PairedSiteMPO (apply.jl:16-33)
+    return _paired_from_single(_download_mpo(out[], flat))        # 2n-site chain -> PairedSiteMPO (apply.jl:34-58)
 end
 build_dt_mpo(n::Int, ωr::Real, sm, sc; kw...) = _build_paired(:dt, n, ωr, sm, sc; kw...)
 build_zt_mpo(n::Int, ωr::Real, sm, sc; kw...) = _build_paired(:zt, n, ωr, sm, sc; kw...)

@@ -276,3 +276,55 @@ def test_zt_medium_matches_oracle(q):
     ref = np.array([np.sum(x * np.exp(-(2 * math.pi * k + 2j * math.pi * l) / 2**n * j)) / 2**n for k, l in zip(ks, ls)])
     # MPO truncated at cutoff 1e-12 on sigma^2: ~1e-6 of the operator norm
     assert np.abs(got - ref).max() <= 5e-5 * np.abs(ref).max()
+
+
+def test_builder_bond_series_extended(q, goldens):
+    """mpo_bond_dim.jld2 pins the max bond of the three builders for n = 2..30 (cutoff 1e-15, omega_r = 2 pi): QFT over
+    the whole range, DT / zT up to n = 16 / 12 here (the builds are sequences of thousands of dependent small SVDs)."""
+    g = goldens["mpo_max_bond_series"]
+    for n in range(2, 31):
+        assert max(q.build_qft_mpo(n, cutoff=1e-15, maxdim=None).bonds) == g["qft"][n - g["n_start"]], n
+    for n in range(8, 17):
+        assert max(q.build_dt_mpo(n, 2 * math.pi, cutoff=1e-15, maxdim=None).bonds) == g["dt"][n - g["n_start"]], n
+    for n in range(7, 13):
+        assert max(q.build_zt_mpo(n, 2 * math.pi, cutoff=1e-15, maxdim=None).bonds) == g["zt"][n - g["n_start"]], n
+
+
+def test_bench_zt_mpo_n28_bonds_match_oracle(q):
+    """The zT MPO the bench applies (n = 28, omega_r = 2 pi, cutoff 1e-12, maxdim 128): bond list identical to the oracle's
+    build, and the two operators agree on a product state."""
+    n = 28
+    W = q.build_zt_mpo(n, 2 * math.pi, cutoff=1e-12, maxdim=128)
+    Wo = O.build_zt_mpo(n, 2 * math.pi, cutoff=1e-12, maxdim=128)
+    assert W.bonds == O.mpo_bonds(Wo)
+    # <bits| W |product state> through both operators: contract the 2n-site chains with fixed in/out bits
+    rng = np.random.default_rng(0)
+    cores = W.cores()
+    for _ in range(8):
+        bi = rng.integers(0, 2, 2 * n)
+        bo = rng.integers(0, 2, 2 * n)
+        va, vb = np.ones(1, dtype=complex), np.ones(1, dtype=complex)
+        for i in range(2 * n):
+            va = va @ cores[i][:, bi[i], bo[i], :]
+            vb = vb @ Wo[i][:, bi[i], bo[i], :]
+        assert abs(va[0] - vb[0]) <= 1e-8 * max(abs(vb[0]), 1e-3)
+
+
+@pytest.mark.parametrize("n", [20, 22])
+def test_encode_svd_sequential_large(q, n):
+    """signal_mps(:svd) (SignalConverters.jl:49-104) beyond the quick-start size: bonds and amplitudes against the
+    oracle's sequential TT-SVD on the structured bench signal."""
+    N = 2**n
+    t = np.arange(N) / (2.5 * N)
+    x = np.sin(t) * np.exp(-0.08 * t) + np.sin(2.5 * t) * np.exp(-0.03 * t)
+    import time
+    t0 = time.perf_counter()
+    psi = q.signal_mps(x, method="svd", cutoff=1e-12)
+    dt_gpu = time.perf_counter() - t0
+    co, c = O.tt_svd(x, cutoff=1e-12)
+    assert psi.bonds == O.bonds_of(co)
+    rng = np.random.default_rng(n)
+    idx = rng.integers(0, N, 2048)
+    bits = ((idx[:, None] >> np.arange(n - 1, -1, -1)[None, :]) & 1).astype(np.uint8)
+    assert np.abs(q.coefficients(psi, bits) - O.coefficient_batch(co, c, bits)).max() <= 1e-10 * np.abs(x).max()
+    print(f"signal_mps(:svd) n={n}: {dt_gpu * 1e3:.1f} ms incl. upload")
