@@ -203,7 +203,7 @@ static Mat<T> mul_A(SplitCtx<T>& sc, const T* A, int64_t R, int64_t C, int l, co
         stream_plan(ctx, R, C * F, &ks, &kc);
         Mat<double> part(ctx, (int64_t)ks * R, nt * 8);
         Mat<double> ssq;
-        const int grid = stream_grid(ctx, R, ks);
+        const int grid = stream_grid(ctx, R, ks, nt);
         if (want_sumsq) ssq = Mat<double>(ctx, grid, 1);
         stream_gemm(ctx, false, reinterpret_cast<const double*>(A), R, C * F, C * F, X.p, lpp, nt, part.p, ks, kc,
                     want_sumsq ? ssq.p : nullptr, l * F);
@@ -391,7 +391,7 @@ static int rsvd_split_fused(SplitCtx<double>& sc, const double* A, int64_t R, in
     QIL_LAUNCH_CHECK(ctx);
     const bool want_sumsq = top && !sc.nrm_ready;
     Mat<double> ssq;
-    const int grid1 = stream_grid(ctx, R, ks1);
+    const int grid1 = stream_grid(ctx, R, ks1, nt);
     if (want_sumsq) ssq = Mat<double>(ctx, grid1, 1);
     stream_gemm(ctx, false, A, R, C, C, XC.p, lpp, nt, partR.p, ks1, kc1, want_sumsq ? ssq.p : nullptr, l0);
     if (want_sumsq) {
