@@ -382,6 +382,48 @@ def c2_leg(q, ctx, torch, dev, timed, steps, hbm_peak, with_oracle):
     return res
 
 
+def fp64_regime_leg(q, ctx, torch, dev, x_dev, n):
+    """The regimes where the FP64 tensor pipe, not HBM, bounds the streaming GEMM: the reference's kernel
+    benchmark setting k=100 p=5 q=2 (scripts/benchmark/svd_rsvd_itensor.jl:23-26; l = 105 sketch columns, 2.2 s per split
+    on an M2 Max) on the real n-qubit signal, and the C3 complex pole signal with k=50 p=5 (l = 55 complex = 110 real
+    columns) and k=100 (column panels).  Reports the streaming kernel's FLOP rate from the library's per-launch events."""
+    import math
+    res = {}
+    cases = [("k100_real", x_dev, n, False, dict(k=100, p=5, q=2, cutoff=1e-12))]
+    nc = min(n, 26)
+    Nc = 2**nc
+    j = torch.arange(Nc, dtype=torch.float64, device=dev)
+    sc = 2.0 ** (20 - nc)
+    la = complex(math.log(1.00015), 0.002)
+    xc = torch.exp(j * sc * torch.tensor(la, dtype=torch.complex128, device=dev)) * torch.cos(0.0061 * j * sc)
+    del j
+    cases.append(("k50_complex_c3", xc, nc, True, dict(k=50, p=5, q=2, cutoff=1e-12, maxdim=128)))
+    cases.append(("k100_complex_c3", xc, nc, True, dict(k=100, p=5, q=2, cutoff=1e-12)))
+    for name, x, nn, cplx, kw in cases:
+        NN = 2**nn
+        try:
+            q.signal_mps_dev(ctx, x.data_ptr(), NN, cplx, method="rsvd", **kw)          # warm-up
+            ctx.profile_reset(); ctx.profile_enable(True)
+            e0 = torch.cuda.Event(enable_timing=True); e1 = torch.cuda.Event(enable_timing=True)
+            torch.cuda.synchronize()
+            e0.record()
+            reps = 3
+            for _ in range(reps):
+                psi = q.signal_mps_dev(ctx, x.data_ptr(), NN, cplx, method="rsvd", **kw)
+            e1.record()
+            torch.cuda.synchronize()
+            g_ms, g_cnt, g_bytes, g_flops = ctx.profile_read_work(0)
+            ctx.profile_enable(False); ctx.profile_reset()
+            tf = g_flops / (g_ms / 1e3) / 1e12 if g_ms else None
+            res[name] = {"n": nn, "complex": cplx, "k": kw["k"], "p": kw["p"], "q": kw["q"],
+                         "encode_ms": e0.elapsed_time(e1) / reps, "stream_gemm_ms_per_encode": g_ms / reps,
+                         "stream_gemm_launches_per_encode": g_cnt / reps, "stream_gemm_tflops": tf,
+                         "fp64_frac_of_37.1": tf / 37.1 if tf else None, "max_bond": max(psi.bonds)}
+        except Exception as e:
+            res[name] = {"error": f"{type(e).__name__}: {e}"}
+    return res
+
+
 def c5_leg(q, ctx, torch, dev, timed, steps):
     """BASELINE configs[4] / SURVEY 8d C5: n = 30 multi-tone decaying signal (multi_sin_exp surrogate with the parameters
     of scripts/benchmark/common.jl:72), the reference's own headline zT benchmark (scripts/benchmark/zt_full_runtime.jl:
@@ -879,6 +921,11 @@ def run_ours(args):
         except Exception as e:  # the baseline is reported, never required
             line["cpu_baseline"] = {"value": None, "unit": "samples/s", "cores": os.cpu_count() or 1, "kind": "port",
                                     "sample": f"failed: {e}"}
+    if not shard and world == 1 and n >= 24:
+        try:
+            line["fp64_regime"] = fp64_regime_leg(q, ctx, torch, dev, x_dev, n)
+        except Exception as e:
+            line["fp64_regime"] = {"error": f"{type(e).__name__}: {e}"}
     if not shard and world == 1 and n >= 28 and not args.no_c5:
         try:
             torch.cuda.empty_cache()

@@ -38,7 +38,7 @@ __global__ void omega_dense_kernel(const T* stream, unsigned long long seed, lon
 // where S is Omega (src == nullptr) or a dense C x l matrix (src, ld = l).
 template <typename T>
 __global__ void prep_x_k1_kernel(const T* src, const T* stream, unsigned long long seed, long long C, int l,
-                                 long long rows_pad, int lpp, double* X) {
+                                 long long rows_pad, int lpp, double* X, int j0 = 0, int ldsrc = 0) {
     constexpr int F = Scalar<T>::is_complex ? 2 : 1;
     const long long total = rows_pad * lpp;
     for (long long idx = (long long)blockIdx.x * blockDim.x + threadIdx.x; idx < total;
@@ -49,7 +49,7 @@ __global__ void prep_x_k1_kernel(const T* src, const T* stream, unsigned long lo
         const int j = col / F;
         double v = 0.0;
         if (c < C && j < l) {
-            const T s = src ? src[c * l + j] : stream_at<T>(stream, seed, c + C * j);
+            const T s = src ? src[c * (long long)(ldsrc ? ldsrc : l) + j0 + j] : stream_at<T>(stream, seed, c + C * (long long)(j0 + j));
             if (F == 1) {
                 v = Scalar<T>::real(s);
             } else {
@@ -65,7 +65,8 @@ __global__ void prep_x_k1_kernel(const T* src, const T* stream, unsigned long lo
 
 // K2 operand: X[r][.] = Q[r][.] viewed as real (R x F*l), zero padded to rows_pad x lpp
 template <typename T>
-__global__ void prep_x_k2_kernel(const T* Q, long long R, int l, long long rows_pad, int lpp, double* X) {
+__global__ void prep_x_k2_kernel(const T* Q, long long R, int l, long long rows_pad, int lpp, double* X, int j0 = 0,
+                                 int ldq = 0) {
     constexpr int F = Scalar<T>::is_complex ? 2 : 1;
     const double* q = reinterpret_cast<const double*>(Q);
     const long long total = rows_pad * lpp;
@@ -73,13 +74,13 @@ __global__ void prep_x_k2_kernel(const T* Q, long long R, int l, long long rows_
          idx += (long long)gridDim.x * blockDim.x) {
         const long long r = idx / lpp;
         const int col = (int)(idx - r * lpp);
-        X[idx] = (r < R && col < F * l) ? q[r * (long long)(F * l) + col] : 0.0;
+        X[idx] = (r < R && col < F * l) ? q[r * (long long)(F * (ldq ? ldq : l)) + F * j0 + col] : 0.0;
     }
 }
 
 // Y (R x l, dense T) = sum_ks part[ks][r][.]  (K1: complex output is already interleaved)
 template <typename T>
-__global__ void reduce_k1_kernel(const double* part, int ksplit, long long R, int ldo, int l, T* Y) {
+__global__ void reduce_k1_kernel(const double* part, int ksplit, long long R, int ldo, int l, T* Y, int j0 = 0, int ldy = 0) {
     constexpr int F = Scalar<T>::is_complex ? 2 : 1;
     double* y = reinterpret_cast<double*>(Y);
     const long long total = R * l * F;
@@ -89,7 +90,7 @@ __global__ void reduce_k1_kernel(const double* part, int ksplit, long long R, in
         const int col = (int)(idx - r * (l * F));
         double s = 0.0;
         for (int ks = 0; ks < ksplit; ++ks) s += part[((long long)ks * R + r) * ldo + col];
-        y[idx] = s;
+        y[r * (long long)(F * (ldy ? ldy : l)) + F * j0 + col] = s;
     }
 }
 
@@ -97,7 +98,7 @@ __global__ void reduce_k1_kernel(const double* part, int ksplit, long long R, in
 //   Zr[c][j] = Z'[2c][2j] + Z'[2c+1][2j+1],  Zi[c][j] = Z'[2c][2j+1] - Z'[2c+1][2j]
 template <typename T>
 __global__ void reduce_k2_kernel(const double* part, int ksplit, long long C, int ldo, int l, const double* scale,
-                                 T* Z) {
+                                 T* Z, int j0 = 0, int ldz = 0) {
     constexpr int F = Scalar<T>::is_complex ? 2 : 1;
     const double sc = scale ? scale[0] : 1.0;
     const long long Mtot = C * F;
@@ -109,7 +110,7 @@ __global__ void reduce_k2_kernel(const double* part, int ksplit, long long C, in
         if (F == 1) {
             double s = 0.0;
             for (int ks = 0; ks < ksplit; ++ks) s += part[((long long)ks * Mtot + c) * ldo + j];
-            reinterpret_cast<double*>(Z)[idx] = s * sc;
+            reinterpret_cast<double*>(Z)[c * (long long)(ldz ? ldz : l) + j0 + j] = s * sc;
         } else {
             double re = 0.0, im = 0.0;
             for (int ks = 0; ks < ksplit; ++ks) {
@@ -118,8 +119,9 @@ __global__ void reduce_k2_kernel(const double* part, int ksplit, long long C, in
                 re += p0[0] + p1[1];
                 im += p0[1] - p1[0];
             }
-            reinterpret_cast<double*>(Z)[2 * idx] = re * sc;
-            reinterpret_cast<double*>(Z)[2 * idx + 1] = im * sc;
+            const long long zo = c * (long long)(ldz ? ldz : l) + j0 + j;
+            reinterpret_cast<double*>(Z)[2 * zo] = re * sc;
+            reinterpret_cast<double*>(Z)[2 * zo + 1] = im * sc;
         }
     }
 }
@@ -191,36 +193,42 @@ static Mat<T> mul_A(SplitCtx<T>& sc, const T* A, int64_t R, int64_t C, int l, co
     qil_ctx* ctx = sc.ctx;
     constexpr int F = Scalar<T>::is_complex ? 2 : 1;
     Mat<T> Y(ctx, R, l);
-    if (stream_supported(R, C * F, C * F, l * F)) {
-        const int nt = stream_nt_for(l * F);
-        const int lpp = stream_lpp(nt);
-        const int64_t rows_pad = (C * F + 31) / 32 * 32;
-        Mat<double> X(ctx, rows_pad, lpp);
-        prep_x_k1_kernel<T><<<grid_for(ctx, rows_pad * lpp), 256, 0, ctx->stream>>>(
-            Xsrc, sc.stream, (unsigned long long)sc.o->seed, C, l, rows_pad, lpp, X.p);
-        QIL_LAUNCH_CHECK(ctx);
-        int ks; long long kc;
-        stream_plan(ctx, R, C * F, &ks, &kc);
-        Mat<double> part(ctx, (int64_t)ks * R, nt * 8);
-        Mat<double> ssq;
-        const int grid = stream_grid(ctx, R, ks, nt);
-        if (want_sumsq) ssq = Mat<double>(ctx, grid, 1);
-        stream_gemm(ctx, false, reinterpret_cast<const double*>(A), R, C * F, C * F, X.p, lpp, nt, part.p, ks, kc,
-                    want_sumsq ? ssq.p : nullptr, l * F);
-        reduce_k1_kernel<T><<<grid_for(ctx, R * l * F), 256, 0, ctx->stream>>>(part.p, ks, R, nt * 8, l, Y.p);
-        QIL_LAUNCH_CHECK(ctx);
-        if (want_sumsq && sc.comm) {
-            // ||x||^2 = sum over ranks of the local sums (8-byte all-reduce)
-            sum_partials_kernel<<<1, 32, 0, ctx->stream>>>(ssq.p, grid, sc.d_nrm);
+    const int lw_max = 112 / F;                         // sketch columns per streaming launch (14 column tiles of 8)
+    if (stream_supported(R, C * F, C * F, std::min(l, lw_max) * F)) {
+        // wider sketches (k = 100: l = 105 real, 210 real columns when complex) go through in column panels
+        for (int j0 = 0; j0 < l; j0 += lw_max) {
+            const int lw = std::min(lw_max, l - j0);
+            const bool sumsq_now = want_sumsq && j0 == 0;
+            const int nt = stream_nt_for(lw * F);
+            const int lpp = stream_lpp(nt);
+            const int64_t rows_pad = (C * F + 31) / 32 * 32;
+            Mat<double> X(ctx, rows_pad, lpp);
+            prep_x_k1_kernel<T><<<grid_for(ctx, rows_pad * lpp), 256, 0, ctx->stream>>>(
+                Xsrc, sc.stream, (unsigned long long)sc.o->seed, C, lw, rows_pad, lpp, X.p, j0, l);
             QIL_LAUNCH_CHECK(ctx);
-            comm_allreduce(sc.comm, sc.d_nrm, 1);
-            norm_from_sumsq_kernel<<<1, 32, 0, ctx->stream>>>(sc.d_nrm);
+            int ks; long long kc;
+            stream_plan(ctx, R, C * F, &ks, &kc);
+            Mat<double> part(ctx, (int64_t)ks * R, nt * 8);
+            Mat<double> ssq;
+            const int grid = stream_grid(ctx, R, ks, nt);
+            if (sumsq_now) ssq = Mat<double>(ctx, grid, 1);
+            stream_gemm(ctx, false, reinterpret_cast<const double*>(A), R, C * F, C * F, X.p, lpp, nt, part.p, ks, kc,
+                        sumsq_now ? ssq.p : nullptr, lw * F);
+            reduce_k1_kernel<T><<<grid_for(ctx, R * lw * F), 256, 0, ctx->stream>>>(part.p, ks, R, nt * 8, lw, Y.p, j0, l);
             QIL_LAUNCH_CHECK(ctx);
-            sc.nrm_ready = true;
-        } else if (want_sumsq) {
-            finalize_norm_kernel<<<1, 32, 0, ctx->stream>>>(ssq.p, grid, sc.d_nrm);
-            QIL_LAUNCH_CHECK(ctx);
-            sc.nrm_ready = true;
+            if (sumsq_now && sc.comm) {
+                // ||x||^2 = sum over ranks of the local sums (8-byte all-reduce)
+                sum_partials_kernel<<<1, 32, 0, ctx->stream>>>(ssq.p, grid, sc.d_nrm);
+                QIL_LAUNCH_CHECK(ctx);
+                comm_allreduce(sc.comm, sc.d_nrm, 1);
+                norm_from_sumsq_kernel<<<1, 32, 0, ctx->stream>>>(sc.d_nrm);
+                QIL_LAUNCH_CHECK(ctx);
+                sc.nrm_ready = true;
+            } else if (sumsq_now) {
+                finalize_norm_kernel<<<1, 32, 0, ctx->stream>>>(ssq.p, grid, sc.d_nrm);
+                QIL_LAUNCH_CHECK(ctx);
+                sc.nrm_ready = true;
+            }
         }
     } else {
         Mat<T> Om;
@@ -243,19 +251,23 @@ static Mat<T> mul_AH(SplitCtx<T>& sc, const T* A, int64_t R, int64_t C, int l, c
     qil_ctx* ctx = sc.ctx;
     constexpr int F = Scalar<T>::is_complex ? 2 : 1;
     Mat<T> Z(ctx, C, l);
-    if (stream_supported(R, C * F, C * F, l * F)) {
-        const int nt = stream_nt_for(l * F);
-        const int lpp = stream_lpp(nt);
-        const int64_t rows_pad = (R + 31) / 32 * 32;
-        Mat<double> X(ctx, rows_pad, lpp);
-        prep_x_k2_kernel<T><<<grid_for(ctx, rows_pad * lpp), 256, 0, ctx->stream>>>(Q, R, l, rows_pad, lpp, X.p);
-        QIL_LAUNCH_CHECK(ctx);
-        int ks; long long kc;
-        stream_plan(ctx, C * F, R, &ks, &kc);
-        Mat<double> part(ctx, (int64_t)ks * C * F, nt * 8);
-        stream_gemm(ctx, true, reinterpret_cast<const double*>(A), R, C * F, C * F, X.p, lpp, nt, part.p, ks, kc, nullptr, l * F);
-        reduce_k2_kernel<T><<<grid_for(ctx, C * l), 256, 0, ctx->stream>>>(part.p, ks, C, nt * 8, l, scale, Z.p);
-        QIL_LAUNCH_CHECK(ctx);
+    const int lw_max = 112 / F;
+    if (stream_supported(R, C * F, C * F, std::min(l, lw_max) * F)) {
+        for (int j0 = 0; j0 < l; j0 += lw_max) {
+            const int lw = std::min(lw_max, l - j0);
+            const int nt = stream_nt_for(lw * F);
+            const int lpp = stream_lpp(nt);
+            const int64_t rows_pad = (R + 31) / 32 * 32;
+            Mat<double> X(ctx, rows_pad, lpp);
+            prep_x_k2_kernel<T><<<grid_for(ctx, rows_pad * lpp), 256, 0, ctx->stream>>>(Q, R, lw, rows_pad, lpp, X.p, j0, l);
+            QIL_LAUNCH_CHECK(ctx);
+            int ks; long long kc;
+            stream_plan(ctx, C * F, R, &ks, &kc);
+            Mat<double> part(ctx, (int64_t)ks * C * F, nt * 8);
+            stream_gemm(ctx, true, reinterpret_cast<const double*>(A), R, C * F, C * F, X.p, lpp, nt, part.p, ks, kc, nullptr, lw * F);
+            reduce_k2_kernel<T><<<grid_for(ctx, C * lw), 256, 0, ctx->stream>>>(part.p, ks, C, nt * 8, lw, scale, Z.p, j0, l);
+            QIL_LAUNCH_CHECK(ctx);
+        }
     } else {
         gemm<T>(ctx, OP_C, OP_N, C, l, R, 1.0, A, C, Q, l, 0.0, Z.p, l);
         if (scale) {

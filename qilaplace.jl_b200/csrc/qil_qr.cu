@@ -183,6 +183,88 @@ static void launch_hhqr(qil_ctx* ctx, const QrParams<T>& p, int max_mloc, bool u
     QIL_LAUNCH_CHECK(ctx);
 }
 
+
+// ---- blocked QR for tall panels wider than the TSQR's 32 columns (k = 100 sketches: l = 105, complex l = 55) ------------
+// Block classical Gram-Schmidt with reorthogonalisation ("twice is enough") over panels of <= 32 (complex: 16) columns,
+// each panel factored by the Householder TSQR:  P <- P - Q (Q^H P) twice, then P = Qp Rp.  The inner products Q^H P are
+// m-long reductions with a handful of outputs: row chunks per CTA, fixed-order second stage (deterministic).
+template <typename T>
+__global__ void __launch_bounds__(256) tall_inner_kernel(const T* __restrict__ Q, long long ldq, int c0, const T* __restrict__ P,
+                                                         long long ldp, int w, long long m, int rows_per, T* __restrict__ part) {
+    extern __shared__ __align__(16) unsigned char smem_raw[];
+    T* sq = reinterpret_cast<T*>(smem_raw);          // [rows][c0]
+    T* sp = sq + (size_t)rows_per * c0;              // [rows][w]
+    const long long r0 = (long long)blockIdx.x * rows_per;
+    const int rows = (int)min((long long)rows_per, m - r0);
+    for (int idx = threadIdx.x; idx < rows * c0; idx += blockDim.x) {
+        const int r = idx / c0, i = idx - r * c0;
+        sq[idx] = Q[(r0 + r) * ldq + i];
+    }
+    for (int idx = threadIdx.x; idx < rows * w; idx += blockDim.x) {
+        const int r = idx / w, j = idx - r * w;
+        sp[idx] = P[(r0 + r) * ldp + j];
+    }
+    __syncthreads();
+    T* out = part + (size_t)blockIdx.x * c0 * w;
+    for (int idx = threadIdx.x; idx < c0 * w; idx += blockDim.x) {
+        const int j = idx / c0, i = idx - j * c0;     // consecutive threads: consecutive i (contiguous in sq rows)
+        T acc = Scalar<T>::zero();
+        for (int r = 0; r < rows; ++r) acc = Scalar<T>::fma(Scalar<T>::conj(sq[r * c0 + i]), sp[r * w + j], acc);
+        out[(size_t)i * w + j] = acc;
+    }
+}
+// S (c0 x w, ld lds) = sum of the chunk partials (fixed order); R block (ld ldr) accumulates it
+template <typename T>
+__global__ void tall_inner_reduce_kernel(const T* __restrict__ part, int nchunks, int c0, int w, T* __restrict__ S,
+                                         T* __restrict__ Rblk, long long ldr, int accumulate) {
+    for (int idx = blockIdx.x * blockDim.x + threadIdx.x; idx < c0 * w; idx += gridDim.x * blockDim.x) {
+        T acc = Scalar<T>::zero();
+        for (int c = 0; c < nchunks; ++c) acc = Scalar<T>::add(acc, part[(size_t)c * c0 * w + idx]);
+        S[idx] = acc;
+        const int i = idx / w, j = idx - i * w;
+        T* r = Rblk + (long long)i * ldr + j;
+        *r = accumulate ? Scalar<T>::add(*r, acc) : acc;
+    }
+}
+
+template <typename T>
+static void qr_blocked_tall(qil_ctx* ctx, int64_t m, int n, const T* A, int64_t lda, bool positive, Mat<T>& Q, Mat<T>& R,
+                            int nsum, int64_t sum_stride) {
+    const int bw = Scalar<T>::is_complex ? 16 : 32;
+    Q = Mat<T>(ctx, m, n);
+    R = Mat<T>(ctx, n, n);
+    QIL_CUDA(cudaMemsetAsync(R.p, 0, (size_t)n * n * sizeof(T), ctx->stream));
+    const size_t budget = std::min<size_t>(ctx->smem_optin, 200 * 1024);
+    int rows_per = 128;
+    while (rows_per > 16 && (size_t)rows_per * (n + bw) * sizeof(T) > budget) rows_per >>= 1;
+    const int nchunks = (int)((m + rows_per - 1) / rows_per);
+    Mat<T> part(ctx, (int64_t)nchunks * n, bw), S(ctx, n, bw), P(ctx, m, bw), Rp(ctx, bw, bw);
+    for (int c0 = 0; c0 < n; c0 += bw) {
+        const int w = std::min(bw, n - c0);
+        // P = A[:, c0:c0+w]
+        if (nsum == 1) {
+            QIL_CUDA(cudaMemcpy2DAsync(P.p, (size_t)w * sizeof(T), A + c0, (size_t)lda * sizeof(T), (size_t)w * sizeof(T),
+                                       (size_t)m, cudaMemcpyDeviceToDevice, ctx->stream));
+        } else {
+            QIL_THROW(QIL_ERR_UNSUPPORTED, "blocked qr: partial-sum input is not supported");
+        }
+        for (int rep = 0; rep < 2 && c0 > 0; ++rep) {
+            const size_t smem = (size_t)rows_per * (c0 + w) * sizeof(T);
+            auto kern = tall_inner_kernel<T>;
+            ensure_dynamic_smem(kern, smem);
+            kern<<<nchunks, 256, smem, ctx->stream>>>(Q.p, n, c0, P.p, w, w, m, rows_per, part.p);
+            QIL_LAUNCH_CHECK(ctx);
+            tall_inner_reduce_kernel<T><<<(c0 * w + 255) / 256, 256, 0, ctx->stream>>>(part.p, nchunks, c0, w, S.p, R.p + c0, n, rep);
+            QIL_LAUNCH_CHECK(ctx);
+            // P -= Q[:, :c0] S
+            gemm<T>(ctx, OP_N, OP_N, m, w, c0, -1.0, Q.p, n, S.p, w, 1.0, P.p, w);
+        }
+        qr_fast<T>(ctx, m, w, P.p, w, 1, 0, positive, Q.p + c0, n, w, Rp.p);
+        QIL_CUDA(cudaMemcpy2DAsync(R.p + (size_t)c0 * n + c0, (size_t)n * sizeof(T), Rp.p, (size_t)w * sizeof(T),
+                                   (size_t)w * sizeof(T), (size_t)w, cudaMemcpyDeviceToDevice, ctx->stream));
+    }
+}
+
 template <typename T>
 void qr_thin(qil_ctx* ctx, int64_t m, int64_t n64, const T* A, int64_t lda, bool positive, Mat<T>& Q, Mat<T>& R,
              int nsum, int64_t sum_stride, bool want_q) {
@@ -201,6 +283,17 @@ void qr_thin(qil_ctx* ctx, int64_t m, int64_t n64, const T* A, int64_t lda, bool
         qr_fast<T>(ctx, m, n, A, lda, nsum, sum_stride, positive, Qf.p, n, n, R.p);
         if (want_q) Q = std::move(Qf);
         return;
+    }
+    {
+        // tall panels wider than the TSQR limit: block Gram-Schmidt over TSQR panels
+        const int bw = Scalar<T>::is_complex ? 16 : 32;
+        if (n > bw && n <= 512 && m >= 8 * (int64_t)n && nsum == 1 && qr_fast_supported<T>(ctx, m, bw) &&
+            (size_t)16 * (n + bw) * sizeof(T) <= std::min<size_t>(ctx->smem_optin, 200 * 1024)) {
+            Mat<T> Qb;
+            qr_blocked_tall<T>(ctx, m, n, A, lda, positive, Qb, R, nsum, sum_stride);
+            if (want_q) Q = std::move(Qb);
+            return;
+        }
     }
     const int cap = qr_capacity<T>(ctx, n);
     const int64_t k = std::min<int64_t>(m, n);
