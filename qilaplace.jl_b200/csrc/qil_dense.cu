@@ -189,7 +189,10 @@ template <typename T>
 __global__ void transpose_conj_kernel(long long m, long long n, const T* __restrict__ A, long long lda,
                                       T* __restrict__ B, long long ldb, int conj) {
     __shared__ T tile[32][33];
-    const long long i0 = (long long)blockIdx.y * 32, j0 = (long long)blockIdx.x * 32;
+    // tiles are numbered linearly on blockIdx.x (grid.y is limited to 65535: a 2 x 2^21 step of the sequential TT-SVD
+    // at n = 22 has more row tiles than that)
+    const long long tiles_x = (n + 31) / 32;
+    const long long i0 = ((long long)blockIdx.x / tiles_x) * 32, j0 = ((long long)blockIdx.x % tiles_x) * 32;
     for (int r = threadIdx.y; r < 32; r += blockDim.y) {
         const long long i = i0 + r, j = j0 + threadIdx.x;
         if (i < m && j < n) tile[r][threadIdx.x] = conj ? Scalar<T>::conj(A[i * lda + j]) : A[i * lda + j];
@@ -203,7 +206,9 @@ __global__ void transpose_conj_kernel(long long m, long long n, const T* __restr
 template <typename T>
 void transpose_conj(qil_ctx* ctx, int64_t m, int64_t n, const T* A, int64_t lda, T* B, int64_t ldb, bool conj) {
     if (m * n == 0) return;
-    dim3 grid((unsigned)((n + 31) / 32), (unsigned)((m + 31) / 32)), block(32, 8);
+    const long long tiles = ((n + 31) / 32) * ((m + 31) / 32);
+    QIL_REQUIRE(tiles < ((long long)1 << 31), QIL_ERR_UNSUPPORTED, "transpose: matrix too large");
+    dim3 grid((unsigned)tiles), block(32, 8);
     transpose_conj_kernel<T><<<grid, block, 0, ctx->stream>>>(m, n, A, lda, B, ldb, conj ? 1 : 0);
     QIL_LAUNCH_CHECK(ctx);
 }
