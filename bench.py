@@ -592,8 +592,9 @@ def run_ours(args):
 
     x_stage = torch.empty(NL, dtype=torch.float64, device=dev) if shard else None
     cores_pin = torch.empty(256 << 20, dtype=torch.uint8, pin_memory=True)     # host landing zone of the result cores
-    from qilaplace_b200.parallel import SignalUploader
-    uploader = None if shard else SignalUploader(ctx, N, is_complex=False)
+    # the staging ring lives behind the C ABI (qil_uploader_*): no torch streams / tensors on the e2e path
+    uploader = None if shard else q.Uploader(ctx, 8 * N)
+    x_pin_ptr, x_pin_bytes = x_pin.data_ptr(), 8 * NL
 
     def step_e2e():
         # the calls a user streaming host signals makes: every step uploads ITS signal from pinned host memory
@@ -604,9 +605,9 @@ def run_ours(args):
             psi = encode_dev(x_stage.data_ptr())
         else:
             if uploader.inflight == 0:
-                uploader.submit(x_pin)                                    # first step: nothing prefetched yet
+                uploader.submit(x_pin_ptr, x_pin_bytes)                   # first step: nothing prefetched yet
             d_x = uploader.acquire()
-            uploader.submit(x_pin)                                        # next step's input (same synthetic signal)
+            uploader.submit(x_pin_ptr, x_pin_bytes)                       # next step's input (same synthetic signal)
             psi = q.signal_mps_dev(ctx, d_x, N, False, method="rsvd", **ALGO)
             uploader.release()
         z = q.ztmps_from_mps(psi, cutoff=ALGO["cutoff"])
@@ -741,12 +742,15 @@ def run_ours(args):
     for _ in range(2):
         step_e2e()
     log("e2e warm-up done")
-    drain = None if shard else (lambda: torch.cuda.current_stream().wait_stream(uploader.copy_stream))
+    def drain_uploader():
+        # the upload the last step started is awaited inside the timed region (acquire makes the stream wait for it)
+        uploader.acquire(); uploader.release()
+    drain = None if shard else drain_uploader
     ms_e2e = timed(step_e2e, args.steps, drain)
     ms_e2e_serial = None
     if not shard:
-        # drain the prefetched buffer so that it is not counted for anybody, then the unpipelined variant
-        uploader.acquire(); uploader.release(); torch.cuda.synchronize()
+        # (the prefetched buffer was drained inside the timed region) then the unpipelined variant
+        torch.cuda.synchronize()
         step_e2e_serial()
         ms_e2e_serial = timed(step_e2e_serial, args.steps) / args.steps
     log(f"e2e encode leg timed: {ms_e2e / args.steps:.3f} ms/step (unpipelined {ms_e2e_serial})")
@@ -818,7 +822,7 @@ def run_ours(args):
         "e2e": {"value": e2e_value, "unit": "samples/s", "ms_per_step": ms_e2e / args.steps,
                 "h2d_bytes_per_step": int(8 * NL), "d2h_bytes_per_step": host_bytes,
                 "pipelining": ("none (sharded: every rank uploads its chunk, then encodes)" if shard else
-                               "double-buffered upload (parallel.SignalUploader): step i+1's signal crosses PCIe while "
+                               "double-buffered upload behind the C ABI (qil_uploader_*): step i+1's signal crosses PCIe while "
                                "step i encodes; K uploads, K encodes and K read-backs complete inside the timed region "
                                "(the first encode consumes the upload the last warm-up step started, the K-th step's "
                                "upload is awaited before the region closes)"),

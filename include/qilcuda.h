@@ -44,6 +44,7 @@ typedef struct qil_ctx qil_ctx;
 typedef struct qil_mps qil_mps;
 typedef struct qil_mpo qil_mpo;
 typedef struct qil_peer qil_peer;
+typedef struct qil_uploader qil_uploader;
 
 /* ---- context ------------------------------------------------------------------------------- */
 const char* qil_last_error(void);
@@ -114,6 +115,25 @@ int qil_coefficient_batch_dev(qil_ctx* ctx, const qil_mps* psi, const uint8_t* d
 int qil_coefficient_grid(qil_ctx* ctx, const qil_mps* psi, const uint8_t* site_mode, const int32_t* out_bit, void* out);
 int qil_coefficient_grid_dev(qil_ctx* ctx, const qil_mps* psi, const uint8_t* site_mode, const int32_t* out_bit,
                              void* d_out);
+
+/* ---- pipelined host -> device staging -----------------------------------------------------------------------
+ * A ring of `depth` device buffers of `bytes` each, filled on a private copy stream: the upload of the next signal
+ * overlaps the work on the current one (end to end the path is PCIe bound: 2 GiB per n=28 signal vs a ~5 ms encode).
+ *   qil_uploader_submit(u, host, bytes)  enqueue the H2D copy of one signal (pinned host memory makes it asynchronous;
+ *                                        see qil_host_register) into the next free buffer; error if all are in flight
+ *   qil_uploader_acquire(u, &d_ptr)      device pointer of the oldest submitted signal; the context's stream waits for
+ *                                        its upload (no host synchronisation)
+ *   ... qil_encode_rsvd_dev(ctx, ..., d_ptr, ...) or any other *_dev call on the context ...
+ *   qil_uploader_release(u)              the buffer may be refilled once the work enqueued so far has finished
+ * qil_host_register / qil_host_unregister page-lock an existing host buffer (cudaHostRegister) for callers whose arrays
+ * are pageable (a Julia Vector): do it once per buffer, not per call. */
+int qil_uploader_create(qil_ctx* ctx, int64_t bytes, int depth, qil_uploader** out);
+int qil_uploader_submit(qil_uploader* u, const void* host, int64_t bytes);
+int qil_uploader_acquire(qil_uploader* u, void** d_ptr);
+int qil_uploader_release(qil_uploader* u);
+int qil_uploader_destroy(qil_uploader* u);
+int qil_host_register(void* host, int64_t bytes);
+int qil_host_unregister(void* host);
 
 /* ---- on-disk container (dims + raw cores; the reference itself persists only JLD2 benchmark dicts,
  * scripts/benchmark/common.jl:193-203).  Layout, little endian: "QILTN001" | u32 kind (0 MPS, 1 MPO) | u32 is_complex |

@@ -13,4 +13,4 @@ from .api import (Context, default_context, SignalMPS, ZTMPS, SingleSiteMPO, Pai
                   signal_mps_dev, signal_mps_batch_dev, ztmps_from_mps, coefficients_dev,
                   coefficient_grid, coefficient_grid_dev, pole_scan, pole_scan_modes, apply_batch,
                   coefficient_grid_argmax, coefficients_argmax, sum_sites, laplace_coefficients, z_from_kl, kl_bits,
-                  pole_scan_argmax, pole_scan_list_argmax, pole_scan_driver, save, load_mps, load_mpo, apply_zipup)
+                  pole_scan_argmax, pole_scan_list_argmax, pole_scan_driver, save, load_mps, load_mpo, apply_zipup, Uploader)

@@ -69,6 +69,13 @@ _SIGS = {
     "qil_coefficient_batch_dev": [c_ctx, c_mps, C.c_void_p, C.c_int64, C.c_void_p],
     "qil_coefficient_grid": [c_ctx, c_mps, C.c_void_p, C.c_void_p, C.c_void_p],
     "qil_coefficient_grid_dev": [c_ctx, c_mps, C.c_void_p, C.c_void_p, C.c_void_p],
+    "qil_uploader_create": [c_ctx, C.c_int64, C.c_int, C.POINTER(C.c_void_p)],
+    "qil_uploader_submit": [C.c_void_p, C.c_void_p, C.c_int64],
+    "qil_uploader_acquire": [C.c_void_p, C.POINTER(C.c_void_p)],
+    "qil_uploader_release": [C.c_void_p],
+    "qil_uploader_destroy": [C.c_void_p],
+    "qil_host_register": [C.c_void_p, C.c_int64],
+    "qil_host_unregister": [C.c_void_p],
     "qil_mps_save": [c_mps, C.c_char_p],
     "qil_mps_load": [c_ctx, C.c_char_p, C.POINTER(c_mps)],
     "qil_mpo_save": [c_mpo, C.c_char_p],

@@ -626,6 +626,49 @@ def pole_scan(psi, k0=0, l0=0, log2_k=None, log2_l=None, stride_log2_k=0, stride
     return coefficient_grid(psi, mode, ob).reshape(2**log2_k, 2**log2_l)
 
 
+class Uploader:
+    """qil_uploader_* (include/qilcuda.h): ring of device buffers filled on the library's own copy stream.
+
+        up = Uploader(ctx, nbytes)
+        up.submit(ptr0, nbytes)                    # host address (pinned memory -> truly asynchronous)
+        for ...:
+            d_x = up.acquire()
+            up.submit(ptr_next, nbytes)            # overlaps the work below
+            psi = signal_mps_dev(ctx, d_x, N, ...)
+            up.release()
+    """
+
+    def __init__(self, ctx, nbytes, depth=2):
+        self.ctx = ctx
+        self.handle = C.c_void_p()
+        self.inflight = 0
+        call("qil_uploader_create", ctx.handle, C.c_int64(int(nbytes)), int(depth), C.byref(self.handle))
+
+    def submit(self, host_ptr, nbytes):
+        call("qil_uploader_submit", self.handle, C.c_void_p(int(host_ptr)), C.c_int64(int(nbytes)))
+        self.inflight += 1
+
+    def acquire(self):
+        p = C.c_void_p()
+        call("qil_uploader_acquire", self.handle, C.byref(p))
+        return p.value
+
+    def release(self):
+        call("qil_uploader_release", self.handle)
+        self.inflight -= 1
+
+    def close(self):
+        if self.handle:
+            _lib.load().qil_uploader_destroy(self.handle)
+            self.handle = None
+
+    def __del__(self):
+        try:
+            self.close()
+        except Exception:
+            pass
+
+
 def save(obj, path):
     """Write an MPS / ZTMPS / MPO to the QILTN001 container (include/qilcuda.h)."""
     fn = "qil_mpo_save" if isinstance(obj, SingleSiteMPO) else "qil_mps_save"

@@ -615,6 +615,49 @@ int qil_mpo_load(qil_ctx* ctx, const char* path, qil_mpo** out) {
     QIL_API_END
 }
 
+int qil_uploader_create(qil_ctx* ctx, int64_t bytes, int depth, qil_uploader** out) {
+    QIL_API_BEGIN
+    QIL_NONNULL(ctx); QIL_NONNULL(out);
+    QIL_CUDA(cudaSetDevice(ctx->device));
+    *out = uploader_create(ctx, bytes, depth);
+    QIL_API_END
+}
+int qil_uploader_submit(qil_uploader* u, const void* host, int64_t bytes) {
+    QIL_API_BEGIN
+    QIL_NONNULL(u); QIL_NONNULL(host);
+    uploader_submit(u, host, bytes);
+    QIL_API_END
+}
+int qil_uploader_acquire(qil_uploader* u, void** d_ptr) {
+    QIL_API_BEGIN
+    QIL_NONNULL(u); QIL_NONNULL(d_ptr);
+    *d_ptr = uploader_acquire(u);
+    QIL_API_END
+}
+int qil_uploader_release(qil_uploader* u) {
+    QIL_API_BEGIN
+    QIL_NONNULL(u);
+    uploader_release(u);
+    QIL_API_END
+}
+int qil_uploader_destroy(qil_uploader* u) {
+    QIL_API_BEGIN
+    uploader_destroy(u);
+    QIL_API_END
+}
+int qil_host_register(void* host, int64_t bytes) {
+    QIL_API_BEGIN
+    QIL_NONNULL(host);
+    QIL_CUDA(cudaHostRegister(host, (size_t)bytes, cudaHostRegisterDefault));
+    QIL_API_END
+}
+int qil_host_unregister(void* host) {
+    QIL_API_BEGIN
+    QIL_NONNULL(host);
+    QIL_CUDA(cudaHostUnregister(host));
+    QIL_API_END
+}
+
 // ---- apply ---------------------------------------------------------------------------------
 int qil_apply_mpo_mps(qil_ctx* ctx, const qil_mpo* W, const qil_mps* psi, qil_mps** out) {
     QIL_API_BEGIN

@@ -187,6 +187,13 @@ void destroy(qil_mps* m);
 void unpool(qil_mps* m);          // give a pooled MPS its own core allocations
 void destroy(qil_mpo* m);
 
+// host -> device staging ring (qil_upload.cu)
+qil_uploader* uploader_create(qil_ctx* ctx, int64_t bytes, int depth);
+void uploader_submit(qil_uploader* u, const void* host, int64_t bytes);
+void* uploader_acquire(qil_uploader* u);
+void uploader_release(qil_uploader* u);
+void uploader_destroy(qil_uploader* u);
+
 // native collectives over peer memory (qil_peer.cu)
 qil_peer* peer_create(qil_ctx* ctx, int rank, int world, int64_t bytes, unsigned char* handle64);
 void peer_connect(qil_peer* p, const unsigned char* all_handles);
