@@ -124,20 +124,30 @@ __global__ void __launch_bounds__(256) apply_jobs_kernel(const ApplyJob* __restr
         const TW* __restrict__ wa = W + (size_t)a * 4 * Db;
         const TP* __restrict__ p0r = P + (size_t)l * 2 * cr;
         TO* __restrict__ o0 = O + (size_t)LA * 2 * R;
-        for (unsigned RB = tx; RB < R; RB += 32) {
-            const unsigned r = RB / Db, b = RB - r * Db;
-            const TO p0 = promote<TO, TP>(p0r[r]);
-            const TO p1 = promote<TO, TP>(p0r[cr + r]);
-            const TO w00 = promote<TO, TW>(wa[b]);            // p=0,s=0
-            const TO w01 = promote<TO, TW>(wa[Db + b]);       // p=0,s=1
-            const TO w10 = promote<TO, TW>(wa[2 * Db + b]);   // p=1,s=0
-            const TO w11 = promote<TO, TW>(wa[3 * Db + b]);   // p=1,s=1
-            TO v0 = Scalar<TO>::mul(w00, p0);
-            v0 = Scalar<TO>::fma(w10, p1, v0);
-            TO v1 = Scalar<TO>::mul(w01, p0);
-            v1 = Scalar<TO>::fma(w11, p1, v1);
-            o0[RB] = v0;
-            o0[R + RB] = v1;
+        // four independent elements per thread and iteration: the kernel is latency bound on the operand loads
+        for (unsigned RB0 = tx; RB0 < R; RB0 += 128) {
+            TO v0[4], v1[4];
+#pragma unroll
+            for (int e = 0; e < 4; ++e) {
+                const unsigned RB = min(RB0 + 32 * e, R - 1);
+                const unsigned r = RB / Db, b = RB - r * Db;
+                const TO p0 = promote<TO, TP>(p0r[r]);
+                const TO p1 = promote<TO, TP>(p0r[cr + r]);
+                const TO w00 = promote<TO, TW>(wa[b]);            // p=0,s=0
+                const TO w01 = promote<TO, TW>(wa[Db + b]);       // p=0,s=1
+                const TO w10 = promote<TO, TW>(wa[2 * Db + b]);   // p=1,s=0
+                const TO w11 = promote<TO, TW>(wa[3 * Db + b]);   // p=1,s=1
+                v0[e] = Scalar<TO>::fma(w10, p1, Scalar<TO>::mul(w00, p0));
+                v1[e] = Scalar<TO>::fma(w11, p1, Scalar<TO>::mul(w01, p0));
+            }
+#pragma unroll
+            for (int e = 0; e < 4; ++e) {
+                const unsigned RB = RB0 + 32 * e;
+                if (RB < R) {
+                    o0[RB] = v0[e];
+                    o0[R + RB] = v1[e];
+                }
+            }
         }
     }
 }
@@ -171,12 +181,12 @@ void apply_mpo_mps_many(qil_ctx* ctx, const qil_mpo* W, const qil_mps* const* ps
     }
     void* pool_raw = ctx->alloc(std::max<size_t>(total, 1) * es);
     std::shared_ptr<void> pool(pool_raw, [ctx](void* p) { ctx->free(p); });
-    // jobs: ~256 KB of output each (at least 8 rows: one per thread row)
+    // jobs: ~128 KB of output each (at least 8 rows: one per thread row)
     std::vector<ApplyJob> jobs;
     for (int64_t s = 0; s < count; ++s)
         for (int i = 0; i < n; ++i) {
             const int64_t L = ob[s][i], R = ob[s][i + 1];
-            int64_t rows_per = std::max<int64_t>(8, (int64_t)(262144 / es) / std::max<int64_t>(2 * R, 1));
+            int64_t rows_per = std::max<int64_t>(8, (int64_t)(131072 / es) / std::max<int64_t>(2 * R, 1));
             rows_per = std::min(rows_per, L);
             for (int64_t r0 = 0; r0 < L; r0 += rows_per) {
                 ApplyJob j;
