@@ -375,7 +375,20 @@ def c2_leg(q, ctx, torch, dev, timed, steps, hbm_peak, with_oracle):
                 got = q.coefficients(par[bb], bits)
                 worst = max(worst, float(np.abs(got - O.coefficient_batch(co, c, bits)).max() / np.abs(xs[bb]).max()))
         t_cpu = time.perf_counter() - t0
+        # yardstick for the bond identity: the oracle against itself on inputs perturbed by one ulp per sample.  With
+        # q = 0 and cutoff 1e-14 the decisions deep in the tree sit at the algorithm's own noise floor.
+        self_same, self_n = 0, 0
+        rng2 = np.random.default_rng(9)
+        diffs = []
+        for bb in range(0, count, 8):
+            co, c = O.tt_rsvd(xs[bb], omega_fn=omega_fn, **kw)
+            cp, _ = O.tt_rsvd(xs[bb] * (1.0 + 1.1e-16 * rng2.standard_normal(N)), omega_fn=omega_fn, **kw)
+            self_same += int(O.bonds_of(co) == O.bonds_of(cp))
+            self_n += 1
+            diffs.append(max(abs(a - b) for a, b in zip(par[bb].bonds, O.bonds_of(co))))
         res["parity"] = {"signals_with_bonds_equal_oracle": same, "of": count, "encode_max_rel_err_sampled": worst,
+                         "oracle_vs_oracle_1ulp_perturbed_input_bonds_equal": self_same, "of_sampled": self_n,
+                         "max_bond_difference_sampled": int(max(diffs)),
                          "note": "both sides use the same host-drawn normal stream"}
         res["cpu_baseline"] = {"value": count * N / t_cpu, "unit": "samples/s", "kind": "port",
                                "sample": f"numpy oracle, encode only, all {count} signals, {t_cpu:.1f} s"}

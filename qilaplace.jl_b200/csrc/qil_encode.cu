@@ -985,7 +985,8 @@ static bool encode_rsvd_tree_batch(qil_ctx* ctx, const RsvdOpts& o, const double
         }
         // ---- norms
         {
-            const int parts = 8;
+            // enough CTAs to stream at HBM rate whatever the batch shape (4 x 2 GiB or 256 x 8 MiB)
+            const int parts = (int)std::max<int64_t>(8, (4 * (int64_t)ctx->sm_count + count - 1) / count);
             Mat<double> partial(ctx, count * parts, 1);
             batch_sumsq_kernel<<<dim3(parts, (unsigned)count), 256, 0, ctx->stream>>>(x_all, N, parts, partial.p);
             QIL_LAUNCH_CHECK(ctx);
