@@ -960,6 +960,11 @@ def run_ours(args):
 def main():
     args = parse()
     if args.impl == "reference":
+        # torchrun exports OMP_NUM_THREADS=1 to every rank; OpenBLAS sizes its thread pool from the environment when numpy
+        # is first imported (nothing above imports it), so give the CPU arm every host core before that happens
+        nc = str(os.cpu_count() or 1)
+        for var in ("OMP_NUM_THREADS", "OPENBLAS_NUM_THREADS", "MKL_NUM_THREADS"):
+            os.environ[var] = nc
         run_reference(args)
     else:
         run_ours(args)
