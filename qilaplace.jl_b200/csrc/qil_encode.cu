@@ -207,7 +207,7 @@ static Mat<T> mul_A(SplitCtx<T>& sc, const T* A, int64_t R, int64_t C, int l, co
                 Xsrc, sc.stream, (unsigned long long)sc.o->seed, C, lw, rows_pad, lpp, X.p, j0, l);
             QIL_LAUNCH_CHECK(ctx);
             int ks; long long kc;
-            stream_plan(ctx, R, C * F, &ks, &kc);
+            stream_plan(ctx, R, C * F, &ks, &kc, nt);
             Mat<double> part(ctx, (int64_t)ks * R, nt * 8);
             Mat<double> ssq;
             const int grid = stream_grid(ctx, R, ks, nt);
@@ -262,7 +262,7 @@ static Mat<T> mul_AH(SplitCtx<T>& sc, const T* A, int64_t R, int64_t C, int l, c
             prep_x_k2_kernel<T><<<grid_for(ctx, rows_pad * lpp), 256, 0, ctx->stream>>>(Q, R, lw, rows_pad, lpp, X.p, j0, l);
             QIL_LAUNCH_CHECK(ctx);
             int ks; long long kc;
-            stream_plan(ctx, C * F, R, &ks, &kc);
+            stream_plan(ctx, C * F, R, &ks, &kc, nt);
             Mat<double> part(ctx, (int64_t)ks * C * F, nt * 8);
             stream_gemm(ctx, true, reinterpret_cast<const double*>(A), R, C * F, C * F, X.p, lpp, nt, part.p, ks, kc, nullptr, lw * F);
             reduce_k2_kernel<T><<<grid_for(ctx, C * lw), 256, 0, ctx->stream>>>(part.p, ks, C, nt * 8, lw, scale, Z.p, j0, l);
@@ -394,8 +394,8 @@ static int rsvd_split_fused(SplitCtx<double>& sc, const double* A, int64_t R, in
     if (rowsR > R) QIL_CUDA(cudaMemsetAsync(XR.p, 0, XR.elems() * sizeof(double), ctx->stream));
     if (rowsC > C) QIL_CUDA(cudaMemsetAsync(XC.p, 0, XC.elems() * sizeof(double), ctx->stream));
     int ks1, ks2; long long kc1, kc2;
-    stream_plan(ctx, R, C, &ks1, &kc1);
-    stream_plan(ctx, C, R, &ks2, &kc2);
+    stream_plan(ctx, R, C, &ks1, &kc1, nt);
+    stream_plan(ctx, C, R, &ks2, &kc2, nt);
     Mat<double> partR(ctx, (int64_t)ks1 * R, nt * 8), partC(ctx, (int64_t)ks2 * C, nt * 8);
     // ---- Y = A Omega
     prep_x_k1_kernel<double><<<grid_for(ctx, rowsC * lpp), 256, 0, ctx->stream>>>(
@@ -1000,7 +1000,7 @@ static bool encode_rsvd_tree_batch(qil_ctx* ctx, const RsvdOpts& o, const double
                                                                                 l0, C, lpp, XC.p);
         QIL_LAUNCH_CHECK(ctx);
         int ks1; long long kc1;
-        stream_plan(ctx, Rall, C, &ks1, &kc1);
+        stream_plan(ctx, Rall, C, &ks1, &kc1, nt);
         Mat<double> partR(ctx, (int64_t)ks1 * Rall, ldo), partC(ctx, count * C, ldo), Yall(ctx, Rall, l0);
         auto sum_R = [&]() {
             reduce_k1_kernel<double><<<grid_for(ctx, Rall * l0), 256, 0, ctx->stream>>>(partR.p, ks1, Rall, ldo, l0, Yall.p);

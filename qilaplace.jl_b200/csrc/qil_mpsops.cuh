@@ -57,7 +57,7 @@ int stream_nt_for(int cols);
 // column g) hit 16 distinct bank pairs per half warp (8*nt + 2 gave a 2-way conflict on every load)
 inline int stream_lpp(int nt) { return nt * 8 + 1; }
 bool stream_supported(long long R, long long C, long long ld, int cols);
-void stream_plan(qil_ctx* ctx, long long Mtot, long long Kdim, int* ksplit, long long* kchunk);
+void stream_plan(qil_ctx* ctx, long long Mtot, long long Kdim, int* ksplit, long long* kchunk, int nt = 1);
 int stream_grid(qil_ctx* ctx, long long Mtot, int ksplit, int nt);
 void stream_gemm(qil_ctx* ctx, bool trans, const double* A, long long R, long long C, long long ld, const double* X,
                  int lpp, int nt, double* out, int ksplit, long long kchunk, double* sumsq_partials,

@@ -340,15 +340,28 @@ void stream_gemm(qil_ctx* ctx, bool trans, const double* A, long long R, long lo
     }
 }
 
-void stream_plan(qil_ctx* ctx, long long Mtot, long long Kdim, int* ksplit, long long* kchunk) {
-    // enough tiles for ~6 waves of persistent CTAs, chunks of at least 256 along K
+void stream_plan(qil_ctx* ctx, long long Mtot, long long Kdim, int* ksplit, long long* kchunk, int nt) {
+    // Tiles (row tile x K chunk) are dealt round robin to the resident persistent CTAs, so the launch takes
+    // ceil(tiles / CTAs) waves: 896 tiles on 296 CTAs are 3.03 waves, i.e. a fourth, almost empty wave (25 % lost).  Among
+    // the split factors around ~6 tiles per CTA (chunks of at least 256 along K) pick the one whose last wave is fullest.
     const long long tilesM = (Mtot + kBM - 1) / kBM;
-    long long want = ((long long)ctx->sm_count * 6 + tilesM - 1) / tilesM;
-    long long maxsplit = std::max<long long>(1, Kdim / 256);
-    long long ks = std::max<long long>(1, std::min(want, maxsplit));
-    long long chunk = ((Kdim + ks - 1) / ks + kBK - 1) / kBK * kBK;
-    ks = (Kdim + chunk - 1) / chunk;
-    *ksplit = (int)ks;
+    const long long ctas = (long long)ctx->sm_count * stream_ctas_per_sm(nt);
+    const long long maxsplit = std::max<long long>(1, Kdim / 256);
+    const long long want = std::max<long long>(1, std::min((ctas * 6 + tilesM - 1) / tilesM, maxsplit));
+    long long best = want;
+    double best_eff = -1.0;
+    for (long long ks = std::max<long long>(1, want / 2); ks <= std::min(maxsplit, 2 * want + 1); ++ks) {
+        const long long chunk = ((Kdim + ks - 1) / ks + kBK - 1) / kBK * kBK;
+        const long long ks_eff = (Kdim + chunk - 1) / chunk;
+        const long long tiles = tilesM * ks_eff;
+        const long long waves = (tiles + ctas - 1) / ctas;
+        double eff = (double)tiles / (double)(waves * ctas);
+        eff -= 0.002 * (double)ks_eff;                       // mild preference for fewer partials at equal balance
+        if (tiles < ctas) eff = (double)tiles / (double)ctas - 0.002 * (double)ks_eff;
+        if (eff > best_eff) { best_eff = eff; best = ks_eff; }
+    }
+    long long chunk = ((Kdim + best - 1) / best + kBK - 1) / kBK * kBK;
+    *ksplit = (int)((Kdim + chunk - 1) / chunk);
     *kchunk = chunk;
 }
 
