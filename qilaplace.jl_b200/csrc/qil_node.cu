@@ -18,7 +18,8 @@
 
 namespace qil {
 
-constexpr int kNodeThreads = 512;
+constexpr int kNodeThreads = 256;   // 8 warps, up to 255 registers: at 512 threads the 128-register cap spilled (24 % of the
+                                    // stall samples of the level-2 launch sat on local-memory stores)
 
 struct NodeParams {
     const NodeDesc* nodes;      // [gridDim.x]

@@ -21,7 +21,10 @@ namespace qil {
 template <typename T> struct Leaf { static constexpr int RPL = 16; static constexpr int ROWS = 512; };
 template <> struct Leaf<cplx> { static constexpr int RPL = 8; static constexpr int ROWS = 256; };
 constexpr int kLeafThreads = 256;             // <= 256 threads: the Householder warp may use up to 255 registers
-constexpr int kTreeThreads = 512;
+// single block of <= 256 rows: 8 factor warps and <= 8 apply chunks of 4 columns for real panels (255 registers, no
+// spills); complex panels have up to 16 chunks of 2 columns and keep 16 warps
+template <typename T> struct TreeThreads { static constexpr int N = 256; };
+template <> struct TreeThreads<cplx> { static constexpr int N = 512; };
 template <typename T> struct LeafChunk { static constexpr int CH = 4; };
 template <> struct LeafChunk<cplx> { static constexpr int CH = 2; };
 
@@ -179,7 +182,7 @@ __global__ void __launch_bounds__(kLeafThreads) tsqr_leaf_apply_kernel(const Tsq
 
 // ---- whole QR inside one CTA (also the tree stage of the three-launch form) -----------------------------------
 template <typename T>
-__global__ void __launch_bounds__(kTreeThreads) tsqr_cta_kernel(const TsqrParams<T> p) {
+__global__ void __launch_bounds__(TreeThreads<T>::N) tsqr_cta_kernel(const TsqrParams<T> p) {
     extern __shared__ __align__(16) unsigned char smem_raw[];
     T* panel = reinterpret_cast<T*>(smem_raw);
     const long long bat = blockIdx.x;
@@ -232,7 +235,7 @@ void qr_fast(qil_ctx* ctx, int64_t m, int n, const T* A, int64_t lda, int nsum, 
         auto kern = tsqr_cta_kernel<T>;
         const size_t smem = tsqr_cta_smem<T>(m, n);
         ensure_dynamic_smem(kern, smem);
-        kern<<<batch, kTreeThreads, smem, ctx->stream>>>(p);
+        kern<<<batch, TreeThreads<T>::N, smem, ctx->stream>>>(p);
         QIL_LAUNCH_CHECK(ctx);
         return;
     }

@@ -357,8 +357,8 @@ __device__ __forceinline__ void cta_qr_apply_level(const CtaQrLevel<T>& lv) {
     const int n = lv.n;
     const int nch = (n + CH - 1) / CH;
     // rounds of whole blocks: all chunks of a block run in the same round, results are stored after the barrier.
-    // More chunks than warps (nch > nwarps): the chunks of a block take several rounds and go through Qout or, for an
-    // in-place level, are not supported (callers keep n / CH <= nwarps).
+    // REQUIRES nch <= nwarps (results of a block are stored in place after its round): callers launch 8 warps for real
+    // panels (<= 8 chunks of 4 columns) and 16 for complex ones (<= 16 chunks of 2).
     const int blocks_per_round = max(1, nwarps / nch);
     for (int b0 = 0; b0 < lv.nb; b0 += blocks_per_round) {
         const int b = b0 + warp / nch;
