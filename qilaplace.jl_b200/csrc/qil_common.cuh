@@ -111,6 +111,14 @@ struct qil_ctx {
     // scratch that lives as long as the context
     void* scratch = nullptr;
     size_t scratch_bytes = 0;
+    // two zero-initialised words (arrival counter, generation) for the software grid barrier of cooperative kernels
+    // launched on `stream` (one such kernel at a time per context: launches on one stream are serialised)
+    unsigned int* grid_sync = nullptr;
+    unsigned int* get_grid_sync();
+    qil_ctx() = default;
+    qil_ctx(const qil_ctx&) = delete;
+    qil_ctx& operator=(const qil_ctx&) = delete;
+    ~qil_ctx();
 
     // optional per-kernel-class timing (CUDA events on `stream`), enabled by qil_profile_enable
     struct ProfRegion { int id; cudaEvent_t e0, e1; double bytes, flops; };

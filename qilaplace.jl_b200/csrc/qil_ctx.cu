@@ -25,6 +25,18 @@ void* qil_ctx::get_scratch(size_t bytes) {
     return scratch;
 }
 
+unsigned int* qil_ctx::get_grid_sync() {
+    if (!grid_sync) {
+        QIL_CUDA(cudaMalloc(&grid_sync, 4 * sizeof(unsigned int)));
+        QIL_CUDA(cudaMemset(grid_sync, 0, 4 * sizeof(unsigned int)));
+    }
+    return grid_sync;
+}
+
+qil_ctx::~qil_ctx() {
+    if (grid_sync) cudaFree(grid_sync);
+}
+
 void qil_ctx::prof_begin(int id, double bytes, double flops) {
     if (!prof_on) return;
     if (prof_depth++ > 0) return;

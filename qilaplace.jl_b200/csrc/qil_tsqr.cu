@@ -198,6 +198,278 @@ __global__ void __launch_bounds__(TreeThreads<T>::N) tsqr_cta_kernel(const TsqrP
               p.Q ? p.Q + bat * p.q_bs : nullptr, p.ldq, p.qcols, work);
 }
 
+// ---- whole tall QR in ONE cooperative launch -------------------------------------------------------------------
+// Three (two) TSQR levels separated by a software grid barrier; the reflectors of every level stay in the shared
+// memory of the CTA that produced them, only the n x n triangles (up) and the n x n seeds of the explicit Q (down)
+// travel through L2:
+//   A  every CTA factors its block of <= R0 rows (8 warps, column parallel)           -> triangle to Rst0
+//   B  CTA b < nb1 factors a block of <= R1 rows of the stacked level-0 triangles       -> triangle to Rst1
+//   C  the LAST CTA (it holds no level-1 block) factors the remaining <= R1 rows, writes R and its explicit Q -> M1
+//   D  CTA b < nb1: rows of the level-1 Q = its reflectors applied to its seed M1[b]     -> M0
+//   E  every CTA: rows of Q = level-0 reflectors applied to the seed M0[b]
+// nb1 == 0: the level-0 triangles fit one block and B / D are skipped.  One launch of ~40 us instead of five launches
+// of ~40 us each for the 2^14 x 20 panels of the top split.
+constexpr int kFusedThreads = 256;
+
+struct TsqrFusedPlan {
+    bool ok = false;
+    int R0 = 0, R1 = 0, nb0 = 0, nb1 = 0;
+    size_t smem = 0;
+};
+
+template <typename T>
+struct TsqrFusedParams {
+    const T* A; long long lda; int nsum; long long sum_stride;
+    long long m; int n;
+    int nb0, nb1, R0, R1;
+    T* Rst0; T* Rst1;       // stacked triangles of level 0 / 1, [nb * n][n]
+    T* M1; T* M0;           // explicit Q of the top block / of level 1 (the seeds of the level below), ld n
+    T* Q; long long ldq; int qcols;
+    T* R;
+    int positive; int pitch;
+    unsigned int* sync;     // {arrival counter, generation}, zero before the first use
+    long long* clk;         // debug (QIL_TSQR_CLK=1): %globaltimer of CTA 0 / the last CTA at the phase boundaries
+};
+__device__ __forceinline__ void fused_clk(long long* clk, int slot) {
+    if (clk && threadIdx.x == 0 && (blockIdx.x == 0 || blockIdx.x == gridDim.x - 1)) {
+        long long t;
+        asm volatile("mov.u64 %0, %globaltimer;" : "=l"(t));
+        clk[(blockIdx.x == 0 ? 0 : 16) + slot] = t;
+    }
+}
+
+__device__ __forceinline__ void wq_grid_barrier(unsigned int* sync) {
+    __syncthreads();
+    if (threadIdx.x == 0) {
+        __threadfence();
+        const unsigned int g = *((volatile unsigned int*)(sync + 1));
+        if (atomicAdd(sync, 1u) == gridDim.x - 1) {
+            *((volatile unsigned int*)sync) = 0u;
+            __threadfence();
+            atomicAdd(sync + 1, 1u);
+        } else {
+            while (*((volatile unsigned int*)(sync + 1)) == g) { }
+        }
+        __threadfence();
+    }
+    __syncthreads();
+}
+
+// all 8 warps factor one block together (column parallel, named barrier 1)
+template <typename T>
+__device__ __noinline__ void fused_factor(T* blk, int pitch, int m, int n, T* beta, double* tau) {
+    wqr_factor_any<T>(blk, pitch, m, n, beta, tau, threadIdx.x >> 5, blockDim.x >> 5, 1);
+}
+
+// n x n triangle of a factored block (diag in beta) -> dst (ld n)
+template <typename T>
+__device__ __forceinline__ void fused_store_triangle(const T* blk, int pitch, int m, int n, const T* beta, T* dst) {
+    for (int idx = threadIdx.x; idx < n * n; idx += blockDim.x) {
+        const int j = idx / n, c = idx - j * n;
+        T v = Scalar<T>::zero();
+        if (j < m) {
+            if (c == j) v = beta[j];
+            else if (c > j) v = blk[j * pitch + c];
+        }
+        dst[idx] = v;
+    }
+}
+
+// rows [0, m) of out (ld ldo) = H_0 ... H_{k-1} [seed; 0]; seed (n x n, shared, ld n) or, when null, diag(phases of
+// btop) (the top block).  Columns n .. ocols-1 of out are zero filled.  CH columns per warp in registers.
+template <typename T, int RPL>
+__device__ __forceinline__ void fused_apply_rpl(const T* blk, int pitch, int m, int n, const double* tau, const T* seed,
+                                                const T* btop, bool positive, T* out, long long ldo, int ocols) {
+    constexpr int CH = LeafChunk<T>::CH;
+    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31, nwarps = blockDim.x >> 5;
+    const int nch = (n + CH - 1) / CH;
+    for (int ch = warp; ch < nch; ch += nwarps) {
+        const int c0 = ch * CH;
+        T reg[RPL][CH];
+#pragma unroll
+        for (int t = 0; t < RPL; ++t) {
+            const int i = lane + 32 * t;
+#pragma unroll
+            for (int q = 0; q < CH; ++q) {
+                const int c = c0 + q;
+                T v = Scalar<T>::zero();
+                if (i < n && i < m && c < n) {
+                    if (seed) v = seed[i * n + c];
+                    else if (i == c) v = positive ? wqr_phase<T>(btop[c]) : Scalar<T>::one();
+                }
+                reg[t][q] = v;
+            }
+        }
+        wqr_apply_chunk<T, RPL, CH>(blk, pitch, m, min(m, n), tau, reg);
+#pragma unroll
+        for (int t = 0; t < RPL; ++t) {
+            const int i = lane + 32 * t;
+            if (i < m) {
+#pragma unroll
+                for (int q = 0; q < CH; ++q) {
+                    const int c = c0 + q;
+                    if (c < n) out[(long long)i * ldo + c] = reg[t][q];
+                    else if (c < ocols) out[(long long)i * ldo + c] = Scalar<T>::zero();
+                }
+            }
+        }
+    }
+    const int cz = nch * CH;
+    if (ocols > cz) {
+        const int wdt = ocols - cz;
+        for (int idx = threadIdx.x; idx < m * wdt; idx += blockDim.x) {
+            const int i = idx / wdt, c = cz + idx % wdt;
+            out[(long long)i * ldo + c] = Scalar<T>::zero();
+        }
+    }
+}
+template <typename T>
+__device__ __noinline__ void fused_apply(const T* blk, int pitch, int m, int n, const double* tau, const T* seed,
+                                         const T* btop, bool positive, T* out, long long ldo, int ocols) {
+    const int rpl = (m + 31) >> 5;
+    if (rpl <= 2) fused_apply_rpl<T, 2>(blk, pitch, m, n, tau, seed, btop, positive, out, ldo, ocols);
+    else if (rpl <= 4) fused_apply_rpl<T, 4>(blk, pitch, m, n, tau, seed, btop, positive, out, ldo, ocols);
+    else fused_apply_rpl<T, 8>(blk, pitch, m, n, tau, seed, btop, positive, out, ldo, ocols);
+}
+
+// rows [s0, s1) of a dense (ld n) matrix written by OTHER CTAs of this launch -> shared panel, padding columns zero
+template <typename T>
+__device__ __forceinline__ void fused_load_stack(const T* src, int s0, int rows, int n, T* blk, int pitch) {
+    for (int idx = threadIdx.x; idx < rows * pitch; idx += blockDim.x) {
+        const int i = idx / pitch, c = idx - i * pitch;
+        blk[idx] = (c < n) ? __ldcg(src + (size_t)(s0 + i) * n + c) : Scalar<T>::zero();
+    }
+}
+
+template <typename T>
+__global__ void __launch_bounds__(kFusedThreads) tsqr_fused_kernel(const TsqrFusedParams<T> p) {
+    extern __shared__ __align__(16) unsigned char smem_raw[];
+    const int n = p.n, pitch = p.pitch;
+    T* blk0 = reinterpret_cast<T*>(smem_raw);
+    T* blk1 = blk0 + (size_t)p.R0 * pitch;
+    T* seed = blk1 + (size_t)p.R1 * pitch;                    // n x n
+    T* beta0 = seed + n * n;
+    T* beta1 = beta0 + n;
+    double* tau0 = reinterpret_cast<double*>(beta1 + n);
+    double* tau1 = tau0 + n;
+    const int b = blockIdx.x;
+    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31, nwarps = blockDim.x >> 5;
+    const long long r0 = ((long long)b * p.m) / p.nb0, r1 = ((long long)(b + 1) * p.m) / p.nb0;
+    const int mloc = (int)(r1 - r0);
+    fused_clk(p.clk, 0);
+    // ---- A: level-0 block
+    for (int i0 = warp; i0 < mloc; i0 += 8 * nwarps) {
+        T v[8];
+#pragma unroll
+        for (int e = 0; e < 8; ++e) {
+            const int i = i0 + e * nwarps;
+            v[e] = Scalar<T>::zero();
+            if (i < mloc && lane < n) v[e] = load_sum<T>(p.A + (r0 + i) * p.lda + lane, p.nsum, p.sum_stride);
+        }
+#pragma unroll
+        for (int e = 0; e < 8; ++e) {
+            const int i = i0 + e * nwarps;
+            if (i < mloc && lane < pitch) blk0[i * pitch + lane] = v[e];
+        }
+    }
+    if (pitch > 32) {
+        for (int idx = threadIdx.x; idx < mloc * (pitch - 32); idx += blockDim.x) {
+            const int i = idx / (pitch - 32), c = 32 + idx % (pitch - 32);
+            blk0[i * pitch + c] = Scalar<T>::zero();
+        }
+    }
+    __syncthreads();
+    fused_clk(p.clk, 1);
+    fused_factor<T>(blk0, pitch, mloc, n, beta0, tau0);
+    __syncthreads();
+    fused_clk(p.clk, 2);
+    fused_store_triangle<T>(blk0, pitch, mloc, n, beta0, p.Rst0 + (size_t)b * n * n);
+    wq_grid_barrier(p.sync);
+    fused_clk(p.clk, 3);
+    // ---- B: level-1 block
+    const int rows1 = p.nb0 * n;
+    int s0 = 0, m1 = 0;
+    if (p.nb1 > 0 && b < p.nb1) {
+        s0 = (int)(((long long)b * rows1) / p.nb1);
+        m1 = (int)(((long long)(b + 1) * rows1) / p.nb1) - s0;
+        fused_load_stack<T>(p.Rst0, s0, m1, n, blk1, pitch);
+        __syncthreads();
+        fused_factor<T>(blk1, pitch, m1, n, beta1, tau1);
+        __syncthreads();
+        fused_store_triangle<T>(blk1, pitch, m1, n, beta1, p.Rst1 + (size_t)b * n * n);
+    }
+    if (p.nb1 > 0) wq_grid_barrier(p.sync);
+    fused_clk(p.clk, 4);
+    // ---- C: top block, on the last CTA
+    const int rowsT = (p.nb1 > 0 ? p.nb1 : p.nb0) * n;
+    T* Mtop = p.nb1 > 0 ? p.M1 : p.M0;
+    if (b == (int)gridDim.x - 1) {
+        fused_load_stack<T>(p.nb1 > 0 ? p.Rst1 : p.Rst0, 0, rowsT, n, blk1, pitch);
+        __syncthreads();
+        fused_clk(p.clk, 5);
+        fused_factor<T>(blk1, pitch, rowsT, n, beta1, tau1);
+        __syncthreads();
+        fused_clk(p.clk, 6);
+        if (p.R) {
+            for (int idx = threadIdx.x; idx < n * n; idx += blockDim.x) {
+                const int j = idx / n, c = idx - j * n;
+                T v = Scalar<T>::zero();
+                if (c == j) v = beta1[j];
+                else if (c > j) v = blk1[j * pitch + c];
+                if (p.positive) v = Scalar<T>::mul(Scalar<T>::conj(wqr_phase<T>(beta1[j])), v);
+                p.R[idx] = v;
+            }
+        }
+        fused_apply<T>(blk1, pitch, rowsT, n, tau1, nullptr, beta1, p.positive != 0, Mtop, n, n);
+    }
+    fused_clk(p.clk, 7);
+    wq_grid_barrier(p.sync);
+    fused_clk(p.clk, 8);
+    // ---- D: level-1 rows of Q
+    if (p.nb1 > 0) {
+        if (b < p.nb1) {
+            for (int idx = threadIdx.x; idx < n * n; idx += blockDim.x) seed[idx] = __ldcg(p.M1 + (size_t)b * n * n + idx);
+            __syncthreads();
+            fused_apply<T>(blk1, pitch, m1, n, tau1, seed, nullptr, false, p.M0 + (size_t)s0 * n, n, n);
+        }
+        wq_grid_barrier(p.sync);
+    }
+    // ---- E: rows of Q
+    fused_clk(p.clk, 9);
+    for (int idx = threadIdx.x; idx < n * n; idx += blockDim.x) seed[idx] = __ldcg(p.M0 + (size_t)b * n * n + idx);
+    __syncthreads();
+    fused_apply<T>(blk0, pitch, mloc, n, tau0, seed, nullptr, false, p.Q + r0 * p.ldq, p.ldq, p.qcols);
+    __syncthreads();
+    fused_clk(p.clk, 10);
+}
+
+template <typename T>
+static TsqrFusedPlan tsqr_fused_plan(qil_ctx* ctx, int64_t m, int n) {
+    TsqrFusedPlan best;
+    static const bool off = [] { const char* e = getenv("QIL_TSQR_FUSED"); return e && e[0] == '0'; }();
+    if (off) return best;
+    const size_t budget = std::min<size_t>(ctx->smem_optin, 225 * 1024);
+    const int pitch = wqr_pitch(n);
+    const int r0s[2] = {128, 256}, r1s[2] = {256, 128};
+    for (int a = 0; a < 2 && !best.ok; ++a) {
+        for (int c = 0; c < 2 && !best.ok; ++c) {
+            const int R0 = r0s[a], R1 = r1s[c];
+            const int64_t nb0 = (m + R0 - 1) / R0;
+            if (nb0 < 2 || nb0 > ctx->sm_count) continue;           // one CTA per SM (255 registers x 256 threads)
+            int64_t nb1 = 0;
+            if (nb0 * n > R1) {
+                nb1 = (nb0 * n + R1 - 1) / R1;
+                if (nb1 * n > R1 || nb1 >= nb0) continue;
+            }
+            const size_t smem = ((size_t)(R0 + R1) * pitch + (size_t)n * n + 4 * (size_t)n + 8) * sizeof(T) + 64;
+            if (smem > budget) continue;
+            best.ok = true;
+            best.R0 = R0; best.R1 = R1; best.nb0 = (int)nb0; best.nb1 = (int)nb1; best.smem = smem;
+        }
+    }
+    return best;
+}
+
 template <typename T>
 static size_t tsqr_cta_smem(int64_t m, int n) {
     const int pitch = wqr_pitch(n);
@@ -238,6 +510,43 @@ void qr_fast(qil_ctx* ctx, int64_t m, int n, const T* A, int64_t lda, int nsum, 
         kern<<<batch, TreeThreads<T>::N, smem, ctx->stream>>>(p);
         QIL_LAUNCH_CHECK(ctx);
         return;
+    }
+    if (batch == 1) {
+        const TsqrFusedPlan fp = tsqr_fused_plan<T>(ctx, m, n);
+        if (fp.ok) {
+            TsqrFusedParams<T> f{};
+            f.A = A; f.lda = lda; f.nsum = nsum; f.sum_stride = sum_stride;
+            f.m = m; f.n = n; f.nb0 = fp.nb0; f.nb1 = fp.nb1; f.R0 = fp.R0; f.R1 = fp.R1;
+            const int64_t rows1 = (int64_t)fp.nb0 * n, rows2 = (int64_t)std::max(fp.nb1, 1) * n;
+            Mat<T> Rst0(ctx, rows1, n), M0(ctx, rows1, n), Rst1(ctx, rows2, n), M1(ctx, rows2, n);
+            f.Rst0 = Rst0.p; f.M0 = M0.p; f.Rst1 = Rst1.p; f.M1 = M1.p;
+            f.Q = Q; f.ldq = ldq; f.qcols = p.qcols; f.R = R; f.positive = p.positive; f.pitch = p.pitch;
+            f.sync = ctx->get_grid_sync();
+            static const bool dbg_clk = [] { const char* e = getenv("QIL_TSQR_CLK"); return e && e[0] == '1'; }();
+            Mat<long long> clk;
+            if (dbg_clk) {
+                clk = Mat<long long>(ctx, 32, 1);
+                QIL_CUDA(cudaMemsetAsync(clk.p, 0, 32 * sizeof(long long), ctx->stream));
+                f.clk = clk.p;
+            }
+            auto kern = tsqr_fused_kernel<T>;
+            ensure_dynamic_smem(kern, fp.smem);
+            void* args[] = {(void*)&f};
+            QIL_CUDA(cudaLaunchCooperativeKernel((const void*)kern, dim3(fp.nb0), dim3(kFusedThreads), args, fp.smem,
+                                                 ctx->stream));
+            QIL_LAUNCH_CHECK(ctx);
+            if (dbg_clk) {
+                long long h[32];
+                QIL_CUDA(cudaMemcpyAsync(h, clk.p, sizeof(h), cudaMemcpyDeviceToHost, ctx->stream));
+                ctx->sync();
+                fprintf(stderr, "[tsqr_fused %lld x %d nb0 %d nb1 %d] cta0 ns:", (long long)m, n, fp.nb0, fp.nb1);
+                for (int i = 1; i <= 10; ++i) fprintf(stderr, " %lld", h[i] ? h[i] - h[0] : -1);
+                fprintf(stderr, " | last:");
+                for (int i = 1; i <= 10; ++i) fprintf(stderr, " %lld", h[16 + i] ? h[16 + i] - h[16] : -1);
+                fprintf(stderr, "\n");
+            }
+            return;
+        }
     }
     const int nblk = (int)((m + Leaf<T>::ROWS - 1) / Leaf<T>::ROWS);
     const int64_t m2 = (int64_t)nblk * n;
