@@ -202,13 +202,17 @@ __global__ void __launch_bounds__(TreeThreads<T>::N) tsqr_cta_kernel(const TsqrP
 // Three (two) TSQR levels separated by a software grid barrier; the reflectors of every level stay in the shared
 // memory of the CTA that produced them, only the n x n triangles (up) and the n x n seeds of the explicit Q (down)
 // travel through L2:
-//   A  every CTA factors its block of <= R0 rows (8 warps, column parallel)           -> triangle to Rst0
+//   A  CTA b < nb0 factors its block of <= R0 rows (8 warps, column parallel)         -> triangle to Rst0
 //   B  CTA b < nb1 factors a block of <= R1 rows of the stacked level-0 triangles       -> triangle to Rst1
-//   C  the LAST CTA (it holds no level-1 block) factors the remaining <= R1 rows, writes R and its explicit Q -> M1
+//   C  CTA nb0 (it holds no other block) factors the remaining <= R1 rows, writes R and its explicit Q -> M1
 //   D  CTA b < nb1: rows of the level-1 Q = its reflectors applied to its seed M1[b]     -> M0
-//   E  every CTA: rows of Q = level-0 reflectors applied to the seed M0[b]
-// nb1 == 0: the level-0 triangles fit one block and B / D are skipped.  One launch of ~40 us instead of five launches
-// of ~40 us each for the 2^14 x 20 panels of the top split.
+//   E  CTA b < nb0: rows of Q = level-0 reflectors applied to the seed M0[b]
+// nb1 == 0: the level-0 triangles fit one block and B / D are skipped.
+// The apply-down (C, D, E) uses the compact WY form  H_0 ... H_{n-1} = I - V T V^H  (LAPACK larft/larfb) instead of n
+// dependent reflector applications: rows of Q = [S; 0] - V (T V1^H) S with V1 = V[0:n, :].  The n x n matrix T V1^H of
+// a block does not depend on the seed S, so a CTA builds it between ARRIVING at the grid barrier after its factor and
+// WAITING for it, i.e. while the levels above are being factored; what is left on the critical path of the way down
+// is one n x n x n product and one row-parallel m x n x n product per level (no cross-lane reductions).
 constexpr int kFusedThreads = 256;
 
 struct TsqrFusedPlan {
@@ -233,23 +237,29 @@ struct TsqrFusedParams {
 __device__ __forceinline__ void fused_clk(long long* clk, int slot) {
     if (clk && threadIdx.x == 0 && (blockIdx.x == 0 || blockIdx.x == gridDim.x - 1)) {
         long long t;
-        asm volatile("mov.u64 %0, %globaltimer;" : "=l"(t));
+        asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(t) :: "memory");
         clk[(blockIdx.x == 0 ? 0 : 16) + slot] = t;
     }
 }
 
-__device__ __forceinline__ void wq_grid_barrier(unsigned int* sync) {
+// split grid barrier: everything a CTA does between arrive and wait overlaps the other CTAs' way to the barrier
+__device__ __forceinline__ unsigned int wq_grid_arrive(unsigned int* sync) {
+    unsigned int g = 0;
     __syncthreads();
     if (threadIdx.x == 0) {
         __threadfence();
-        const unsigned int g = *((volatile unsigned int*)(sync + 1));
+        g = *((volatile unsigned int*)(sync + 1));
         if (atomicAdd(sync, 1u) == gridDim.x - 1) {
             *((volatile unsigned int*)sync) = 0u;
             __threadfence();
             atomicAdd(sync + 1, 1u);
-        } else {
-            while (*((volatile unsigned int*)(sync + 1)) == g) { }
         }
+    }
+    return g;
+}
+__device__ __forceinline__ void wq_grid_wait(unsigned int* sync, unsigned int g) {
+    if (threadIdx.x == 0) {
+        while (*((volatile unsigned int*)(sync + 1)) == g) { }
         __threadfence();
     }
     __syncthreads();
@@ -275,69 +285,201 @@ __device__ __forceinline__ void fused_store_triangle(const T* blk, int pitch, in
     }
 }
 
-// rows [0, m) of out (ld ldo) = H_0 ... H_{k-1} [seed; 0]; seed (n x n, shared, ld n) or, when null, diag(phases of
-// btop) (the top block).  Columns n .. ocols-1 of out are zero filled.  CH columns per warp in registers.
-template <typename T, int RPL>
-__device__ __forceinline__ void fused_apply_rpl(const T* blk, int pitch, int m, int n, const double* tau, const T* seed,
-                                                const T* btop, bool positive, T* out, long long ldo, int ocols) {
-    constexpr int CH = LeafChunk<T>::CH;
-    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31, nwarps = blockDim.x >> 5;
-    const int nch = (n + CH - 1) / CH;
-    for (int ch = warp; ch < nch; ch += nwarps) {
-        const int c0 = ch * CH;
-        T reg[RPL][CH];
+// T of the compact WY form from G (strict upper triangle of Tm, pitch pt), in place, by ONE warp: lane i keeps row i of
+// T in registers -- T[i][j] = -tau_j sum_{k=i}^{j-1} T[i][k] G[k][j] needs no other row, so there is no cross-lane
+// traffic and no barrier; the G loads are warp-wide broadcasts that do not depend on the running sums.
+template <typename T>
+__device__ __forceinline__ void wy_t_rows(T* Tm, int pt, int n, const double* tau) {
+    constexpr int NMAX = kWqrMaxN;
+    const int lane = threadIdx.x & 31;
+    T row[NMAX];
 #pragma unroll
-        for (int t = 0; t < RPL; ++t) {
-            const int i = lane + 32 * t;
+    for (int j = 0; j < NMAX; ++j) {
+        row[j] = Scalar<T>::zero();
+        if (j < n) {
+            const double tj = tau[j];
+            T a0 = Scalar<T>::zero(), a1 = a0;
 #pragma unroll
-            for (int q = 0; q < CH; ++q) {
-                const int c = c0 + q;
-                T v = Scalar<T>::zero();
-                if (i < n && i < m && c < n) {
-                    if (seed) v = seed[i * n + c];
-                    else if (i == c) v = positive ? wqr_phase<T>(btop[c]) : Scalar<T>::one();
-                }
-                reg[t][q] = v;
+            for (int k = 0; k < j; ++k) {
+                const T g = Tm[k * pt + j];
+                if (k & 1) a1 = Scalar<T>::fma(row[k], g, a1);
+                else a0 = Scalar<T>::fma(row[k], g, a0);
             }
+            const T v = Scalar<T>::scale(Scalar<T>::add(a0, a1), -tj);
+            row[j] = (lane < j) ? v : (lane == j ? Scalar<T>::from_real(tj) : Scalar<T>::zero());
         }
-        wqr_apply_chunk<T, RPL, CH>(blk, pitch, m, min(m, n), tau, reg);
+    }
+    __syncwarp();
 #pragma unroll
-        for (int t = 0; t < RPL; ++t) {
-            const int i = lane + 32 * t;
-            if (i < m) {
+    for (int j = 0; j < NMAX; ++j)
+        if (j < n && lane < n) Tm[lane * pt + j] = row[j];
+}
+
+// Compact WY of a factored block (m >= n rows; reflectors below the diagonal, heads on it):  TV = T V1^H  (n x n, ld n).
+// The strict upper triangle of the block (the R entries, already stored elsewhere) is zeroed so that blk IS V.
+//   G[i][j] = v_i^H v_j (i < j);  T[j][j] = tau_j,  T[0:j, j] = -tau_j T[0:j, 0:j] G[0:j, j]  (in place, one warp)
+// Tm: n x (n | 1) scratch (odd pitch: lane <-> row of T is conflict free).  All pointers are shared memory.
+template <typename T>
+__device__ __noinline__ void wy_build(T* blk, int pitch, int m, int n, const double* tau, T* Tm, T* TV, long long* clk = nullptr) {
+    __builtin_assume(__isShared(blk));
+    __builtin_assume(__isShared(tau));
+    __builtin_assume(__isShared(Tm));
+    __builtin_assume(__isShared(TV));
+    const int tid = threadIdx.x, nth = blockDim.x;
+    const int pt = n | 1;
+    __syncthreads();
+    for (int idx = tid; idx < n * n; idx += nth) {
+        const int i = idx / n, c = idx - i * n;
+        if (c > i) blk[i * pitch + c] = Scalar<T>::zero();
+    }
+    __syncthreads();
+    // Gram G = V^H V (only the strict upper triangle is used below)
+    if (!Scalar<T>::is_complex) {
+        // real: FP64 tensor pipe, fragments straight from the panel
+        cta_gemm(true, reinterpret_cast<const double*>(blk), pitch, n, m, reinterpret_cast<const double*>(blk), pitch, n,
+                 reinterpret_cast<double*>(Tm), pt, 1.0);
+    } else {
+        // the same row r for all lanes of a warp (column index = lane-contiguous: conflict free); rows above the
+        // diagonal contribute zeros
+        for (int idx = tid; idx < n * n; idx += nth) {
+            const int i = idx / n, j = idx - i * n;
+            T a0 = Scalar<T>::zero(), a1 = a0, a2 = a0, a3 = a0;
+            if (i < j) {
+                const T* vi = blk + i;
+                const T* vj = blk + j;
+                int r = (i + 1) & ~3;                     // v_j is zero above row j > i; keep r aligned for all lanes
+                for (; r + 3 < m; r += 4) {
+                    const T x0 = vi[(r + 0) * pitch], x1 = vi[(r + 1) * pitch], x2 = vi[(r + 2) * pitch], x3 = vi[(r + 3) * pitch];
+                    const T y0 = vj[(r + 0) * pitch], y1 = vj[(r + 1) * pitch], y2 = vj[(r + 2) * pitch], y3 = vj[(r + 3) * pitch];
+                    a0 = Scalar<T>::fma(Scalar<T>::conj(x0), y0, a0);
+                    a1 = Scalar<T>::fma(Scalar<T>::conj(x1), y1, a1);
+                    a2 = Scalar<T>::fma(Scalar<T>::conj(x2), y2, a2);
+                    a3 = Scalar<T>::fma(Scalar<T>::conj(x3), y3, a3);
+                }
+                for (; r < m; ++r) a0 = Scalar<T>::fma(Scalar<T>::conj(vi[r * pitch]), vj[r * pitch], a0);
+            }
+            Tm[i * pt + j] = Scalar<T>::add(Scalar<T>::add(a0, a1), Scalar<T>::add(a2, a3));
+        }
+    }
+    __syncthreads();
+    fused_clk(clk, 12);
+    if (tid < 32) wy_t_rows<T>(Tm, pt, n, tau);
+    __syncthreads();
+    fused_clk(clk, 13);
+    for (int idx = tid; idx < n * n; idx += nth) {
+        const int i = idx / n, c = idx - i * n;
+        T acc = Scalar<T>::zero();
+        for (int k = i; k <= c; ++k) acc = Scalar<T>::fma(Tm[i * pt + k], Scalar<T>::conj(blk[c * pitch + k]), acc);
+        TV[idx] = acc;
+    }
+    __syncthreads();
+}
+
+// rows [0, m) of out (ld ldo) = [S; 0] - V (TV S);  S: n x n (shared, ld n), W2: n x n scratch.  Columns n .. ocols-1
+// of out are zero filled.  One thread per (row, chunk of CW columns): no reductions across threads.
+template <typename T>
+__device__ __noinline__ void wy_apply(const T* blk, int pitch, int m, int n, const T* TV, const T* S, T* W2, T* out,
+                                      long long ldo, int ocols) {
+    __builtin_assume(__isShared(blk));
+    __builtin_assume(__isShared(TV));
+    __builtin_assume(__isShared(S));
+    __builtin_assume(__isShared(W2));
+    constexpr int CW = 4;
+    const int tid = threadIdx.x, nth = blockDim.x;
+    for (int idx = tid; idx < n * n; idx += nth) {
+        const int i = idx / n, c = idx - i * n;
+        T a0 = Scalar<T>::zero(), a1 = a0, a2 = a0, a3 = a0;
+        int k = 0;
+        for (; k + 3 < n; k += 4) {
+            a0 = Scalar<T>::fma(TV[i * n + k], S[k * n + c], a0);
+            a1 = Scalar<T>::fma(TV[i * n + k + 1], S[(k + 1) * n + c], a1);
+            a2 = Scalar<T>::fma(TV[i * n + k + 2], S[(k + 2) * n + c], a2);
+            a3 = Scalar<T>::fma(TV[i * n + k + 3], S[(k + 3) * n + c], a3);
+        }
+        for (; k < n; ++k) a0 = Scalar<T>::fma(TV[i * n + k], S[k * n + c], a0);
+        W2[idx] = Scalar<T>::add(Scalar<T>::add(a0, a1), Scalar<T>::add(a2, a3));
+    }
+    __syncthreads();
+    if (!Scalar<T>::is_complex) {
+        // out = -V W2 on the FP64 tensor pipe (the zeroed upper triangle of V takes care of k > row), then + S on top
+        cta_gemm(false, reinterpret_cast<const double*>(blk), pitch, m, n, reinterpret_cast<const double*>(W2), n, n,
+                 reinterpret_cast<double*>(out), (int)ldo, -1.0);
+        __syncthreads();
+        for (int idx = tid; idx < n * n; idx += nth) {
+            const int i = idx / n, c = idx - i * n;
+            out[(long long)i * ldo + c] = Scalar<T>::add(out[(long long)i * ldo + c], S[idx]);
+        }
+    } else {
+        const int nch = (n + CW - 1) / CW;
+        for (int item = tid; item < m * nch; item += nth) {
+            const int row = item % m, c0 = (item / m) * CW;
+            T acc[CW];
 #pragma unroll
-                for (int q = 0; q < CH; ++q) {
-                    const int c = c0 + q;
-                    if (c < n) out[(long long)i * ldo + c] = reg[t][q];
-                    else if (c < ocols) out[(long long)i * ldo + c] = Scalar<T>::zero();
+            for (int q = 0; q < CW; ++q) acc[q] = Scalar<T>::zero();
+            const T* v = blk + (size_t)row * pitch;
+            const T* w = W2 + min(c0, n - CW < 0 ? 0 : n - CW);   // last chunk shifted left when n % CW != 0 ...
+            const int sh = c0 - (int)(w - W2);                     // ... its first `sh` columns are duplicates
+            const int kend = min(row + 1, n);                      // V[row][k] == 0 for k > row
+            int k = 0;
+            for (; k + 3 < kend; k += 4) {
+                const T v0 = v[k], v1 = v[k + 1], v2 = v[k + 2], v3 = v[k + 3];
+#pragma unroll
+                for (int q = 0; q < CW; ++q) {
+                    acc[q] = Scalar<T>::fma(v0, w[k * n + q], acc[q]);
+                    acc[q] = Scalar<T>::fma(v1, w[(k + 1) * n + q], acc[q]);
+                    acc[q] = Scalar<T>::fma(v2, w[(k + 2) * n + q], acc[q]);
+                    acc[q] = Scalar<T>::fma(v3, w[(k + 3) * n + q], acc[q]);
+                }
+            }
+            for (; k < kend; ++k) {
+                const T vk = v[k];
+#pragma unroll
+                for (int q = 0; q < CW; ++q) acc[q] = Scalar<T>::fma(vk, w[k * n + q], acc[q]);
+            }
+#pragma unroll
+            for (int q = 0; q < CW; ++q) {
+                const int c = c0 - sh + q;
+                if (q >= sh && c < n) {
+                    const T s = (row < n) ? S[row * n + c] : Scalar<T>::zero();
+                    out[(long long)row * ldo + c] = Scalar<T>::sub(s, acc[q]);
                 }
             }
         }
     }
-    const int cz = nch * CH;
-    if (ocols > cz) {
-        const int wdt = ocols - cz;
-        for (int idx = threadIdx.x; idx < m * wdt; idx += blockDim.x) {
-            const int i = idx / wdt, c = cz + idx % wdt;
+    if (ocols > n) {
+        const int wdt = ocols - n;
+        for (int idx = tid; idx < m * wdt; idx += nth) {
+            const int i = idx / wdt, c = n + idx % wdt;
             out[(long long)i * ldo + c] = Scalar<T>::zero();
         }
     }
-}
-template <typename T>
-__device__ __noinline__ void fused_apply(const T* blk, int pitch, int m, int n, const double* tau, const T* seed,
-                                         const T* btop, bool positive, T* out, long long ldo, int ocols) {
-    const int rpl = (m + 31) >> 5;
-    if (rpl <= 2) fused_apply_rpl<T, 2>(blk, pitch, m, n, tau, seed, btop, positive, out, ldo, ocols);
-    else if (rpl <= 4) fused_apply_rpl<T, 4>(blk, pitch, m, n, tau, seed, btop, positive, out, ldo, ocols);
-    else fused_apply_rpl<T, 8>(blk, pitch, m, n, tau, seed, btop, positive, out, ldo, ocols);
 }
 
 // rows [s0, s1) of a dense (ld n) matrix written by OTHER CTAs of this launch -> shared panel, padding columns zero
 template <typename T>
 __device__ __forceinline__ void fused_load_stack(const T* src, int s0, int rows, int n, T* blk, int pitch) {
-    for (int idx = threadIdx.x; idx < rows * pitch; idx += blockDim.x) {
-        const int i = idx / pitch, c = idx - i * pitch;
-        blk[idx] = (c < n) ? __ldcg(src + (size_t)(s0 + i) * n + c) : Scalar<T>::zero();
+    const T* base = src + (size_t)s0 * n;                  // rows * n contiguous elements
+    const int total = rows * n;
+    for (int i0 = threadIdx.x; i0 < total; i0 += 8 * blockDim.x) {
+        T v[8];
+#pragma unroll
+        for (int e = 0; e < 8; ++e) {
+            const int idx = i0 + e * blockDim.x;
+            v[e] = (idx < total) ? __ldcg(base + idx) : Scalar<T>::zero();
+        }
+#pragma unroll
+        for (int e = 0; e < 8; ++e) {
+            const int idx = i0 + e * blockDim.x;
+            if (idx < total) {
+                const int i = idx / n, c = idx - i * n;
+                blk[i * pitch + c] = v[e];
+            }
+        }
+    }
+    const int padw = pitch - n;
+    for (int idx = threadIdx.x; idx < rows * padw; idx += blockDim.x) {
+        const int i = idx / padw, c = n + idx - i * padw;
+        blk[i * pitch + c] = Scalar<T>::zero();
     }
 }
 
@@ -347,17 +489,26 @@ __global__ void __launch_bounds__(kFusedThreads) tsqr_fused_kernel(const TsqrFus
     const int n = p.n, pitch = p.pitch;
     T* blk0 = reinterpret_cast<T*>(smem_raw);
     T* blk1 = blk0 + (size_t)p.R0 * pitch;
-    T* seed = blk1 + (size_t)p.R1 * pitch;                    // n x n
-    T* beta0 = seed + n * n;
+    T* Tm = blk1 + (size_t)p.R1 * pitch;                      // n x (n | 1), then four n x n matrices
+    T* TV0 = Tm + n * (n | 1);
+    T* TV1 = TV0 + n * n;
+    T* S = TV1 + n * n;
+    T* W2 = S + n * n;
+    T* beta0 = W2 + n * n;
     T* beta1 = beta0 + n;
     double* tau0 = reinterpret_cast<double*>(beta1 + n);
     double* tau1 = tau0 + n;
     const int b = blockIdx.x;
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31, nwarps = blockDim.x >> 5;
-    const long long r0 = ((long long)b * p.m) / p.nb0, r1 = ((long long)(b + 1) * p.m) / p.nb0;
+    // CTA nb0 (the last one) owns no level-0 block: it factors the top block, so that no block's WY build sits between
+    // the top factor and the way down
+    const bool is_top = (b == p.nb0);
+    const bool is_l1 = (p.nb1 > 0 && b < p.nb1);
+    const long long r0 = is_top ? 0 : ((long long)b * p.m) / p.nb0, r1 = is_top ? 0 : ((long long)(b + 1) * p.m) / p.nb0;
     const int mloc = (int)(r1 - r0);
     fused_clk(p.clk, 0);
     // ---- A: level-0 block
+    if (!is_top) {
     for (int i0 = warp; i0 < mloc; i0 += 8 * nwarps) {
         T v[8];
 #pragma unroll
@@ -384,61 +535,77 @@ __global__ void __launch_bounds__(kFusedThreads) tsqr_fused_kernel(const TsqrFus
     __syncthreads();
     fused_clk(p.clk, 2);
     fused_store_triangle<T>(blk0, pitch, mloc, n, beta0, p.Rst0 + (size_t)b * n * n);
-    wq_grid_barrier(p.sync);
+    }
+    unsigned int tok = wq_grid_arrive(p.sync);
+    if (!is_top && !is_l1) wy_build<T>(blk0, pitch, mloc, n, tau0, Tm, TV0);
+    wq_grid_wait(p.sync, tok);
     fused_clk(p.clk, 3);
     // ---- B: level-1 block
     const int rows1 = p.nb0 * n;
     int s0 = 0, m1 = 0;
-    if (p.nb1 > 0 && b < p.nb1) {
-        s0 = (int)(((long long)b * rows1) / p.nb1);
-        m1 = (int)(((long long)(b + 1) * rows1) / p.nb1) - s0;
-        fused_load_stack<T>(p.Rst0, s0, m1, n, blk1, pitch);
-        __syncthreads();
-        fused_factor<T>(blk1, pitch, m1, n, beta1, tau1);
-        __syncthreads();
-        fused_store_triangle<T>(blk1, pitch, m1, n, beta1, p.Rst1 + (size_t)b * n * n);
+    if (p.nb1 > 0) {
+        if (is_l1) {
+            s0 = (int)(((long long)b * rows1) / p.nb1);
+            m1 = (int)(((long long)(b + 1) * rows1) / p.nb1) - s0;
+            fused_load_stack<T>(p.Rst0, s0, m1, n, blk1, pitch);
+            __syncthreads();
+            fused_factor<T>(blk1, pitch, m1, n, beta1, tau1);
+            __syncthreads();
+            fused_store_triangle<T>(blk1, pitch, m1, n, beta1, p.Rst1 + (size_t)b * n * n);
+        }
+        tok = wq_grid_arrive(p.sync);
+        if (is_l1) {
+            wy_build<T>(blk1, pitch, m1, n, tau1, Tm, TV1);
+            wy_build<T>(blk0, pitch, mloc, n, tau0, Tm, TV0);
+        }
+        wq_grid_wait(p.sync, tok);
     }
-    if (p.nb1 > 0) wq_grid_barrier(p.sync);
     fused_clk(p.clk, 4);
     // ---- C: top block, on the last CTA
     const int rowsT = (p.nb1 > 0 ? p.nb1 : p.nb0) * n;
-    T* Mtop = p.nb1 > 0 ? p.M1 : p.M0;
-    if (b == (int)gridDim.x - 1) {
+    if (is_top) {
         fused_load_stack<T>(p.nb1 > 0 ? p.Rst1 : p.Rst0, 0, rowsT, n, blk1, pitch);
         __syncthreads();
         fused_clk(p.clk, 5);
         fused_factor<T>(blk1, pitch, rowsT, n, beta1, tau1);
         __syncthreads();
         fused_clk(p.clk, 6);
-        if (p.R) {
-            for (int idx = threadIdx.x; idx < n * n; idx += blockDim.x) {
-                const int j = idx / n, c = idx - j * n;
+        for (int idx = threadIdx.x; idx < n * n; idx += blockDim.x) {
+            const int j = idx / n, c = idx - j * n;
+            const T ph = p.positive ? wqr_phase<T>(beta1[j]) : Scalar<T>::one();
+            if (p.R) {
                 T v = Scalar<T>::zero();
                 if (c == j) v = beta1[j];
                 else if (c > j) v = blk1[j * pitch + c];
-                if (p.positive) v = Scalar<T>::mul(Scalar<T>::conj(wqr_phase<T>(beta1[j])), v);
-                p.R[idx] = v;
+                p.R[idx] = Scalar<T>::mul(Scalar<T>::conj(ph), v);
             }
+            S[idx] = (c == j) ? ph : Scalar<T>::zero();            // seed of the top block: diag(phases)
         }
-        fused_apply<T>(blk1, pitch, rowsT, n, tau1, nullptr, beta1, p.positive != 0, Mtop, n, n);
+        fused_clk(p.clk, 14);
+        wy_build<T>(blk1, pitch, rowsT, n, tau1, Tm, TV1, p.clk);
+        fused_clk(p.clk, 11);
+        wy_apply<T>(blk1, pitch, rowsT, n, TV1, S, W2, p.nb1 > 0 ? p.M1 : p.M0, n, n);
     }
     fused_clk(p.clk, 7);
-    wq_grid_barrier(p.sync);
+    tok = wq_grid_arrive(p.sync);
+    wq_grid_wait(p.sync, tok);
     fused_clk(p.clk, 8);
     // ---- D: level-1 rows of Q
     if (p.nb1 > 0) {
-        if (b < p.nb1) {
-            for (int idx = threadIdx.x; idx < n * n; idx += blockDim.x) seed[idx] = __ldcg(p.M1 + (size_t)b * n * n + idx);
+        if (is_l1) {
+            for (int idx = threadIdx.x; idx < n * n; idx += blockDim.x) S[idx] = __ldcg(p.M1 + (size_t)b * n * n + idx);
             __syncthreads();
-            fused_apply<T>(blk1, pitch, m1, n, tau1, seed, nullptr, false, p.M0 + (size_t)s0 * n, n, n);
+            wy_apply<T>(blk1, pitch, m1, n, TV1, S, W2, p.M0 + (size_t)s0 * n, n, n);
         }
-        wq_grid_barrier(p.sync);
+        tok = wq_grid_arrive(p.sync);
+        wq_grid_wait(p.sync, tok);
     }
     // ---- E: rows of Q
     fused_clk(p.clk, 9);
-    for (int idx = threadIdx.x; idx < n * n; idx += blockDim.x) seed[idx] = __ldcg(p.M0 + (size_t)b * n * n + idx);
+    if (is_top) return;
+    for (int idx = threadIdx.x; idx < n * n; idx += blockDim.x) S[idx] = __ldcg(p.M0 + (size_t)b * n * n + idx);
     __syncthreads();
-    fused_apply<T>(blk0, pitch, mloc, n, tau0, seed, nullptr, false, p.Q + r0 * p.ldq, p.ldq, p.qcols);
+    wy_apply<T>(blk0, pitch, mloc, n, TV0, S, W2, p.Q + r0 * p.ldq, p.ldq, p.qcols);
     __syncthreads();
     fused_clk(p.clk, 10);
 }
@@ -455,13 +622,13 @@ static TsqrFusedPlan tsqr_fused_plan(qil_ctx* ctx, int64_t m, int n) {
         for (int c = 0; c < 2 && !best.ok; ++c) {
             const int R0 = r0s[a], R1 = r1s[c];
             const int64_t nb0 = (m + R0 - 1) / R0;
-            if (nb0 < 2 || nb0 > ctx->sm_count) continue;           // one CTA per SM (255 registers x 256 threads)
+            if (nb0 < 2 || nb0 + 1 > ctx->sm_count) continue;       // one CTA per SM, plus the CTA of the top block
             int64_t nb1 = 0;
             if (nb0 * n > R1) {
                 nb1 = (nb0 * n + R1 - 1) / R1;
-                if (nb1 * n > R1 || nb1 >= nb0) continue;
+                if (nb1 * n > R1) continue;
             }
-            const size_t smem = ((size_t)(R0 + R1) * pitch + (size_t)n * n + 4 * (size_t)n + 8) * sizeof(T) + 64;
+            const size_t smem = ((size_t)(R0 + R1) * pitch + 5 * (size_t)n * (n + 1) + 4 * (size_t)n + 8) * sizeof(T) + 64;
             if (smem > budget) continue;
             best.ok = true;
             best.R0 = R0; best.R1 = R1; best.nb0 = (int)nb0; best.nb1 = (int)nb1; best.smem = smem;
@@ -532,9 +699,14 @@ void qr_fast(qil_ctx* ctx, int64_t m, int n, const T* A, int64_t lda, int nsum, 
             auto kern = tsqr_fused_kernel<T>;
             ensure_dynamic_smem(kern, fp.smem);
             void* args[] = {(void*)&f};
-            QIL_CUDA(cudaLaunchCooperativeKernel((const void*)kern, dim3(fp.nb0), dim3(kFusedThreads), args, fp.smem,
+            QIL_CUDA(cudaLaunchCooperativeKernel((const void*)kern, dim3(fp.nb0 + 1), dim3(kFusedThreads), args, fp.smem,
                                                  ctx->stream));
             QIL_LAUNCH_CHECK(ctx);
+            static const bool dbg_twice = [] { const char* e = getenv("QIL_TSQR_TWICE"); return e && e[0] == '1'; }();
+            if (dbg_twice) {      // debug: the same launch again with warm instruction caches (same inputs, same outputs)
+                QIL_CUDA(cudaLaunchCooperativeKernel((const void*)kern, dim3(fp.nb0 + 1), dim3(kFusedThreads), args, fp.smem,
+                                                     ctx->stream));
+            }
             if (dbg_clk) {
                 long long h[32];
                 QIL_CUDA(cudaMemcpyAsync(h, clk.p, sizeof(h), cudaMemcpyDeviceToHost, ctx->stream));
@@ -542,7 +714,7 @@ void qr_fast(qil_ctx* ctx, int64_t m, int n, const T* A, int64_t lda, int nsum, 
                 fprintf(stderr, "[tsqr_fused %lld x %d nb0 %d nb1 %d] cta0 ns:", (long long)m, n, fp.nb0, fp.nb1);
                 for (int i = 1; i <= 10; ++i) fprintf(stderr, " %lld", h[i] ? h[i] - h[0] : -1);
                 fprintf(stderr, " | last:");
-                for (int i = 1; i <= 10; ++i) fprintf(stderr, " %lld", h[16 + i] ? h[16 + i] - h[16] : -1);
+                for (int i = 1; i <= 14; ++i) fprintf(stderr, " %lld", h[16 + i] ? h[16 + i] - h[16] : -1);
                 fprintf(stderr, "\n");
             }
             return;
