@@ -239,6 +239,7 @@ __device__ __forceinline__ void fused_clk(long long* clk, int slot) {
         long long t;
         asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(t) :: "memory");
         clk[(blockIdx.x == 0 ? 0 : 16) + slot] = t;
+        clk[32 + (blockIdx.x == 0 ? 0 : 16) + slot] = clock64();
     }
 }
 
@@ -265,10 +266,27 @@ __device__ __forceinline__ void wq_grid_wait(unsigned int* sync, unsigned int g)
     __syncthreads();
 }
 
-// all 8 warps factor one block together (column parallel, named barrier 1)
+// one block factored by the CTA.  Real panels: row-parallel register-resident Householder (rqr_factor, thread <-> row,
+// the first ceil(m / 32) warps); complex panels: the column-parallel shared-memory form (all 8 warps, named barrier 1).
+// `scr`: rqr_scratch_elems(8, NC) doubles (real only).
 template <typename T>
-__device__ __noinline__ void fused_factor(T* blk, int pitch, int m, int n, T* beta, double* tau) {
+__device__ __noinline__ void fused_factor(T* blk, int pitch, int m, int n, T* beta, double* tau, T* scr) {
     wqr_factor_any<T>(blk, pitch, m, n, beta, tau, threadIdx.x >> 5, blockDim.x >> 5, 1);
+}
+__host__ __device__ inline int rqr_nc_for(int n) { return (n + 7) & ~7; }
+template <>
+__device__ __noinline__ void fused_factor<double>(double* blk, int pitch, int m, int n, double* beta, double* tau,
+                                                  double* scr) {
+    __builtin_assume(__isShared(blk));
+    __builtin_assume(__isShared(beta));
+    __builtin_assume(__isShared(tau));
+    __builtin_assume(__isShared(scr));
+    const int NW = (m + 31) >> 5;
+    if ((int)(threadIdx.x >> 5) >= NW) return;               // the caller's __syncthreads() follows
+    if (n <= 8) rqr_factor<8>(blk, pitch, m, n, beta, tau, scr, NW, 1);
+    else if (n <= 16) rqr_factor<16>(blk, pitch, m, n, beta, tau, scr, NW, 1);
+    else if (n <= 24) rqr_factor<24>(blk, pitch, m, n, beta, tau, scr, NW, 1);
+    else rqr_factor<32>(blk, pitch, m, n, beta, tau, scr, NW, 1);
 }
 
 // n x n triangle of a factored block (diag in beta) -> dst (ld n)
@@ -489,15 +507,17 @@ __global__ void __launch_bounds__(kFusedThreads) tsqr_fused_kernel(const TsqrFus
     const int n = p.n, pitch = p.pitch;
     T* blk0 = reinterpret_cast<T*>(smem_raw);
     T* blk1 = blk0 + (size_t)p.R0 * pitch;
-    T* Tm = blk1 + (size_t)p.R1 * pitch;                      // n x (n | 1), then four n x n matrices
-    T* TV0 = Tm + n * (n | 1);
-    T* TV1 = TV0 + n * n;
-    T* S = TV1 + n * n;
-    T* W2 = S + n * n;
-    T* beta0 = W2 + n * n;
+    T* beta0 = blk1 + (size_t)p.R1 * pitch;
     T* beta1 = beta0 + n;
     double* tau0 = reinterpret_cast<double*>(beta1 + n);
     double* tau1 = tau0 + n;
+    // n x (n | 1) + four n x n matrices of the WY phases; the same region is the scratch of the real factor (none of the
+    // matrices is live while a block is being factored)
+    T* Tm = reinterpret_cast<T*>((reinterpret_cast<uintptr_t>(tau1 + n) + 15) & ~(uintptr_t)15);   // 16-byte aligned
+    T* TV0 = Tm + n * (n | 1) + (n & 1);
+    T* TV1 = TV0 + n * n;
+    T* S = TV1 + n * n;
+    T* W2 = S + n * n;
     const int b = blockIdx.x;
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31, nwarps = blockDim.x >> 5;
     // CTA nb0 (the last one) owns no level-0 block: it factors the top block, so that no block's WY build sits between
@@ -531,7 +551,7 @@ __global__ void __launch_bounds__(kFusedThreads) tsqr_fused_kernel(const TsqrFus
     }
     __syncthreads();
     fused_clk(p.clk, 1);
-    fused_factor<T>(blk0, pitch, mloc, n, beta0, tau0);
+    fused_factor<T>(blk0, pitch, mloc, n, beta0, tau0, Tm);
     __syncthreads();
     fused_clk(p.clk, 2);
     fused_store_triangle<T>(blk0, pitch, mloc, n, beta0, p.Rst0 + (size_t)b * n * n);
@@ -549,7 +569,7 @@ __global__ void __launch_bounds__(kFusedThreads) tsqr_fused_kernel(const TsqrFus
             m1 = (int)(((long long)(b + 1) * rows1) / p.nb1) - s0;
             fused_load_stack<T>(p.Rst0, s0, m1, n, blk1, pitch);
             __syncthreads();
-            fused_factor<T>(blk1, pitch, m1, n, beta1, tau1);
+            fused_factor<T>(blk1, pitch, m1, n, beta1, tau1, Tm);
             __syncthreads();
             fused_store_triangle<T>(blk1, pitch, m1, n, beta1, p.Rst1 + (size_t)b * n * n);
         }
@@ -567,7 +587,7 @@ __global__ void __launch_bounds__(kFusedThreads) tsqr_fused_kernel(const TsqrFus
         fused_load_stack<T>(p.nb1 > 0 ? p.Rst1 : p.Rst0, 0, rowsT, n, blk1, pitch);
         __syncthreads();
         fused_clk(p.clk, 5);
-        fused_factor<T>(blk1, pitch, rowsT, n, beta1, tau1);
+        fused_factor<T>(blk1, pitch, rowsT, n, beta1, tau1, Tm);
         __syncthreads();
         fused_clk(p.clk, 6);
         for (int idx = threadIdx.x; idx < n * n; idx += blockDim.x) {
@@ -628,7 +648,9 @@ static TsqrFusedPlan tsqr_fused_plan(qil_ctx* ctx, int64_t m, int n) {
                 nb1 = (nb0 * n + R1 - 1) / R1;
                 if (nb1 * n > R1) continue;
             }
-            const size_t smem = ((size_t)(R0 + R1) * pitch + 5 * (size_t)n * (n + 1) + 4 * (size_t)n + 8) * sizeof(T) + 64;
+            size_t small = 5 * (size_t)n * (n + 1) + 8;               // elements of T
+            if (!Scalar<T>::is_complex) small = std::max(small, rqr_scratch_elems(8, rqr_nc_for(n)) + 8);
+            const size_t smem = ((size_t)(R0 + R1) * pitch + small + 4 * (size_t)n + 8) * sizeof(T) + 64;
             if (smem > budget) continue;
             best.ok = true;
             best.R0 = R0; best.R1 = R1; best.nb0 = (int)nb0; best.nb1 = (int)nb1; best.smem = smem;
@@ -692,8 +714,8 @@ void qr_fast(qil_ctx* ctx, int64_t m, int n, const T* A, int64_t lda, int nsum, 
             static const bool dbg_clk = [] { const char* e = getenv("QIL_TSQR_CLK"); return e && e[0] == '1'; }();
             Mat<long long> clk;
             if (dbg_clk) {
-                clk = Mat<long long>(ctx, 32, 1);
-                QIL_CUDA(cudaMemsetAsync(clk.p, 0, 32 * sizeof(long long), ctx->stream));
+                clk = Mat<long long>(ctx, 64, 1);
+                QIL_CUDA(cudaMemsetAsync(clk.p, 0, 64 * sizeof(long long), ctx->stream));
                 f.clk = clk.p;
             }
             auto kern = tsqr_fused_kernel<T>;
@@ -708,9 +730,10 @@ void qr_fast(qil_ctx* ctx, int64_t m, int n, const T* A, int64_t lda, int nsum, 
                                                      ctx->stream));
             }
             if (dbg_clk) {
-                long long h[32];
+                long long h[64];
                 QIL_CUDA(cudaMemcpyAsync(h, clk.p, sizeof(h), cudaMemcpyDeviceToHost, ctx->stream));
                 ctx->sync();
+                fprintf(stderr, "[tsqr_fused] cta0 factor A: %lld ns = %lld cycles\n", h[2] - h[1], h[34] - h[33]);
                 fprintf(stderr, "[tsqr_fused %lld x %d nb0 %d nb1 %d] cta0 ns:", (long long)m, n, fp.nb0, fp.nb1);
                 for (int i = 1; i <= 10; ++i) fprintf(stderr, " %lld", h[i] ? h[i] - h[0] : -1);
                 fprintf(stderr, " | last:");

@@ -232,6 +232,87 @@ __device__ __forceinline__ void wqr_factor(T* blk, int pitch, int m, int n, T* b
     if (W > 1) wq_bar(bar, W * 32);
 }
 
+// ---- row-parallel, register-resident Householder (real panels) ---------------------------------------------
+// wqr_factor above keeps the trailing matrix in shared memory and re-reads it every column step through a different
+// code path per (column count, first pass) case: ~1900 cycles per step, much of it instruction fetch (the kernel is
+// ~380 KB of SASS) and per-warp redundant scalar work.  Here thread r of the first NW warps holds row r of the block
+// in REGISTERS for the whole factorisation; after every step the trailing columns move one register down
+// (a[c-1] <- a[c] + f_c u: the update writes the shifted position), so the pivot column is always a[0] and ONE short
+// loop body serves every step.  Per step:
+//   products x_r a_rc (x = pivot column below the diagonal)            -> this warp's [32][NC+2] staging tile (STS.128)
+//   lane c sums column c of the tile (32 rows), writes one partial     -> partial[warp][c]
+//   ONE named barrier over the NW warps
+//   lane c adds the NW partials: x^H a_c (c = 0: |x|^2), reads the pivot row element a_jc;  the reflector scalars
+//   come from lane 0 by shuffle;  f_c = -tau (x^H a_c - beta a_jc) goes to a per-warp buffer, every lane reads all f
+//   (LDS.128 broadcasts) and updates its row.
+// Output convention is wqr_factor's: reflectors below the diagonal (head on it), R strictly above, diag(R) in beta.
+//   blk: m x n row-major, pitch; m <= 32 * NW; n <= NC;  scr: rqr_scratch_elems(NW, NC) doubles, 16-byte aligned.
+// Called by the first NW warps of the CTA (all 32 lanes each); `bar` is a named-barrier id private to them.
+__host__ __device__ inline size_t rqr_scratch_elems(int nw, int nc) {
+    return (size_t)nw * 32 * (nc + 2) + 3 * (size_t)nw * nc + 2 * (size_t)nc;
+}
+template <int NC>
+__device__ __forceinline__ void rqr_factor(double* blk, int pitch, int m, int n, double* beta, double* tau, double* scr,
+                                           int NW, int bar) {
+    constexpr int PP = NC + 2;
+    const int tid = threadIdx.x, lane = tid & 31, w = tid >> 5;
+    const int row = tid;
+    double* P = scr + (size_t)w * 32 * PP;                  // this warp's staging tile
+    double* part = scr + (size_t)NW * 32 * PP;              // [2][NW][NC]
+    double* piv = part + 2 * (size_t)NW * NC;               // [2][NC]
+    double* fbuf = piv + 2 * NC + (size_t)w * NC;           // [NC] per warp
+    double a[NC];
+#pragma unroll
+    for (int c = 0; c < NC; ++c) a[c] = (row < m && c < n) ? blk[row * pitch + c] : 0.0;
+    for (int j = 0; j < n; ++j) {
+        const int par = j & 1;
+        const double x = (row >= j) ? a[0] : 0.0;           // rows above the pivot are finished (rows >= m hold zeros)
+#pragma unroll
+        for (int c = 0; c < NC; c += 2)
+            *reinterpret_cast<double2*>(P + lane * PP + c) = make_double2(x * a[c], x * a[c + 1]);
+        if (row == j) {
+#pragma unroll
+            for (int c = 0; c < NC; c += 2)
+                *reinterpret_cast<double2*>(piv + par * NC + c) = make_double2(a[c], a[c + 1]);
+        }
+        __syncwarp();
+        if (lane < NC) {
+            double s0 = 0.0, s1 = 0.0, s2 = 0.0, s3 = 0.0;
+#pragma unroll
+            for (int r = 0; r < 32; r += 4) {
+                s0 += P[(r + 0) * PP + lane];
+                s1 += P[(r + 1) * PP + lane];
+                s2 += P[(r + 2) * PP + lane];
+                s3 += P[(r + 3) * PP + lane];
+            }
+            part[((size_t)par * NW + w) * NC + lane] = (s0 + s1) + (s2 + s3);
+        }
+        wq_bar(bar, NW * 32);
+        double tot = 0.0, pv = 0.0;
+        if (lane < NC) {
+            for (int ww = 0; ww < NW; ++ww) tot += part[((size_t)par * NW + ww) * NC + lane];
+            pv = piv[par * NC + lane];
+        }
+        const double s0 = __shfl_sync(0xffffffffu, tot, 0), x0 = __shfl_sync(0xffffffffu, pv, 0);
+        double bj, tj, head;
+        wqr_reflector<double>(s0, x0, bj, tj, head);
+        if (lane < NC) fbuf[lane] = (tj != 0.0) ? -tj * (tot - bj * pv) : 0.0;
+        __syncwarp();
+        const double u = (row > j) ? a[0] : (row == j ? head : 0.0);
+        if (row < m) blk[row * pitch + j] = (row == j) ? head : a[0];
+        a[0] = fma(fbuf[1], u, a[1]);                       // increasing c: position c is read before it is overwritten
+#pragma unroll
+        for (int c = 2; c < NC; c += 2) {
+            const double2 f = *reinterpret_cast<const double2*>(fbuf + c);
+            a[c - 1] = fma(f.x, u, a[c]);
+            a[c] = fma(f.y, u, a[c + 1 < NC ? c + 1 : c]);
+        }
+        a[NC - 1] = 0.0;
+        if (tid == 0) { beta[j] = bj; tau[j] = tj; }
+    }
+    wq_bar(bar, NW * 32);
+}
+
 // run-time row-slot count -> compile-time RPL (1, 2, 4, 8): a block of m rows costs ceil(m/32) slots, not 8
 template <typename T>
 __device__ __forceinline__ void wqr_factor_any(T* blk, int pitch, int m, int n, T* beta, double* tau, int wi, int W,
