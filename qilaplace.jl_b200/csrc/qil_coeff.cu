@@ -169,7 +169,11 @@ __device__ __forceinline__ void dmma16816c(double* c, const double* a, const dou
           "d"(b[2]), "d"(b[3]));
 }
 
-__global__ void __launch_bounds__(kCgThreads, 1)
+// NW warps: warp w works on DMMA row tile w % 8 and on column groups [(w / 8) * NG, (w / 8 + 1) * NG) of every pass,
+// NG = 64 / NW (8 warps: all 8 groups, 255 registers; 16 warps: 4 groups each, 128 registers, twice the warps per
+// scheduler to cover the load / barrier bubbles of the tensor pipe)
+template <int NW>
+__global__ void __launch_bounds__(NW * 32, 1)
 coeff_gemm_kernel(const ChainDesc d, const uint8_t* __restrict__ bits, long long B, cplx* __restrict__ out,
                   double amplitude, cplx* __restrict__ vscratch, int chi_pad) {
     extern __shared__ __align__(1024) unsigned char smem_raw[];
@@ -180,8 +184,11 @@ coeff_gemm_kernel(const ChainDesc d, const uint8_t* __restrict__ bits, long long
     int* tilebit = rowmap + kCgRows;                                     // [8]
     __shared__ int s_cnt[2];
 
+    constexpr int THREADS = NW * 32;
+    constexpr int NG = 64 / NW;                 // column groups per warp and pass
     const int n = d.n;
     const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
+    const int mtile = warp & 7, gq0 = (warp >> 3) * NG;
     const int g = lane >> 2, t = lane & 3;
     cplx* V0 = vscratch + (size_t)blockIdx.x * 2 * kCgS * chi_pad;
     cplx* V1 = V0 + (size_t)kCgS * chi_pad;
@@ -191,9 +198,9 @@ coeff_gemm_kernel(const ChainDesc d, const uint8_t* __restrict__ bits, long long
         const long long s0 = tile * kCgS;
         const int ns = (int)min((long long)kCgS, B - s0);
         __syncthreads();
-        for (int idx = tid; idx < kCgS * n; idx += kCgThreads)
+        for (int idx = tid; idx < kCgS * n; idx += THREADS)
             sbits[idx] = (idx < ns * n) ? bits[s0 * n + idx] : (uint8_t)0;
-        for (int s = tid; s < kCgS; s += kCgThreads) V0[(size_t)s * chi_pad] = make_double2(1.0, 0.0);
+        for (int s = tid; s < kCgS; s += THREADS) V0[(size_t)s * chi_pad] = make_double2(1.0, 0.0);
         __syncthreads();
 
         cplx* Vc = V0;
@@ -235,36 +242,39 @@ coeff_gemm_kernel(const ChainDesc d, const uint8_t* __restrict__ bits, long long
             const int kchunks = (cl + kCgKc - 1) / kCgKc;
             const int npass = (cr + kCgNc - 1) / kCgNc;
             const int iters = kchunks * npass;
-            const int mybit = tilebit[warp];
-            const int R0 = warp * 16 + g, R1 = R0 + 8;
+            const int mybit = tilebit[mtile];
+            const int R0 = mtile * 16 + g, R1 = R0 + 8;
             const int str0 = rowmap[R0], str1 = rowmap[R1];
 
-            auto issue = [&](int it) {
+            // one of the 16 cp.async of a stage per thread: pieces 0..7 = A (128 rows x 16 complex), 8..15 = B ((bit, 16 l) x 64)
+            auto issue_piece = [&](int it, int e) {
                 const int stage = it % kCgStages;
                 const int pass = it / kchunks, kc = it - pass * kchunks;
-                unsigned char* a = sA + stage * kCgABytes;
-                unsigned char* b = sB + stage * kCgBBytes;
-                // A: 128 rows x 16 complex
-#pragma unroll
-                for (int e = 0; e < (kCgRows * kCgKc) / kCgThreads; ++e) {
-                    const int idx = e * kCgThreads + tid;
+                if (e < 8) {
+                    unsigned char* a = sA + stage * kCgABytes;
+                    const int idx = e * THREADS + tid;
                     const int row = idx >> 4, j = idx & 15;
                     const int sidx = rowmap[row];
                     const int l = kc * kCgKc + j;
                     const bool ok = (sidx >= 0) && (l < cl);
                     const cplx* src = ok ? (Vc + (size_t)sidx * chi_pad + l) : Vc;
                     cp_async16(a + row * 256 + ((j ^ (row & 7)) << 4), src, ok);
-                }
-                // B: (bit, 16 l) x 64 complex
-#pragma unroll
-                for (int e = 0; e < (2 * kCgKc * kCgNc) / kCgThreads; ++e) {
-                    const int idx = e * kCgThreads + tid;
+                } else {
+                    unsigned char* b = sB + stage * kCgBBytes;
+                    const int idx = (e - 8) * THREADS + tid;
                     const int rowb = idx >> 6, c = idx & 63;        // rowb = bit*16 + lr
                     const int bit = rowb >> 4, lr = rowb & 15;
                     const int l = kc * kCgKc + lr, r = pass * kCgNc + c;
                     const bool ok = (l < cl) && (r < cr);
                     const cplx* src = ok ? (M + ((size_t)l * 2 + bit) * cr + r) : M;
-                    cp_async16(b + rowb * 1024 + ((c ^ (((lr >> 1) & 3) << 2)) << 4), src, ok);
+                    cp_async16(b + rowb * 1024 + ((c ^ (((lr >> 1) & 3) << 1)) << 4), src, ok);
+                }
+            };
+            auto issue = [&](int it) {
+#pragma unroll
+                for (int e = 0; e < 8; ++e) {
+                    if (e * THREADS < kCgRows * kCgKc) issue_piece(it, e);
+                    if (e * THREADS < 2 * kCgKc * kCgNc) issue_piece(it, 8 + e);
                 }
             };
 
@@ -273,23 +283,35 @@ coeff_gemm_kernel(const ChainDesc d, const uint8_t* __restrict__ bits, long long
                 if (it < iters) issue(it);
                 cp_async_commit();
             }
-            double acc[16][4];
+            // One pass = 64 complex output columns = 8 groups of 8; a group is TWO n8 DMMA tiles, the real parts and
+            // the imaginary parts of its 8 columns:
+            //   re = sum_l Vr Br - Vi Bi = (Vr, -Vi) . (Br, Bi)     A fragment with negated imaginary entries, B as loaded
+            //   im = sum_l Vr Bi + Vi Br = (Vr,  Vi) . (Bi, Br)     plain A fragment, B with re / im swapped (register names)
+            // so one pair of 16-byte loads (B[l0][c], B[l1][c], c = group column of this lane) feeds two DMMAs, and the
+            // only sign flips are the four imaginary A entries per k-block (not one select + negation per B element).
+            double accr[NG][4], acci[NG][4];
             for (int it = 0; it < iters; ++it) {
                 const int pass = it / kchunks, kc = it - pass * kchunks;
                 if (kc == 0) {
 #pragma unroll
-                    for (int x = 0; x < 16; ++x) { acc[x][0] = acc[x][1] = acc[x][2] = acc[x][3] = 0.0; }
+                    for (int x = 0; x < NG; ++x) {
+                        accr[x][0] = accr[x][1] = accr[x][2] = accr[x][3] = 0.0;
+                        acci[x][0] = acci[x][1] = acci[x][2] = acci[x][3] = 0.0;
+                    }
                 }
                 cp_async_wait<kCgStages - 2>();
                 __syncthreads();
-                if (it + kCgStages - 1 < iters) issue(it + kCgStages - 1);
-                cp_async_commit();
+                // the 16 copies of stage it+2 are issued one per column group BETWEEN the DMMAs below (the warp waits on the
+                // tensor pipe there anyway), not as a block in front of them
+                const bool more = (it + kCgStages - 1 < iters);
+                if (more) issue(it + kCgStages - 1);
                 const int stage = it % kCgStages;
                 const unsigned char* a = sA + stage * kCgABytes;
                 const unsigned char* b = sB + stage * kCgBBytes + mybit * (kCgKc * 1024);
+                const int ngroups = min(8, (cr - pass * kCgNc + 7) >> 3);       // column groups that exist in this pass
 #pragma unroll
                 for (int kb = 0; kb < 2; ++kb) {
-                    double af[8];
+                    double af[8], afn[8];
                     const int j0 = kb * 8 + 2 * t;
                     const double2 x00 = *reinterpret_cast<const double2*>(a + R0 * 256 + (((j0) ^ (R0 & 7)) << 4));
                     const double2 x01 = *reinterpret_cast<const double2*>(a + R0 * 256 + (((j0 + 1) ^ (R0 & 7)) << 4));
@@ -297,29 +319,44 @@ coeff_gemm_kernel(const ChainDesc d, const uint8_t* __restrict__ bits, long long
                     const double2 x11 = *reinterpret_cast<const double2*>(a + R1 * 256 + (((j0 + 1) ^ (R1 & 7)) << 4));
                     af[0] = x00.x; af[2] = x00.y; af[4] = x01.x; af[6] = x01.y;
                     af[1] = x10.x; af[3] = x10.y; af[5] = x11.x; af[7] = x11.y;
+                    afn[0] = af[0]; afn[1] = af[1]; afn[4] = af[4]; afn[5] = af[5];
+                    afn[2] = -af[2]; afn[3] = -af[3]; afn[6] = -af[6]; afn[7] = -af[7];
                     const int lr0 = kb * 8 + 2 * t, lr1 = lr0 + 1;
                     const unsigned char* b0p = b + lr0 * 1024;
                     const unsigned char* b1p = b + lr1 * 1024;
-                    const int sw0 = ((lr0 >> 1) & 3) << 2, sw1 = ((lr1 >> 1) & 3) << 2;
+                    const int sw0 = ((lr0 >> 1) & 3) << 1, sw1 = ((lr1 >> 1) & 3) << 1;
+                    // B elements of the next group are loaded before the DMMAs of this one are issued
+                    double2 e0n = *reinterpret_cast<const double2*>(b0p + (((gq0 * 8 + g) ^ sw0) << 4));
+                    double2 e1n = *reinterpret_cast<const double2*>(b1p + (((gq0 * 8 + g) ^ sw1) << 4));
 #pragma unroll
-                    for (int nt = 0; nt < 16; ++nt) {
-                        const int c = nt * 4 + (g >> 1);
-                        const double2 e0 = *reinterpret_cast<const double2*>(b0p + ((c ^ sw0) << 4));
-                        const double2 e1 = *reinterpret_cast<const double2*>(b1p + ((c ^ sw1) << 4));
-                        double bf[4];
-                        if (g & 1) { bf[0] = e0.y; bf[1] = e0.x; bf[2] = e1.y; bf[3] = e1.x; }
-                        else       { bf[0] = e0.x; bf[1] = -e0.y; bf[2] = e1.x; bf[3] = -e1.y; }
-                        dmma16816c(acc[nt], af, bf);
+                    for (int gq = 0; gq < NG; ++gq) {
+                        const double2 e0 = e0n, e1 = e1n;
+                        if (gq + 1 < NG) {
+                            const int cn = (gq0 + gq + 1) * 8 + g;
+                            e0n = *reinterpret_cast<const double2*>(b0p + ((cn ^ sw0) << 4));
+                            e1n = *reinterpret_cast<const double2*>(b1p + ((cn ^ sw1) << 4));
+                        }
+                        if (gq0 + gq < ngroups) {
+                            const double br[4] = {e0.x, e0.y, e1.x, e1.y};
+                            const double bi[4] = {e0.y, e0.x, e1.y, e1.x};
+                            dmma16816c(accr[gq], afn, br);
+                            dmma16816c(acci[gq], af, bi);
+                        }
                     }
                 }
+                cp_async_commit();
                 if (kc == kchunks - 1) {
-                    // epilogue of this pass: complex column = pass*64 + nt*4 + t
+                    // epilogue of this pass: complex columns pass*64 + gq*8 + {2t, 2t+1} of rows R0 / R1
 #pragma unroll
-                    for (int nt = 0; nt < 16; ++nt) {
-                        const int r = pass * kCgNc + nt * 4 + t;
+                    for (int gq = 0; gq < NG; ++gq) {
+                        const int r = pass * kCgNc + (gq0 + gq) * 8 + 2 * t;
                         if (r < cr) {
-                            if (str0 >= 0) Vn[(size_t)str0 * chi_pad + r] = make_double2(acc[nt][0], acc[nt][1]);
-                            if (str1 >= 0) Vn[(size_t)str1 * chi_pad + r] = make_double2(acc[nt][2], acc[nt][3]);
+                            if (str0 >= 0) Vn[(size_t)str0 * chi_pad + r] = make_double2(accr[gq][0], acci[gq][0]);
+                            if (str1 >= 0) Vn[(size_t)str1 * chi_pad + r] = make_double2(accr[gq][2], acci[gq][2]);
+                        }
+                        if (r + 1 < cr) {
+                            if (str0 >= 0) Vn[(size_t)str0 * chi_pad + r + 1] = make_double2(accr[gq][1], acci[gq][1]);
+                            if (str1 >= 0) Vn[(size_t)str1 * chi_pad + r + 1] = make_double2(accr[gq][3], acci[gq][3]);
                         }
                     }
                 }
@@ -328,7 +365,7 @@ coeff_gemm_kernel(const ChainDesc d, const uint8_t* __restrict__ bits, long long
             __syncthreads();
             cplx* tmp = Vc; Vc = Vn; Vn = tmp;
         }
-        for (int s = tid; s < ns; s += kCgThreads) {
+        for (int s = tid; s < ns; s += THREADS) {
             const cplx v = Vc[(size_t)s * chi_pad];
             out[s0 + s] = make_double2(v.x * amplitude, v.y * amplitude);
         }
@@ -345,9 +382,10 @@ static void launch_coeff_gemm(qil_ctx* ctx, const qil_mps* psi, const uint8_t* d
                         (kCgRows + 8) * sizeof(int) + 64;
     QIL_REQUIRE(smem <= ctx->smem_optin, QIL_ERR_UNSUPPORTED, "coefficient: chain of %d sites does not fit", psi->n);
     cplx* scratch = (cplx*)ctx->alloc((size_t)grid * 2 * kCgS * chi_pad * sizeof(cplx));
-    auto kern = coeff_gemm_kernel;
+    static const int nw = [] { const char* e = getenv("QIL_COEFF_WARPS"); return (e && atoi(e) == 8) ? 8 : 16; }();
+    auto kern = (nw == 16) ? coeff_gemm_kernel<16> : coeff_gemm_kernel<8>;
     ensure_dynamic_smem(kern, smem);
-    kern<<<grid, kCgThreads, smem, ctx->stream>>>(make_desc(psi), d_bits, (long long)B, reinterpret_cast<cplx*>(d_out),
+    kern<<<grid, nw * 32, smem, ctx->stream>>>(make_desc(psi), d_bits, (long long)B, reinterpret_cast<cplx*>(d_out),
                                                   psi->amplitude, scratch, chi_pad);
     QIL_LAUNCH_CHECK(ctx);
     ctx->free(scratch);

@@ -45,7 +45,9 @@ def test_batch_encode_matches_single_and_oracle(q, n, count, workers, qit):
         got = q.coefficients(batch[b], bits)
         # batched and single encodes sum their split-K partials in different orders; with power iterations that rounding
         # noise is amplified by the conditioning of the algorithm (oracle vs oracle on a 1-ulp perturbed input: 4e-11 at n=20)
-        assert np.abs(got - q.coefficients(one, bits)).max() <= (1e-12 if qit == 0 else 1e-9) * np.abs(xs[b]).max()
+        # (the single encode factors its tall panels with the one-launch WY TSQR, a batch with the three-launch reflector
+        # form: two Householder QRs that differ at rounding level, hence 1e-11 and not 1e-12 without power iterations)
+        assert np.abs(got - q.coefficients(one, bits)).max() <= (1e-11 if qit == 0 else 1e-9) * np.abs(xs[b]).max()
         assert np.abs(got - xs[b][idx]).max() <= 1e-6 * np.abs(xs[b]).max()
         if b in (0, count - 1):
             co, c = O.tt_rsvd(xs[b], **kw)
