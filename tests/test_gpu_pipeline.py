@@ -328,3 +328,22 @@ def test_encode_svd_sequential_large(q, n):
     bits = ((idx[:, None] >> np.arange(n - 1, -1, -1)[None, :]) & 1).astype(np.uint8)
     assert np.abs(q.coefficients(psi, bits) - O.coefficient_batch(co, c, bits)).max() <= 1e-10 * np.abs(x).max()
     print(f"signal_mps(:svd) n={n}: {dt_gpu * 1e3:.1f} ms incl. upload")
+
+
+def test_two_contexts_on_two_devices(q):
+    """Dynamic shared-memory limits are per (device, kernel): a context on a second device must raise them again
+    (round-1 advisor finding: the cache was keyed by the kernel only)."""
+    import torch
+    if torch.cuda.device_count() < 2:
+        pytest.skip("needs two GPUs")
+    n = 14
+    x = q.generate_signal(n, kind="sin_decay", freq=[1.0, 2.5], decay_rate=[0.08, 0.03])
+    kw = dict(k=15, p=5, q=2, cutoff=1e-12)
+    res = []
+    for dev in (0, 1):
+        ctx = q.Context(dev)
+        psi = q.signal_mps(x, method="rsvd", ctx=ctx, **kw)      # streaming GEMM, TSQR and node kernels: > 48 KB smem
+        bits = np.array([[(i >> (n - 1 - s)) & 1 for s in range(n)] for i in range(0, 2**n, 97)], dtype=np.uint8)
+        res.append((psi.bonds, q.coefficients(psi, bits)))
+    assert res[0][0] == res[1][0]
+    assert np.abs(res[0][1] - res[1][1]).max() <= 1e-12 * np.abs(x).max()
