@@ -232,14 +232,15 @@ struct TsqrFusedParams {
     T* R;
     int positive; int pitch;
     unsigned int* sync;     // {arrival counter, generation}, zero before the first use
+    int warm;               // instruction-cache warm-up passes in idle CTAs (QIL_TSQR_WARM=0 disables)
     long long* clk;         // debug (QIL_TSQR_CLK=1): %globaltimer of CTA 0 / the last CTA at the phase boundaries
 };
 __device__ __forceinline__ void fused_clk(long long* clk, int slot) {
     if (clk && threadIdx.x == 0 && (blockIdx.x == 0 || blockIdx.x == gridDim.x - 1)) {
         long long t;
         asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(t) :: "memory");
-        clk[(blockIdx.x == 0 ? 0 : 16) + slot] = t;
-        clk[32 + (blockIdx.x == 0 ? 0 : 16) + slot] = clock64();
+        clk[(blockIdx.x == 0 ? 0 : 24) + slot] = t;
+        clk[48 + (blockIdx.x == 0 ? 0 : 24) + slot] = clock64();
     }
 }
 
@@ -273,7 +274,6 @@ template <typename T>
 __device__ __noinline__ void fused_factor(T* blk, int pitch, int m, int n, T* beta, double* tau, T* scr) {
     wqr_factor_any<T>(blk, pitch, m, n, beta, tau, threadIdx.x >> 5, blockDim.x >> 5, 1);
 }
-__host__ __device__ inline int rqr_nc_for(int n) { return (n + 7) & ~7; }
 template <>
 __device__ __noinline__ void fused_factor<double>(double* blk, int pitch, int m, int n, double* beta, double* tau,
                                                   double* scr) {
@@ -281,12 +281,7 @@ __device__ __noinline__ void fused_factor<double>(double* blk, int pitch, int m,
     __builtin_assume(__isShared(beta));
     __builtin_assume(__isShared(tau));
     __builtin_assume(__isShared(scr));
-    const int NW = (m + 31) >> 5;
-    if ((int)(threadIdx.x >> 5) >= NW) return;               // the caller's __syncthreads() follows
-    if (n <= 8) rqr_factor<8>(blk, pitch, m, n, beta, tau, scr, NW, 1);
-    else if (n <= 16) rqr_factor<16>(blk, pitch, m, n, beta, tau, scr, NW, 1);
-    else if (n <= 24) rqr_factor<24>(blk, pitch, m, n, beta, tau, scr, NW, 1);
-    else rqr_factor<32>(blk, pitch, m, n, beta, tau, scr, NW, 1);
+    rqr_factor_any(blk, pitch, m, n, beta, tau, scr, 1);      // the caller's __syncthreads() follows
 }
 
 // n x n triangle of a factored block (diag in beta) -> dst (ld n)
@@ -316,13 +311,21 @@ __device__ __forceinline__ void wy_t_rows(T* Tm, int pt, int n, const double* ta
         row[j] = Scalar<T>::zero();
         if (j < n) {
             const double tj = tau[j];
-            T a0 = Scalar<T>::zero(), a1 = a0;
+            // column j of G first (independent broadcast loads, all in flight together), then the dot product: a load
+            // issued right in front of the FMA that consumes it costs a shared-memory latency per term
+            T g[NMAX];
+#pragma unroll
+            for (int k = 0; k < j; ++k) g[k] = Tm[k * pt + j];
+            T a0 = Scalar<T>::zero(), a1 = a0, a2 = a0, a3 = a0;
 #pragma unroll
             for (int k = 0; k < j; ++k) {
-                const T g = Tm[k * pt + j];
-                if (k & 1) a1 = Scalar<T>::fma(row[k], g, a1);
-                else a0 = Scalar<T>::fma(row[k], g, a0);
+                if ((k & 3) == 0) a0 = Scalar<T>::fma(row[k], g[k], a0);
+                else if ((k & 3) == 1) a1 = Scalar<T>::fma(row[k], g[k], a1);
+                else if ((k & 3) == 2) a2 = Scalar<T>::fma(row[k], g[k], a2);
+                else a3 = Scalar<T>::fma(row[k], g[k], a3);
             }
+            a0 = Scalar<T>::add(a0, a2);
+            a1 = Scalar<T>::add(a1, a3);
             const T v = Scalar<T>::scale(Scalar<T>::add(a0, a1), -tj);
             row[j] = (lane < j) ? v : (lane == j ? Scalar<T>::from_real(tj) : Scalar<T>::zero());
         }
@@ -333,16 +336,76 @@ __device__ __forceinline__ void wy_t_rows(T* Tm, int pt, int n, const double* ta
         if (j < n && lane < n) Tm[lane * pt + j] = row[j];
 }
 
+// G = V^T V (real; n x n, pitch pt) on the FP64 tensor pipe with the m rows split over the warps: warp w takes row tile
+// w % mtiles of G and the k-segment w / mtiles of the m rows, partial tiles go to `part` ([nseg][32][pt]) and are summed
+// in segment order (deterministic).  cta_gemm alone would leave this to the one or two warps that own a row tile of G.
+__device__ __forceinline__ void wy_gram(const double* V, int pitch, int m, int n, double* G, int pt, double* part) {
+    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31, nwarps = blockDim.x >> 5;
+    const int g = lane >> 2, t = lane & 3;
+    const int mtiles = (n + 15) >> 4, ntl = (n + 7) >> 3;
+    const int nseg = nwarps / mtiles;
+    const int mt = warp % mtiles, seg = warp / mtiles;
+    const int ksteps = (m + 15) >> 4;
+    if (seg < nseg) {
+        double acc[4][4];
+#pragma unroll
+        for (int i = 0; i < 4; ++i) { acc[i][0] = acc[i][1] = acc[i][2] = acc[i][3] = 0.0; }
+        const int r0 = mt * 16 + g, r1 = r0 + 8;
+        const int ks0 = (seg * ksteps) / nseg, ks1 = ((seg + 1) * ksteps) / nseg;
+        for (int ks = ks0; ks < ks1; ++ks) {
+            const int k0 = ks * 16;
+            double af[8];
+#pragma unroll
+            for (int i = 0; i < 4; ++i) {
+                const int k = k0 + 4 * t + i;
+                af[2 * i] = (k < m && r0 < n) ? V[k * pitch + r0] : 0.0;
+                af[2 * i + 1] = (k < m && r1 < n) ? V[k * pitch + r1] : 0.0;
+            }
+#pragma unroll
+            for (int nt = 0; nt < 4; ++nt) {
+                if (nt < ntl) {
+                    double bf[4];
+                    const int col = nt * 8 + g;
+#pragma unroll
+                    for (int i = 0; i < 4; ++i) {
+                        const int k = k0 + 4 * t + i;
+                        bf[i] = (k < m && col < n) ? V[k * pitch + col] : 0.0;
+                    }
+                    wq_dmma(acc[nt], af, bf);
+                }
+            }
+        }
+        double* P = part + (size_t)seg * 32 * pt;
+#pragma unroll
+        for (int nt = 0; nt < 4; ++nt) {
+            if (nt < ntl) {
+                const int c0 = nt * 8 + 2 * t;
+                if (c0 < n) { P[r0 * pt + c0] = acc[nt][0]; P[r1 * pt + c0] = acc[nt][2]; }
+                if (c0 + 1 < n) { P[r0 * pt + c0 + 1] = acc[nt][1]; P[r1 * pt + c0 + 1] = acc[nt][3]; }
+            }
+        }
+    }
+    __syncthreads();
+    for (int idx = threadIdx.x; idx < n * n; idx += blockDim.x) {
+        const int i = idx / n, j = idx - i * n;
+        double a = 0.0;
+        for (int sg = 0; sg < nseg; ++sg) a += part[((size_t)sg * 32 + i) * pt + j];
+        G[i * pt + j] = a;
+    }
+}
+
 // Compact WY of a factored block (m >= n rows; reflectors below the diagonal, heads on it):  TV = T V1^H  (n x n, ld n).
 // The strict upper triangle of the block (the R entries, already stored elsewhere) is zeroed so that blk IS V.
 //   G[i][j] = v_i^H v_j (i < j);  T[j][j] = tau_j,  T[0:j, j] = -tau_j T[0:j, 0:j] G[0:j, j]  (in place, one warp)
 // Tm: n x (n | 1) scratch (odd pitch: lane <-> row of T is conflict free).  All pointers are shared memory.
 template <typename T>
-__device__ __noinline__ void wy_build(T* blk, int pitch, int m, int n, const double* tau, T* Tm, T* TV, long long* clk = nullptr) {
+__device__ __noinline__ void wy_build(T* blk, int pitch, int m, int n, const double* tau, T* Tm, T* TV, T* gpart,
+                                      long long* clk = nullptr) {
     __builtin_assume(__isShared(blk));
     __builtin_assume(__isShared(tau));
     __builtin_assume(__isShared(Tm));
     __builtin_assume(__isShared(TV));
+    __builtin_assume(__isShared(gpart));
     const int tid = threadIdx.x, nth = blockDim.x;
     const int pt = n | 1;
     __syncthreads();
@@ -354,8 +417,8 @@ __device__ __noinline__ void wy_build(T* blk, int pitch, int m, int n, const dou
     // Gram G = V^H V (only the strict upper triangle is used below)
     if (!Scalar<T>::is_complex) {
         // real: FP64 tensor pipe, fragments straight from the panel
-        cta_gemm(true, reinterpret_cast<const double*>(blk), pitch, n, m, reinterpret_cast<const double*>(blk), pitch, n,
-                 reinterpret_cast<double*>(Tm), pt, 1.0);
+        wy_gram(reinterpret_cast<const double*>(blk), pitch, m, n, reinterpret_cast<double*>(Tm), pt,
+                reinterpret_cast<double*>(gpart));
     } else {
         // the same row r for all lanes of a warp (column index = lane-contiguous: conflict free); rows above the
         // diagonal contribute zeros
@@ -397,7 +460,7 @@ __device__ __noinline__ void wy_build(T* blk, int pitch, int m, int n, const dou
 // of out are zero filled.  One thread per (row, chunk of CW columns): no reductions across threads.
 template <typename T>
 __device__ __noinline__ void wy_apply(const T* blk, int pitch, int m, int n, const T* TV, const T* S, T* W2, T* out,
-                                      long long ldo, int ocols) {
+                                      long long ldo, int ocols, long long* clk = nullptr) {
     __builtin_assume(__isShared(blk));
     __builtin_assume(__isShared(TV));
     __builtin_assume(__isShared(S));
@@ -418,11 +481,13 @@ __device__ __noinline__ void wy_apply(const T* blk, int pitch, int m, int n, con
         W2[idx] = Scalar<T>::add(Scalar<T>::add(a0, a1), Scalar<T>::add(a2, a3));
     }
     __syncthreads();
+    fused_clk(clk, 15);
     if (!Scalar<T>::is_complex) {
         // out = -V W2 on the FP64 tensor pipe (the zeroed upper triangle of V takes care of k > row), then + S on top
         cta_gemm(false, reinterpret_cast<const double*>(blk), pitch, m, n, reinterpret_cast<const double*>(W2), n, n,
                  reinterpret_cast<double*>(out), (int)ldo, -1.0);
         __syncthreads();
+        fused_clk(clk, 16);
         for (int idx = tid; idx < n * n; idx += nth) {
             const int i = idx / n, c = idx - i * n;
             out[(long long)i * ldo + c] = Scalar<T>::add(out[(long long)i * ldo + c], S[idx]);
@@ -507,6 +572,7 @@ __global__ void __launch_bounds__(kFusedThreads) tsqr_fused_kernel(const TsqrFus
     const int n = p.n, pitch = p.pitch;
     T* blk0 = reinterpret_cast<T*>(smem_raw);
     T* blk1 = blk0 + (size_t)p.R0 * pitch;
+    T* blkT = p.nb1 > 0 ? blk1 : blk0;          // the top CTA owns no level-0 block: two-level plans reuse that region
     T* beta0 = blk1 + (size_t)p.R1 * pitch;
     T* beta1 = beta0 + n;
     double* tau0 = reinterpret_cast<double*>(beta1 + n);
@@ -518,6 +584,7 @@ __global__ void __launch_bounds__(kFusedThreads) tsqr_fused_kernel(const TsqrFus
     T* TV1 = TV0 + n * n;
     T* S = TV1 + n * n;
     T* W2 = S + n * n;
+    T* Gp = W2 + n * n;                                       // partial Gram tiles (real): the tail of the factor scratch
     const int b = blockIdx.x;
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31, nwarps = blockDim.x >> 5;
     // CTA nb0 (the last one) owns no level-0 block: it factors the top block, so that no block's WY build sits between
@@ -529,16 +596,17 @@ __global__ void __launch_bounds__(kFusedThreads) tsqr_fused_kernel(const TsqrFus
     fused_clk(p.clk, 0);
     // ---- A: level-0 block
     if (!is_top) {
-    for (int i0 = warp; i0 < mloc; i0 += 8 * nwarps) {
-        T v[8];
+    constexpr int kInFlight = Scalar<T>::is_complex ? 8 : 16;
+    for (int i0 = warp; i0 < mloc; i0 += kInFlight * nwarps) {
+        T v[kInFlight];
 #pragma unroll
-        for (int e = 0; e < 8; ++e) {
+        for (int e = 0; e < kInFlight; ++e) {
             const int i = i0 + e * nwarps;
             v[e] = Scalar<T>::zero();
             if (i < mloc && lane < n) v[e] = load_sum<T>(p.A + (r0 + i) * p.lda + lane, p.nsum, p.sum_stride);
         }
 #pragma unroll
-        for (int e = 0; e < 8; ++e) {
+        for (int e = 0; e < kInFlight; ++e) {
             const int i = i0 + e * nwarps;
             if (i < mloc && lane < pitch) blk0[i * pitch + lane] = v[e];
         }
@@ -557,7 +625,29 @@ __global__ void __launch_bounds__(kFusedThreads) tsqr_fused_kernel(const TsqrFus
     fused_store_triangle<T>(blk0, pitch, mloc, n, beta0, p.Rst0 + (size_t)b * n * n);
     }
     unsigned int tok = wq_grid_arrive(p.sync);
-    if (!is_top && !is_l1) wy_build<T>(blk0, pitch, mloc, n, tau0, Tm, TV0);
+    if (!is_top && !is_l1) wy_build<T>(blk0, pitch, mloc, n, tau0, Tm, TV0, Gp);
+    if (is_top && p.warm) {
+        // Instruction-cache warm-up.  Every phase of this kernel is code its SM has not run yet (and the streaming passes
+        // between two QRs flush it from L2), so a phase costs more in instruction fetch than in arithmetic.  The CTA of
+        // the top block is idle until the levels below have been factored: it runs its whole phase (factor, WY build,
+        // WY apply) once on a synthetic block of the same shape, so that the real pass finds the code in its caches.
+        // Everything it writes (shared memory, M1 / M0) is overwritten by the real pass before anybody reads it.
+        const int rowsW = (p.nb1 > 0 ? p.nb1 : p.nb0) * n;
+        for (int idx = threadIdx.x; idx < rowsW * pitch; idx += blockDim.x) {
+            const int i = idx / pitch, c = idx - i * pitch;
+            blkT[idx] = (c < n) ? Scalar<T>::from_real(((i % n) == c ? 1.0 : 0.0) + 1e-3 * (double)((i * 7 + c * 3) % 11)) : Scalar<T>::zero();
+        }
+        __syncthreads();
+        fused_factor<T>(blkT, pitch, rowsW, n, beta1, tau1, Tm);
+        __syncthreads();
+        for (int idx = threadIdx.x; idx < n * n; idx += blockDim.x) {
+            const int j = idx / n, c = idx - j * n;
+            S[idx] = (c == j) ? wqr_phase<T>(beta1[j]) : Scalar<T>::zero();
+        }
+        wy_build<T>(blkT, pitch, rowsW, n, tau1, Tm, TV1, Gp);
+        wy_apply<T>(blkT, pitch, rowsW, n, TV1, S, W2, p.nb1 > 0 ? p.M1 : p.M0, n, n);
+        __syncthreads();
+    }
     wq_grid_wait(p.sync, tok);
     fused_clk(p.clk, 3);
     // ---- B: level-1 block
@@ -575,8 +665,8 @@ __global__ void __launch_bounds__(kFusedThreads) tsqr_fused_kernel(const TsqrFus
         }
         tok = wq_grid_arrive(p.sync);
         if (is_l1) {
-            wy_build<T>(blk1, pitch, m1, n, tau1, Tm, TV1);
-            wy_build<T>(blk0, pitch, mloc, n, tau0, Tm, TV0);
+            wy_build<T>(blk1, pitch, m1, n, tau1, Tm, TV1, Gp);
+            wy_build<T>(blk0, pitch, mloc, n, tau0, Tm, TV0, Gp);
         }
         wq_grid_wait(p.sync, tok);
     }
@@ -584,10 +674,10 @@ __global__ void __launch_bounds__(kFusedThreads) tsqr_fused_kernel(const TsqrFus
     // ---- C: top block, on the last CTA
     const int rowsT = (p.nb1 > 0 ? p.nb1 : p.nb0) * n;
     if (is_top) {
-        fused_load_stack<T>(p.nb1 > 0 ? p.Rst1 : p.Rst0, 0, rowsT, n, blk1, pitch);
+        fused_load_stack<T>(p.nb1 > 0 ? p.Rst1 : p.Rst0, 0, rowsT, n, blkT, pitch);
         __syncthreads();
         fused_clk(p.clk, 5);
-        fused_factor<T>(blk1, pitch, rowsT, n, beta1, tau1, Tm);
+        fused_factor<T>(blkT, pitch, rowsT, n, beta1, tau1, Tm);
         __syncthreads();
         fused_clk(p.clk, 6);
         for (int idx = threadIdx.x; idx < n * n; idx += blockDim.x) {
@@ -596,15 +686,15 @@ __global__ void __launch_bounds__(kFusedThreads) tsqr_fused_kernel(const TsqrFus
             if (p.R) {
                 T v = Scalar<T>::zero();
                 if (c == j) v = beta1[j];
-                else if (c > j) v = blk1[j * pitch + c];
+                else if (c > j) v = blkT[j * pitch + c];
                 p.R[idx] = Scalar<T>::mul(Scalar<T>::conj(ph), v);
             }
             S[idx] = (c == j) ? ph : Scalar<T>::zero();            // seed of the top block: diag(phases)
         }
         fused_clk(p.clk, 14);
-        wy_build<T>(blk1, pitch, rowsT, n, tau1, Tm, TV1, p.clk);
+        wy_build<T>(blkT, pitch, rowsT, n, tau1, Tm, TV1, Gp, p.clk);
         fused_clk(p.clk, 11);
-        wy_apply<T>(blk1, pitch, rowsT, n, TV1, S, W2, p.nb1 > 0 ? p.M1 : p.M0, n, n);
+        wy_apply<T>(blkT, pitch, rowsT, n, TV1, S, W2, p.nb1 > 0 ? p.M1 : p.M0, n, n, p.clk);
     }
     fused_clk(p.clk, 7);
     tok = wq_grid_arrive(p.sync);
@@ -637,6 +727,36 @@ static TsqrFusedPlan tsqr_fused_plan(qil_ctx* ctx, int64_t m, int n) {
     if (off) return best;
     const size_t budget = std::min<size_t>(ctx->smem_optin, 225 * 1024);
     const int pitch = wqr_pitch(n);
+    // rows one block may have: the register-resident real factor takes 768 (512 beyond 24 columns), the complex
+    // shared-memory form 256
+    const int maxrows = Scalar<T>::is_complex ? kWqrMaxRows : rqr_max_rows(n);
+    auto small_elems = [&]() {
+        size_t small = 5 * (size_t)n * (n + 1) + 8;               // elements of T
+        if (!Scalar<T>::is_complex) {
+            const int mtiles = (n + 15) / 16;
+            small += (size_t)(8 / mtiles) * 32 * (n | 1);         // partial Gram tiles of wy_gram behind the matrices
+            small = std::max(small, rqr_scratch_elems(8, rqr_nc_for(n)) + 8);
+        }
+        return small;
+    };
+    // two levels: nb0 blocks of <= R0 rows, their triangles go straight to the top block (which sits in the level-0
+    // region of its own CTA).  The smallest R0 that fits: most CTAs, shortest column steps.  Blocks stay <= 256 rows
+    // although the factor could take 768: one SM has 64 FP64 FMA / clock, and a 640-row top block (two levels for a
+    // 2^14-row panel) was measured SLOWER than three levels of small blocks (127 vs 116 us; per column step 3300 cycles
+    // for 640 rows against 1840 for 128, and every product of the WY phase scales the same way).
+    const int maxrows2 = std::min(maxrows, kWqrMaxRows);
+    for (int R0 = 128; R0 <= maxrows2 && !best.ok; R0 *= 2) {
+        const int64_t nb0 = (m + R0 - 1) / R0;
+        if (nb0 < 2 || nb0 + 1 > ctx->sm_count) continue;
+        const int64_t rowsT = nb0 * n;
+        if (rowsT > maxrows2) continue;
+        const int RA = (int)std::max<int64_t>(R0, rowsT);
+        const size_t smem = ((size_t)RA * pitch + small_elems() + 4 * (size_t)n + 8) * sizeof(T) + 64;
+        if (smem > budget) continue;
+        best.ok = true;
+        best.R0 = RA; best.R1 = 0; best.nb0 = (int)nb0; best.nb1 = 0; best.smem = smem;
+    }
+    // three levels
     const int r0s[2] = {128, 256}, r1s[2] = {256, 128};
     for (int a = 0; a < 2 && !best.ok; ++a) {
         for (int c = 0; c < 2 && !best.ok; ++c) {
@@ -647,10 +767,10 @@ static TsqrFusedPlan tsqr_fused_plan(qil_ctx* ctx, int64_t m, int n) {
             if (nb0 * n > R1) {
                 nb1 = (nb0 * n + R1 - 1) / R1;
                 if (nb1 * n > R1) continue;
+            } else {
+                continue;                                           // would have been a two-level plan
             }
-            size_t small = 5 * (size_t)n * (n + 1) + 8;               // elements of T
-            if (!Scalar<T>::is_complex) small = std::max(small, rqr_scratch_elems(8, rqr_nc_for(n)) + 8);
-            const size_t smem = ((size_t)(R0 + R1) * pitch + small + 4 * (size_t)n + 8) * sizeof(T) + 64;
+            const size_t smem = ((size_t)(R0 + R1) * pitch + small_elems() + 4 * (size_t)n + 8) * sizeof(T) + 64;
             if (smem > budget) continue;
             best.ok = true;
             best.R0 = R0; best.R1 = R1; best.nb0 = (int)nb0; best.nb1 = (int)nb1; best.smem = smem;
@@ -711,11 +831,13 @@ void qr_fast(qil_ctx* ctx, int64_t m, int n, const T* A, int64_t lda, int nsum, 
             f.Rst0 = Rst0.p; f.M0 = M0.p; f.Rst1 = Rst1.p; f.M1 = M1.p;
             f.Q = Q; f.ldq = ldq; f.qcols = p.qcols; f.R = R; f.positive = p.positive; f.pitch = p.pitch;
             f.sync = ctx->get_grid_sync();
+            static const bool warm = [] { const char* e = getenv("QIL_TSQR_WARM"); return !(e && e[0] == '0'); }();
+            f.warm = warm ? 1 : 0;
             static const bool dbg_clk = [] { const char* e = getenv("QIL_TSQR_CLK"); return e && e[0] == '1'; }();
             Mat<long long> clk;
             if (dbg_clk) {
-                clk = Mat<long long>(ctx, 64, 1);
-                QIL_CUDA(cudaMemsetAsync(clk.p, 0, 64 * sizeof(long long), ctx->stream));
+                clk = Mat<long long>(ctx, 96, 1);
+                QIL_CUDA(cudaMemsetAsync(clk.p, 0, 96 * sizeof(long long), ctx->stream));
                 f.clk = clk.p;
             }
             auto kern = tsqr_fused_kernel<T>;
@@ -730,14 +852,14 @@ void qr_fast(qil_ctx* ctx, int64_t m, int n, const T* A, int64_t lda, int nsum, 
                                                      ctx->stream));
             }
             if (dbg_clk) {
-                long long h[64];
+                long long h[96];
                 QIL_CUDA(cudaMemcpyAsync(h, clk.p, sizeof(h), cudaMemcpyDeviceToHost, ctx->stream));
                 ctx->sync();
-                fprintf(stderr, "[tsqr_fused] cta0 factor A: %lld ns = %lld cycles\n", h[2] - h[1], h[34] - h[33]);
+                fprintf(stderr, "[tsqr_fused] cta0 factor A: %lld ns = %lld cycles\n", h[2] - h[1], h[50] - h[49]);
                 fprintf(stderr, "[tsqr_fused %lld x %d nb0 %d nb1 %d] cta0 ns:", (long long)m, n, fp.nb0, fp.nb1);
                 for (int i = 1; i <= 10; ++i) fprintf(stderr, " %lld", h[i] ? h[i] - h[0] : -1);
                 fprintf(stderr, " | last:");
-                for (int i = 1; i <= 14; ++i) fprintf(stderr, " %lld", h[16 + i] ? h[16 + i] - h[16] : -1);
+                for (int i = 1; i <= 18; ++i) fprintf(stderr, " %lld", h[24 + i] ? h[24 + i] - h[24] : -1);
                 fprintf(stderr, "\n");
             }
             return;

@@ -251,31 +251,58 @@ __device__ __forceinline__ void wqr_factor(T* blk, int pitch, int m, int n, T* b
 __host__ __device__ inline size_t rqr_scratch_elems(int nw, int nc) {
     return (size_t)nw * 32 * (nc + 2) + 3 * (size_t)nw * nc + 2 * (size_t)nc;
 }
-template <int NC>
+// RT rows per thread: thread tid of the NW participating warps holds rows tid, tid + 32 NW, ... (RT of them), so a block
+// has up to 32 * NW * RT rows; the products of a thread's rows are summed before they are staged, i.e. the shared-memory
+// traffic per step does not grow with RT, only the FMAs do.
+#ifdef QIL_RQR_PROFILE
+#define RQR_CLK(slot) do { const long long c_ = clock64(); rqr_seg[slot] += c_ - rqr_t; rqr_t = c_; } while (0)
+#else
+#define RQR_CLK(slot) do { } while (0)
+#endif
+template <int NC, int RT>
 __device__ __forceinline__ void rqr_factor(double* blk, int pitch, int m, int n, double* beta, double* tau, double* scr,
                                            int NW, int bar) {
     constexpr int PP = NC + 2;
     const int tid = threadIdx.x, lane = tid & 31, w = tid >> 5;
-    const int row = tid;
+    const int nthr = NW * 32;
     double* P = scr + (size_t)w * 32 * PP;                  // this warp's staging tile
     double* part = scr + (size_t)NW * 32 * PP;              // [2][NW][NC]
     double* piv = part + 2 * (size_t)NW * NC;               // [2][NC]
     double* fbuf = piv + 2 * NC + (size_t)w * NC;           // [NC] per warp
-    double a[NC];
+    double a[RT][NC];
+    int row[RT];
 #pragma unroll
-    for (int c = 0; c < NC; ++c) a[c] = (row < m && c < n) ? blk[row * pitch + c] : 0.0;
+    for (int t = 0; t < RT; ++t) {
+        row[t] = tid + t * nthr;
+#pragma unroll
+        for (int c = 0; c < NC; ++c) a[t][c] = (row[t] < m && c < n) ? blk[row[t] * pitch + c] : 0.0;
+    }
+#ifdef QIL_RQR_PROFILE
+    long long rqr_seg[8] = {0, 0, 0, 0, 0, 0, 0, 0};
+    long long rqr_t = clock64();
+#endif
     for (int j = 0; j < n; ++j) {
         const int par = j & 1;
-        const double x = (row >= j) ? a[0] : 0.0;           // rows above the pivot are finished (rows >= m hold zeros)
+        double x[RT];
 #pragma unroll
-        for (int c = 0; c < NC; c += 2)
-            *reinterpret_cast<double2*>(P + lane * PP + c) = make_double2(x * a[c], x * a[c + 1]);
-        if (row == j) {
+        for (int t = 0; t < RT; ++t) x[t] = (row[t] >= j) ? a[t][0] : 0.0;   // rows above the pivot are finished
 #pragma unroll
-            for (int c = 0; c < NC; c += 2)
-                *reinterpret_cast<double2*>(piv + par * NC + c) = make_double2(a[c], a[c + 1]);
+        for (int c = 0; c < NC; c += 2) {
+            double p0 = x[0] * a[0][c], p1 = x[0] * a[0][c + 1];
+#pragma unroll
+            for (int t = 1; t < RT; ++t) { p0 = fma(x[t], a[t][c], p0); p1 = fma(x[t], a[t][c + 1], p1); }
+            *reinterpret_cast<double2*>(P + lane * PP + c) = make_double2(p0, p1);
+        }
+#pragma unroll
+        for (int t = 0; t < RT; ++t) {
+            if (row[t] == j) {
+#pragma unroll
+                for (int c = 0; c < NC; c += 2)
+                    *reinterpret_cast<double2*>(piv + par * NC + c) = make_double2(a[t][c], a[t][c + 1]);
+            }
         }
         __syncwarp();
+        RQR_CLK(0);
         if (lane < NC) {
             double s0 = 0.0, s1 = 0.0, s2 = 0.0, s3 = 0.0;
 #pragma unroll
@@ -287,30 +314,74 @@ __device__ __forceinline__ void rqr_factor(double* blk, int pitch, int m, int n,
             }
             part[((size_t)par * NW + w) * NC + lane] = (s0 + s1) + (s2 + s3);
         }
-        wq_bar(bar, NW * 32);
+        RQR_CLK(1);
+        if (NW > 1) wq_bar(bar, nthr); else __syncwarp();
+        RQR_CLK(2);
         double tot = 0.0, pv = 0.0;
         if (lane < NC) {
             for (int ww = 0; ww < NW; ++ww) tot += part[((size_t)par * NW + ww) * NC + lane];
             pv = piv[par * NC + lane];
         }
         const double s0 = __shfl_sync(0xffffffffu, tot, 0), x0 = __shfl_sync(0xffffffffu, pv, 0);
+        RQR_CLK(3);
         double bj, tj, head;
         wqr_reflector<double>(s0, x0, bj, tj, head);
+        RQR_CLK(4);
         if (lane < NC) fbuf[lane] = (tj != 0.0) ? -tj * (tot - bj * pv) : 0.0;
         __syncwarp();
-        const double u = (row > j) ? a[0] : (row == j ? head : 0.0);
-        if (row < m) blk[row * pitch + j] = (row == j) ? head : a[0];
-        a[0] = fma(fbuf[1], u, a[1]);                       // increasing c: position c is read before it is overwritten
+        RQR_CLK(5);
+        double u[RT];
+#pragma unroll
+        for (int t = 0; t < RT; ++t) {
+            u[t] = (row[t] > j) ? a[t][0] : (row[t] == j ? head : 0.0);
+            if (row[t] < m) blk[row[t] * pitch + j] = (row[t] == j) ? head : a[t][0];
+        }
+        {
+            const double f1 = fbuf[1];                      // increasing c: position c is read before it is overwritten
+#pragma unroll
+            for (int t = 0; t < RT; ++t) a[t][0] = fma(f1, u[t], a[t][1]);
+        }
 #pragma unroll
         for (int c = 2; c < NC; c += 2) {
             const double2 f = *reinterpret_cast<const double2*>(fbuf + c);
-            a[c - 1] = fma(f.x, u, a[c]);
-            a[c] = fma(f.y, u, a[c + 1 < NC ? c + 1 : c]);
+#pragma unroll
+            for (int t = 0; t < RT; ++t) {
+                a[t][c - 1] = fma(f.x, u[t], a[t][c]);
+                a[t][c] = fma(f.y, u[t], a[t][c + 1 < NC ? c + 1 : c]);
+            }
         }
-        a[NC - 1] = 0.0;
+#pragma unroll
+        for (int t = 0; t < RT; ++t) a[t][NC - 1] = 0.0;
         if (tid == 0) { beta[j] = bj; tau[j] = tj; }
+        RQR_CLK(6);
     }
-    wq_bar(bar, NW * 32);
+#ifdef QIL_RQR_PROFILE
+    if (tid == 0) for (int i = 0; i < 8; ++i) g_rqr_seg[i] = rqr_seg[i];
+#endif
+    if (NW > 1) wq_bar(bar, nthr); else __syncwarp();
+}
+// run-time column capacity / rows per thread -> compile-time.  m <= 32 * NW * RT with NW <= 8 warps; RT = 3 only up to 24
+// columns (register budget)
+constexpr int kRqrMaxRows24 = 768, kRqrMaxRows32 = 512;
+__host__ __device__ inline int rqr_max_rows(int n) { return n <= 24 ? kRqrMaxRows24 : kRqrMaxRows32; }
+__host__ __device__ inline int rqr_nc_for(int n) { return (n + 7) & ~7; }
+template <int NC>
+__device__ __forceinline__ void rqr_factor_rt(double* blk, int pitch, int m, int n, double* beta, double* tau, double* scr,
+                                              int NW, int bar) {
+    const int rt = (m + NW * 32 - 1) / (NW * 32);
+    if (rt <= 1) rqr_factor<NC, 1>(blk, pitch, m, n, beta, tau, scr, NW, bar);
+    else if (rt == 2) rqr_factor<NC, 2>(blk, pitch, m, n, beta, tau, scr, NW, bar);
+    else if (NC <= 24) rqr_factor<(NC <= 24 ? NC : 8), 3>(blk, pitch, m, n, beta, tau, scr, NW, bar);
+}
+// all threads of the CTA call; the first NW = min(8, ceil(m / 32)) warps work.  No trailing CTA barrier.
+__device__ __forceinline__ void rqr_factor_any(double* blk, int pitch, int m, int n, double* beta, double* tau, double* scr,
+                                               int bar) {
+    const int NW = min(8, (m + 31) >> 5);
+    if ((int)(threadIdx.x >> 5) >= NW) return;
+    if (n <= 8) rqr_factor_rt<8>(blk, pitch, m, n, beta, tau, scr, NW, bar);
+    else if (n <= 16) rqr_factor_rt<16>(blk, pitch, m, n, beta, tau, scr, NW, bar);
+    else if (n <= 24) rqr_factor_rt<24>(blk, pitch, m, n, beta, tau, scr, NW, bar);
+    else rqr_factor_rt<32>(blk, pitch, m, n, beta, tau, scr, NW, bar);
 }
 
 // run-time row-slot count -> compile-time RPL (1, 2, 4, 8): a block of m rows costs ceil(m/32) slots, not 8
