@@ -625,7 +625,11 @@ __global__ void __launch_bounds__(kFusedThreads) tsqr_fused_kernel(const TsqrFus
     fused_store_triangle<T>(blk0, pitch, mloc, n, beta0, p.Rst0 + (size_t)b * n * n);
     }
     unsigned int tok = wq_grid_arrive(p.sync);
-    if (!is_top && !is_l1) wy_build<T>(blk0, pitch, mloc, n, tau0, Tm, TV0, Gp);
+    if (!is_top && !is_l1) {
+        wy_build<T>(blk0, pitch, mloc, n, tau0, Tm, TV0, Gp);
+        // warm-up of the way down (see below): the rows of Q written here are written again in phase E
+        if (p.warm) wy_apply<T>(blk0, pitch, mloc, n, TV0, S, W2, p.Q + r0 * p.ldq, p.ldq, p.qcols);
+    }
     if (is_top && p.warm) {
         // Instruction-cache warm-up.  Every phase of this kernel is code its SM has not run yet (and the streaming passes
         // between two QRs flush it from L2), so a phase costs more in instruction fetch than in arithmetic.  The CTA of
@@ -667,6 +671,11 @@ __global__ void __launch_bounds__(kFusedThreads) tsqr_fused_kernel(const TsqrFus
         if (is_l1) {
             wy_build<T>(blk1, pitch, m1, n, tau1, Tm, TV1, Gp);
             wy_build<T>(blk0, pitch, mloc, n, tau0, Tm, TV0, Gp);
+            if (p.warm) {       // warm-up of phases D and E; both outputs are written again there
+                wy_apply<T>(blk1, pitch, m1, n, TV1, S, W2, p.M0 + (size_t)s0 * n, n, n);
+                wy_apply<T>(blk0, pitch, mloc, n, TV0, S, W2, p.Q + r0 * p.ldq, p.ldq, p.qcols);
+                __syncthreads();
+            }
         }
         wq_grid_wait(p.sync, tok);
     }

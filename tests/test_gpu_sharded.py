@@ -22,6 +22,14 @@ def _signal(n, cplx):
     return x * np.exp(0.3j * t) if cplx else x
 
 
+def _free_port():
+    """A port nobody listens on right now (a fixed pid-derived port collided once when the whole file ran back to back)."""
+    import socket
+    with socket.socket(socket.AF_INET, socket.SOCK_STREAM) as sk:
+        sk.bind(("127.0.0.1", 0))
+        return sk.getsockname()[1]
+
+
 def _worker(rank, world, port, ret, default_stream=False, peer=False):
     sys.path.insert(0, ROOT)
     sys.path.insert(0, os.path.join(ROOT, "oracle"))
@@ -79,7 +87,7 @@ def _worker(rank, world, port, ret, default_stream=False, peer=False):
                                                        (4, False, False), (4, False, True)])
 def test_row_sharded_encode_matches_single_device_and_oracle(world, default_stream, peer):
     import torch.multiprocessing as mp
-    port = 33500 + (os.getpid() % 2000) + 4 * world + 2 * int(default_stream) + int(peer)
+    port = _free_port()
     mgr = mp.Manager()
     ret = mgr.dict()
     mp.spawn(_worker, args=(world, port, ret, default_stream, peer), nprocs=world, join=True)
@@ -134,7 +142,7 @@ def test_row_sharded_encode_many_gpus_bonds_identical(world, peer):
     import torch.multiprocessing as mp
     if torch.cuda.device_count() < world:
         pytest.skip(f"needs {world} GPUs")
-    port = 35500 + (os.getpid() % 2000) + 8 * world + int(peer)
+    port = _free_port()
     mgr = mp.Manager()
     ret = mgr.dict()
     mp.spawn(_worker_big, args=(world, port, ret, peer), nprocs=world, join=True)
@@ -183,7 +191,7 @@ def _worker_scan(rank, world, port, ret):
 @pytest.mark.parametrize("world", [2, 4])
 def test_broadcast_mps_and_sharded_pole_scan(world):
     import torch.multiprocessing as mp
-    port = 36500 + (os.getpid() % 2000) + world
+    port = _free_port()
     mgr = mp.Manager()
     ret = mgr.dict()
     mp.spawn(_worker_scan, args=(world, port, ret), nprocs=world, join=True)
