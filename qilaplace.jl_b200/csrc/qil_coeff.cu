@@ -160,6 +160,29 @@ __device__ __forceinline__ void cp_async_commit() { asm volatile("cp.async.commi
 template <int N> __device__ __forceinline__ void cp_async_wait() {
     asm volatile("cp.async.wait_group %0;" ::"n"(N) : "memory");
 }
+// mbarrier helpers for the full / empty ring of coeff_gemm_kernel<NW, true>
+__device__ __forceinline__ unsigned cg_smem_u32(const void* p) { return (unsigned)__cvta_generic_to_shared(p); }
+__device__ __forceinline__ void cg_mbar_init(uint64_t* bar, unsigned count) {
+    asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(cg_smem_u32(bar)), "r"(count));
+}
+__device__ __forceinline__ void cg_mbar_arrive(uint64_t* bar) {
+    asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" ::"r"(cg_smem_u32(bar)) : "memory");
+}
+// arrival that fires when all cp.async issued so far by this thread have landed (counts as one expected arrival)
+__device__ __forceinline__ void cg_cp_async_arrive(uint64_t* bar) {
+    asm volatile("cp.async.mbarrier.arrive.noinc.shared::cta.b64 [%0];" ::"r"(cg_smem_u32(bar)) : "memory");
+}
+__device__ __forceinline__ void cg_mbar_wait(uint64_t* bar, unsigned parity) {
+    asm volatile(
+        "{\n"
+        ".reg .pred p;\n"
+        "CG_WAIT:\n"
+        "mbarrier.try_wait.parity.shared::cta.b64 p, [%0], %1;\n"
+        "@p bra CG_DONE;\n"
+        "bra CG_WAIT;\n"
+        "CG_DONE:\n"
+        "}\n" ::"r"(cg_smem_u32(bar)), "r"(parity) : "memory");
+}
 __device__ __forceinline__ void dmma16816c(double* c, const double* a, const double* b) {
     asm volatile(
         "mma.sync.aligned.m16n8k16.row.col.f64.f64.f64.f64 {%0,%1,%2,%3}, {%4,%5,%6,%7,%8,%9,%10,%11}, "
@@ -172,7 +195,10 @@ __device__ __forceinline__ void dmma16816c(double* c, const double* a, const dou
 // NW warps: warp w works on DMMA row tile w % 8 and on column groups [(w / 8) * NG, (w / 8 + 1) * NG) of every pass,
 // NG = 64 / NW (8 warps: all 8 groups, 255 registers; 16 warps: 4 groups each, 128 registers, twice the warps per
 // scheduler to cover the load / barrier bubbles of the tensor pipe)
-template <int NW>
+// MB: the stages of the ring are handed over through mbarriers (every thread's cp.async arrive on full[stage], every warp
+// arrives on empty[stage] after its last read) instead of cp.async.wait_group + __syncthreads() per k-chunk, so warps
+// drift against each other by up to one chunk and no warp waits for the slowest one at every chunk.
+template <int NW, bool MB>
 __global__ void __launch_bounds__(NW * 32, 1)
 coeff_gemm_kernel(const ChainDesc d, const uint8_t* __restrict__ bits, long long B, cplx* __restrict__ out,
                   double amplitude, cplx* __restrict__ vscratch, int chi_pad) {
@@ -183,6 +209,7 @@ coeff_gemm_kernel(const ChainDesc d, const uint8_t* __restrict__ bits, long long
     int* rowmap = reinterpret_cast<int*>(sbits + ((kCgS * d.n + 15) & ~15));  // [128] string of each tile row
     int* tilebit = rowmap + kCgRows;                                     // [8]
     __shared__ int s_cnt[2];
+    __shared__ uint64_t s_full[kCgStages], s_empty[kCgStages];
 
     constexpr int THREADS = NW * 32;
     constexpr int NG = 64 / NW;                 // column groups per warp and pass
@@ -193,6 +220,14 @@ coeff_gemm_kernel(const ChainDesc d, const uint8_t* __restrict__ bits, long long
     cplx* V0 = vscratch + (size_t)blockIdx.x * 2 * kCgS * chi_pad;
     cplx* V1 = V0 + (size_t)kCgS * chi_pad;
     const long long ntiles = (B + kCgS - 1) / kCgS;
+    if (MB) {
+        if (threadIdx.x == 0) {
+            for (int st = 0; st < kCgStages; ++st) { cg_mbar_init(&s_full[st], NW * 32); cg_mbar_init(&s_empty[st], NW); }
+            asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+        }
+        __syncthreads();
+    }
+    unsigned gprod = 0, gcons = 0;        // ring positions (chunks issued / consumed so far), identical in every thread
 
     for (long long tile = blockIdx.x; tile < ntiles; tile += gridDim.x) {
         const long long s0 = tile * kCgS;
@@ -248,7 +283,7 @@ coeff_gemm_kernel(const ChainDesc d, const uint8_t* __restrict__ bits, long long
 
             // one of the 16 cp.async of a stage per thread: pieces 0..7 = A (128 rows x 16 complex), 8..15 = B ((bit, 16 l) x 64)
             auto issue_piece = [&](int it, int e) {
-                const int stage = it % kCgStages;
+                const int stage = MB ? (int)(gprod % kCgStages) : it % kCgStages;
                 const int pass = it / kchunks, kc = it - pass * kchunks;
                 if (e < 8) {
                     unsigned char* a = sA + stage * kCgABytes;
@@ -271,17 +306,19 @@ coeff_gemm_kernel(const ChainDesc d, const uint8_t* __restrict__ bits, long long
                 }
             };
             auto issue = [&](int it) {
+                if (MB) cg_mbar_wait(&s_empty[gprod % kCgStages], ((gprod / kCgStages) & 1) ^ 1);
 #pragma unroll
                 for (int e = 0; e < 8; ++e) {
                     if (e * THREADS < kCgRows * kCgKc) issue_piece(it, e);
                     if (e * THREADS < 2 * kCgKc * kCgNc) issue_piece(it, 8 + e);
                 }
+                if (MB) { cg_cp_async_arrive(&s_full[gprod % kCgStages]); ++gprod; }
             };
 
             // prologue
             for (int it = 0; it < kCgStages - 1; ++it) {
                 if (it < iters) issue(it);
-                cp_async_commit();
+                if (!MB) cp_async_commit();
             }
             // One pass = 64 complex output columns = 8 groups of 8; a group is TWO n8 DMMA tiles, the real parts and
             // the imaginary parts of its 8 columns:
@@ -299,13 +336,17 @@ coeff_gemm_kernel(const ChainDesc d, const uint8_t* __restrict__ bits, long long
                         acci[x][0] = acci[x][1] = acci[x][2] = acci[x][3] = 0.0;
                     }
                 }
-                cp_async_wait<kCgStages - 2>();
-                __syncthreads();
-                // the 16 copies of stage it+2 are issued one per column group BETWEEN the DMMAs below (the warp waits on the
-                // tensor pipe there anyway), not as a block in front of them
                 const bool more = (it + kCgStages - 1 < iters);
-                if (more) issue(it + kCgStages - 1);
-                const int stage = it % kCgStages;
+                int stage;
+                if (MB) {
+                    stage = (int)(gcons % kCgStages);
+                    cg_mbar_wait(&s_full[stage], (gcons / kCgStages) & 1);
+                } else {
+                    cp_async_wait<kCgStages - 2>();
+                    __syncthreads();
+                    if (more) issue(it + kCgStages - 1);
+                    stage = it % kCgStages;
+                }
                 const unsigned char* a = sA + stage * kCgABytes;
                 const unsigned char* b = sB + stage * kCgBBytes + mybit * (kCgKc * 1024);
                 const int ngroups = min(8, (cr - pass * kCgNc + 7) >> 3);       // column groups that exist in this pass
@@ -344,7 +385,14 @@ coeff_gemm_kernel(const ChainDesc d, const uint8_t* __restrict__ bits, long long
                         }
                     }
                 }
-                cp_async_commit();
+                if (MB) {
+                    __syncwarp();
+                    if (lane == 0) cg_mbar_arrive(&s_empty[stage]);     // this warp is done reading the stage
+                    ++gcons;
+                    if (more) issue(it + kCgStages - 1);                 // the stage of chunk it-1: long released by everybody
+                } else {
+                    cp_async_commit();
+                }
                 if (kc == kchunks - 1) {
                     // epilogue of this pass: complex columns pass*64 + gq*8 + {2t, 2t+1} of rows R0 / R1
 #pragma unroll
@@ -383,7 +431,9 @@ static void launch_coeff_gemm(qil_ctx* ctx, const qil_mps* psi, const uint8_t* d
     QIL_REQUIRE(smem <= ctx->smem_optin, QIL_ERR_UNSUPPORTED, "coefficient: chain of %d sites does not fit", psi->n);
     cplx* scratch = (cplx*)ctx->alloc((size_t)grid * 2 * kCgS * chi_pad * sizeof(cplx));
     static const int nw = [] { const char* e = getenv("QIL_COEFF_WARPS"); return (e && atoi(e) == 8) ? 8 : 16; }();
-    auto kern = (nw == 16) ? coeff_gemm_kernel<16> : coeff_gemm_kernel<8>;
+    static const bool mb = [] { const char* e = getenv("QIL_COEFF_MBAR"); return !(e && e[0] == '0'); }();
+    auto kern = (nw == 16) ? (mb ? coeff_gemm_kernel<16, true> : coeff_gemm_kernel<16, false>)
+                           : (mb ? coeff_gemm_kernel<8, true> : coeff_gemm_kernel<8, false>);
     ensure_dynamic_smem(kern, smem);
     kern<<<grid, nw * 32, smem, ctx->stream>>>(make_desc(psi), d_bits, (long long)B, reinterpret_cast<cplx*>(d_out),
                                                   psi->amplitude, scratch, chi_pad);

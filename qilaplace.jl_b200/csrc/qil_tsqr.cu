@@ -298,42 +298,59 @@ __device__ __forceinline__ void fused_store_triangle(const T* blk, int pitch, in
     }
 }
 
-// T of the compact WY form from G (strict upper triangle of Tm, pitch pt), in place, by ONE warp: lane i keeps row i of
-// T in registers -- T[i][j] = -tau_j sum_{k=i}^{j-1} T[i][k] G[k][j] needs no other row, so there is no cross-lane
-// traffic and no barrier; the G loads are warp-wide broadcasts that do not depend on the running sums.
+// T of the compact WY form from G (strict upper triangle of Tm, pitch pt), in place:  T = (striu(G) + diag(1 / tau))^-1,
+// i.e. T[j][j] = tau_j, T[0:j, j] = -tau_j T[0:j, 0:j] G[0:j, j].  Column by column that is a chain of n dependent dot
+// products (4.5 us for n = 20 with one warp, whatever the scheduling of its loads); blocked it is short:
+//   8 x 8 diagonal blocks by one warp each (lane i keeps row i of its block in registers, no cross-lane traffic), then
+//   T12 = -T11 (G12 T22) for neighbouring blocks, doubling the block size per level: two tiny products by all threads.
+// X: scratch of >= 256 elements.  Called by all threads of the CTA.
 template <typename T>
-__device__ __forceinline__ void wy_t_rows(T* Tm, int pt, int n, const double* tau) {
-    constexpr int NMAX = kWqrMaxN;
-    const int lane = threadIdx.x & 31;
-    T row[NMAX];
+__device__ __forceinline__ void wy_t_blocked(T* Tm, int pt, int n, const double* tau, T* X) {
+    constexpr int BS = 8;
+    const int tid = threadIdx.x, nth = blockDim.x, warp = tid >> 5, lane = tid & 31;
+    const int nblk = (n + BS - 1) / BS;
+    if (warp < nblk) {
+        const int lo = warp * BS, w = min(BS, n - lo);
+        T row[BS];
 #pragma unroll
-    for (int j = 0; j < NMAX; ++j) {
-        row[j] = Scalar<T>::zero();
-        if (j < n) {
-            const double tj = tau[j];
-            // column j of G first (independent broadcast loads, all in flight together), then the dot product: a load
-            // issued right in front of the FMA that consumes it costs a shared-memory latency per term
-            T g[NMAX];
+        for (int j = 0; j < BS; ++j) {
+            row[j] = Scalar<T>::zero();
+            if (j < w) {
+                const double tj = tau[lo + j];
+                T acc = Scalar<T>::zero();
 #pragma unroll
-            for (int k = 0; k < j; ++k) g[k] = Tm[k * pt + j];
-            T a0 = Scalar<T>::zero(), a1 = a0, a2 = a0, a3 = a0;
-#pragma unroll
-            for (int k = 0; k < j; ++k) {
-                if ((k & 3) == 0) a0 = Scalar<T>::fma(row[k], g[k], a0);
-                else if ((k & 3) == 1) a1 = Scalar<T>::fma(row[k], g[k], a1);
-                else if ((k & 3) == 2) a2 = Scalar<T>::fma(row[k], g[k], a2);
-                else a3 = Scalar<T>::fma(row[k], g[k], a3);
+                for (int k = 0; k < j; ++k) acc = Scalar<T>::fma(row[k], Tm[(lo + k) * pt + lo + j], acc);
+                row[j] = (lane < j) ? Scalar<T>::scale(acc, -tj) : (lane == j ? Scalar<T>::from_real(tj) : Scalar<T>::zero());
             }
-            a0 = Scalar<T>::add(a0, a2);
-            a1 = Scalar<T>::add(a1, a3);
-            const T v = Scalar<T>::scale(Scalar<T>::add(a0, a1), -tj);
-            row[j] = (lane < j) ? v : (lane == j ? Scalar<T>::from_real(tj) : Scalar<T>::zero());
+        }
+        __syncwarp();
+        if (lane < w) {
+#pragma unroll
+            for (int j = 0; j < BS; ++j)
+                if (j < w && j >= lane) Tm[(lo + lane) * pt + lo + j] = row[j];
         }
     }
-    __syncwarp();
-#pragma unroll
-    for (int j = 0; j < NMAX; ++j)
-        if (j < n && lane < n) Tm[lane * pt + j] = row[j];
+    __syncthreads();
+    for (int span = BS; span < n; span *= 2) {
+        for (int lo = 0; lo + span < n; lo += 2 * span) {
+            const int mid = lo + span, hi = min(lo + 2 * span, n);
+            const int h = mid - lo, wd = hi - mid;
+            for (int idx = tid; idx < h * wd; idx += nth) {            // X = G12 T22  (T22 upper triangular)
+                const int i = lo + idx / wd, j = mid + idx % wd;
+                T acc = Scalar<T>::zero();
+                for (int k = mid; k <= j; ++k) acc = Scalar<T>::fma(Tm[i * pt + k], Tm[k * pt + j], acc);
+                X[idx] = acc;
+            }
+            __syncthreads();
+            for (int idx = tid; idx < h * wd; idx += nth) {            // T12 = -T11 X  (T11 upper triangular)
+                const int ii = idx / wd, jj = idx % wd;
+                T acc = Scalar<T>::zero();
+                for (int k = ii; k < h; ++k) acc = Scalar<T>::fma(Tm[(lo + ii) * pt + lo + k], X[k * wd + jj], acc);
+                Tm[(lo + ii) * pt + mid + jj] = Scalar<T>::scale(acc, -1.0);
+            }
+            __syncthreads();
+        }
+    }
 }
 
 // G = V^T V (real; n x n, pitch pt) on the FP64 tensor pipe with the m rows split over the warps: warp w takes row tile
@@ -444,7 +461,7 @@ __device__ __noinline__ void wy_build(T* blk, int pitch, int m, int n, const dou
     }
     __syncthreads();
     fused_clk(clk, 12);
-    if (tid < 32) wy_t_rows<T>(Tm, pt, n, tau);
+    wy_t_blocked<T>(Tm, pt, n, tau, gpart);
     __syncthreads();
     fused_clk(clk, 13);
     for (int idx = tid; idx < n * n; idx += nth) {
@@ -740,7 +757,7 @@ static TsqrFusedPlan tsqr_fused_plan(qil_ctx* ctx, int64_t m, int n) {
     // shared-memory form 256
     const int maxrows = Scalar<T>::is_complex ? kWqrMaxRows : rqr_max_rows(n);
     auto small_elems = [&]() {
-        size_t small = 5 * (size_t)n * (n + 1) + 8;               // elements of T
+        size_t small = 5 * (size_t)n * (n + 1) + 8 + 256;         // elements of T: WY matrices + scratch of wy_t_blocked
         if (!Scalar<T>::is_complex) {
             const int mtiles = (n + 15) / 16;
             small += (size_t)(8 / mtiles) * 32 * (n | 1);         // partial Gram tiles of wy_gram behind the matrices

@@ -265,6 +265,7 @@ __device__ __forceinline__ void rqr_factor(double* blk, int pitch, int m, int n,
     constexpr int PP = NC + 2;
     const int tid = threadIdx.x, lane = tid & 31, w = tid >> 5;
     const int nthr = NW * 32;
+    const int cl = min(lane, NC - 1);
     double* P = scr + (size_t)w * 32 * PP;                  // this warp's staging tile
     double* part = scr + (size_t)NW * 32 * PP;              // [2][NW][NC]
     double* piv = part + 2 * (size_t)NW * NC;               // [2][NC]
@@ -303,31 +304,29 @@ __device__ __forceinline__ void rqr_factor(double* blk, int pitch, int m, int n,
         }
         __syncwarp();
         RQR_CLK(0);
-        if (lane < NC) {
+        {   // lanes >= NC repeat column NC - 1 (same values, same addresses): no divergent region in the step
             double s0 = 0.0, s1 = 0.0, s2 = 0.0, s3 = 0.0;
 #pragma unroll
             for (int r = 0; r < 32; r += 4) {
-                s0 += P[(r + 0) * PP + lane];
-                s1 += P[(r + 1) * PP + lane];
-                s2 += P[(r + 2) * PP + lane];
-                s3 += P[(r + 3) * PP + lane];
+                s0 += P[(r + 0) * PP + cl];
+                s1 += P[(r + 1) * PP + cl];
+                s2 += P[(r + 2) * PP + cl];
+                s3 += P[(r + 3) * PP + cl];
             }
-            part[((size_t)par * NW + w) * NC + lane] = (s0 + s1) + (s2 + s3);
+            part[((size_t)par * NW + w) * NC + cl] = (s0 + s1) + (s2 + s3);
         }
         RQR_CLK(1);
         if (NW > 1) wq_bar(bar, nthr); else __syncwarp();
         RQR_CLK(2);
-        double tot = 0.0, pv = 0.0;
-        if (lane < NC) {
-            for (int ww = 0; ww < NW; ++ww) tot += part[((size_t)par * NW + ww) * NC + lane];
-            pv = piv[par * NC + lane];
-        }
+        double tot = 0.0;
+        for (int ww = 0; ww < NW; ++ww) tot += part[((size_t)par * NW + ww) * NC + cl];
+        const double pv = piv[par * NC + cl];
         const double s0 = __shfl_sync(0xffffffffu, tot, 0), x0 = __shfl_sync(0xffffffffu, pv, 0);
         RQR_CLK(3);
         double bj, tj, head;
         wqr_reflector<double>(s0, x0, bj, tj, head);
         RQR_CLK(4);
-        if (lane < NC) fbuf[lane] = (tj != 0.0) ? -tj * (tot - bj * pv) : 0.0;
+        fbuf[cl] = (tj != 0.0) ? -tj * (tot - bj * pv) : 0.0;
         __syncwarp();
         RQR_CLK(5);
         double u[RT];
@@ -373,10 +372,13 @@ __device__ __forceinline__ void rqr_factor_rt(double* blk, int pitch, int m, int
     else if (rt == 2) rqr_factor<NC, 2>(blk, pitch, m, n, beta, tau, scr, NW, bar);
     else if (NC <= 24) rqr_factor<(NC <= 24 ? NC : 8), 3>(blk, pitch, m, n, beta, tau, scr, NW, bar);
 }
-// all threads of the CTA call; the first NW = min(8, ceil(m / 32)) warps work.  No trailing CTA barrier.
+// all threads of the CTA call; the first NW warps work.  No trailing CTA barrier.  Few warps with two or three rows per
+// thread beat many warps with one (tools/ubench_rqr.cu, cycles per column step at n = 20: 128 rows 1840 with 4 warps,
+// 1570 with 2; 256 rows 2364 with 8 warps, 1651 with 4; 384 rows 1823 with 4): fewer partial sums to combine, less
+// barrier skew, and the FMAs of the extra rows are cheap next to the latency chain of a step.
 __device__ __forceinline__ void rqr_factor_any(double* blk, int pitch, int m, int n, double* beta, double* tau, double* scr,
                                                int bar) {
-    const int NW = min(8, (m + 31) >> 5);
+    const int NW = (m <= 128) ? min(2, (m + 31) >> 5) : ((m <= (n <= 24 ? 384 : 256)) ? 4 : 8);
     if ((int)(threadIdx.x >> 5) >= NW) return;
     if (n <= 8) rqr_factor_rt<8>(blk, pitch, m, n, beta, tau, scr, NW, bar);
     else if (n <= 16) rqr_factor_rt<16>(blk, pitch, m, n, beta, tau, scr, NW, bar);

@@ -51,13 +51,23 @@ void run(int m, int n, int NW) {
 
 int main() {
     run<24, 1>(128, 20, 4);
+    run<24, 2>(128, 20, 2);
+    run<24, 4>(128, 20, 1);
     run<24, 1>(200, 20, 7);
+    run<24, 2>(200, 20, 4);
+    run<24, 4>(200, 20, 2);
     run<24, 1>(256, 20, 8);
     run<24, 2>(256, 20, 4);
+    run<24, 4>(256, 20, 2);
+    run<24, 3>(384, 20, 4);
     run<24, 2>(512, 20, 8);
-    run<24, 3>(640, 20, 7);
     run<8, 1>(128, 6, 4);
+    run<8, 4>(128, 6, 1);
     run<32, 1>(128, 30, 4);
+    run<32, 2>(128, 30, 2);
     run<24, 1>(32, 20, 1);
+    run<32, 1>(128, 20, 4);
+    run<32, 2>(128, 20, 2);
+    run<32, 2>(256, 20, 4);
     return 0;
 }
