@@ -82,7 +82,10 @@ __global__ void __launch_bounds__(256) gemm_kernel(Op opa, Op opb, int64_t M, in
     __shared__ T As[GK][GT + 1];
     __shared__ T Bs[GK][GT + 1];
     const int tx = threadIdx.x & 15, ty = threadIdx.x >> 4;
-    const int64_t i0 = (int64_t)blockIdx.y * GT, j0 = (int64_t)blockIdx.x * GT;
+    // tiles are numbered linearly on blockIdx.x (grid.y is limited to 65535: the 2^23-row steps of the sequential TT-SVD
+    // at n = 24 have more row tiles than that)
+    const int64_t tiles_n = (N + GT - 1) / GT;
+    const int64_t i0 = ((int64_t)blockIdx.x / tiles_n) * GT, j0 = ((int64_t)blockIdx.x % tiles_n) * GT;
     T acc[4][4];
 #pragma unroll
     for (int a = 0; a < 4; ++a)
@@ -133,8 +136,9 @@ template <typename T>
 void gemm(qil_ctx* ctx, Op opa, Op opb, int64_t M, int64_t N, int64_t K, double alpha, const T* A, int64_t lda,
           const T* B, int64_t ldb, double beta, T* C, int64_t ldc) {
     if (M == 0 || N == 0) return;
-    dim3 grid((unsigned)((N + GT - 1) / GT), (unsigned)((M + GT - 1) / GT));
-    gemm_kernel<T><<<grid, 256, 0, ctx->stream>>>(opa, opb, M, N, K, alpha, A, lda, B, ldb, beta, C, ldc);
+    const int64_t tiles = ((N + GT - 1) / GT) * ((M + GT - 1) / GT);
+    QIL_REQUIRE(tiles < ((int64_t)1 << 31), QIL_ERR_UNSUPPORTED, "gemm: %lld x %lld has too many tiles", (long long)M, (long long)N);
+    gemm_kernel<T><<<(unsigned)tiles, 256, 0, ctx->stream>>>(opa, opb, M, N, K, alpha, A, lda, B, ldb, beta, C, ldc);
     QIL_LAUNCH_CHECK(ctx);
 }
 template void gemm<double>(qil_ctx*, Op, Op, int64_t, int64_t, int64_t, double, const double*, int64_t,

@@ -310,7 +310,7 @@ def test_bench_zt_mpo_n28_bonds_match_oracle(q):
         assert abs(va[0] - vb[0]) <= 1e-8 * max(abs(vb[0]), 1e-3)
 
 
-@pytest.mark.parametrize("n", [20, 22])
+@pytest.mark.parametrize("n", [20, 22, 24])
 def test_encode_svd_sequential_large(q, n):
     """signal_mps(:svd) (SignalConverters.jl:49-104) beyond the quick-start size: bonds and amplitudes against the
     oracle's sequential TT-SVD on the structured bench signal."""
