@@ -146,6 +146,7 @@ def blas_threads(limit=None):
     except Exception:
         import contextlib
         return int(os.environ.get("OMP_NUM_THREADS", os.cpu_count() or 1)), contextlib.nullcontext()
+    import numpy  # noqa: F401  -- threadpoolctl only sees BLAS libraries that are already loaded
     want = limit or (os.cpu_count() or 1)
     ctxm = threadpool_limits(limits=want)
     nth = max([i.get("num_threads", 1) for i in threadpool_info()] or [1])

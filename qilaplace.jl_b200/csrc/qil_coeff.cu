@@ -149,7 +149,6 @@ constexpr int kCgNc = 64;        // complex n per pass (128 real, 16 n8 tiles)
 constexpr int kCgStages = 3;
 constexpr int kCgABytes = kCgRows * kCgKc * 16;        // 32 KB
 constexpr int kCgBBytes = 2 * kCgKc * kCgNc * 16;      // 32 KB (both bit slices)
-constexpr int kCgThreads = 256;
 
 __device__ __forceinline__ void cp_async16(void* dst, const void* src, bool valid) {
     const unsigned d = (unsigned)__cvta_generic_to_shared(dst);

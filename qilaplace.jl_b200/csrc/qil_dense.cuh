@@ -120,6 +120,8 @@ struct SmallSvdItem {
     int rank = 0;
 };
 template <typename T>
-void svd_small_batch(qil_ctx* ctx, std::vector<SmallSvdItem<T>>& items, double cutoff, int64_t maxdim, int64_t mindim);
+// pool_out != nullptr: all outputs are non-owning views into ONE allocation, handed back through *pool_out
+void svd_small_batch(qil_ctx* ctx, std::vector<SmallSvdItem<T>>& items, double cutoff, int64_t maxdim, int64_t mindim,
+                     std::shared_ptr<void>* pool_out = nullptr);
 
 }  // namespace qil

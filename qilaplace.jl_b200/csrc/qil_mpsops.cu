@@ -139,7 +139,10 @@ static qil_mps* ztmps_split_t(qil_ctx* ctx, const qil_mps* psi, double cutoff, i
             cores[2 * i + 1] = SVh.take();
         }
     }
-    svd_small_batch<T>(ctx, batch, cutoff, maxdim, 1);
+    // every site in the batch (the usual case): the 2n cores share one pooled allocation
+    const bool pooled = (int)batch.size() == n;
+    std::shared_ptr<void> pool;
+    svd_small_batch<T>(ctx, batch, cutoff, maxdim, 1, pooled ? &pool : nullptr);
     for (size_t b = 0; b < batch.size(); ++b) {
         const int i = batch_site[b];
         bond[2 * i + 1] = batch[b].rank;
@@ -149,6 +152,7 @@ static qil_mps* ztmps_split_t(qil_ctx* ctx, const qil_mps* psi, double cutoff, i
     qil_mps* m = new_mps(ctx, 2 * n, psi->is_complex, bond.data(), false);
     m->core = cores;
     m->amplitude = psi->amplitude;
+    if (pooled) m->pool = pool;
     return m;
 }
 

@@ -336,7 +336,8 @@ int svd_small(qil_ctx* ctx, int64_t m, int64_t n, const T* A, int64_t lda, doubl
 
 // Batched variant: every item is an independent small SVD (one CTA each, one launch, one host sync).
 template <typename T>
-void svd_small_batch(qil_ctx* ctx, std::vector<SmallSvdItem<T>>& items, double cutoff, int64_t maxdim, int64_t mindim) {
+void svd_small_batch(qil_ctx* ctx, std::vector<SmallSvdItem<T>>& items, double cutoff, int64_t maxdim, int64_t mindim,
+                     std::shared_ptr<void>* pool_out) {
     struct Region {
         qil_ctx* c;
         explicit Region(qil_ctx* cc) : c(cc) { c->prof_begin(PROF_SVD); }
@@ -347,6 +348,19 @@ void svd_small_batch(qil_ctx* ctx, std::vector<SmallSvdItem<T>>& items, double c
     std::vector<SmallSvdParams<T>> h(nb);
     int* d_rank = (int*)ctx->alloc(sizeof(int) * nb);
     size_t smem = 0;
+    T* pool_base = nullptr;
+    size_t pool_used = 0;
+    if (pool_out) {
+        size_t total = 0;
+        for (int i = 0; i < nb; ++i) {
+            const SmallSvdItem<T>& it = items[i];
+            const int64_t k = std::min(it.m, it.n);
+            const size_t mk = (size_t)((it.m * k + 1) & ~(int64_t)1), kn = (size_t)((k * it.n + 1) & ~(int64_t)1);
+            total += (it.want_U ? mk : 0) + (it.want_US ? mk : 0) + (it.want_Vh ? kn : 0) + (it.want_SVh ? kn : 0);
+        }
+        pool_base = (T*)ctx->alloc(std::max<size_t>(total, 1) * sizeof(T));
+        *pool_out = std::shared_ptr<void>(pool_base, [ctx](void* q) { ctx->free(q); });
+    }
     for (int i = 0; i < nb; ++i) {
         SmallSvdItem<T>& it = items[i];
         const int64_t m = it.m, n = it.n;
@@ -356,10 +370,25 @@ void svd_small_batch(qil_ctx* ctx, std::vector<SmallSvdItem<T>>& items, double c
         p.mt = (int)std::max(m, n); p.nt = k; p.mpad = p.mt | 1; p.npad = p.nt | 1;
         p.cutoff = cutoff; p.maxdim = maxdim < 1 ? 1 : maxdim; p.mindim = std::max<int64_t>(mindim, 1);
         p.margin = ctx->d_margin;
-        if (it.want_U) it.U = Mat<T>(ctx, m, k);
-        if (it.want_US) it.US = Mat<T>(ctx, m, k);
-        if (it.want_Vh) it.Vh = Mat<T>(ctx, k, n);
-        if (it.want_SVh) it.SVh = Mat<T>(ctx, k, n);
+        if (pool_out) {
+            // all outputs of the batch in ONE allocation (the ~2 stream-ordered allocations per item were most of the host
+            // time of a ZTMPS split: 56 of them at n = 28); the matrices are non-owning views into it
+            auto view = [&](int64_t rr, int64_t cc) {
+                Mat<T> v;
+                v.ctx = nullptr; v.p = pool_base + pool_used; v.rows = rr; v.cols = cc;
+                pool_used += (size_t)((rr * cc + 1) & ~(int64_t)1);
+                return v;
+            };
+            if (it.want_U) it.U = view(m, k);
+            if (it.want_US) it.US = view(m, k);
+            if (it.want_Vh) it.Vh = view(k, n);
+            if (it.want_SVh) it.SVh = view(k, n);
+        } else {
+            if (it.want_U) it.U = Mat<T>(ctx, m, k);
+            if (it.want_US) it.US = Mat<T>(ctx, m, k);
+            if (it.want_Vh) it.Vh = Mat<T>(ctx, k, n);
+            if (it.want_SVh) it.SVh = Mat<T>(ctx, k, n);
+        }
         p.U = it.want_U ? it.U.p : nullptr; p.US = it.want_US ? it.US.p : nullptr;
         p.Vh = it.want_Vh ? it.Vh.p : nullptr; p.SVh = it.want_SVh ? it.SVh.p : nullptr;
         p.S = nullptr; p.rank = d_rank + i;
@@ -387,8 +416,10 @@ void svd_small_batch(qil_ctx* ctx, std::vector<SmallSvdItem<T>>& items, double c
         if (it.want_SVh) it.SVh.rows = r;
     }
 }
-template void svd_small_batch<double>(qil_ctx*, std::vector<SmallSvdItem<double>>&, double, int64_t, int64_t);
-template void svd_small_batch<cplx>(qil_ctx*, std::vector<SmallSvdItem<cplx>>&, double, int64_t, int64_t);
+template void svd_small_batch<double>(qil_ctx*, std::vector<SmallSvdItem<double>>&, double, int64_t, int64_t,
+                                      std::shared_ptr<void>*);
+template void svd_small_batch<cplx>(qil_ctx*, std::vector<SmallSvdItem<cplx>>&, double, int64_t, int64_t,
+                                    std::shared_ptr<void>*);
 
 template bool svd_small_fits<double>(qil_ctx*, int64_t, int64_t);
 template bool svd_small_fits<cplx>(qil_ctx*, int64_t, int64_t);
