@@ -35,6 +35,31 @@ def test_qr(q, shape, cplx):
 
 
 @pytest.mark.parametrize("cplx", [False, True])
+@pytest.mark.parametrize("shape", [(257, 20), (300, 7), (1024, 30), (2560, 8), (4096, 20), (16384, 20), (32768, 20),
+                                   (37000, 5), (40000, 20), (16384, 6), (9000, 17)])
+def test_qr_tall_panels_one_launch_tsqr(q, shape, cplx):
+    """Shapes that walk the plans of the cooperative one-launch TSQR (qil_tsqr.cu): two and three levels, 128- and 256-row
+    level-0 blocks, every column capacity of the register-resident factor (8 / 16 / 24 / 32), the sizes of the n = 28
+    and n = 30 top splits, and panels beyond one CTA per SM (three-launch fallback).  Rank-deficient columns included:
+    Q must stay orthonormal to rounding (rsvd.jl:83)."""
+    m, n = shape
+    rng = np.random.default_rng(m * 7 + n + cplx)
+    A = _rand(rng, m, n, cplx)
+    if n >= 6:
+        A[:, n - 2] = A[:, 0] * 0.5 - A[:, 1]            # exact dependence
+        A[:, n - 1] *= 1e-14                              # a column at rounding level
+    for positive in (True, False):
+        Q, R = q.qr(A, positive=positive)
+        assert Q.shape == (m, n) and R.shape == (n, n)
+        assert np.abs(Q @ R - A).max() <= 1e-12 * np.abs(A).max() * np.sqrt(m)
+        assert np.abs(Q.conj().T @ Q - np.eye(n)).max() <= 1e-13 * np.sqrt(m)
+        assert np.abs(np.tril(R, -1)).max() == 0.0
+        if positive:
+            d = np.diagonal(R)
+            assert np.all(np.abs(d.imag) <= 1e-15 * np.abs(d).max()) and np.all(d.real >= 0)
+
+
+@pytest.mark.parametrize("cplx", [False, True])
 def test_qr_rank_deficient_tall(q, cplx):
     # Y = A*Omega of a low-rank A: Q must stay orthonormal to rounding (rsvd.jl:83)
     rng = np.random.default_rng(5 + cplx)
