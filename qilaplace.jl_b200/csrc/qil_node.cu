@@ -15,6 +15,7 @@
 #include "qil_fast.cuh"
 #include "qil_rng.cuh"
 #include "qil_wqr.cuh"
+#include "qil_wy.cuh"
 
 namespace qil {
 
@@ -34,6 +35,7 @@ struct NodeParams {
     long long stream_len;
     unsigned long long seed;
     int smem_elems;             // doubles of dynamic shared memory available
+    int fast;                   // register-resident factor + compact-WY explicit Q (cta_qr_fast) where the panel allows
 };
 
 __global__ void __launch_bounds__(kNodeThreads) node_split_kernel(const NodeParams p) {
@@ -66,8 +68,16 @@ __global__ void __launch_bounds__(kNodeThreads) node_split_kernel(const NodePara
         else { panC = sm + off; off += (size_t)C * pitch; }
         need = off;
     }
+    need = (need + 1) & ~(size_t)1;                            // 16-byte aligned work area
     double* work = sm + need;
-    need += cta_qr_extra_elems<double>(mt, l);
+    // panels of up to 768 rows (512 beyond 24 columns) are factored in ONE level by the register-resident Householder and
+    // their explicit Q is formed in compact-WY form; larger ones keep the multi-level reflector form
+    const bool fastqr = p.fast && mt <= rqr_max_rows(l);
+    {
+        const size_t slow = cta_qr_extra_elems<double>(mt, l), fast = fastqr ? cta_qr_fast_elems(l) : 0;
+        need += (slow > fast ? slow : fast) + 1;
+        need = (need + 1) & ~(size_t)1;
+    }
     double* Rm = sm + need;  need += (size_t)l * l;             // triangle of the last QR
     double* G0 = sm + need;  need += (size_t)l * pg;            // column-major
     double* Gw = sm + need;  need += (size_t)l * pg;
@@ -116,7 +126,8 @@ __global__ void __launch_bounds__(kNodeThreads) node_split_kernel(const NodePara
             cta_gemm(!onR, A, C, rows, onR ? C : R, onR ? panC : panR, pitch, l, pan, pitch, 1.0);
             __syncthreads();
         }
-        cta_qr<double>(pan, pitch, rows, l, !last, last ? Rm : nullptr, l, nullptr, 0, 0, work);
+        if (fastqr) cta_qr_fast(pan, pitch, rows, l, !last, last ? Rm : nullptr, l, work);
+        else cta_qr<double>(pan, pitch, rows, l, !last, last ? Rm : nullptr, l, nullptr, 0, 0, work);
     }
     // ---- G: the l x l matrix whose left singular vectors are wanted.  tall: G = Rm; otherwise G = Rm^H.
     for (int idx = tid; idx < l * pg; idx += nth) {
@@ -179,6 +190,8 @@ void node_level_launch(qil_ctx* ctx, const NodeDesc* d_nodes, int count, int* d_
     p.nodes = d_nodes; p.bonds = d_bonds; p.overflow = d_overflow; p.margin = ctx->d_margin;
     p.kp = o.k + o.p; p.q = o.q; p.cutoff = o.cutoff; p.maxdim = o.maxdim; p.mindim = o.mindim;
     p.stream = d_stream; p.stream_len = stream_len; p.seed = (unsigned long long)o.seed;
+    static const bool fast = [] { const char* e = getenv("QIL_NODE_FAST"); return !(e && e[0] == '0'); }();
+    p.fast = fast ? 1 : 0;
     const size_t smem = std::min<size_t>(ctx->smem_optin, 227 * 1024) - 1024;
     p.smem_elems = (int)(smem / sizeof(double));
     ensure_dynamic_smem(node_split_kernel, smem);
