@@ -267,8 +267,8 @@ __device__ __noinline__ void fused_factor(T* blk, int pitch, int m, int n, T* be
     wqr_factor_any<T>(blk, pitch, m, n, beta, tau, threadIdx.x >> 5, blockDim.x >> 5, 1);
 }
 template <>
-__device__ __forceinline__ void fused_factor<double>(double* blk, int pitch, int m, int n, double* beta, double* tau,
-                                                     double* scr) {
+__device__ __noinline__ void fused_factor<double>(double* blk, int pitch, int m, int n, double* beta, double* tau,
+                                                  double* scr) {
     rqr_factor_call(blk, pitch, m, n, beta, tau, scr, 1);     // the caller's __syncthreads() follows
 }
 
@@ -289,28 +289,29 @@ __device__ __forceinline__ void fused_store_triangle(const T* blk, int pitch, in
 // rows [s0, s1) of a dense (ld n) matrix written by OTHER CTAs of this launch -> shared panel, padding columns zero
 template <typename T>
 __device__ __forceinline__ void fused_load_stack(const T* src, int s0, int rows, int n, T* blk, int pitch) {
-    const T* base = src + (size_t)s0 * n;                  // rows * n contiguous elements
-    const int total = rows * n;
-    for (int i0 = threadIdx.x; i0 < total; i0 += 8 * blockDim.x) {
-        T v[8];
+    // one row per warp and slot, lanes = columns (no index division), 16 rows of every warp in flight (L2 round trips,
+    // not bytes, are what this load costs)
+    constexpr int kInFlight = Scalar<T>::is_complex ? 8 : 16;
+    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31, nwarps = blockDim.x >> 5;
+    const T* base = src + (size_t)s0 * n;
+    for (int i0 = warp; i0 < rows; i0 += kInFlight * nwarps) {
+        T v[kInFlight];
 #pragma unroll
-        for (int e = 0; e < 8; ++e) {
-            const int idx = i0 + e * blockDim.x;
-            v[e] = (idx < total) ? __ldcg(base + idx) : Scalar<T>::zero();
+        for (int e = 0; e < kInFlight; ++e) {
+            const int i = i0 + e * nwarps;
+            v[e] = (i < rows && lane < n) ? __ldcg(base + (size_t)i * n + lane) : Scalar<T>::zero();
         }
 #pragma unroll
-        for (int e = 0; e < 8; ++e) {
-            const int idx = i0 + e * blockDim.x;
-            if (idx < total) {
-                const int i = idx / n, c = idx - i * n;
-                blk[i * pitch + c] = v[e];
-            }
+        for (int e = 0; e < kInFlight; ++e) {
+            const int i = i0 + e * nwarps;
+            if (i < rows && lane < pitch) blk[i * pitch + lane] = v[e];
         }
     }
-    const int padw = pitch - n;
-    for (int idx = threadIdx.x; idx < rows * padw; idx += blockDim.x) {
-        const int i = idx / padw, c = n + idx - i * padw;
-        blk[i * pitch + c] = Scalar<T>::zero();
+    if (pitch > 32) {
+        for (int idx = threadIdx.x; idx < rows * (pitch - 32); idx += blockDim.x) {
+            const int i = idx / (pitch - 32), c = 32 + idx % (pitch - 32);
+            blk[i * pitch + c] = Scalar<T>::zero();
+        }
     }
 }
 
