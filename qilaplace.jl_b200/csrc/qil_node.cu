@@ -72,10 +72,14 @@ __global__ void __launch_bounds__(kNodeThreads) node_split_kernel(const NodePara
     double* work = sm + need;
     // panels of up to 768 rows (512 beyond 24 columns) are factored in ONE level by the register-resident Householder and
     // their explicit Q is formed in compact-WY form; larger ones keep the multi-level reflector form
-    const bool fastqr = p.fast && mt <= rqr_max_rows(l);
+    bool fastqr = p.fast && mt <= rqr_max_rows(l);
     {
-        const size_t slow = cta_qr_extra_elems<double>(mt, l), fast = fastqr ? cta_qr_fast_elems(l) : 0;
-        need += (slow > fast ? slow : fast) + 1;
+        const size_t slow = cta_qr_extra_elems<double>(mt, l), fast = cta_qr_fast_elems(l);
+        // the fast form needs the larger work area: a node that only fits with the reflector form keeps it (an overflow
+        // would send the whole encode to the general multi-launch path)
+        const size_t rest = (size_t)l * l + 3 * (size_t)l * pg + (size_t)l * l + l + (l + 1) / 2 + 8;
+        if (fastqr && need + std::max(slow, fast) + rest > (size_t)p.smem_elems) fastqr = false;
+        need += (fastqr ? std::max(slow, fast) : slow) + 1;
         need = (need + 1) & ~(size_t)1;
     }
     double* Rm = sm + need;  need += (size_t)l * l;             // triangle of the last QR
