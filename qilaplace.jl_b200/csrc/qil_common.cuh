@@ -114,6 +114,7 @@ struct qil_ctx {
     // two zero-initialised words (arrival counter, generation) for the software grid barrier of cooperative kernels
     // launched on `stream` (one such kernel at a time per context: launches on one stream are serialised)
     unsigned int* grid_sync = nullptr;
+    bool tsqr_fused_ok = true;        // false: tall QRs take the three-launch TSQR (see tsqr_sharded in qil_encode.cu)
     unsigned int* get_grid_sync();
     qil_ctx() = default;
     qil_ctx(const qil_ctx&) = delete;

@@ -482,7 +482,7 @@ template <typename T>
 static TsqrFusedPlan tsqr_fused_plan(qil_ctx* ctx, int64_t m, int n) {
     TsqrFusedPlan best;
     static const bool off = [] { const char* e = getenv("QIL_TSQR_FUSED"); return e && e[0] == '0'; }();
-    if (off) return best;
+    if (off || !ctx->tsqr_fused_ok) return best;
     const size_t budget = std::min<size_t>(ctx->smem_optin, 225 * 1024);
     const int pitch = wqr_pitch(n);
     // rows one block may have: the register-resident real factor takes 768 (512 beyond 24 columns), the complex
