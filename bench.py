@@ -138,6 +138,13 @@ class ClockSampler(threading.Thread):
 _CPU_SETUP = {}
 
 
+def workload_name(n):
+    """config.workload: the same string in both arms (the driver compares the two lines' configs)."""
+    return (f"C4 n={n} real sin_decay: signal_ztmps(:rsvd k={ALGO['k']} p={ALGO['p']} q={ALGO['q']} "
+            f"cutoff={ALGO['cutoff']:g}) + zT apply (omega_r=2pi, MPO cutoff {MPO_CUTOFF:g} maxdim {MPO_MAXDIM}, "
+            f"built in setup)")
+
+
 def blas_threads(limit=None):
     """(threads in use, context manager setting them).  torchrun exports OMP_NUM_THREADS=1 for every rank, which
     silently makes numpy/OpenBLAS single-threaded: the reference arm sets the pool size explicitly and reports it."""
@@ -215,8 +222,8 @@ def run_reference(args):
         "impl": "reference", "metric": "encode_zt_apply_samples_per_s", "value": value, "unit": unit,
         "n_gpus": args.gpus, "steps": args.steps, "warmup": 1, "ms_per_step": ms,
         "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f64", "data": "synthetic",
-        "config": {"workload": f"C4 n={args.n} real sin_decay: signal_ztmps(:rsvd k=15 p=5 q=2 cutoff=1e-12) + zT apply",
-                   "cpu_sample_n": n},
+        "config": {"workload": workload_name(args.n), "signals_per_rank": 1, "cpu_sample_n": n,
+                   "coefficients_sample": 20000},
         "cpu_baseline": {"value": value, "unit": unit, "cores": cores, "threads": threads, "kind": "port", "sample": sample,
                          "detail": detail},
         "e2e": {"value": value, "unit": unit, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
@@ -856,8 +863,7 @@ def run_ours(args):
         "metric": "encode_zt_apply_samples_per_s", "value": value, "unit": "samples/s", "n_gpus": world,
         "steps": args.steps, "warmup": max(args.warmup, 3), "ms_per_step": ms_step, "higher_is_better": True,
         "scaling": "strong" if shard else "weak", "vs_baseline": None, "dtype": "f64", "data": "synthetic",
-        "config": {"workload": f"C4 n={n} real sin_decay: signal_ztmps(:rsvd k=15 p=5 q=2 cutoff=1e-12) + zT apply "
-                               f"(omega_r=2pi, MPO cutoff 1e-12 maxdim 128, built in setup); then {B} coefficients",
+        "config": {"workload": workload_name(n), "coefficients": B,
                    "signals_per_rank": (1.0 / world) if shard else 1,
                    "sharding": (("one signal row-sharded over the ranks: TSQR all-gather + projection all-reduce, "
                                  + ("library kernels over NVLink peer memory (CUDA IPC)" if args.comm == "peer"

@@ -10,6 +10,7 @@ from __future__ import annotations
 import ctypes as C
 import math
 import re
+import weakref
 
 import numpy as np
 
@@ -34,6 +35,7 @@ class Context:
         else:
             call("qil_create_on_stream", int(device), C.c_void_p(int(stream)), C.byref(self.handle))
         self.device = int(device)
+        self._chains = weakref.WeakSet()   # live SignalMPS / MPO objects: released before the context goes
 
     def sync(self):
         call("qil_sync", self.handle)
@@ -68,9 +70,16 @@ class Context:
         return float(t.value), int(c.value), float(b.value), float(f.value)
 
     def close(self):
+        """Destroy the context.  Chains that still hang off it are released first (their handles point into the
+        context), and become unusable: any later call on them raises instead of dereferencing a freed qil_ctx."""
         if self.handle:
+            for ch in list(self._chains):
+                ch._release()
             _lib.load().qil_destroy(self.handle)
             self.handle = None
+            for dev, c in list(_default_ctx.items()):
+                if c is self:
+                    del _default_ctx[dev]
 
 
 _default_ctx = {}
@@ -113,8 +122,9 @@ class _DeviceChain:
     def __init__(self, ctx, handle):
         self.ctx = ctx
         self.handle = handle
+        ctx._chains.add(self)
 
-    def __del__(self):
+    def _release(self):
         h = getattr(self, "handle", None)
         if h:
             try:
@@ -122,6 +132,9 @@ class _DeviceChain:
             except Exception:
                 pass
             self.handle = None
+
+    def __del__(self):
+        self._release()
 
     def _bond_dims(self):
         n = self.nsites_flat
