@@ -477,14 +477,14 @@ qil_mpo* build_zt_mpo(qil_ctx* ctx, int n, double wr, double cutoff, int64_t max
         combine_down<cplx>(ctx, Wq, blk);
         compress_mpo<cplx>(ctx, Wq, true, cutoff, maxdim);
     }
-    qil_mpo* hdt = to_handle<double>(ctx, Wdt);
-    qil_mpo* hq = to_handle<cplx>(ctx, Wq);
-    qil_mpo* fused = apply_mpo_mpo(ctx, hdt, hq, 0, 0);   // apply(W_dt, mpo_qft) (zt_transformer.jl:103)
-    destroy(hdt);
-    destroy(hq);
-    if (n == 1) return fused;
-    Chain<cplx> Wzt = from_handle<cplx>(ctx, fused);
-    destroy(fused);
+    chain_owner<qil_mpo> hdt(to_handle<double>(ctx, Wdt));
+    chain_owner<qil_mpo> hq(to_handle<cplx>(ctx, Wq));
+    chain_owner<qil_mpo> fused(apply_mpo_mpo(ctx, hdt.get(), hq.get(), 0, 0));   // apply(W_dt, mpo_qft) (zt_transformer.jl:103)
+    hdt.reset();
+    hq.reset();
+    if (n == 1) return fused.release();
+    Chain<cplx> Wzt = from_handle<cplx>(ctx, fused.get());
+    fused.reset();
     compress_mpo<cplx>(ctx, Wzt, true, cutoff, maxdim);
     return to_handle<cplx>(ctx, Wzt);
 }

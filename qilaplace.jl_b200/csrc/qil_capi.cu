@@ -227,13 +227,13 @@ int qil_mps_from_host(qil_ctx* ctx, int n, int is_complex, const int64_t* bond, 
     QIL_API_BEGIN
     QIL_NONNULL(ctx); QIL_NONNULL(bond); QIL_NONNULL(cores); QIL_NONNULL(out);
     QIL_CUDA(cudaSetDevice(ctx->device));
-    qil_mps* m = new_mps(ctx, n, is_complex, bond, true);
+    chain_owner<qil_mps> m(new_mps(ctx, n, is_complex, bond, true));
     m->amplitude = amplitude;
     for (int i = 0; i < n; ++i)
         QIL_CUDA(cudaMemcpyAsync(m->core[i], cores[i], m->core_elems(i) * elem_size(is_complex),
                                  cudaMemcpyHostToDevice, ctx->stream));
     ctx->sync();
-    *out = m;
+    *out = m.release();
     QIL_API_END
 }
 
@@ -317,12 +317,12 @@ int qil_mpo_from_host(qil_ctx* ctx, int n, int is_complex, const int64_t* bond, 
     QIL_API_BEGIN
     QIL_NONNULL(ctx); QIL_NONNULL(bond); QIL_NONNULL(cores); QIL_NONNULL(out);
     QIL_CUDA(cudaSetDevice(ctx->device));
-    qil_mpo* m = new_mpo(ctx, n, is_complex, bond, true);
+    chain_owner<qil_mpo> m(new_mpo(ctx, n, is_complex, bond, true));
     for (int i = 0; i < n; ++i)
         QIL_CUDA(cudaMemcpyAsync(m->core[i], cores[i], m->core_elems(i) * elem_size(is_complex),
                                  cudaMemcpyHostToDevice, ctx->stream));
     ctx->sync();
-    *out = m;
+    *out = m.release();
     QIL_API_END
 }
 

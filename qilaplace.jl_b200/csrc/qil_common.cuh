@@ -196,6 +196,30 @@ void destroy(qil_mps* m);
 void unpool(qil_mps* m);          // give a pooled MPS its own core allocations
 void destroy(qil_mpo* m);
 
+// owner of a chain handle until it is handed to the caller: an exception on the way releases it
+template <typename H>
+struct chain_owner {
+    H* p;
+    explicit chain_owner(H* h = nullptr) : p(h) {}
+    chain_owner(const chain_owner&) = delete;
+    chain_owner& operator=(const chain_owner&) = delete;
+    ~chain_owner() { reset(); }
+    void reset(H* h = nullptr) { if (p) destroy(p); p = h; }
+    H* release() { H* h = p; p = nullptr; return h; }
+    H* get() const { return p; }
+    H* operator->() const { return p; }
+};
+
+// ordering-only event that is destroyed on every way out of its scope
+struct scoped_event {
+    cudaEvent_t e = nullptr;
+    scoped_event() { QIL_CUDA(cudaEventCreateWithFlags(&e, cudaEventDisableTiming)); }
+    scoped_event(const scoped_event&) = delete;
+    scoped_event& operator=(const scoped_event&) = delete;
+    ~scoped_event() { if (e) cudaEventDestroy(e); }
+    operator cudaEvent_t() const { return e; }
+};
+
 // host -> device staging ring (qil_upload.cu)
 qil_uploader* uploader_create(qil_ctx* ctx, int64_t bytes, int depth);
 void uploader_submit(qil_uploader* u, const void* host, int64_t bytes);

@@ -690,8 +690,7 @@ static void dc_encode(SplitCtx<T>& sc, std::vector<DcNode<T>> level, std::vector
         };
         const int nworkers = (int)std::min<size_t>(heavy.size(), 4);
         if (nworkers >= 2 && !ctx->is_aux && !sc.comm) {
-            cudaEvent_t ready;
-            QIL_CUDA(cudaEventCreateWithFlags(&ready, cudaEventDisableTiming));
+            scoped_event ready;
             QIL_CUDA(cudaEventRecord(ready, ctx->stream));
             std::vector<int> code(nworkers, QIL_OK);
             std::vector<std::string> err(nworkers);
@@ -723,7 +722,6 @@ static void dc_encode(SplitCtx<T>& sc, std::vector<DcNode<T>> level, std::vector
                 ctx->launches += sub[w]->launches;
                 sub[w]->launches = 0;
             }
-            cudaEventDestroy(ready);
             for (size_t h : heavy) { Us[h].ctx = ctx; SVs[h].ctx = ctx; }     // results live on the parent context
             for (int w = 0; w < nworkers; ++w)
                 if (code[w] != QIL_OK) throw Error(code[w], err[w]);
@@ -1209,8 +1207,7 @@ void encode_rsvd_batch(qil_ctx* ctx, const T* d_x, int64_t N, int64_t count, con
     workers = (int)std::max<int64_t>(1, std::min<int64_t>(workers <= 0 ? 16 : workers, count));
     for (int64_t i = 0; i < count; ++i) out[i] = nullptr;
     if (encode_rsvd_batch_tree_dispatch<T>(ctx, d_x, N, count, o, out)) return;      // level-synchronous path
-    cudaEvent_t ready;
-    QIL_CUDA(cudaEventCreateWithFlags(&ready, cudaEventDisableTiming));
+    scoped_event ready;
     QIL_CUDA(cudaEventRecord(ready, ctx->stream));
     std::vector<qil_ctx> sub(workers);
     std::vector<std::string> err(workers);
@@ -1252,7 +1249,6 @@ void encode_rsvd_batch(qil_ctx* ctx, const T* d_x, int64_t N, int64_t count, con
         cudaStreamDestroy(sub[w].stream);
         ctx->launches += sub[w].launches;
     }
-    cudaEventDestroy(ready);
     for (int w = 0; w < workers; ++w)
         if (code[w] != QIL_OK) {
             for (int64_t i = 0; i < count; ++i) { if (out[i]) { destroy(out[i]); out[i] = nullptr; } }
