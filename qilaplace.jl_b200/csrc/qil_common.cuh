@@ -49,6 +49,13 @@ struct Error : public std::exception {
 
 constexpr int kMaxSites = QIL_MAX_SITES;
 
+// A collective callback can only return a status; the library's own callbacks leave the reason here (per host thread)
+// and the caller of the callback appends it to the error it raises.
+inline std::string& callback_error_note() {
+    static thread_local std::string note;
+    return note;
+}
+
 // ---- complex helpers (double2 == interleaved complex) -------------------------------------
 typedef double2 cplx;
 

@@ -163,13 +163,18 @@ struct SplitCtx {
 };
 
 // ---- collectives of a row-sharded encode (callbacks supplied by the host, ordered on ctx->stream) ----
+static void comm_failed(const char* which) {
+    const std::string note = callback_error_note();
+    callback_error_note().clear();
+    QIL_THROW(QIL_ERR_RUNTIME, "sharded encode: the %s callback failed%s%s", which, note.empty() ? "" : ": ", note.c_str());
+}
 static void comm_allreduce(const qil_comm* c, void* d_buf, int64_t count_f64) {
-    QIL_REQUIRE(c->allreduce_sum_f64(c->user, d_buf, count_f64) == 0, QIL_ERR_RUNTIME,
-                "sharded encode: the all-reduce callback failed");
+    callback_error_note().clear();
+    if (c->allreduce_sum_f64(c->user, d_buf, count_f64) != 0) comm_failed("all-reduce");
 }
 static void comm_allgather(const qil_comm* c, const void* d_send, void* d_recv, int64_t count_f64) {
-    QIL_REQUIRE(c->allgather_f64(c->user, d_send, d_recv, count_f64) == 0, QIL_ERR_RUNTIME,
-                "sharded encode: the all-gather callback failed");
+    callback_error_note().clear();
+    if (c->allgather_f64(c->user, d_send, d_recv, count_f64) != 0) comm_failed("all-gather");
 }
 // nrm[0] = sum of the per-CTA partial sums of squares (before the cross-rank reduction)
 __global__ void sum_partials_kernel(const double* partials, int n, double* nrm) {

@@ -137,7 +137,8 @@ static int peer_exchange(qil_peer* p, const void* d_src, void* d_dst, int64_t co
                                                                    (long long)count, epoch, gather);
         QIL_LAUNCH_CHECK(ctx);
         return 0;
-    } catch (const Error&) {
+    } catch (const Error& e) {
+        callback_error_note() = e.msg;
         return 1;
     }
 }
