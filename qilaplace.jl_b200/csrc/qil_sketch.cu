@@ -26,10 +26,9 @@
 namespace qil {
 
 constexpr int kBM = 128;          // output rows per tile (8 consumer warps x 16)
-constexpr int kBK = 32;           // reduction depth per pipeline stage
+constexpr int kBK = 32;           // granularity of the K chunks and of the zero padding of X (a stage holds BK = 32 or 16)
 constexpr int kConsumerWarps = 8;
 constexpr int kStreamThreads = (kConsumerWarps + 1) * 32;
-constexpr int kStageABytes = kBM * kBK * 8;   // 32 KB
 
 // ---- PTX helpers ------------------------------------------------------------------------------------
 __device__ __forceinline__ uint32_t smem_u32(const void* p) { return (uint32_t)__cvta_generic_to_shared(p); }
@@ -90,13 +89,15 @@ struct StreamParams {
     long long x_bs;      // ... and the distance (doubles) between their X operands
 };
 
-template <int NT, bool TRANS, int STAGES>
-__global__ void __launch_bounds__(kStreamThreads, (STAGES <= 2 ? 2 : 1))
+// BK: reduction depth of one pipeline stage (A tile of 128 x BK doubles); CTAS: resident CTAs per SM the launch is sized for
+template <int NT, bool TRANS, int STAGES, int BK, int CTAS>
+__global__ void __launch_bounds__(kStreamThreads, CTAS)
 stream_gemm_kernel(const __grid_constant__ CUtensorMap tmA, const StreamParams p) {
+    constexpr int kStageABytes = kBM * BK * 8;   // 32 KB / 16 KB
     extern __shared__ __align__(1024) unsigned char smem_raw[];
     // 128B-swizzled TMA boxes need a 1024-byte aligned base; do not rely on the toolchain for that
     unsigned char* smem = smem_raw + ((1024u - (smem_u32(smem_raw) & 1023u)) & 1023u);
-    const int xbytes = kBK * p.lpp * 8;
+    const int xbytes = BK * p.lpp * 8;
     const int xstride = (xbytes + 127) & ~127;
     unsigned char* sA = smem;                                   // STAGES x 32 KB (1024-aligned)
     unsigned char* sX = smem + (size_t)STAGES * kStageABytes;   // STAGES x xstride
@@ -125,19 +126,20 @@ stream_gemm_kernel(const __grid_constant__ CUtensorMap tmA, const StreamParams p
                 const int ks = (int)(tile / p.tilesM);
                 const long long k0 = (long long)ks * p.kchunk;
                 const long long k1 = min(k0 + p.kchunk, p.Kdim);
-                for (long long k = k0; k < k1; k += kBK) {
+                for (long long k = k0; k < k1; k += BK) {
                     mbar_wait(&empty[stage], phase ^ 1);
                     mbar_expect_tx(&full[stage], kStageABytes + xbytes);
                     unsigned char* a = sA + (size_t)stage * kStageABytes;
                     if (!TRANS) {
-                        // two boxes [128 rows][16 cols]
-                        tma_load_2d(a, &tmA, &full[stage], (int)k, tm * kBM);
-                        tma_load_2d(a + 16384, &tmA, &full[stage], (int)k + 16, tm * kBM);
+                        // BK/16 boxes [128 rows][16 cols]
+#pragma unroll
+                        for (int b = 0; b < BK / 16; ++b)
+                            tma_load_2d(a + b * 16384, &tmA, &full[stage], (int)k + 16 * b, tm * kBM);
                     } else {
-                        // eight boxes [32 rows][16 cols], one per consumer warp
+                        // eight boxes [BK rows][16 cols], one per consumer warp
 #pragma unroll
                         for (int w = 0; w < 8; ++w)
-                            tma_load_2d(a + w * 4096, &tmA, &full[stage], tm * kBM + w * 16, (int)k);
+                            tma_load_2d(a + w * (BK * 128), &tmA, &full[stage], tm * kBM + w * 16, (int)k);
                     }
                     const double* xsrc = p.X + k * p.lpp;
                     if (!TRANS && p.x_rows) xsrc += ((long long)tm * kBM / p.x_rows) * p.x_bs;
@@ -160,12 +162,12 @@ stream_gemm_kernel(const __grid_constant__ CUtensorMap tmA, const StreamParams p
             double acc[NT][4];
 #pragma unroll
             for (int i = 0; i < NT; ++i) { acc[i][0] = acc[i][1] = acc[i][2] = acc[i][3] = 0.0; }
-            for (long long k = k0; k < k1; k += kBK) {
+            for (long long k = k0; k < k1; k += BK) {
                 mbar_wait(&full[stage], phase);
                 const unsigned char* a = sA + (size_t)stage * kStageABytes;
                 const double* xs = reinterpret_cast<const double*>(sX + (size_t)stage * xstride);
 #pragma unroll
-                for (int kb = 0; kb < 2; ++kb) {
+                for (int kb = 0; kb < BK / 16; ++kb) {
                     double af[8];
                     if (!TRANS) {
                         // box kb: rows = output rows, 16 k-columns; this thread owns k = 4t..4t+3 of rows g, g+8
@@ -178,8 +180,8 @@ stream_gemm_kernel(const __grid_constant__ CUtensorMap tmA, const StreamParams p
                         af[0] = v00.x; af[2] = v00.y; af[4] = v01.x; af[6] = v01.y;
                         af[1] = v10.x; af[3] = v10.y; af[5] = v11.x; af[7] = v11.y;
                     } else {
-                        // box `warp`: 32 k-rows x 16 output columns; rows kb*16 + 4t + i, columns g and g+8
-                        const unsigned char* box = a + warp * 4096;
+                        // box `warp`: BK k-rows x 16 output columns; rows kb*16 + 4t + i, columns g and g+8
+                        const unsigned char* box = a + warp * (BK * 128);
 #pragma unroll
                         for (int i = 0; i < 4; ++i) {
                             const int row = kb * 16 + 4 * t + i;
@@ -257,33 +259,59 @@ static CUtensorMap make_tmap(const double* A, long long R, long long C, long lon
     return tm;
 }
 
-template <int NT, bool TRANS, int STAGES>
-static void launch_stream_s(qil_ctx* ctx, const CUtensorMap& tm, const StreamParams& p);
-
-// narrow sketches (NT <= 4): two CTAs per SM with a 2-stage ring each (one CTA's epilogue / barrier bubbles are covered
-// by the other's DMMA work; measured 2.77 vs 2.83 ms for the six n=28 passes); QIL_STREAM_STAGES=4 restores one CTA per
-// SM with a 4-stage ring, which wide sketches (NT > 4) always use (3 stages beyond NT = 8)
+// ---- launch configuration ------------------------------------------------------------------------------
+// Narrow sketches (NT <= 4) run two CTAs per SM (one CTA's epilogue / barrier bubbles are covered by the other's DMMA
+// work; measured 2.77 vs 2.83 ms for the six n=28 passes against one CTA with a 4-stage ring).  QIL_STREAM_VARIANT picks
+// the ring of that mode:  2 (default) five 16-deep stages | 1: four 16-deep stages | 0: two 32-deep stages (the ring until
+// the end of round 2) | 3: one CTA per SM with five 32-deep stages | 4 (or QIL_STREAM_STAGES=4): one CTA per SM with a
+// 4-stage ring, which wide sketches (NT > 4) always use (3 stages beyond NT = 8).  With 16-deep stages a released stage is
+// needed again only 4 stages later instead of 1, for about the same shared memory: six n=28 passes at l=20 take
+// 2.463 ms (variant 2), 2.477 (1), 2.517 (0), 2.512 (3 and 4) -- profiles/r02_stream_ring_variants.txt.  The pass is bound by the
+// FP64 pipe (profiles/r02_stream_gemm_ncu_full.txt), so the ring depth moves it by 2 % only.
+static int stream_variant() {
+    static const int v = [] {
+        const char* e = getenv("QIL_STREAM_VARIANT");
+        if (e) return atoi(e);
+        const char* st = getenv("QIL_STREAM_STAGES");
+        return (st && atoi(st) == 4) ? 4 : 2;
+    }();
+    return v;
+}
 static int stream_ctas_per_sm(int nt) {
-    static const int want = [] { const char* e = getenv("QIL_STREAM_STAGES"); return e ? atoi(e) : 2; }();
-    return (nt <= 4 && want == 2) ? 2 : 1;
+    const int v = stream_variant();
+    return (nt <= 4 && v >= 0 && v <= 2) ? 2 : 1;
 }
-template <int NT, bool TRANS>
-static void launch_stream(qil_ctx* ctx, const CUtensorMap& tm, const StreamParams& p) {
-    if (stream_ctas_per_sm(NT) == 2) launch_stream_s<(NT <= 4 ? NT : 1), TRANS, 2>(ctx, tm, p);
-    else launch_stream_s<NT, TRANS, ((NT <= 8) ? 4 : 3)>(ctx, tm, p);
+static int stream_bk(int nt) {
+    const int v = stream_variant();
+    return (nt <= 4 && (v == 1 || v == 2)) ? 16 : 32;
 }
 
-template <int NT, bool TRANS, int STAGES>
+template <int NT, bool TRANS, int STAGES, int BK, int CTAS>
 static void launch_stream_s(qil_ctx* ctx, const CUtensorMap& tm, const StreamParams& p) {
-    const int xbytes = kBK * p.lpp * 8;
+    const int xbytes = BK * p.lpp * 8;
     const int xstride = (xbytes + 127) & ~127;
-    const size_t smem = (size_t)STAGES * (kStageABytes + xstride) + 2 * STAGES * 8 + kConsumerWarps * 8 + 1024;
-    auto kern = stream_gemm_kernel<NT, TRANS, STAGES>;
+    const size_t smem = (size_t)STAGES * (kBM * BK * 8 + xstride) + 2 * STAGES * 8 + kConsumerWarps * 8 + 1024;
+    auto kern = stream_gemm_kernel<NT, TRANS, STAGES, BK, CTAS>;
     ensure_dynamic_smem(kern, smem);
     const long long ntiles = (long long)p.tilesM * p.ksplit;
-    const int grid = (int)std::min<long long>(ntiles, (long long)ctx->sm_count * (STAGES <= 2 ? 2 : 1));
+    const int grid = (int)std::min<long long>(ntiles, (long long)ctx->sm_count * CTAS);
     kern<<<grid, kStreamThreads, smem, ctx->stream>>>(tm, p);
     QIL_LAUNCH_CHECK(ctx);
+}
+
+template <int NT, bool TRANS>
+static void launch_stream(qil_ctx* ctx, const CUtensorMap& tm, const StreamParams& p) {
+    constexpr int NN = (NT <= 4 ? NT : 1);            // the narrow-sketch variants are instantiated for NT <= 4 only
+    if (NT <= 4) {
+        switch (stream_variant()) {
+            case 0: launch_stream_s<NN, TRANS, 2, 32, 2>(ctx, tm, p); return;
+            case 1: launch_stream_s<NN, TRANS, 4, 16, 2>(ctx, tm, p); return;
+            case 2: launch_stream_s<NN, TRANS, 5, 16, 2>(ctx, tm, p); return;
+            case 3: launch_stream_s<NN, TRANS, 5, 32, 1>(ctx, tm, p); return;
+            default: break;
+        }
+    }
+    launch_stream_s<NT, TRANS, ((NT <= 8) ? 4 : 3), 32, 1>(ctx, tm, p);
 }
 
 template <bool TRANS>
@@ -332,7 +360,7 @@ void stream_gemm(qil_ctx* ctx, bool trans, const double* A, long long R, long lo
     p.out = out;
     p.X = X;
     p.sumsq = sumsq_partials;
-    const CUtensorMap tm = trans ? make_tmap(A, R, C, ld, 16, kBK) : make_tmap(A, R, C, ld, 16, kBM);
+    const CUtensorMap tm = trans ? make_tmap(A, R, C, ld, 16, stream_bk(nt)) : make_tmap(A, R, C, ld, 16, kBM);
     // algorithmic work: one read of the R x C view, 2 flops per element and sketch column
     { qil_prof_region prof_guard_(ctx, PROF_STREAM_GEMM, 8.0 * (double)R * (double)C, 2.0 * (double)R * (double)C * (double)ncols);
     if (!trans) dispatch_stream<false>(ctx, nt, tm, p);

@@ -29,4 +29,9 @@ for it in range(reps):
     for cls, nm in ((0, "stream_gemm"), (3, "qr (outside svd)"), (4, "svd (incl. its qr)")):
         ms, cnt = ctx.profile_read(cls)
         print("   class %-20s %8.3f ms in %d regions" % (nm, ms, cnt))
-print("ok", psi.bonds)
+import numpy as np
+idx = (np.arange(64, dtype=np.int64) * 4194301) % N
+bits = ((idx[:, None] >> np.arange(n - 1, -1, -1)[None, :]) & 1).astype(np.uint8)
+c = q.coefficients(psi, bits)
+ref = x[torch.from_numpy(idx).to(dev)].cpu().numpy()
+print("ok", psi.bonds, "max |coefficient - x| / max|x| on 64 samples: %.3e" % (np.abs(c - ref).max() / np.abs(ref).max()))
