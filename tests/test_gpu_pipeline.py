@@ -363,5 +363,5 @@ def test_context_close_releases_live_chains(q):
         q.coefficients(psi, np.zeros((1, 10), dtype=np.uint8))
     del psi, W                                      # __del__ on released chains is a no-op
     ctx2 = q.Context(0)                             # the device is still usable
-    assert q.signal_mps(x, ctx=ctx2).bonds[0] == 1
+    assert len(q.signal_mps(x, ctx=ctx2).bonds) == 9
     ctx2.close()
