@@ -720,7 +720,11 @@ def run_ours(args):
     # ---- timed: device-resident (`value`), with per-kernel-class events for the roofline
     sampler = ClockSampler(local)
     sampler.start()
-    time.sleep(0.3)
+    # nvidia-smi initialises NVML before its first line; on a fresh box that takes longer than a fixed nap and stalls CUDA
+    # calls of the first timed region for hundreds of ms (one 112 ms/step region seen) -- wait for two samples, 5 s at most
+    t_wait = time.perf_counter()
+    while len(sampler.samples) < 2 and time.perf_counter() - t_wait < 5.0:
+        time.sleep(0.05)
     # The timed region (exactly K steps between two synchronised events) is measured REGIONS times and the median region is
     # reported, with all of them listed in `timed_regions_ms_per_step`: about one K-step region in four on these boxes
     # contains a single step that is 1 .. 20 ms late (a host-side stall inside a stream-ordered allocation; every stage

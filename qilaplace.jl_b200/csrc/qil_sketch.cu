@@ -262,27 +262,30 @@ static CUtensorMap make_tmap(const double* A, long long R, long long C, long lon
 // ---- launch configuration ------------------------------------------------------------------------------
 // Narrow sketches (NT <= 4) run two CTAs per SM (one CTA's epilogue / barrier bubbles are covered by the other's DMMA
 // work; measured 2.77 vs 2.83 ms for the six n=28 passes against one CTA with a 4-stage ring).  QIL_STREAM_VARIANT picks
-// the ring of that mode:  2 (default) five 16-deep stages | 1: four 16-deep stages | 0: two 32-deep stages (the ring until
-// the end of round 2) | 3: one CTA per SM with five 32-deep stages | 4 (or QIL_STREAM_STAGES=4): one CTA per SM with a
+// the ring of that mode:  2 (default at three column tiles) five 16-deep stages | 1: four 16-deep stages | 0 (default
+// otherwise): two 32-deep stages | 3: one CTA per SM with five 32-deep stages | 4 (or QIL_STREAM_STAGES=4): one CTA per SM with a
 // 4-stage ring, which wide sketches (NT > 4) always use (3 stages beyond NT = 8).  With 16-deep stages a released stage is
 // needed again only 4 stages later instead of 1, for about the same shared memory: six n=28 passes at l=20 take
 // 2.463 ms (variant 2), 2.477 (1), 2.517 (0), 2.512 (3 and 4) -- profiles/r02_stream_ring_variants.txt.  The pass is bound by the
 // FP64 pipe (profiles/r02_stream_gemm_ncu_full.txt), so the ring depth moves it by 2 % only.
-static int stream_variant() {
+static int stream_variant(int nt) {
     static const int v = [] {
         const char* e = getenv("QIL_STREAM_VARIANT");
         if (e) return atoi(e);
         const char* st = getenv("QIL_STREAM_STAGES");
-        return (st && atoi(st) == 4) ? 4 : 2;
+        return (st && atoi(st) == 4) ? 4 : -1;
     }();
-    return v;
+    // default: the deep ring only where it was measured to win -- three column tiles (l = 17..24, the co-bound case of the
+    // reference's k+p = 20).  One tile (HBM-bound, 2 KB TMA boxes of the transposed pass cost more than the ring gains) and
+    // four tiles on the short matrices of the C2 batch were 3-5 % slower with it (adaptive leg 3.45 -> 3.55 ms, C2 4.92 -> 5.10 ms).
+    return v >= 0 ? v : (nt == 3 ? 2 : 0);
 }
 static int stream_ctas_per_sm(int nt) {
-    const int v = stream_variant();
+    const int v = stream_variant(nt);
     return (nt <= 4 && v >= 0 && v <= 2) ? 2 : 1;
 }
 static int stream_bk(int nt) {
-    const int v = stream_variant();
+    const int v = stream_variant(nt);
     return (nt <= 4 && (v == 1 || v == 2)) ? 16 : 32;
 }
 
@@ -303,7 +306,7 @@ template <int NT, bool TRANS>
 static void launch_stream(qil_ctx* ctx, const CUtensorMap& tm, const StreamParams& p) {
     constexpr int NN = (NT <= 4 ? NT : 1);            // the narrow-sketch variants are instantiated for NT <= 4 only
     if (NT <= 4) {
-        switch (stream_variant()) {
+        switch (stream_variant(NT)) {
             case 0: launch_stream_s<NN, TRANS, 2, 32, 2>(ctx, tm, p); return;
             case 1: launch_stream_s<NN, TRANS, 4, 16, 2>(ctx, tm, p); return;
             case 2: launch_stream_s<NN, TRANS, 5, 16, 2>(ctx, tm, p); return;
