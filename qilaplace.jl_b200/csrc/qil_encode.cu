@@ -261,7 +261,7 @@ static Mat<T> mul_AH(SplitCtx<T>& sc, const T* A, int64_t R, int64_t C, int l, c
         for (int j0 = 0; j0 < l; j0 += lw_max) {
             const int lw = std::min(lw_max, l - j0);
             const int nt = stream_nt_for(lw * F);
-            const int lpp = stream_lpp(nt);
+            const int lpp = stream_lpp(nt, true);
             const int64_t rows_pad = (R + 31) / 32 * 32;
             Mat<double> X(ctx, rows_pad, lpp);
             prep_x_k2_kernel<T><<<grid_for(ctx, rows_pad * lpp), 256, 0, ctx->stream>>>(Q, R, lw, rows_pad, lpp, X.p, j0, l);
@@ -393,9 +393,9 @@ static int rsvd_split_fused(SplitCtx<double>& sc, const double* A, int64_t R, in
     qil_ctx* ctx = sc.ctx;
     const RsvdOpts& o = *sc.o;
     int nt = stream_nt_for(l0);
-    int lpp = stream_lpp(nt);
+    int lppC = stream_lpp(nt, false), lppR = stream_lpp(nt, true);   // XC is the K1 operand, XR the K2 operand
     const int64_t rowsR = (R + 31) / 32 * 32, rowsC = (C + 31) / 32 * 32;
-    Mat<double> XR(ctx, rowsR, lpp), XC(ctx, rowsC, lpp);
+    Mat<double> XR(ctx, rowsR, lppR), XC(ctx, rowsC, lppC);
     if (rowsR > R) QIL_CUDA(cudaMemsetAsync(XR.p, 0, XR.elems() * sizeof(double), ctx->stream));
     if (rowsC > C) QIL_CUDA(cudaMemsetAsync(XC.p, 0, XC.elems() * sizeof(double), ctx->stream));
     int ks1, ks2; long long kc1, kc2;
@@ -403,14 +403,14 @@ static int rsvd_split_fused(SplitCtx<double>& sc, const double* A, int64_t R, in
     stream_plan(ctx, C, R, &ks2, &kc2, nt);
     Mat<double> partR(ctx, (int64_t)ks1 * R, nt * 8), partC(ctx, (int64_t)ks2 * C, nt * 8);
     // ---- Y = A Omega
-    prep_x_k1_kernel<double><<<grid_for(ctx, rowsC * lpp), 256, 0, ctx->stream>>>(
-        nullptr, sc.stream, (unsigned long long)o.seed, C, l0, rowsC, lpp, XC.p);
+    prep_x_k1_kernel<double><<<grid_for(ctx, rowsC * lppC), 256, 0, ctx->stream>>>(
+        nullptr, sc.stream, (unsigned long long)o.seed, C, l0, rowsC, lppC, XC.p);
     QIL_LAUNCH_CHECK(ctx);
     const bool want_sumsq = top && !sc.nrm_ready;
     Mat<double> ssq;
     const int grid1 = stream_grid(ctx, R, ks1, nt);
     if (want_sumsq) ssq = Mat<double>(ctx, grid1, 1);
-    stream_gemm(ctx, false, A, R, C, C, XC.p, lpp, nt, partR.p, ks1, kc1, want_sumsq ? ssq.p : nullptr, l0);
+    stream_gemm(ctx, false, A, R, C, C, XC.p, lppC, nt, partR.p, ks1, kc1, want_sumsq ? ssq.p : nullptr, l0);
     if (want_sumsq) {
         finalize_norm_kernel<<<1, 32, 0, ctx->stream>>>(ssq.p, grid1, sc.d_nrm);
         QIL_LAUNCH_CHECK(ctx);
@@ -434,40 +434,41 @@ static int rsvd_split_fused(SplitCtx<double>& sc, const double* A, int64_t R, in
         if (adapt) Rtop = Mat<double>(ctx, l0, l0);
         { qil_prof_region prof_guard_(ctx, PROF_QR);
         sum_R(l0);
-        qr_fast<double>(ctx, R, l0, YR.p, l0, 1, 0, true, XR.p, lpp, lpp, adapt ? Rtop.p : nullptr);
+        qr_fast<double>(ctx, R, l0, YR.p, l0, 1, 0, true, XR.p, lppR, lppR, adapt ? Rtop.p : nullptr);
         }
         if (adapt) {
             l = shrink_sketch_width<double>(ctx, o, l0, Rtop);
             if (l < l0) {
-                const int nt2 = stream_nt_for(l), lpp2 = stream_lpp(nt2);
-                Mat<double> XR2(ctx, rowsR, lpp2), XC2(ctx, rowsC, lpp2);
+                const int nt2 = stream_nt_for(l), lppC2 = stream_lpp(nt2, false), lppR2 = stream_lpp(nt2, true);
+                Mat<double> XR2(ctx, rowsR, lppR2), XC2(ctx, rowsC, lppC2);
                 QIL_CUDA(cudaMemsetAsync(XR2.p, 0, XR2.elems() * sizeof(double), ctx->stream));
                 if (rowsC > C) QIL_CUDA(cudaMemsetAsync(XC2.p, 0, XC2.elems() * sizeof(double), ctx->stream));
-                QIL_CUDA(cudaMemcpy2DAsync(XR2.p, (size_t)lpp2 * sizeof(double), XR.p, (size_t)lpp * sizeof(double),
+                QIL_CUDA(cudaMemcpy2DAsync(XR2.p, (size_t)lppR2 * sizeof(double), XR.p, (size_t)lppR * sizeof(double),
                                            (size_t)l * sizeof(double), (size_t)R, cudaMemcpyDeviceToDevice, ctx->stream));
                 XR = std::move(XR2);
                 XC = std::move(XC2);
                 nt = nt2;
-                lpp = lpp2;
+                lppC = lppC2;
+                lppR = lppR2;
             }
         }
     }
     for (int it = 0; it < o.q; ++it) {
-        stream_gemm(ctx, true, A, R, C, C, XR.p, lpp, nt, partC.p, ks2, kc2, nullptr, l);
+        stream_gemm(ctx, true, A, R, C, C, XR.p, lppR, nt, partC.p, ks2, kc2, nullptr, l);
         { qil_prof_region prof_guard_(ctx, PROF_QR);
         sum_C(l);
-        qr_fast<double>(ctx, C, l, ZC.p, l, 1, 0, true, XC.p, lpp, lpp, nullptr);
+        qr_fast<double>(ctx, C, l, ZC.p, l, 1, 0, true, XC.p, lppC, lppC, nullptr);
         }
-        stream_gemm(ctx, false, A, R, C, C, XC.p, lpp, nt, partR.p, ks1, kc1, nullptr, l);
+        stream_gemm(ctx, false, A, R, C, C, XC.p, lppC, nt, partR.p, ks1, kc1, nullptr, l);
         { qil_prof_region prof_guard_(ctx, PROF_QR);
         sum_R(l);
-        qr_fast<double>(ctx, R, l, YR.p, l, 1, 0, true, XR.p, lpp, lpp, nullptr);
+        qr_fast<double>(ctx, R, l, YR.p, l, 1, 0, true, XR.p, lppR, lppR, nullptr);
         }
     }
     // ---- B^H = A^H Q, then the device-side tail
-    stream_gemm(ctx, true, A, R, C, C, XR.p, lpp, nt, partC.p, ks2, kc2, nullptr, l);
+    stream_gemm(ctx, true, A, R, C, C, XR.p, lppR, nt, partC.p, ks2, kc2, nullptr, l);
     sum_C(l);
-    return rsvd_tail<double>(sc, R, C, l, XR.p, lpp, ZC.p, l, 1, 0, top ? sc.d_nrm + 1 : nullptr, U, SVh, Vh, S, dev);
+    return rsvd_tail<double>(sc, R, C, l, XR.p, lppR, ZC.p, l, 1, 0, top ? sc.d_nrm + 1 : nullptr, U, SVh, Vh, S, dev);
 }
 template <typename T>
 static int rsvd_split_fused_dispatch(SplitCtx<T>&, const T*, int64_t, int64_t, bool, int, Mat<T>&, Mat<T>*, Mat<T>*,
@@ -1007,10 +1008,10 @@ static bool encode_rsvd_tree_batch(qil_ctx* ctx, const RsvdOpts& o, const double
             QIL_LAUNCH_CHECK(ctx);
         }
         // ---- top split of every signal
-        const int nt = stream_nt_for(l0), lpp = stream_lpp(nt), ldo = nt * 8;
-        Mat<double> XC(ctx, C, lpp), XCall, XRall(ctx, Rall, lpp);
-        prep_x_k1_kernel<double><<<grid_for(ctx, C * lpp), 256, 0, ctx->stream>>>(nullptr, nstream, (unsigned long long)o.seed, C,
-                                                                                l0, C, lpp, XC.p);
+        const int nt = stream_nt_for(l0), lppC = stream_lpp(nt, false), lppR = stream_lpp(nt, true), ldo = nt * 8;
+        Mat<double> XC(ctx, C, lppC), XCall, XRall(ctx, Rall, lppR);
+        prep_x_k1_kernel<double><<<grid_for(ctx, C * lppC), 256, 0, ctx->stream>>>(nullptr, nstream, (unsigned long long)o.seed, C,
+                                                                                 l0, C, lppC, XC.p);
         QIL_LAUNCH_CHECK(ctx);
         int ks1; long long kc1;
         stream_plan(ctx, Rall, C, &ks1, &kc1, nt);
@@ -1019,19 +1020,19 @@ static bool encode_rsvd_tree_batch(qil_ctx* ctx, const RsvdOpts& o, const double
             reduce_k1_kernel<double><<<grid_for(ctx, Rall * l0), 256, 0, ctx->stream>>>(partR.p, ks1, Rall, ldo, l0, Yall.p);
             QIL_LAUNCH_CHECK(ctx);
         };
-        stream_gemm(ctx, false, x_all, Rall, C, C, XC.p, lpp, nt, partR.p, ks1, kc1, nullptr, l0);
+        stream_gemm(ctx, false, x_all, Rall, C, C, XC.p, lppC, nt, partR.p, ks1, kc1, nullptr, l0);
         sum_R();
-        qr_fast<double>(ctx, R, l0, Yall.p, l0, 1, 0, true, XRall.p, lpp, lpp, nullptr, (int)count, R * l0, R * lpp, 0);
-        if (o.q > 0) XCall = Mat<double>(ctx, count * C, lpp);
+        qr_fast<double>(ctx, R, l0, Yall.p, l0, 1, 0, true, XRall.p, lppR, lppR, nullptr, (int)count, R * l0, R * lppR, 0);
+        if (o.q > 0) XCall = Mat<double>(ctx, count * C, lppC);
         for (int it = 0; it < o.q; ++it) {
             // Z_s = X_s^H Q_s: split-K with one chunk per signal -> partial s IS Z_s
-            stream_gemm(ctx, true, x_all, Rall, C, C, XRall.p, lpp, nt, partC.p, (int)count, R, nullptr, l0);
-            qr_fast<double>(ctx, C, l0, partC.p, ldo, 1, 0, true, XCall.p, lpp, lpp, nullptr, (int)count, C * ldo, C * lpp, 0);
-            stream_gemm(ctx, false, x_all, Rall, C, C, XCall.p, lpp, nt, partR.p, ks1, kc1, nullptr, l0, R, C * lpp);
+            stream_gemm(ctx, true, x_all, Rall, C, C, XRall.p, lppR, nt, partC.p, (int)count, R, nullptr, l0);
+            qr_fast<double>(ctx, C, l0, partC.p, ldo, 1, 0, true, XCall.p, lppC, lppC, nullptr, (int)count, C * ldo, C * lppC, 0);
+            stream_gemm(ctx, false, x_all, Rall, C, C, XCall.p, lppC, nt, partR.p, ks1, kc1, nullptr, l0, R, C * lppC);
             sum_R();
-            qr_fast<double>(ctx, R, l0, Yall.p, l0, 1, 0, true, XRall.p, lpp, lpp, nullptr, (int)count, R * l0, R * lpp, 0);
+            qr_fast<double>(ctx, R, l0, Yall.p, l0, 1, 0, true, XRall.p, lppR, lppR, nullptr, (int)count, R * l0, R * lppR, 0);
         }
-        stream_gemm(ctx, true, x_all, Rall, C, C, XRall.p, lpp, nt, partC.p, (int)count, R, nullptr, l0);   // B_s^H
+        stream_gemm(ctx, true, x_all, Rall, C, C, XRall.p, lppR, nt, partC.p, (int)count, R, nullptr, l0);   // B_s^H
         {
             Mat<double> Qb(ctx, count * C, l0), Rb(ctx, count * l0, l0), Us(ctx, count * l0, l0), T2(ctx, count * l0, l0);
             Mat<double> Sv(ctx, count * l0, 1);
@@ -1039,8 +1040,8 @@ static bool encode_rsvd_tree_batch(qil_ctx* ctx, const RsvdOpts& o, const double
                             (int64_t)l0 * l0);
             svd_finish<double>(ctx, l0, Rb.p, nrm.p + 1, o.cutoff, o.maxdim, o.mindim, Us.p, T2.p, Sv.p, d_state + mid + 1,
                                (int)count, 2, nb1);
-            rsvd_outputs<double>(ctx, R, C, l0, XRall.p, lpp, Qb.p, l0, Us.p, T2.p, Sv.p, d_state + mid + 1,
-                                 buf_ptr(b_utop, 0), buf_ptr(b_svtop, 0), nullptr, (int)count, R * lpp, C * l0,
+            rsvd_outputs<double>(ctx, R, C, l0, XRall.p, lppR, Qb.p, l0, Us.p, T2.p, Sv.p, d_state + mid + 1,
+                                 buf_ptr(b_utop, 0), buf_ptr(b_svtop, 0), nullptr, (int)count, R * lppR, C * l0,
                                  bufs[b_utop].size, bufs[b_svtop].size, nb1);
         }
         // ---- the tree levels

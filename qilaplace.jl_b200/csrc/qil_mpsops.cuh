@@ -55,7 +55,10 @@ namespace qil {
 int stream_nt_for(int cols);
 // pitch (doubles) of the X operand: 8*nt + 1 -- odd, so that the B-fragment loads of the DMMA consumers (rows 4t+i,
 // column g) hit 16 distinct bank pairs per half warp (8*nt + 2 gave a 2-way conflict on every load)
-inline int stream_lpp(int nt) { return nt * 8 + 1; }
+// pitch (doubles) of the small operand X of the streaming GEMM, chosen so that the B-fragment loads of a half-warp fall into
+// distinct banks: K1 reads k-rows 4t+i (pitch = 1 mod 8), K2 reads k-rows 2t + (i&1) + 8(i>>1) (pitch = 2 mod 8), the order
+// that also makes its A-fragment loads from the 128B-swizzled transposed boxes conflict-free (qil_sketch.cu)
+inline int stream_lpp(int nt, bool trans = false) { return nt * 8 + (trans ? 2 : 1); }
 bool stream_supported(long long R, long long C, long long ld, int cols);
 void stream_plan(qil_ctx* ctx, long long Mtot, long long Kdim, int* ksplit, long long* kchunk, int nt = 1);
 int stream_grid(qil_ctx* ctx, long long Mtot, int ksplit, int nt);

@@ -180,11 +180,15 @@ stream_gemm_kernel(const __grid_constant__ CUtensorMap tmA, const StreamParams p
                         af[0] = v00.x; af[2] = v00.y; af[4] = v01.x; af[6] = v01.y;
                         af[1] = v10.x; af[3] = v10.y; af[5] = v11.x; af[7] = v11.y;
                     } else {
-                        // box `warp`: BK k-rows x 16 output columns; rows kb*16 + 4t + i, columns g and g+8
+                        // box `warp`: BK k-rows x 16 output columns, columns g and g+8.  The sum over k does not care which
+                        // k-row a thread takes as long as A and B agree: element i of thread t is k-row 2t + (i&1) + 8(i>>1)
+                        // instead of the fragment's natural 4t + i, so that the four rows one load touches in a half-warp
+                        // (t = 0..3) sit in four different phases of the 128B swizzle -> no bank conflicts (the natural order
+                        // put t and t+2 on the same banks: 29 % of this pass's shared-memory wavefronts were replays)
                         const unsigned char* box = a + warp * (BK * 128);
 #pragma unroll
                         for (int i = 0; i < 4; ++i) {
-                            const int row = kb * 16 + 4 * t + i;
+                            const int row = kb * 16 + 2 * t + (i & 1) + 8 * (i >> 1);
                             const unsigned char* rp = box + row * 128;
                             af[2 * i] = *reinterpret_cast<const double*>(rp + ((((g) >> 1) ^ (row & 7)) << 4) + ((g & 1) << 3));
                             af[2 * i + 1] = *reinterpret_cast<const double*>(rp + ((((g + 8) >> 1) ^ (row & 7)) << 4) + ((g & 1) << 3));
@@ -194,12 +198,14 @@ stream_gemm_kernel(const __grid_constant__ CUtensorMap tmA, const StreamParams p
 #pragma unroll
                         for (int i = 0; i < 8; ++i) ssq = fma(af[i], af[i], ssq);
                     }
-                    const double* xr = xs + (size_t)(kb * 16 + 4 * t) * p.lpp + g;
+                    // B fragment: k-rows 4t + i (K1) or the permuted rows of the A fragment above (K2); the pitch of X
+                    // (stream_lpp) spreads either set over distinct banks
+                    const double* xr = xs + (size_t)(kb * 16 + (TRANS ? 2 : 4) * t) * p.lpp + g;
 #pragma unroll
                     for (int nt = 0; nt < NT; ++nt) {
                         double bf[4];
 #pragma unroll
-                        for (int i = 0; i < 4; ++i) bf[i] = xr[(size_t)i * p.lpp + nt * 8];
+                        for (int i = 0; i < 4; ++i) bf[i] = xr[(size_t)(TRANS ? ((i & 1) + 8 * (i >> 1)) : i) * p.lpp + nt * 8];
                         dmma16816(acc[nt], af, bf);
                     }
                 }
