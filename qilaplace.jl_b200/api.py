@@ -10,7 +10,6 @@ from __future__ import annotations
 import ctypes as C
 import math
 import re
-import weakref
 
 import numpy as np
 
@@ -35,7 +34,8 @@ class Context:
         else:
             call("qil_create_on_stream", int(device), C.c_void_p(int(stream)), C.byref(self.handle))
         self.device = int(device)
-        self._chains = weakref.WeakSet()   # live SignalMPS / MPO objects: released before the context goes
+        self._live = 0                 # SignalMPS / MPO objects that still hold a handle into this context
+        self._close_pending = False
 
     def sync(self):
         call("qil_sync", self.handle)
@@ -70,16 +70,28 @@ class Context:
         return float(t.value), int(c.value), float(b.value), float(f.value)
 
     def close(self):
-        """Destroy the context.  Chains that still hang off it are released first (their handles point into the
-        context), and become unusable: any later call on them raises instead of dereferencing a freed qil_ctx."""
+        """Destroy the context -- now if nothing hangs off it, otherwise as soon as the last SignalMPS / MPO that holds a
+        handle into it is released (their handles point into the qil_ctx, so it must outlive them).  A plain counter:
+        creating a chain costs one integer increment (a batch step creates hundreds)."""
+        if not self.handle:
+            return
+        for dev, c in list(_default_ctx.items()):
+            if c is self:
+                del _default_ctx[dev]
+        if self._live > 0:
+            self._close_pending = True
+            return
+        self._destroy()
+
+    def _destroy(self):
         if self.handle:
-            for ch in list(self._chains):
-                ch._release()
             _lib.load().qil_destroy(self.handle)
             self.handle = None
-            for dev, c in list(_default_ctx.items()):
-                if c is self:
-                    del _default_ctx[dev]
+        self._close_pending = False
+
+    @property
+    def closed(self):
+        return self.handle is None
 
 
 _default_ctx = {}
@@ -122,9 +134,9 @@ class _DeviceChain:
     def __init__(self, ctx, handle):
         self.ctx = ctx
         self.handle = handle
-        ctx._chains.add(self)
+        ctx._live += 1
 
-    def _release(self):
+    def __del__(self):
         h = getattr(self, "handle", None)
         if h:
             try:
@@ -132,9 +144,13 @@ class _DeviceChain:
             except Exception:
                 pass
             self.handle = None
-
-    def __del__(self):
-        self._release()
+            ctx = self.ctx
+            ctx._live -= 1
+            if ctx._close_pending and ctx._live <= 0:
+                try:
+                    ctx._destroy()
+                except Exception:
+                    pass
 
     def _bond_dims(self):
         n = self.nsites_flat

@@ -349,19 +349,24 @@ def test_two_contexts_on_two_devices(q):
     assert np.abs(res[0][1] - res[1][1]).max() <= 1e-12 * np.abs(x).max()
 
 
-def test_context_close_releases_live_chains(q):
-    """Closing a context while SignalMPS / MPO objects are alive releases them first; later use raises instead of
-    dereferencing a freed qil_ctx (round-1 advisor finding)."""
+def test_context_close_waits_for_live_chains(q):
+    """Closing a context while SignalMPS / MPO objects are alive must not leave them with a dangling qil_ctx (round-1
+    advisor finding): the destroy is deferred until the last handle into the context is released."""
     ctx = q.Context(0)
     x = q.generate_signal(10, kind="sin", freq=3.0)
     psi = q.signal_mps(x, ctx=ctx)
     W = q.build_qft_mpo(10, ctx=ctx)
-    assert psi.handle and W.handle
     ctx.close()
-    assert psi.handle is None and W.handle is None and ctx.handle is None
-    with pytest.raises(Exception):
-        q.coefficients(psi, np.zeros((1, 10), dtype=np.uint8))
-    del psi, W                                      # __del__ on released chains is a no-op
+    assert not ctx.closed                           # two chains still point into it
+    out = W * psi                                   # ... and stay usable
+    assert len(out.bonds) == 9
+    del out, psi
+    assert not ctx.closed
+    del W
+    assert ctx.closed                               # the last release destroyed it
     ctx2 = q.Context(0)                             # the device is still usable
     assert len(q.signal_mps(x, ctx=ctx2).bonds) == 9
     ctx2.close()
+    ctx3 = q.Context(0)
+    ctx3.close()
+    assert ctx3.closed                              # nothing alive: closed at once
