@@ -856,6 +856,10 @@ def run_ours(args):
         "launches_per_step": g_cnt / args.steps, "avg_launch_ms": gemm_ms, "share_of_step": g_ms / ms_dev,
         "fp64_tflops": flops / (g_ms / 1e3) / 1e12, "fp64_peak_tflops_measured_dmma": 37.1,
         "fp64_frac": flops / (g_ms / 1e3) / 1e12 / 37.1,
+        "note": ("at l = k+p = 20 the pass has two floors of nearly the same height: HBM (8*2^n bytes at the measured copy rate) and the "
+                 "FP64 tensor pipe, which must execute 24 padded columns (3 n8 tiles) -- the higher one; ncu: DMMA path 82-84 % of peak, "
+                 "math_pipe_throttle the dominant stall (profiles/r02_stream_gemm_ncu_full.txt).  frac is against HBM, fp64_frac "
+                 "counts the 20 algorithmic columns against the measured 37.1 TFLOP/s"),
         "coefficient_kernel": {"avg_launch_ms": coeff_ms, "coefficients_per_s": B / (coeff_ms / 1e3) if coeff_ms else None,
                                "algorithmic_GBps": coeff_bytes * B / (coeff_ms / 1e3) / 1e9 if coeff_ms else None,
                                "executed_tflops": (coeff_bytes / 2.0) * B / (coeff_ms / 1e3) / 1e12 if coeff_ms else None},
