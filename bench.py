@@ -933,7 +933,6 @@ def run_ours(args):
             del js, ts
             xs_pin = torch.empty(NLs, dtype=torch.float64, pin_memory=True)
             xs_pin.copy_(xs_dev)
-            xs_stage = torch.empty(NLs, dtype=torch.float64, device=dev)
             sstate = {}
 
             def step_sharded():
@@ -941,25 +940,51 @@ def run_ours(args):
                 sstate["psi"] = ps
                 sstate["out"] = q.apply(W, q.ztmps_from_mps(ps, cutoff=ALGO["cutoff"]))
 
+            xs_pin_ptr = xs_pin.data_ptr()
+            up = {}
+
             def step_sharded_e2e():
-                xs_stage.copy_(xs_pin, non_blocking=True)
-                ps = parallel.signal_mps_sharded_dev(scomm, xs_stage.data_ptr(), N, False, **ALGO)
+                up_s = up["s"]
+                if up_s.inflight == 0:
+                    up_s.submit(xs_pin_ptr, 8 * NLs)
+                d_xs = up_s.acquire()
+                up_s.submit(xs_pin_ptr, 8 * NLs)     # the next step's chunk crosses PCIe while this one is encoded
+                ps = parallel.signal_mps_sharded_dev(scomm, d_xs, N, False, **ALGO)
+                up_s.release()
                 o2 = q.apply(W, q.ztmps_from_mps(ps, cutoff=ALGO["cutoff"]))
                 sstate["host_cores"] = o2.cores_into(cores_pin)
 
+            def drain_sharded():
+                up["s"].acquire(); up["s"].release()   # the upload the last step started is awaited inside the timed region
+
             for _ in range(3):
                 step_sharded()
-            ms_sh = timed(step_sharded, args.steps) / args.steps
+            # median of three K-step regions, like the headline (a single region now and then contains one late step)
+            sh_regions = sorted(timed(step_sharded, args.steps) / args.steps for _ in range(3))
+            ms_sh = sh_regions[1]
+            up["s"] = q.Uploader(ctx, 8 * NLs)       # this rank's chunk, double-buffered behind the C ABI like the N=1 e2e
             for _ in range(2):
                 step_sharded_e2e()
-            ms_sh_e2e = timed(step_sharded_e2e, args.steps) / args.steps
+            def e2e_region():
+                # every region starts like the first one: one upload already in flight (submitted here, outside the region;
+                # the barrier that opens the region waits for it), so that a region holds exactly K uploads, not K + 1
+                if up["s"].inflight == 0:
+                    up["s"].submit(xs_pin_ptr, 8 * NLs)
+                return timed(step_sharded_e2e, args.steps, drain_sharded) / args.steps
+
+            sh_e2e_regions = sorted(e2e_region() for _ in range(3))
+            ms_sh_e2e = sh_e2e_regions[1]
+            up["s"].close()
             line["sharded"] = {
                 "what": f"ONE n={n} signal row-sharded over {world} ranks (qil_encode_rsvd_sharded_dev: TSQR all-gather + "
                         f"projection all-reduce over " + ("NVLink peer memory, library kernels" if args.comm == "peer"
                                                           else "NCCL") + "), then split + zT apply; strong scaling",
                 "scaling": "strong", "ms_per_step": ms_sh, "samples_per_s": N / (ms_sh / 1e3),
+                "timed_regions_ms_per_step": [round(v, 4) for v in sh_regions],
+                "e2e_timed_regions_ms_per_step": [round(v, 4) for v in sh_e2e_regions],
                 "e2e_ms_per_step": ms_sh_e2e, "e2e_samples_per_s": N / (ms_sh_e2e / 1e3),
                 "h2d_bytes_per_step_per_rank": int(8 * NLs),
+                "e2e_pipelining": "each rank's chunk double-buffered behind the C ABI (qil_uploader_*), as in the N=1 e2e",
                 "bonds_equal_single_gpu": sstate["psi"].bonds == psi.bonds,
                 "speedup_vs_one_signal_on_one_rank": ms_step / ms_sh}
             if args.comm == "peer":
