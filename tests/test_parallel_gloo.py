@@ -69,7 +69,8 @@ def _worker_sharded(rank, world, port, ret):
     import sharded_ref
     dist.init_process_group("gloo", rank=rank, world_size=world)
     try:
-        for n, cplx, qit in ((12, False, 2), (13, True, 1)):
+        # every rank needs at least l = k + p = 20 rows of the 2^(n/2)-row top-level matrix
+        for n, cplx, qit in (((12, False, 2), (13, True, 1)) if world <= 2 else ((14, False, 2), (15, True, 1))):
             N = 2**n
             t = np.arange(N) / (2.5 * N)
             x = np.sin(1.0 * t) * np.exp(-0.08 * t) + np.sin(2.5 * t) * np.exp(-0.03 * t)
@@ -87,13 +88,14 @@ def _worker_sharded(rank, world, port, ret):
         dist.destroy_process_group()
 
 
-def test_row_sharded_encode_formulation_over_gloo():
+@pytest.mark.parametrize("world", [2, 4])
+def test_row_sharded_encode_formulation_over_gloo(world):
     """The exchange steps of the row-sharded top split (TSQR all-gather of R factors, all-reduce of the partial
-    projections, all-gather of U) reproduce the single-process oracle: identical bonds, amplitudes to 1e-10."""
+    projections, all-gather of U) reproduce the single-process oracle: identical bonds, amplitudes to 1e-10 -- at 2 and at
+    4 ranks (the bench signal family, whose closest cutoff decision once flipped a bond at 4 ranks with an unordered sum)."""
     import torch.multiprocessing as mp
-    world = 2
-    port = 31500 + (os.getpid() % 2000)
+    port = 31500 + (os.getpid() % 2000) + 7 * world
     mgr = mp.Manager()
     ret = mgr.dict()
     mp.spawn(_worker_sharded, args=(world, port, ret), nprocs=world, join=True)
-    assert dict(ret) == {0: "ok", 1: "ok"}
+    assert dict(ret) == {r: "ok" for r in range(world)}
