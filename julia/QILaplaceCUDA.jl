@@ -103,8 +103,9 @@ function signal_mps(x::AbstractVector{<:Number}; method::Symbol=:svd, cutoff::Re
                      (Ptr{Cvoid}, Cint, Ptr{Cvoid}, Int64, Cdouble, Int64, Ref{Ptr{Cvoid}}),
                      ctx(), _iscomplex(T), xv, length(xv), cutoff, _maxdim(maxdim), out))
     else
-        # same side effect as the reference: the global RNG is reseeded (rsvd.jl:74); the normal stream is the
-        # one `random_itensor(eltype, cR, alpha)` would consume, so Omega matches the reference bit for bit
+        # same side effect as the reference: the global RNG is reseeded (rsvd.jl:74).  The normal stream is MEANT to be the
+        # one `random_itensor(eltype, cR, alpha)` would consume (column-major fill, Omega[c, j] = stream[c + C*(j-1)]); that
+        # this reproduces the reference's Omega bit for bit is a CLAIM nobody has run (no Julia in the build image)
         Random.seed!(random_seed)
         cols_top = 2^(n - n ÷ 2)
         stream = randn(T, cols_top * min(k + p, cols_top))
