@@ -229,6 +229,8 @@ def run_reference(args):
         "e2e": {"value": value, "unit": unit, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
         "coefficients_per_s": detail.get("coefficients_per_s") if detail else None,
         "gpu_launches": 0,
+        "note": ("one host, one signal per step whatever --gpus is: the CPU arm does not scale with N (rank 0 alone runs it "
+                 "with every host core), so its value is the same at every N"),
     }
     print(json.dumps(line))
 
